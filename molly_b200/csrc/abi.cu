@@ -1,0 +1,335 @@
+// extern "C" surface declared in include/molly_b200.h.  Orchestrates the per-layer kernel sequence of the encoder
+// (HF EsmModel.forward, HF:615-677 -> EsmEncoder.forward, HF:494-514 -> EsmLayer, HF:446-482) on one stream.
+#include <math.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/molly_b200.h"
+#include "common.h"
+#include "kernels.h"
+
+using namespace molly;
+
+struct molly_encoder {
+    molly_encoder_config cfg;
+    molly_encoder_weights w;                     // scalar members + pointers into the vectors below
+    std::vector<const float*> ln1_w, ln1_b, b_qkv, b_o, ln2_w, ln2_b, b_ffn1, b_ffn2;
+    std::vector<const void*> w_qkv, w_o, w_ffn1, w_ffn2;
+    std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_w1, tm_w2;   // weight (B operand) tensor maps, built once
+    CUtensorMap tm_wproj;
+    int ffn1_n;                                  // F (gelu) or 2F (glu)
+    float q_scale;                               // head_dim^-1/2
+    // activation tensor maps depend on (workspace, n_seq, K): cached for the last plan
+    struct Plan {
+        void* ws = nullptr;
+        int n_seq = 0, k = 0;
+        void* final_out = nullptr;
+        CUtensorMap tm_xn, tm_attn, tm_mid, tm_qkv, tm_final;
+    } plan;
+};
+
+namespace {
+
+constexpr size_t kAlign = 1024;
+size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+struct Workspace {
+    size_t off_x, off_xn, off_qkv, off_attn, off_mid, off_kvinfo, off_mask, total;
+};
+
+Workspace layout(const molly_encoder_config& c, int n_seq, int k) {
+    const size_t M = static_cast<size_t>(n_seq) * k, h = c.hidden_size, F = c.intermediate_size;
+    Workspace w;
+    size_t o = 0;
+    w.off_x = o;      o += align_up(M * h * 4);
+    w.off_xn = o;     o += align_up(M * h * 2);
+    w.off_qkv = o;    o += align_up(M * 3 * h * 2);
+    w.off_attn = o;   o += align_up(M * h * 2);
+    w.off_mid = o;    o += align_up(M * F * 2);
+    w.off_kvinfo = o; o += align_up(static_cast<size_t>(n_seq) * 2 * 4);
+    w.off_mask = o;   o += align_up(M);
+    w.total = o;
+    return w;
+}
+
+int validate_cfg(const molly_encoder_config& c) {
+    MOLLY_CHECK(c.hidden_size > 0 && c.num_layers > 0 && c.num_heads > 0 && c.intermediate_size > 0 && c.vocab_size > 0,
+                MOLLY_ERR_INVALID, "encoder config has non-positive sizes");
+    MOLLY_CHECK(c.hidden_size % c.num_heads == 0, MOLLY_ERR_INVALID, "hidden_size %d not divisible by heads %d",
+                c.hidden_size, c.num_heads);
+    const int d = c.hidden_size / c.num_heads;
+    MOLLY_CHECK(d == 16 || d == 32 || d == 64 || d == 128, MOLLY_ERR_UNSUPPORTED, "head_dim %d not in {16,32,64,128}", d);
+    MOLLY_CHECK(c.hidden_size % 32 == 0 && c.intermediate_size % 32 == 0 && c.llm_hidden_size % 32 == 0,
+                MOLLY_ERR_UNSUPPORTED, "hidden / intermediate / llm hidden sizes must be multiples of 32");
+    MOLLY_CHECK(c.hidden_size <= 2560, MOLLY_ERR_UNSUPPORTED, "hidden_size %d > 2560 (LayerNorm register tile)", c.hidden_size);
+    MOLLY_CHECK(c.position_type == MOLLY_POS_ROTARY || c.position_type == MOLLY_POS_ABSOLUTE, MOLLY_ERR_INVALID,
+                "unknown position_type %d", c.position_type);
+    MOLLY_CHECK(c.ffn_type == MOLLY_FFN_GELU || c.ffn_type == MOLLY_FFN_GLU, MOLLY_ERR_INVALID, "unknown ffn_type %d",
+                c.ffn_type);
+    return MOLLY_OK;
+}
+
+int build_plan(molly_encoder* e, void* ws, int n_seq, int k, void* final_out) {
+    auto& p = e->plan;
+    if (p.ws == ws && p.n_seq == n_seq && p.k == k && p.final_out == final_out) return MOLLY_OK;
+    const auto& c = e->cfg;
+    const Workspace L = layout(c, n_seq, k);
+    const int M = n_seq * k, h = c.hidden_size, F = c.intermediate_size;
+    auto* base = static_cast<uint8_t*>(ws);
+    int rc;
+    if ((rc = gemm_make_map_a(&p.tm_xn, base + L.off_xn, h, M, h))) return rc;
+    if ((rc = gemm_make_map_a(&p.tm_attn, base + L.off_attn, h, M, h))) return rc;
+    if ((rc = gemm_make_map_a(&p.tm_mid, base + L.off_mid, F, M, F))) return rc;
+    if ((rc = attention_make_map(&p.tm_qkv, base + L.off_qkv, M, h, c.num_heads))) return rc;
+    if ((rc = gemm_make_map_a(&p.tm_final, final_out, h, M, h))) return rc;
+    p.ws = ws; p.n_seq = n_seq; p.k = k; p.final_out = final_out;
+    return MOLLY_OK;
+}
+
+// Encoder forward up to and including emb_layer_norm_after; result (bf16 [M,h]) lands in `final_out`.
+int encode(molly_encoder* e, const int64_t* ids, int n_seq, int k, void* final_out, void* ws, size_t ws_bytes,
+           int32_t* err_flag, cudaStream_t stream) {
+    const auto& c = e->cfg;
+    MOLLY_CHECK(ids != nullptr && ws != nullptr && final_out != nullptr, MOLLY_ERR_INVALID, "encode: NULL pointer");
+    MOLLY_CHECK(n_seq > 0 && k > 0, MOLLY_ERR_INVALID, "encode: n_seq=%d k_tokens=%d", n_seq, k);
+    MOLLY_CHECK((reinterpret_cast<uintptr_t>(ws) & (kAlign - 1)) == 0, MOLLY_ERR_INVALID, "workspace must be 1024-B aligned");
+    const Workspace L = layout(c, n_seq, k);
+    MOLLY_CHECK(ws_bytes >= L.total, MOLLY_ERR_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, L.total);
+    if (c.position_type == MOLLY_POS_ROTARY)
+        MOLLY_CHECK(e->w.rope_len >= k && e->w.rope_cos_dev && e->w.rope_sin_dev, MOLLY_ERR_INVALID,
+                    "rotary tables cover %d positions < k_tokens %d", e->w.rope_len, k);
+    int rc = build_plan(e, ws, n_seq, k, final_out);
+    if (rc) return rc;
+    const auto& p = e->plan;
+    const int M = n_seq * k, h = c.hidden_size, F = c.intermediate_size;
+    auto* base = static_cast<uint8_t*>(ws);
+    float* x = reinterpret_cast<float*>(base + L.off_x);
+    void* xn = base + L.off_xn;
+    void* qkv = base + L.off_qkv;
+    void* attn = base + L.off_attn;
+    void* mid = base + L.off_mid;
+    int32_t* kv_info = reinterpret_cast<int32_t*>(base + L.off_kvinfo);
+    uint8_t* key_mask = base + L.off_mask;
+
+    EmbedArgs ea{h, c.vocab_size, c.pad_token_id, c.mask_token_id, c.position_type, c.max_positions, c.token_dropout,
+                 c.emb_layer_norm_before ? 0 : 1};
+    if ((rc = embed_launch(ids, n_seq, k, ea, e->w.word_emb_dev, e->w.pos_emb_dev, x, kv_info, key_mask, err_flag, stream)))
+        return rc;
+    if (c.emb_layer_norm_before) {     // HF:229-233: LayerNorm, then multiply by the attention mask
+        if ((rc = layernorm_launch(x, e->w.emb_ln_w_dev, e->w.emb_ln_b_dev, M, h, c.layer_norm_eps, x, DT_F32, stream)))
+            return rc;
+        if ((rc = mask_rows_launch(x, key_mask, M, h, stream))) return rc;
+    }
+    for (int l = 0; l < c.num_layers; ++l) {
+        // --- attention block: x = x + Wo * Attn(LN(x)) + bo   (HF:386-403)
+        if ((rc = layernorm_launch(x, e->ln1_w[l], e->ln1_b[l], M, h, c.layer_norm_eps, xn, DT_BF16, stream))) return rc;
+        // q, k, v = Linear(LN(x)); q *= d^-1/2 BEFORE rotary (HF:329-341) -- folded into the epilogue of one fused GEMM
+        if ((rc = gemm_launch(p.tm_xn, e->tm_wqkv[l], M, 3 * h, h, EPI_BIAS, e->b_qkv[l], nullptr, qkv, DT_BF16, 3 * h,
+                              nullptr, 0, 0, 0, 0, nullptr, stream, h, e->q_scale)))
+            return rc;
+        if (c.position_type == MOLLY_POS_ROTARY)
+            if ((rc = rotary_launch(qkv, M, k, h, c.num_heads, e->w.rope_cos_dev, e->w.rope_sin_dev, stream))) return rc;
+        if ((rc = attention_launch(p.tm_qkv, n_seq, k, h, c.num_heads, kv_info, key_mask, attn, stream))) return rc;
+        if ((rc = gemm_launch(p.tm_attn, e->tm_wo[l], M, h, h, EPI_BIAS_RESID, e->b_o[l], x, x, DT_F32, h, nullptr, 0, 0,
+                              0, 0, nullptr, stream)))
+            return rc;
+        // --- feed-forward block: x = x + W2 * act(W1 * LN(x) + b1) + b2   (HF:478-482)
+        if ((rc = layernorm_launch(x, e->ln2_w[l], e->ln2_b[l], M, h, c.layer_norm_eps, xn, DT_BF16, stream))) return rc;
+        const int epi1 = c.ffn_type == MOLLY_FFN_GLU ? EPI_GLU : EPI_BIAS_GELU;
+        if ((rc = gemm_launch(p.tm_xn, e->tm_w1[l], M, e->ffn1_n, h, epi1, e->b_ffn1[l], nullptr, mid, DT_BF16, F,
+                              nullptr, 0, 0, 0, 0, nullptr, stream)))
+            return rc;
+        if ((rc = gemm_launch(p.tm_mid, e->tm_w2[l], M, h, F, EPI_BIAS_RESID, e->b_ffn2[l], x, x, DT_F32, h, nullptr, 0,
+                              0, 0, 0, nullptr, stream)))
+            return rc;
+    }
+    // emb_layer_norm_after (HF:511-512) -> hidden_states[-1] (omics_one.py:91)
+    return layernorm_launch(x, e->w.final_ln_w_dev, e->w.final_ln_b_dev, M, h, c.layer_norm_eps, final_out, DT_BF16, stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* molly_last_error(void) { return get_last_error(); }
+int molly_abi_version(void) { return MOLLY_ABI_VERSION; }
+int molly_kernel_launch_count(void) { return launch_count(); }
+
+int molly_encoder_create(const molly_encoder_config* cfg, const molly_encoder_weights* w, molly_encoder_t** out) {
+    MOLLY_CHECK(cfg && w && out, MOLLY_ERR_INVALID, "molly_encoder_create: NULL argument");
+    int rc = validate_cfg(*cfg);
+    if (rc) return rc;
+    const int L = cfg->num_layers, h = cfg->hidden_size, F = cfg->intermediate_size, D = cfg->llm_hidden_size;
+    MOLLY_CHECK(w->word_emb_dev && w->final_ln_w_dev && w->final_ln_b_dev && w->w_proj_dev, MOLLY_ERR_INVALID,
+                "molly_encoder_create: missing weights");
+    MOLLY_CHECK(w->ln1_w_dev && w->ln1_b_dev && w->w_qkv_dev && w->b_qkv_dev && w->w_attn_out_dev && w->b_attn_out_dev &&
+                    w->ln2_w_dev && w->ln2_b_dev && w->w_ffn1_dev && w->b_ffn1_dev && w->w_ffn2_dev && w->b_ffn2_dev,
+                MOLLY_ERR_INVALID, "molly_encoder_create: missing per-layer pointer arrays");
+    if (cfg->emb_layer_norm_before)
+        MOLLY_CHECK(w->emb_ln_w_dev && w->emb_ln_b_dev, MOLLY_ERR_INVALID, "emb_layer_norm_before needs emb_ln weights");
+    if (cfg->position_type == MOLLY_POS_ABSOLUTE)
+        MOLLY_CHECK(w->pos_emb_dev != nullptr, MOLLY_ERR_INVALID, "absolute positions need pos_emb");
+    auto* e = new (std::nothrow) molly_encoder();
+    MOLLY_CHECK(e != nullptr, MOLLY_ERR_INVALID, "out of host memory");
+    e->cfg = *cfg;
+    e->w = *w;
+    e->ffn1_n = cfg->ffn_type == MOLLY_FFN_GLU ? 2 * F : F;
+    e->q_scale = 1.0f / sqrtf(static_cast<float>(cfg->hidden_size / cfg->num_heads));
+    auto copyf = [&](std::vector<const float*>& dst, const float* const* src) { dst.assign(src, src + L); };
+    auto copyv = [&](std::vector<const void*>& dst, const void* const* src) { dst.assign(src, src + L); };
+    copyf(e->ln1_w, w->ln1_w_dev); copyf(e->ln1_b, w->ln1_b_dev); copyf(e->b_qkv, w->b_qkv_dev);
+    copyf(e->b_o, w->b_attn_out_dev); copyf(e->ln2_w, w->ln2_w_dev); copyf(e->ln2_b, w->ln2_b_dev);
+    copyf(e->b_ffn1, w->b_ffn1_dev); copyf(e->b_ffn2, w->b_ffn2_dev);
+    copyv(e->w_qkv, w->w_qkv_dev); copyv(e->w_o, w->w_attn_out_dev); copyv(e->w_ffn1, w->w_ffn1_dev);
+    copyv(e->w_ffn2, w->w_ffn2_dev);
+    e->tm_wqkv.resize(L); e->tm_wo.resize(L); e->tm_w1.resize(L); e->tm_w2.resize(L);
+    for (int l = 0; l < L && rc == 0; ++l) {
+        if (!e->w_qkv[l] || !e->w_o[l] || !e->w_ffn1[l] || !e->w_ffn2[l] || !e->ln1_w[l] || !e->ln1_b[l] || !e->ln2_w[l] ||
+            !e->ln2_b[l] || !e->b_qkv[l] || !e->b_o[l]) {
+            set_last_error("molly_encoder_create: NULL weight pointer in a layer");
+            rc = MOLLY_ERR_INVALID;
+            break;
+        }
+        if (cfg->ffn_type == MOLLY_FFN_GELU && (!e->b_ffn1[l] || !e->b_ffn2[l])) {
+            set_last_error("molly_encoder_create: GELU FFN needs biases");
+            rc = MOLLY_ERR_INVALID;
+            break;
+        }
+        if ((rc = gemm_make_map_b(&e->tm_wqkv[l], e->w_qkv[l], h, 3 * h, h))) break;
+        if ((rc = gemm_make_map_b(&e->tm_wo[l], e->w_o[l], h, h, h))) break;
+        if ((rc = gemm_make_map_b(&e->tm_w1[l], e->w_ffn1[l], h, e->ffn1_n, h))) break;
+        if ((rc = gemm_make_map_b(&e->tm_w2[l], e->w_ffn2[l], F, h, F))) break;
+    }
+    if (rc == 0) rc = gemm_make_map_b(&e->tm_wproj, w->w_proj_dev, h, D, h);
+    if (rc) { delete e; return rc; }
+    *out = e;
+    return MOLLY_OK;
+}
+
+void molly_encoder_destroy(molly_encoder_t* enc) { delete enc; }
+
+size_t molly_encoder_workspace_bytes(const molly_encoder_t* enc, int32_t n_seq, int32_t k_tokens) {
+    if (!enc || n_seq <= 0 || k_tokens <= 0) return 0;
+    return layout(enc->cfg, n_seq, k_tokens).total;
+}
+
+int molly_encode_fwd(molly_encoder_t* enc, const int64_t* ids_dev, int32_t n_seq, int32_t k_tokens, void* out_dev,
+                     void* workspace_dev, size_t workspace_bytes, int32_t* err_flag_dev, void* stream) {
+    MOLLY_CHECK(enc != nullptr, MOLLY_ERR_INVALID, "molly_encode_fwd: NULL encoder");
+    return encode(enc, ids_dev, n_seq, k_tokens, out_dev, workspace_dev, workspace_bytes, err_flag_dev,
+                  static_cast<cudaStream_t>(stream));
+}
+
+int molly_encode_project_merge_fwd(molly_encoder_t* enc, const int64_t* ids_dev, const int32_t* seq_table_dev,
+                                   int32_t n_seq, int32_t k_tokens, void* hidden_states_dev, int32_t hs_dtype,
+                                   int32_t B, int32_t T, int32_t D, void* workspace_dev, size_t workspace_bytes,
+                                   int32_t* err_flag_dev, void* enc_out_save_dev, void* stream) {
+    MOLLY_CHECK(enc != nullptr, MOLLY_ERR_INVALID, "molly_encode_project_merge_fwd: NULL encoder");
+    MOLLY_CHECK(seq_table_dev && hidden_states_dev, MOLLY_ERR_INVALID, "molly_encode_project_merge_fwd: NULL pointer");
+    MOLLY_CHECK(D == enc->cfg.llm_hidden_size, MOLLY_ERR_INVALID, "hidden_states D=%d != projector out_features %d", D,
+                enc->cfg.llm_hidden_size);
+    MOLLY_CHECK(hs_dtype == MOLLY_DTYPE_BF16 || hs_dtype == MOLLY_DTYPE_F32, MOLLY_ERR_INVALID, "bad hs_dtype %d", hs_dtype);
+    MOLLY_CHECK(B > 0 && T > 0, MOLLY_ERR_INVALID, "B=%d T=%d", B, T);
+    auto s = static_cast<cudaStream_t>(stream);
+    const Workspace L = layout(enc->cfg, n_seq > 0 ? n_seq : 1, k_tokens > 0 ? k_tokens : 1);
+    void* final_out = enc_out_save_dev ? enc_out_save_dev : static_cast<uint8_t*>(workspace_dev) + L.off_xn;
+    int rc = encode(enc, ids_dev, n_seq, k_tokens, final_out, workspace_dev, workspace_bytes, err_flag_dev, s);
+    if (rc) return rc;
+    // projector + merge: hidden[b, start+1+j, :] = LN_out[n*K+j, :] Wp^T + bp  for j < min(K cap, K)  (omics_one.py:91-97)
+    const int k_cap = enc->cfg.project_token_num < k_tokens ? enc->cfg.project_token_num : k_tokens;
+    return gemm_launch(enc->plan.tm_final, enc->tm_wproj, n_seq * k_tokens, D, enc->cfg.hidden_size, EPI_SCATTER,
+                       enc->w.b_proj_dev, nullptr, hidden_states_dev, hs_dtype, D, seq_table_dev, k_tokens, B, T, k_cap,
+                       err_flag_dev, s);
+}
+
+int molly_pool_fwd(const void* enc_out_dev, const int64_t* ids_dev, int32_t n_seq, int32_t k_tokens, int32_t h,
+                   int32_t mode, float* out_dev, void* stream) {
+    MOLLY_CHECK(enc_out_dev && ids_dev && out_dev && n_seq > 0 && k_tokens > 0 && h > 0, MOLLY_ERR_INVALID,
+                "molly_pool_fwd: bad argument");
+    return pool_launch(enc_out_dev, ids_dev, n_seq, k_tokens, h, mode, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int molly_placeholder_scan(const int64_t* input_ids_dev, int32_t B, int32_t T, const int64_t pad_token_ids[3],
+                           int32_t* out_pos_dev, int32_t* out_kind_dev, int32_t* out_counts_dev, void* stream) {
+    MOLLY_CHECK(input_ids_dev && pad_token_ids && out_pos_dev && out_kind_dev && out_counts_dev, MOLLY_ERR_INVALID,
+                "molly_placeholder_scan: NULL pointer");
+    return placeholder_scan_launch(input_ids_dev, B, T, pad_token_ids[0], pad_token_ids[1], pad_token_ids[2], out_pos_dev,
+                                   out_kind_dev, out_counts_dev, static_cast<cudaStream_t>(stream));
+}
+
+int molly_project_bwd(molly_encoder_t* enc, void* d_hidden_dev, int32_t hs_dtype, const int32_t* seq_table_dev,
+                      int32_t n_seq, int32_t k_tokens, int32_t B, int32_t T, int32_t D, const void* enc_out_save_dev,
+                      float* d_weight_dev, float* d_bias_dev, int32_t zero_rows, void* workspace_dev,
+                      size_t workspace_bytes, void* stream) {
+    MOLLY_CHECK(enc && d_hidden_dev && seq_table_dev && enc_out_save_dev && d_weight_dev && d_bias_dev && workspace_dev,
+                MOLLY_ERR_INVALID, "molly_project_bwd: NULL pointer");
+    MOLLY_CHECK(D == enc->cfg.llm_hidden_size && n_seq > 0 && k_tokens > 0, MOLLY_ERR_INVALID, "molly_project_bwd: bad shape");
+    auto s = static_cast<cudaStream_t>(stream);
+    const int M = n_seq * k_tokens, h = enc->cfg.hidden_size;
+    const size_t dy_bytes = align_up(static_cast<size_t>(M) * D * 2);
+    MOLLY_CHECK(workspace_bytes > dy_bytes, MOLLY_ERR_WORKSPACE, "molly_project_bwd: workspace too small");
+    const int k_cap = enc->cfg.project_token_num < k_tokens ? enc->cfg.project_token_num : k_tokens;
+    int rc = gather_grad_rows_launch(d_hidden_dev, hs_dtype, seq_table_dev, n_seq, k_tokens, k_cap, B, T, D, workspace_dev,
+                                     zero_rows, s);
+    if (rc) return rc;
+    return project_bwd_launch(workspace_dev, enc_out_save_dev, M, D, h, d_weight_dev, d_bias_dev,
+                              static_cast<uint8_t*>(workspace_dev) + dy_bytes, workspace_bytes - dy_bytes, s);
+}
+
+// ------------------------------------ single kernels ------------------------------------
+int molly_gemm_bf16(const void* a_dev, int32_t lda, const void* w_dev, int32_t ldw, int32_t M, int32_t N, int32_t K,
+                    int32_t epilogue, const float* bias_dev, const float* residual_dev, void* out_dev,
+                    int32_t out_dtype, int32_t ldo, const int32_t* seq_table_dev, int32_t seq_k_tokens, int32_t B,
+                    int32_t T, int32_t k_cap, int32_t* err_flag_dev, int32_t scale_cols, float scale, void* stream) {
+    MOLLY_CHECK(a_dev && w_dev && out_dev, MOLLY_ERR_INVALID, "molly_gemm_bf16: NULL pointer");
+    CUtensorMap ta, tb;
+    int rc = gemm_make_maps(&ta, &tb, a_dev, lda, w_dev, ldw, M, N, K);
+    if (rc) return rc;
+    return gemm_launch(ta, tb, M, N, K, epilogue, bias_dev, residual_dev, out_dev, out_dtype, ldo, seq_table_dev,
+                       seq_k_tokens, B, T, k_cap, err_flag_dev, static_cast<cudaStream_t>(stream), scale_cols, scale);
+}
+
+int molly_layernorm(const float* x_dev, const float* w_dev, const float* b_dev, int32_t rows, int32_t h, float eps,
+                    void* out_dev, int32_t out_dtype, void* stream) {
+    MOLLY_CHECK(x_dev && w_dev && b_dev && out_dev, MOLLY_ERR_INVALID, "molly_layernorm: NULL pointer");
+    return layernorm_launch(x_dev, w_dev, b_dev, rows, h, eps, out_dev, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int molly_embed(const int64_t* ids_dev, int32_t n_seq, int32_t k_tokens, const molly_encoder_config* cfg,
+                const void* word_emb_dev, const void* pos_emb_dev, float* x_dev, int32_t* kv_info_dev,
+                uint8_t* key_mask_dev, int32_t* err_flag_dev, void* stream) {
+    MOLLY_CHECK(ids_dev && cfg && word_emb_dev && x_dev && kv_info_dev && key_mask_dev, MOLLY_ERR_INVALID,
+                "molly_embed: NULL pointer");
+    EmbedArgs ea{cfg->hidden_size, cfg->vocab_size, cfg->pad_token_id, cfg->mask_token_id, cfg->position_type,
+                 cfg->max_positions, cfg->token_dropout, cfg->emb_layer_norm_before ? 0 : 1};
+    return embed_launch(ids_dev, n_seq, k_tokens, ea, word_emb_dev, pos_emb_dev, x_dev, kv_info_dev, key_mask_dev,
+                        err_flag_dev, static_cast<cudaStream_t>(stream));
+}
+
+int molly_rotary(void* qkv_dev, int32_t rows, int32_t k_tokens, int32_t h, int32_t heads, const float* cos_dev,
+                 const float* sin_dev, void* stream) {
+    MOLLY_CHECK(qkv_dev && cos_dev && sin_dev, MOLLY_ERR_INVALID, "molly_rotary: NULL pointer");
+    return rotary_launch(qkv_dev, rows, k_tokens, h, heads, cos_dev, sin_dev, static_cast<cudaStream_t>(stream));
+}
+
+int molly_attention(const void* qkv_dev, int32_t n_seq, int32_t k_tokens, int32_t h, int32_t heads,
+                    const int32_t* kv_info_dev, const uint8_t* key_mask_dev, void* out_dev, void* stream) {
+    MOLLY_CHECK(qkv_dev && kv_info_dev && key_mask_dev && out_dev, MOLLY_ERR_INVALID, "molly_attention: NULL pointer");
+    CUtensorMap tm;
+    int rc = attention_make_map(&tm, qkv_dev, n_seq * k_tokens, h, heads);
+    if (rc) return rc;
+    return attention_launch(tm, n_seq, k_tokens, h, heads, kv_info_dev, key_mask_dev, out_dev,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int molly_merge_rows(const void* src_dev, const int32_t* seq_table_dev, int32_t n_seq, int32_t k_tokens, int32_t k_cap,
+                     void* hidden_states_dev, int32_t dtype, int32_t B, int32_t T, int32_t D, int32_t* err_flag_dev,
+                     void* stream) {
+    MOLLY_CHECK(src_dev && seq_table_dev && hidden_states_dev, MOLLY_ERR_INVALID, "molly_merge_rows: NULL pointer");
+    return merge_rows_launch(src_dev, seq_table_dev, n_seq, k_tokens, k_cap, hidden_states_dev, dtype, B, T, D,
+                             err_flag_dev, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

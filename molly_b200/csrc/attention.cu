@@ -1,0 +1,347 @@
+// Fused bidirectional multi-head attention over K-token padded sequences with per-sequence key masking
+// (HF:257-282 eager attention with the additive key-padding mask of HF:679-709), flash-style online softmax.
+//
+// Input is the packed bf16 QKV activation [n_seq*k_tokens, 3h] written by the fused QKV GEMM (q already scaled by
+// d^-1/2 through the packed weights, rotary already applied); output is bf16 [n_seq*k_tokens, h].
+//
+// One CTA = 128 query rows of one (sequence, head):
+//   * TMA brings Q once and K/V tiles (128 keys) through a 2-stage mbarrier ring
+//   * S = Q K^T  : tcgen05.mma, both operands K-major from swizzled smem, fp32 accumulator in TMEM (128 columns)
+//   * softmax    : 4 warps, thread r owns row r (tcgen05.ld 32x32b: TMEM lane == row, so row max / row sum need no
+//                  shuffles); exp2 with the running max in the log2 domain; P written to smem as the bf16 K-major
+//                  A operand (128-B swizzle); O rescaled in TMEM only when a warp's running max moved
+//   * O += P V   : tcgen05.mma, B operand = V tile straight from TMA ([key][d] row-major == MN-major B), fp32 in TMEM
+//   * keys >= kv_len are never loaded (whole blocks skipped); interior pad keys use the byte mask
+// Two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+#include <math_constants.h>
+
+#include "common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace molly {
+
+namespace {
+
+constexpr int ATT_BLOCK = 128;                 // query rows per CTA == keys per KV block
+constexpr int ATT_THREADS = 160;               // 4 softmax warps + 1 control warp
+constexpr float LOG2E = 1.4426950408889634f;
+
+template <int D>
+struct AttnCfg {
+    static constexpr int BOX_D = D < 64 ? D : 64;
+    static constexpr int NBOX = D / BOX_D;
+    static constexpr int ROW_BYTES = BOX_D * 2;                       // 32 / 64 / 128
+    static constexpr uint32_t LAYOUT = ROW_BYTES == 128 ? kLayoutSW128 : (ROW_BYTES == 64 ? kLayoutSW64 : kLayoutSW32);
+    static constexpr int BOX_BYTES = ATT_BLOCK * ROW_BYTES;
+    static constexpr int TILE_BYTES = NBOX * BOX_BYTES;               // one Q / K / V tile
+    static constexpr int P_BYTES = ATT_BLOCK * ATT_BLOCK * 2;         // two 128x64 bf16 swizzle atoms
+    static constexpr int OFF_Q = 0;
+    static constexpr int OFF_K = TILE_BYTES;
+    static constexpr int OFF_V = 3 * TILE_BYTES;
+    static constexpr int OFF_P = 5 * TILE_BYTES;
+    static constexpr int OFF_BAR = OFF_P + P_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 128;
+    static constexpr int TMEM_COLS = 256;                             // S: 128, O: D (<= 128)
+    static constexpr int MIN_CTAS = SMEM_BYTES <= 115000 ? 2 : 1;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_CTAS)
+attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int h, const int32_t* __restrict__ kv_info,
+                 const uint8_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out) {
+    using Cfg = AttnCfg<D>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+    uint64_t* bar_q = bars + 0;
+    uint64_t* bar_kv_full = bars + 1;     // [2]
+    uint64_t* bar_kv_empty = bars + 3;    // [2]
+    uint64_t* bar_s_full = bars + 5;
+    uint64_t* bar_p_full = bars + 6;
+    uint64_t* bar_o_full = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * ATT_BLOCK, head = blockIdx.y, n = blockIdx.z;
+    const int kvl = kv_info[2 * n], n_nonpad = kv_info[2 * n + 1];
+    const bool interior = n_nonpad != kvl;                  // pad ids before the last real token
+    const int nkv = (kvl + ATT_BLOCK - 1) / ATT_BLOCK;
+    const long long row_base = static_cast<long long>(n) * k_tokens;
+
+    if (nkv == 0) {                                         // all-pad sequence: the reference never encodes one
+        if (warp < 4 && q0 + threadIdx.x < k_tokens) {
+            uint4* o = reinterpret_cast<uint4*>(out + (row_base + q0 + threadIdx.x) * h + head * D);
+            for (int i = 0; i < D / 8; ++i) o[i] = make_uint4(0, 0, 0, 0);
+        }
+        return;
+    }
+
+    if (warp == 4) {
+        if (lane == 0) {
+            if ((smem_u32(smem) & 1023u) != 0) { printf("molly attention: smem base not 1024-B aligned\n"); __trap(); }
+            tma_prefetch_desc(&tma_qkv);
+            mbar_init(bar_q, 1);
+            mbar_init(&bar_kv_full[0], 1); mbar_init(&bar_kv_full[1], 1);
+            mbar_init(&bar_kv_empty[0], 1); mbar_init(&bar_kv_empty[1], 1);
+            mbar_init(bar_s_full, 1);
+            mbar_init(bar_p_full, 128);
+            mbar_init(bar_o_full, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_s = tmem_base;
+    const uint32_t tmem_o = tmem_base + 128;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // ---------------- control thread: TMA producer + MMA issuer ----------------
+            auto load_tile = [&](int smem_off, uint64_t* bar, int col, int row) {
+#pragma unroll
+                for (int b = 0; b < Cfg::NBOX; ++b)
+                    tma_load_2d(smem + smem_off + b * Cfg::BOX_BYTES, &tma_qkv, bar, col + b * Cfg::BOX_D, row);
+            };
+            const int qcol = head * D, kcol = h + head * D, vcol = 2 * h + head * D;
+            mbar_arrive_expect_tx(bar_q, Cfg::TILE_BYTES);
+            load_tile(Cfg::OFF_Q, bar_q, qcol, static_cast<int>(row_base) + q0);
+            mbar_arrive_expect_tx(&bar_kv_full[0], 2 * Cfg::TILE_BYTES);
+            load_tile(Cfg::OFF_K, &bar_kv_full[0], kcol, static_cast<int>(row_base));
+            load_tile(Cfg::OFF_V, &bar_kv_full[0], vcol, static_cast<int>(row_base));
+
+            constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK, ATT_BLOCK, false, false);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK, D, false, true);      // B (= V) is MN-major
+            const uint32_t s_q = smem_u32(smem + Cfg::OFF_Q), s_k = smem_u32(smem + Cfg::OFF_K);
+            const uint32_t s_v = smem_u32(smem + Cfg::OFF_V), s_p = smem_u32(smem + Cfg::OFF_P);
+
+            for (int j = 0; j < nkv; ++j) {
+                const int st = j & 1;
+                if (j + 1 < nkv) {                                        // prefetch next K/V block
+                    const int st1 = (j + 1) & 1;
+                    if (j + 1 >= 2) mbar_wait(&bar_kv_empty[st1], (((j + 1) >> 1) - 1) & 1);
+                    mbar_arrive_expect_tx(&bar_kv_full[st1], 2 * Cfg::TILE_BYTES);
+                    load_tile(Cfg::OFF_K + st1 * Cfg::TILE_BYTES, &bar_kv_full[st1], kcol,
+                              static_cast<int>(row_base) + (j + 1) * ATT_BLOCK);
+                    load_tile(Cfg::OFF_V + st1 * Cfg::TILE_BYTES, &bar_kv_full[st1], vcol,
+                              static_cast<int>(row_base) + (j + 1) * ATT_BLOCK);
+                }
+                if (j == 0) mbar_wait(bar_q, 0);
+                mbar_wait(&bar_kv_full[st], (j >> 1) & 1);
+                tc_fence_after();
+                // S = Q K^T : K-major x K-major, D/16 k-steps
+#pragma unroll
+                for (int s = 0; s < D / 16; ++s) {
+                    const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
+                    const uint64_t qd = make_smem_desc(s_q + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
+                    const uint64_t kd =
+                        make_smem_desc(s_k + st * Cfg::TILE_BYTES + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
+                    umma_bf16_ss(tmem_s, qd, kd, idesc_s, s != 0);
+                }
+                umma_commit(bar_s_full);
+                // O += P V : P K-major (two 64-key atoms), V MN-major; 8 k-steps of 16 keys
+                mbar_wait(bar_p_full, j & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < ATT_BLOCK / 16; ++s) {
+                    const uint64_t pd = make_smem_desc(s_p + (s >> 2) * (ATT_BLOCK * 128) + (s & 3) * 32, 16, 1024,
+                                                       kLayoutSW128);
+                    const uint64_t vd = make_smem_desc(s_v + st * Cfg::TILE_BYTES + s * 16 * Cfg::ROW_BYTES,
+                                                       Cfg::BOX_BYTES, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
+                    umma_bf16_ss(tmem_o, pd, vd, idesc_pv, (j | s) != 0);
+                }
+                umma_commit(&bar_kv_empty[st]);
+                if (j == nkv - 1) umma_commit(bar_o_full);
+            }
+        }
+    } else {
+        // ---------------- softmax warps: thread r owns query row r ----------------
+        const int r = threadIdx.x;
+        const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+        uint8_t* p_row = smem + Cfg::OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
+        const int sw = r & 7;
+        float m_run = -CUDART_INF_F;      // running max, log2 domain
+        float l_run = 0.f;
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(bar_s_full, j & 1);
+            tc_fence_after();
+            float s[ATT_BLOCK];
+            {
+                uint32_t raw[ATT_BLOCK];
+                tmem_ld32(tmem_s + lane_addr + 0, raw);
+                tmem_ld32(tmem_s + lane_addr + 32, raw + 32);
+                tmem_ld32(tmem_s + lane_addr + 64, raw + 64);
+                tmem_ld32(tmem_s + lane_addr + 96, raw + 96);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < ATT_BLOCK; ++i) s[i] = __uint_as_float(raw[i]);
+            }
+            const int j0 = j * ATT_BLOCK;
+            if (interior) {
+                const uint4* mk = reinterpret_cast<const uint4*>(key_mask + row_base + j0);
+                const bool vec_ok = ((row_base + j0) & 15) == 0 && j0 + ATT_BLOCK <= k_tokens;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    uint32_t w[4];
+                    if (vec_ok) {
+                        const uint4 u = __ldg(mk + g);
+                        w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            w[i] = 0;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                const int c = j0 + g * 16 + i * 4 + b;
+                                const uint32_t v = (c < k_tokens) ? key_mask[row_base + c] : 0;
+                                w[i] |= (v & 0xffu) << (8 * b);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const bool ok = ((w[i >> 2] >> (8 * (i & 3))) & 0xffu) != 0 && (j0 + g * 16 + i < kvl);
+                        if (!ok) s[g * 16 + i] = -CUDART_INF_F;
+                    }
+                }
+            } else if (j0 + ATT_BLOCK > kvl) {
+                const int lim = kvl - j0;
+#pragma unroll
+                for (int i = 0; i < ATT_BLOCK; ++i)
+                    if (i >= lim) s[i] = -CUDART_INF_F;
+            }
+            float mx = s[0];
+#pragma unroll
+            for (int i = 1; i < ATT_BLOCK; ++i) mx = fmaxf(mx, s[i]);
+            const float m_new = fmaxf(m_run, mx * LOG2E);
+            const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
+            const float alpha = ex2(m_run - m_use);                    // m_run = -inf -> 0
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < ATT_BLOCK; ++i) {
+                s[i] = ex2(fmaf(s[i], LOG2E, -m_use));
+                sum += s[i];
+            }
+            l_run = l_run * alpha + sum;
+            m_run = m_new;
+            // P -> smem, bf16, K-major with the 128-B swizzle: 16-B chunk c of row r lands at chunk (c ^ (r & 7))
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int e = a * 64 + c * 8;
+                    uint4 u;
+                    u.x = pack_bf16x2(s[e + 0], s[e + 1]);
+                    u.y = pack_bf16x2(s[e + 2], s[e + 3]);
+                    u.z = pack_bf16x2(s[e + 4], s[e + 5]);
+                    u.w = pack_bf16x2(s[e + 6], s[e + 7]);
+                    *reinterpret_cast<uint4*>(p_row + a * (ATT_BLOCK * 128) + ((c ^ sw) << 4)) = u;
+                }
+            }
+            // rescale the running O accumulator (complete through block j-1: bar_s_full(j) was committed after PV(j-1))
+            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+                for (int c = 0; c < D / 16; ++c) {
+                    uint32_t o[16];
+                    tmem_ld16(tmem_o + lane_addr + c * 16, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st16(tmem_o + lane_addr + c * 16, o);
+                }
+                tmem_st_wait();
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_p_full);
+        }
+        // epilogue: O / l -> bf16 -> HBM
+        mbar_wait(bar_o_full, 0);
+        tc_fence_after();
+        const float inv_l = 1.0f / l_run;
+        const bool row_ok = q0 + r < k_tokens;
+        __nv_bfloat16* orow = out + (row_base + q0 + r) * h + head * D;
+#pragma unroll
+        for (int c = 0; c < D / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tmem_o + lane_addr + c * 16, o);
+            tmem_ld_wait();
+            if (row_ok) {
+                uint4 u0, u1;
+                u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l);
+                u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l);
+                u0.z = pack_bf16x2(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l);
+                u0.w = pack_bf16x2(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l);
+                u1.x = pack_bf16x2(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l);
+                u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l);
+                u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l);
+                u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l);
+                reinterpret_cast<uint4*>(orow + c * 16)[0] = u0;
+                reinterpret_cast<uint4*>(orow + c * 16)[1] = u1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+template <int D>
+int launch_attention(const CUtensorMap& tm, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
+                     const uint8_t* key_mask, void* out, cudaStream_t stream) {
+    using Cfg = AttnCfg<D>;
+    auto kernel = attention_kernel<D>;
+    static bool configured = false;
+    if (!configured) {
+        MOLLY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid((k_tokens + ATT_BLOCK - 1) / ATT_BLOCK, heads, n_seq);
+    kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, k_tokens, h, kv_info, key_mask,
+                                                           static_cast<__nv_bfloat16*>(out));
+    count_launch();
+    MOLLY_CUDA(cudaGetLastError());
+    return MOLLY_OK;
+}
+
+}  // namespace
+
+int attention_make_map(CUtensorMap* tq, const void* qkv, int rows, int h, int heads) {
+    const int d = h / heads;
+    MOLLY_CHECK(d == 16 || d == 32 || d == 64 || d == 128, MOLLY_ERR_UNSUPPORTED,
+                "attention: head_dim %d not in {16,32,64,128}", d);
+    const int box_d = d < 64 ? d : 64;
+    return make_tma_2d(tq, qkv, rows, 3 * h, 3 * h, ATT_BLOCK, box_d, 2);
+}
+
+int attention_launch(const CUtensorMap& tqkv, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
+                     const uint8_t* key_mask, void* out, cudaStream_t stream) {
+    MOLLY_CHECK(n_seq > 0 && k_tokens > 0 && heads > 0 && h % heads == 0, MOLLY_ERR_INVALID,
+                "attention: bad shape n_seq=%d k=%d h=%d heads=%d", n_seq, k_tokens, h, heads);
+    MOLLY_CHECK(static_cast<long long>(n_seq) * k_tokens < (1ll << 31), MOLLY_ERR_UNSUPPORTED,
+                "attention: n_seq*k_tokens exceeds int32 TMA coordinates");
+    MOLLY_CHECK(n_seq <= 65535 && heads <= 65535, MOLLY_ERR_UNSUPPORTED, "attention: grid too large");
+    switch (h / heads) {
+        case 16: return launch_attention<16>(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
+        case 32: return launch_attention<32>(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
+        case 64: return launch_attention<64>(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
+        case 128: return launch_attention<128>(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
+        default: MOLLY_CHECK(false, MOLLY_ERR_UNSUPPORTED, "attention: head_dim %d unsupported", h / heads);
+    }
+}
+
+}  // namespace molly

@@ -1,0 +1,79 @@
+#include "common.h"
+
+#include <atomic>
+#include <mutex>
+
+#include "kernels.h"
+
+namespace molly {
+
+namespace {
+thread_local std::string g_last_error;
+std::atomic<int> g_launches{0};
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        // resolved through the runtime so that the library has no link-time dependency on libcuda
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+}  // namespace
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* get_last_error() { return g_last_error.c_str(); }
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+int device_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+int make_tma_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                uint32_t box_cols, uint32_t elem_bytes, bool swizzle) {
+    EncodeTiledFn fn = get_encode_fn();
+    MOLLY_CHECK(fn != nullptr, MOLLY_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    MOLLY_CHECK(elem_bytes == 2, MOLLY_ERR_UNSUPPORTED, "tma: only 2-byte elements are used by this library");
+    const uint32_t inner = box_cols * elem_bytes;
+    CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+    if (swizzle) {
+        if (inner == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+        else if (inner == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+        else if (inner == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+        else MOLLY_CHECK(false, MOLLY_ERR_UNSUPPORTED, "tma: swizzled box inner extent must be 32/64/128 B, got %u", inner);
+    }
+    MOLLY_CHECK((ld * elem_bytes) % 16 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, MOLLY_ERR_INVALID,
+                "tma: base and row pitch must be 16-B aligned");
+    MOLLY_CHECK(box_rows <= 256 && box_cols <= 256, MOLLY_ERR_INVALID, "tma: box dims must be <= 256");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * elem_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MOLLY_CHECK(r == CUDA_SUCCESS, MOLLY_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", static_cast<int>(r),
+                static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols),
+                static_cast<unsigned long long>(ld), box_rows, box_cols);
+    return MOLLY_OK;
+}
+
+}  // namespace molly

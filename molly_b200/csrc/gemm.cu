@@ -1,0 +1,369 @@
+// bf16 x bf16 -> fp32 GEMM for sm_100a:  out[M,N] = epilogue(A[M,K] * W[N,K]^T)
+//
+//   * operands move HBM -> shared memory with TMA (128-byte swizzle, 64-element K slabs), 4-6 stage mbarrier ring
+//   * one elected thread issues tcgen05.mma (cta_group::1, M=128, N=BLOCK_N, K=16); accumulators live in TMEM,
+//     double-buffered (2 x BLOCK_N fp32 columns) so the epilogue of tile i overlaps the main loop of tile i+1
+//   * persistent: grid = #SMs, static round-robin over (m,n) tiles, n fastest so the CTAs that are co-resident
+//     share A row-blocks through L2 while the (small) weight matrix stays L2 resident
+//   * warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM alloc/dealloc, 4..11 = epilogue
+//     (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4)
+//   * fused epilogues replace the reference's separate elementwise kernels:
+//       bias                      (HF:329-335 q/k/v Linear; omics_one.py:91 projector)
+//       bias + exact-erf GELU     (HF:406-414, 57-61)
+//       bias + residual, fp32     (HF:365-375, 417-427)
+//       gated SiLU                (NT-v2 FFN, weight rows interleaved at pack time)
+//       bias + row scatter        (omics_one.py:91-97: projector output written straight into hidden_states)
+#include "common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace molly {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                      // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
+
+template <int BLOCK_N>
+struct GemmCfg {
+    static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;           // 512 or 256: powers of two
+    static constexpr int BAR_OFFSET = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+    static constexpr int SMEM_BYTES = BAR_OFFSET + 256;
+};
+
+struct GemmParams {
+    int M, N, K;
+    const float* bias;
+    const float* residual;
+    void* out;
+    int ldo;
+    const int32_t* seq_table;   // EPI_SCATTER: [n_seq][2] = (b, start)
+    int seq_k, B, T, k_cap;
+    int32_t* err_flag;
+    int scale_cols;             // EPI_BIAS: columns [0, scale_cols) are multiplied by `scale` after the bias
+    float scale;                //           (q = (x Wq^T + bq) * d^-1/2, HF:341); scale_cols % 32 == 0
+};
+
+template <typename OutT>
+__device__ __forceinline__ void store_chunk(OutT* dst, const float (&v)[32]);
+
+template <>
+__device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[32]) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+        u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+        u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        d4[i] = u;
+    }
+}
+template <>
+__device__ __forceinline__ void store_chunk<float>(float* dst, const float (&v)[32]) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+template <int BLOCK_N, int EPI, typename OutT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const GemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) {
+            printf("molly gemm: dynamic smem base not 1024-B aligned\n");
+            __trap();
+        }
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
+                    tma_load_2d(sA + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+                    tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tma_b, &full_bar[stage], kb * BLOCK_K,
+                                n_blk * BLOCK_N);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer ------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, false, false);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+                const int acc = local & 1;
+                const uint32_t acc_phase = (local >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_desc =
+                        make_smem_desc(smem_u32(sA + stage * A_STAGE_BYTES), 16, 8 * BLOCK_K * 2, kLayoutSW128);
+                    const uint64_t b_desc =
+                        make_smem_desc(smem_u32(sB + stage * Cfg::B_STAGE_BYTES), 16, 8 * BLOCK_K * 2, kLayoutSW128);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        umma_bf16_ss(d_tmem, desc_advance(a_desc, k * UMMA_K * 2), desc_advance(b_desc, k * UMMA_K * 2),
+                                     idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);          // frees this smem stage once the MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------ epilogue ------------------------------
+        const int q = warp & 3;                     // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;           // which half of the tile's columns
+        constexpr int COLS_PER_WARP = BLOCK_N / 2;
+        constexpr int CHUNKS = COLS_PER_WARP / 32;
+        OutT* const out = reinterpret_cast<OutT*>(p.out);
+        int local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+            const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+            const int acc = local & 1;
+            const uint32_t acc_phase = (local >> 1) & 1;
+            const int row = m_blk * BLOCK_M + q * 32 + lane;
+            long long dst_row = (row < p.M) ? row : -1;
+            if constexpr (EPI == EPI_SCATTER) {
+                dst_row = -1;
+                if (row < p.M) {
+                    const int n = row / p.seq_k;
+                    const int j = row - n * p.seq_k;
+                    const int b = __ldg(p.seq_table + 2 * n);
+                    const int start = __ldg(p.seq_table + 2 * n + 1);
+                    if (start >= 0 && j < p.k_cap) {
+                        const int t = start + 1 + j;
+                        if (t < p.T && b >= 0 && b < p.B) dst_row = static_cast<long long>(b) * p.T + t;
+                        else if (p.err_flag) atomicOr(p.err_flag, 2);
+                    }
+                }
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < CHUNKS; ++c) {
+                const int col_in_tile = half * COLS_PER_WARP + c * 32;
+                const int col0 = n_blk * BLOCK_N + col_in_tile;
+                if (col0 >= p.N) break;                                       // warp-uniform
+                uint32_t raw[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + col_in_tile, raw);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                if constexpr (EPI != EPI_GLU) {
+                    if (p.bias != nullptr) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 bb = __ldg(b4 + i);
+                            v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+                        }
+                    }
+                }
+                if constexpr (EPI == EPI_BIAS) {
+                    if (col0 < p.scale_cols) {                                  // warp-uniform
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+                    }
+                }
+                if (dst_row >= 0) {
+                    if constexpr (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+                        store_chunk<OutT>(out + dst_row * p.ldo + col0, v);
+                    } else if constexpr (EPI == EPI_BIAS_RESID) {
+                        const float4* r4 = reinterpret_cast<const float4*>(p.residual + dst_row * p.ldo + col0);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 rr = r4[i];
+                            v[4 * i] += rr.x; v[4 * i + 1] += rr.y; v[4 * i + 2] += rr.z; v[4 * i + 3] += rr.w;
+                        }
+                        store_chunk<OutT>(out + dst_row * p.ldo + col0, v);
+                    } else if constexpr (EPI == EPI_GLU) {
+                        uint4 u[2];
+                        uint32_t* uw = reinterpret_cast<uint32_t*>(u);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float g0 = silu(v[4 * i]) * v[4 * i + 1];
+                            const float g1 = silu(v[4 * i + 2]) * v[4 * i + 3];
+                            uw[i] = pack_bf16x2(g0, g1);
+                        }
+                        uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                                             dst_row * p.ldo + (col0 >> 1));
+                        d4[0] = u[0];
+                        d4[1] = u[1];
+                    } else {
+                        store_chunk<OutT>(out + dst_row * p.ldo + col0, v);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+template <int BLOCK_N, int EPI, typename OutT>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    auto kernel = gemm_tcgen05_kernel<BLOCK_N, EPI, OutT>;
+    static bool configured = false;
+    if (!configured) {
+        MOLLY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+    const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+    kernel<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+    count_launch();
+    MOLLY_CUDA(cudaGetLastError());
+    return MOLLY_OK;
+}
+
+template <int BLOCK_N>
+int dispatch_epilogue(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi, int out_dtype,
+                      cudaStream_t stream) {
+    const bool f32 = out_dtype == 1;
+    switch (epi) {
+        case EPI_BIAS:
+            return f32 ? launch_gemm<BLOCK_N, EPI_BIAS, float>(ta, tb, p, stream)
+                       : launch_gemm<BLOCK_N, EPI_BIAS, __nv_bfloat16>(ta, tb, p, stream);
+        case EPI_BIAS_GELU:
+            MOLLY_CHECK(!f32, MOLLY_ERR_UNSUPPORTED, "gemm: GELU epilogue writes bf16 only");
+            return launch_gemm<BLOCK_N, EPI_BIAS_GELU, __nv_bfloat16>(ta, tb, p, stream);
+        case EPI_BIAS_RESID:
+            MOLLY_CHECK(f32, MOLLY_ERR_UNSUPPORTED, "gemm: residual epilogue writes the fp32 residual stream only");
+            return launch_gemm<BLOCK_N, EPI_BIAS_RESID, float>(ta, tb, p, stream);
+        case EPI_GLU:
+            MOLLY_CHECK(!f32, MOLLY_ERR_UNSUPPORTED, "gemm: GLU epilogue writes bf16 only");
+            return launch_gemm<BLOCK_N, EPI_GLU, __nv_bfloat16>(ta, tb, p, stream);
+        case EPI_SCATTER:
+            return f32 ? launch_gemm<BLOCK_N, EPI_SCATTER, float>(ta, tb, p, stream)
+                       : launch_gemm<BLOCK_N, EPI_SCATTER, __nv_bfloat16>(ta, tb, p, stream);
+        default:
+            MOLLY_CHECK(false, MOLLY_ERR_INVALID, "gemm: unknown epilogue %d", epi);
+    }
+}
+
+}  // namespace
+
+int gemm_block_n(int N) {
+    // 256-wide tiles unless the last tile would be mostly padding
+    const int t256 = (N + 255) / 256 * 256, t128 = (N + 127) / 128 * 128;
+    return (t256 * 10 > t128 * 11) ? 128 : 256;
+}
+
+int gemm_make_map_a(CUtensorMap* ta, const void* a, int lda, int M, int K) {
+    MOLLY_CHECK(K % 8 == 0 && lda % 8 == 0, MOLLY_ERR_UNSUPPORTED,
+                "gemm: K and lda must be multiples of 8 (16-B TMA strides); got K=%d lda=%d", K, lda);
+    MOLLY_CHECK((reinterpret_cast<uintptr_t>(a) & 15) == 0, MOLLY_ERR_INVALID, "gemm: A must be 16-B aligned");
+    return make_tma_2d(ta, a, M, K, lda, BLOCK_M, BLOCK_K, 2);
+}
+
+int gemm_make_map_b(CUtensorMap* tb, const void* w, int ldw, int N, int K) {
+    MOLLY_CHECK(K % 8 == 0 && ldw % 8 == 0, MOLLY_ERR_UNSUPPORTED,
+                "gemm: K and ldw must be multiples of 8 (16-B TMA strides); got K=%d ldw=%d", K, ldw);
+    MOLLY_CHECK((reinterpret_cast<uintptr_t>(w) & 15) == 0, MOLLY_ERR_INVALID, "gemm: W must be 16-B aligned");
+    return make_tma_2d(tb, w, N, K, ldw, gemm_block_n(N), BLOCK_K, 2);
+}
+
+int gemm_make_maps(CUtensorMap* ta, CUtensorMap* tb, const void* a, int lda, const void* w, int ldw, int M, int N,
+                   int K) {
+    int rc = gemm_make_map_a(ta, a, lda, M, K);
+    if (rc) return rc;
+    return gemm_make_map_b(tb, w, ldw, N, K);
+}
+
+int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int epi, const float* bias,
+                const float* residual, void* out, int out_dtype, int ldo, const int32_t* seq_table, int seq_k, int B,
+                int T, int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols, float scale) {
+    MOLLY_CHECK(M > 0 && N > 0 && K > 0, MOLLY_ERR_INVALID, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+    MOLLY_CHECK(N % 32 == 0, MOLLY_ERR_UNSUPPORTED, "gemm: N must be a multiple of 32, got %d", N);
+    MOLLY_CHECK(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, MOLLY_ERR_INVALID,
+                "gemm: output must be 16-B aligned with ldo %% 8 == 0 (ldo=%d)", ldo);
+    MOLLY_CHECK(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, MOLLY_ERR_INVALID,
+                "gemm: bias must be 16-B aligned");
+    if (epi == EPI_BIAS_RESID)
+        MOLLY_CHECK(residual != nullptr && (reinterpret_cast<uintptr_t>(residual) & 15) == 0, MOLLY_ERR_INVALID,
+                    "gemm: residual epilogue needs a 16-B aligned residual");
+    if (epi == EPI_SCATTER)
+        MOLLY_CHECK(seq_table != nullptr && seq_k > 0 && B > 0 && T > 0, MOLLY_ERR_INVALID,
+                    "gemm: scatter epilogue needs seq_table / k_tokens / B / T");
+    MOLLY_CHECK(scale_cols % 32 == 0, MOLLY_ERR_UNSUPPORTED, "gemm: scale_cols must be a multiple of 32");
+    GemmParams p{M, N, K, bias, residual, out, ldo, seq_table, seq_k, B, T, k_cap, err_flag, scale_cols, scale};
+    if (gemm_block_n(N) == 256) return dispatch_epilogue<256>(ta, tb, p, epi, out_dtype, stream);
+    return dispatch_epilogue<128>(ta, tb, p, epi, out_dtype, stream);
+}
+
+}  // namespace molly

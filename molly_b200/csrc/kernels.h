@@ -1,0 +1,57 @@
+// Internal (C++) launch interface between the translation units; the C ABI in abi.cu wraps these.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace molly {
+
+enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_GLU = 3, EPI_SCATTER = 4 };
+enum { DT_BF16 = 0, DT_F32 = 1 };
+
+void count_launch();
+int launch_count();
+
+// ---- gemm.cu ----
+int gemm_block_n(int N);
+int gemm_make_map_a(CUtensorMap* ta, const void* a, int lda, int M, int K);
+int gemm_make_map_b(CUtensorMap* tb, const void* w, int ldw, int N, int K);
+int gemm_make_maps(CUtensorMap* ta, CUtensorMap* tb, const void* a, int lda, const void* w, int ldw, int M, int N, int K);
+int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int epi, const float* bias,
+                const float* residual, void* out, int out_dtype, int ldo, const int32_t* seq_table, int seq_k, int B,
+                int T, int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols = 0, float scale = 1.0f);
+
+// ---- attention.cu ----
+int attention_make_map(CUtensorMap* tq, const void* qkv, int rows, int h, int heads);
+int attention_launch(const CUtensorMap& tqkv, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_len,
+                     const uint8_t* key_mask, void* out, cudaStream_t stream);
+
+// ---- rowwise.cu ----
+struct EmbedArgs {
+    int hidden, vocab, pad_id, mask_id, position_type, max_positions, token_dropout;
+    int apply_mask;   // 1: x *= (id != 1) inside the gather; 0: caller masks after emb_layer_norm_before
+};
+int embed_launch(const int64_t* ids, int n_seq, int k_tokens, const EmbedArgs& a, const void* word_emb,
+                 const void* pos_emb, float* x, int32_t* kv_len, uint8_t* key_mask, int32_t* err_flag,
+                 cudaStream_t stream);
+int mask_rows_launch(float* x, const uint8_t* key_mask, int rows, int h, cudaStream_t stream);
+int layernorm_launch(const float* x, const float* w, const float* b, int rows, int h, float eps, void* out,
+                     int out_dtype, cudaStream_t stream);
+int rotary_launch(void* qkv, int rows, int k_tokens, int h, int heads, const float* cos_t, const float* sin_t,
+                  cudaStream_t stream);
+int pool_launch(const void* enc_out, const int64_t* ids, int n_seq, int k_tokens, int h, int mode, float* out,
+                cudaStream_t stream);
+
+// ---- merge.cu ----
+int placeholder_scan_launch(const int64_t* input_ids, int B, int T, int64_t pad0, int64_t pad1, int64_t pad2,
+                            int32_t* out_pos, int32_t* out_kind, int32_t* out_counts, cudaStream_t stream);
+int merge_rows_launch(const void* src, const int32_t* seq_table, int n_seq, int k_tokens, int k_cap, void* hidden,
+                      int dtype, int B, int T, int D, int32_t* err_flag, cudaStream_t stream);
+int gather_grad_rows_launch(void* d_hidden, int dtype, const int32_t* seq_table, int n_seq, int k_tokens, int k_cap,
+                            int B, int T, int D, void* dy_bf16, int zero_rows, cudaStream_t stream);
+
+// ---- bwd.cu ----
+int project_bwd_launch(const void* dy_bf16, const void* x_bf16, int M, int D, int h, float* d_weight, float* d_bias,
+                       void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+}  // namespace molly

@@ -1,0 +1,172 @@
+"""Drop-in for ``OmicsOne.process_omic_sequences`` (reference ``src/model/omics_one.py:49-136``).
+
+``FastOmicsPath.process_omic_sequences(hidden_states, omic_ids_list, omic_info_list, device)`` keeps the reference's
+signature, tensor layouts, in-place + same-object return, modality order (DNA/RNA first, then protein, :120-134),
+pairing-by-index quirk and exception types, while the work underneath is the sm_100a library:
+
+    host: route pairs -> one id matrix + one (b, start) table per modality, one H2D each
+    device: embed -> L x [LN, fused QKV GEMM, rotary, fused MHA, out-proj GEMM(+bias+residual), LN,
+                          FFN1 GEMM(+bias+erf-GELU | gated SiLU), FFN2 GEMM(+bias+residual)] -> final LN
+            -> projector GEMM whose epilogue stores rows straight into hidden_states[b, start+1+j, :]
+
+``install(omics_one)`` swaps the method on a live reference ``OmicsOne`` instance; weights are read from its
+``dna_rna_model`` / ``protein_model`` / ``*_projector`` modules' state dicts.
+"""
+from __future__ import annotations
+
+import types
+from typing import Any, List, Mapping, Optional
+
+import torch
+
+from . import ops, planner
+from .config import EncoderConfig
+from .packing import PackedEncoder
+
+
+class _InjectFn(torch.autograd.Function):
+    """Autograd of one modality: grads reach the projector ``weight`` / ``bias``; the overwritten rows of
+    ``hidden_states`` get zero grad (what autograd derives for the reference's slice-assign); encoders are frozen
+    (reference: ``set_up_trainable_param`` / ``pre_train_lora``, src/utils/tools.py:313-338, 345-396)."""
+
+    @staticmethod
+    def forward(ctx, hidden_states, proj_weight, proj_bias, ids, seq_table, enc_id: int):
+        need_grad = proj_weight.requires_grad or proj_bias.requires_grad
+        enc_out = ops.encode_project_merge(hidden_states, ids, seq_table, enc_id, bool(need_grad))
+        ctx.mark_dirty(hidden_states)
+        ctx.enc_id = enc_id
+        ctx.k_tokens = ids.shape[1]
+        ctx.save_for_backward(seq_table, enc_out)
+        ctx.w_dtype, ctx.b_dtype = proj_weight.dtype, proj_bias.dtype
+        return hidden_states
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        seq_table, enc_out = ctx.saved_tensors
+        need_h = ctx.needs_input_grad[0]
+        g = grad_out.contiguous()
+        if need_h:
+            g = g.clone() if g.data_ptr() == grad_out.data_ptr() else g
+        dW = db = None
+        if enc_out.numel() > 0:
+            dW, db = ops.project_bwd(g, seq_table, enc_out, ctx.enc_id, ctx.k_tokens, bool(need_h))
+            dW, db = dW.to(ctx.w_dtype), db.to(ctx.b_dtype)
+        return (g if need_h else None), dW, db, None, None, None
+
+
+class FastOmicsPath:
+    """B200-native encode -> project -> merge behind the reference's call boundary."""
+
+    def __init__(self, dna_rna: Optional[PackedEncoder], protein: Optional[PackedEncoder], strict: bool = False):
+        self.dna_rna, self.protein = dna_rna, protein
+        self._ids = {}
+        for name, enc in (("dna_rna", dna_rna), ("protein", protein)):
+            if enc is not None:
+                self._ids[name] = ops.register_encoder(enc)
+        self.strict = strict                # True: synchronise and raise device-side errors inside the call
+        self._proj_modules = {}             # name -> nn.Linear (live parameters, for --train-mlp)
+        self._proj_versions = {}
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_state_dicts(cls, *, dna_rna_cfg: Optional[EncoderConfig], dna_rna_state: Optional[Mapping[str, Any]],
+                         dna_rna_projector: Optional[Mapping[str, Any]], dna_rna_project_token_num: int,
+                         protein_cfg: Optional[EncoderConfig], protein_state: Optional[Mapping[str, Any]],
+                         protein_projector: Optional[Mapping[str, Any]], protein_project_token_num: int,
+                         device, strict: bool = False) -> "FastOmicsPath":
+        device = torch.device(device)
+        nt = pr = None
+        if dna_rna_cfg is not None:
+            nt = PackedEncoder(dna_rna_cfg, dna_rna_state, dna_rna_projector, dna_rna_project_token_num, device)
+        if protein_cfg is not None:
+            pr = PackedEncoder(protein_cfg, protein_state, protein_projector, protein_project_token_num, device)
+        return cls(nt, pr, strict=strict)
+
+    @classmethod
+    def from_omics_one(cls, om, device, strict: bool = False) -> "FastOmicsPath":
+        """Build from a reference ``OmicsOne`` (omics_one.py:10-30): same three modules per modality."""
+        def one(model, projector, k):
+            if model is None:
+                return None
+            sd = model.state_dict()
+            return PackedEncoder(EncoderConfig.from_hf_config(model.config, sd), sd, projector.state_dict(), k,
+                                 torch.device(device))
+        self = cls(one(om.dna_rna_model, om.dna_rna_projector, om.dna_rna_project_token_num),
+                   one(om.protein_model, om.protein_projector, om.protein_project_token_num), strict=strict)
+        self._proj_modules = {"dna_rna": om.dna_rna_projector, "protein": om.protein_projector}
+        return self
+
+    def install(self, om) -> None:
+        """Replace ``om.process_omic_sequences`` (the frozen signature of omics_one.py:49-55) with this path."""
+        path = self
+
+        def process_omic_sequences(self_om, hidden_states, omic_ids_list, omic_info_list, device):
+            return path.process_omic_sequences(hidden_states, omic_ids_list, omic_info_list, device)
+
+        om.process_omic_sequences = types.MethodType(process_omic_sequences, om)
+
+    def close(self) -> None:
+        for eid in self._ids.values():
+            ops.unregister_encoder(eid)
+        self._ids = {}
+
+    # ------------------------------------------------------------------ the boundary
+    def process_omic_sequences(self, hidden_states: torch.Tensor, omic_ids_list, omic_info_list: List[List[dict]],
+                               device) -> torch.Tensor:
+        if not hidden_states.is_cuda:
+            raise RuntimeError("molly_b200.process_omic_sequences needs hidden_states on a CUDA device "
+                               "(the B200 path has no CPU fallback)")
+        dev = hidden_states.device
+        batch_size = hidden_states.shape[0]
+        nt_plan, pr_plan = planner.route(batch_size, omic_ids_list, omic_info_list)          # may raise ValueError
+        # reference order: all DNA/RNA sequences, then all protein sequences (omics_one.py:120-134)
+        for name, plan in (("dna_rna", nt_plan), ("protein", pr_plan)):
+            if len(plan) == 0:                                                               # :67-68
+                continue
+            self._inject(name, plan, hidden_states, omic_ids_list, dev)
+        if self.strict:
+            ops.check_device_errors(dev)
+        return hidden_states
+
+    def _inject(self, name: str, plan: planner.ModalityPlan, hidden_states: torch.Tensor, omic_ids_list, dev) -> None:
+        enc_id = self._ids.get(name)
+        if enc_id is None:
+            raise RuntimeError(f"Error processing omic sequences: no {name} encoder is loaded")
+        enc = ops.get_encoder(enc_id)
+        ids = planner.gather_ids(omic_ids_list, plan)                                        # may raise RuntimeError
+        if not ids.is_cuda:
+            planner.check_vocab(ids, enc.cfg.vocab_size)                                     # AssertionError, :71-72
+            ids = ids.pin_memory().to(dev, non_blocking=True) if torch.cuda.is_available() else ids.to(dev)
+        _, T, D = hidden_states.shape
+        k = min(enc.project_token_num, ids.shape[1])
+        planner.check_placement(plan, k, hidden_states.shape[0], T)                          # RuntimeError, :97
+        seq_table = plan.seq_table().pin_memory().to(dev, non_blocking=True)
+        target = hidden_states
+        if not hidden_states.is_contiguous():
+            target = hidden_states.contiguous()
+        proj = self._proj_modules.get(name)
+        if proj is not None:
+            self._refresh_projector(name, enc, proj)
+        if proj is not None and torch.is_grad_enabled() and (proj.weight.requires_grad or proj.bias.requires_grad
+                                                              or hidden_states.requires_grad):
+            _InjectFn.apply(target, proj.weight, proj.bias, ids, seq_table, enc_id)
+        else:
+            ops.encode_project_merge(target, ids, seq_table, enc_id, False)
+        if target is not hidden_states:
+            hidden_states.copy_(target)
+
+    def _refresh_projector(self, name: str, enc: PackedEncoder, proj) -> None:
+        ver = (proj.weight._version, proj.bias._version, proj.weight.data_ptr())
+        if self._proj_versions.get(name) != ver:
+            enc.load_projector(proj.weight, proj.bias)
+            self._proj_versions[name] = ver
+
+    # ------------------------------------------------------------------ other consumers of the encoder
+    def encode(self, name: str, ids: torch.Tensor) -> torch.Tensor:
+        """``hidden_states[-1]`` of the named encoder for ``ids`` [n, K] -> bf16 [n, K, h]."""
+        return ops.encode(ids.to(torch.int64).contiguous(), self._ids[name])
+
+    def pooled(self, name: str, ids: torch.Tensor, mode: str = "mean") -> torch.Tensor:
+        """Masked mean-pool (embed_text.py:112-129) or CLS read-out (baselines/model.py:104-120), fp32 [n, h]."""
+        ids = ids.to(torch.int64).contiguous()
+        return ops.pool(self.encode(name, ids), ids, 0 if mode == "mean" else 1)

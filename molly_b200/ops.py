@@ -1,0 +1,302 @@
+"""PyTorch custom ops (``torch.ops.molly_b200.*``) over the C ABI of ``libmolly_b200.so``.
+
+torch is plumbing here: it owns device memory and the current stream; every op body is one ctypes call with raw
+pointers.  There is no CPU implementation registered for any op -- calling one with CPU tensors raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .packing import PackedEncoder
+
+_ENCODERS: Dict[int, PackedEncoder] = {}
+_NEXT_ID = [1]
+_WORKSPACES: Dict[Tuple[int, int], Tensor] = {}
+_ERR_FLAGS: Dict[int, Tensor] = {}
+
+
+# ------------------------------------------------------------------------------------------------
+# registries / helpers
+# ------------------------------------------------------------------------------------------------
+def register_encoder(enc: PackedEncoder) -> int:
+    eid = _NEXT_ID[0]
+    _NEXT_ID[0] += 1
+    _ENCODERS[eid] = enc
+    return eid
+
+
+def unregister_encoder(eid: int) -> None:
+    enc = _ENCODERS.pop(eid, None)
+    if enc is not None:
+        enc.close()
+
+
+def get_encoder(eid: int) -> PackedEncoder:
+    return _ENCODERS[eid]
+
+
+def _require_cuda(*tensors: Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("molly_b200 ops take CUDA tensors only (there is no CPU fallback)")
+        if dev is not None and t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {t.device} vs {dev}")
+        dev = t.device
+    return dev
+
+
+def _stream(dev: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _dtype_code(t: Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return _lib.DTYPE_BF16
+    if t.dtype == torch.float32:
+        return _lib.DTYPE_F32
+    raise ValueError(f"unsupported dtype {t.dtype}: the path writes bf16 or fp32 hidden_states")
+
+
+def workspace(dev: torch.device, nbytes: int) -> Tensor:
+    """Grow-only scratch buffer per (device, stream); stable pointers keep the library's TMA-descriptor plan cached."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            del _WORKSPACES[key]
+            del ws
+        ws = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=dev)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def _aligned(ws: Tensor, align: int = 1024) -> Tuple[int, int]:
+    p = ws.data_ptr()
+    off = (-p) % align
+    return p + off, ws.numel() - off
+
+
+def error_flag(dev: torch.device) -> Tensor:
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    f = _ERR_FLAGS.get(idx)
+    if f is None:
+        f = torch.zeros(1, dtype=torch.int32, device=dev)
+        _ERR_FLAGS[idx] = f
+    return f
+
+
+def check_device_errors(dev: torch.device, what: str = "process_omic_sequences") -> None:
+    """Synchronising read of the device-side error flag; raises what the reference raises for the same input."""
+    f = error_flag(dev)
+    bits = int(f.item())
+    if bits == 0:
+        return
+    f.zero_()
+    if bits & _lib.ERRBIT_OOV:
+        raise AssertionError(f"{what}: out-of-range token id (>= vocab_size) in omic_ids")          # omics_one.py:71-72
+    if bits & _lib.ERRBIT_OVERFLOW:
+        raise RuntimeError(f"{what}: omics placeholder run exceeds the text sequence length")       # slice shape mismatch
+    if bits & _lib.ERRBIT_POSITION:
+        raise RuntimeError(f"Error processing omic sequences: position id exceeds max_position_embeddings")  # :89-90
+    raise RuntimeError(f"{what}: device error flag {bits}")
+
+
+def kernel_launch_count() -> int:
+    return int(_lib.load().molly_kernel_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+# hot-path ops
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("molly_b200::encode_project_merge", mutates_args=("hidden_states",), device_types="cuda")
+def encode_project_merge(hidden_states: Tensor, ids: Tensor, seq_table: Tensor, enc_id: int,
+                         save_enc_out: bool) -> Tensor:
+    """One modality of ``_inject_omic`` (omics_one.py:57-97): encoder forward -> projector -> in-place scatter."""
+    enc = _ENCODERS[enc_id]
+    dev = _require_cuda(hidden_states, ids, seq_table)
+    if hidden_states.dim() != 3 or not hidden_states.is_contiguous():
+        raise ValueError("hidden_states must be a contiguous [B, T, D] tensor")
+    if ids.dtype != torch.int64 or ids.dim() != 2 or not ids.is_contiguous():
+        raise ValueError("ids must be a contiguous int64 [n_seq, K] tensor")
+    if seq_table.dtype != torch.int32 or tuple(seq_table.shape) != (ids.shape[0], 2) or not seq_table.is_contiguous():
+        raise ValueError("seq_table must be a contiguous int32 [n_seq, 2] tensor")
+    B, T, D = hidden_states.shape
+    n_seq, K = ids.shape
+    lib = _lib.load()
+    ws = workspace(dev, enc.workspace_bytes(n_seq, K))
+    ws_ptr, ws_bytes = _aligned(ws)
+    enc_out = (torch.empty(n_seq * K, enc.cfg.hidden_size, dtype=torch.bfloat16, device=dev) if save_enc_out
+               else torch.empty(0, dtype=torch.bfloat16, device=dev))
+    with torch.cuda.device(dev):
+        _lib.check(lib.molly_encode_project_merge_fwd(
+            enc.handle, ids.data_ptr(), seq_table.data_ptr(), n_seq, K, hidden_states.data_ptr(),
+            _dtype_code(hidden_states), B, T, D, ws_ptr, ws_bytes, error_flag(dev).data_ptr(),
+            enc_out.data_ptr() if save_enc_out else None, _stream(dev)), "molly_encode_project_merge_fwd")
+    return enc_out
+
+
+@torch.library.custom_op("molly_b200::encode", mutates_args=(), device_types="cuda")
+def encode(ids: Tensor, enc_id: int) -> Tensor:
+    """``EsmForMaskedLM(ids, attention_mask=ids != 1, output_hidden_states=True).hidden_states[-1]`` -> bf16 [n, K, h]."""
+    enc = _ENCODERS[enc_id]
+    dev = _require_cuda(ids)
+    if ids.dtype != torch.int64 or ids.dim() != 2 or not ids.is_contiguous():
+        raise ValueError("ids must be a contiguous int64 [n_seq, K] tensor")
+    n_seq, K = ids.shape
+    lib = _lib.load()
+    ws = workspace(dev, enc.workspace_bytes(n_seq, K))
+    ws_ptr, ws_bytes = _aligned(ws)
+    out = torch.empty(n_seq, K, enc.cfg.hidden_size, dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.molly_encode_fwd(enc.handle, ids.data_ptr(), n_seq, K, out.data_ptr(), ws_ptr, ws_bytes,
+                                        error_flag(dev).data_ptr(), _stream(dev)), "molly_encode_fwd")
+    return out
+
+
+@torch.library.custom_op("molly_b200::pool", mutates_args=(), device_types="cuda")
+def pool(enc_out: Tensor, ids: Tensor, mode: int) -> Tensor:
+    """mode 0: masked mean over non-pad tokens (embed_text.py:112-129); mode 1: CLS token (baselines/model.py:104-120)."""
+    dev = _require_cuda(enc_out, ids)
+    n_seq, K, h = enc_out.shape
+    if enc_out.dtype != torch.bfloat16 or not enc_out.is_contiguous() or not ids.is_contiguous():
+        raise ValueError("pool: enc_out must be contiguous bf16 [n, K, h]")
+    out = torch.empty(n_seq, h, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_pool_fwd(enc_out.data_ptr(), ids.data_ptr(), n_seq, K, h, mode, out.data_ptr(),
+                                              _stream(dev)), "molly_pool_fwd")
+    return out
+
+
+@torch.library.custom_op("molly_b200::project_bwd", mutates_args=("d_hidden",), device_types="cuda")
+def project_bwd(d_hidden: Tensor, seq_table: Tensor, enc_out: Tensor, enc_id: int, k_tokens: int,
+                zero_rows: bool) -> Tuple[Tensor, Tensor]:
+    """Projector grads through the slice-assign: returns (dW [D,h] fp32, db [D] fp32); optionally zeroes the written rows
+    of ``d_hidden`` in place (they carry no gradient to the LLM embedding table)."""
+    enc = _ENCODERS[enc_id]
+    dev = _require_cuda(d_hidden, seq_table, enc_out)
+    if not d_hidden.is_contiguous() or d_hidden.dim() != 3:
+        raise ValueError("d_hidden must be contiguous [B, T, D]")
+    B, T, D = d_hidden.shape
+    n_seq = seq_table.shape[0]
+    h = enc.cfg.hidden_size
+    M = n_seq * k_tokens
+    Mp = (M + 7) // 8 * 8
+    need = M * D * 2 + 1024 + (D + h) * Mp * 2 + 4096
+    ws = workspace(dev, need)
+    ws_ptr, ws_bytes = _aligned(ws)
+    dW = torch.empty(D, h, dtype=torch.float32, device=dev)
+    db = torch.empty(D, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_project_bwd(
+            enc.handle, d_hidden.data_ptr(), _dtype_code(d_hidden), seq_table.data_ptr(), n_seq, k_tokens, B, T, D,
+            enc_out.data_ptr(), dW.data_ptr(), db.data_ptr(), int(zero_rows), ws_ptr, ws_bytes, _stream(dev)),
+            "molly_project_bwd")
+    return dW, db
+
+
+@torch.library.custom_op("molly_b200::placeholder_scan", mutates_args=(), device_types="cuda")
+def placeholder_scan(input_ids: Tensor, pad0: int, pad1: int, pad2: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Positions / kinds / per-sample counts of the three omics pad-token ids in ``input_ids`` [B, T]."""
+    dev = _require_cuda(input_ids)
+    if input_ids.dtype != torch.int64 or input_ids.dim() != 2 or not input_ids.is_contiguous():
+        raise ValueError("input_ids must be contiguous int64 [B, T]")
+    B, T = input_ids.shape
+    pos = torch.empty(B, T, dtype=torch.int32, device=dev)
+    kind = torch.empty(B, T, dtype=torch.int32, device=dev)
+    cnt = torch.empty(B, dtype=torch.int32, device=dev)
+    pads = (C.c_int64 * 3)(pad0, pad1, pad2)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_placeholder_scan(input_ids.data_ptr(), B, T, pads, pos.data_ptr(), kind.data_ptr(),
+                                                      cnt.data_ptr(), _stream(dev)), "molly_placeholder_scan")
+    return pos, kind, cnt
+
+
+# ------------------------------------------------------------------------------------------------
+# single-kernel ops (unit-parity surface)
+# ------------------------------------------------------------------------------------------------
+def gemm_bf16(a: Tensor, w: Tensor, epilogue: int, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None,
+              out: Optional[Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
+              seq_table: Optional[Tensor] = None, seq_k: int = 0, k_cap: int = 0, scale_cols: int = 0,
+              scale: float = 1.0) -> Tensor:
+    dev = _require_cuda(a, w, bias, residual, out, seq_table)
+    M, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if epilogue == _lib.EPI_GLU else N
+    B = T = 0
+    if epilogue == _lib.EPI_SCATTER:
+        B, T, _ = out.shape
+        ldo = out.shape[-1]
+    else:
+        if out is None:
+            out = torch.empty(M, n_out, dtype=out_dtype, device=dev)
+        ldo = out.stride(0)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_gemm_bf16(
+            a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, epilogue,
+            None if bias is None else bias.data_ptr(), None if residual is None else residual.data_ptr(),
+            out.data_ptr(), _dtype_code(out), ldo, None if seq_table is None else seq_table.data_ptr(), seq_k, B, T,
+            k_cap, error_flag(dev).data_ptr(), scale_cols, scale, _stream(dev)), "molly_gemm_bf16")
+    return out
+
+
+def layernorm(x: Tensor, w: Tensor, b: Tensor, eps: float, out_dtype: torch.dtype = torch.bfloat16) -> Tensor:
+    dev = _require_cuda(x, w, b)
+    rows, h = x.shape
+    out = torch.empty(rows, h, dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), rows, h, eps, out.data_ptr(),
+                                               _dtype_code(out), _stream(dev)), "molly_layernorm")
+    return out
+
+
+def embed(ids: Tensor, c_config: "_lib.EncoderConfig", word_emb: Tensor, pos_emb: Optional[Tensor]):
+    dev = _require_cuda(ids, word_emb, pos_emb)
+    n_seq, K = ids.shape
+    h = c_config.hidden_size
+    x = torch.empty(n_seq * K, h, dtype=torch.float32, device=dev)
+    kv_info = torch.empty(n_seq, 2, dtype=torch.int32, device=dev)
+    key_mask = torch.empty(n_seq * K, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_embed(ids.data_ptr(), n_seq, K, C.byref(c_config), word_emb.data_ptr(),
+                                           None if pos_emb is None else pos_emb.data_ptr(), x.data_ptr(),
+                                           kv_info.data_ptr(), key_mask.data_ptr(), error_flag(dev).data_ptr(),
+                                           _stream(dev)), "molly_embed")
+    return x, kv_info, key_mask
+
+
+def rotary_(qkv: Tensor, k_tokens: int, heads: int, cos: Tensor, sin: Tensor) -> Tensor:
+    dev = _require_cuda(qkv, cos, sin)
+    rows, h3 = qkv.shape
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_rotary(qkv.data_ptr(), rows, k_tokens, h3 // 3, heads, cos.data_ptr(),
+                                            sin.data_ptr(), _stream(dev)), "molly_rotary")
+    return qkv
+
+
+def attention(qkv: Tensor, n_seq: int, k_tokens: int, heads: int, kv_info: Tensor, key_mask: Tensor) -> Tensor:
+    dev = _require_cuda(qkv, kv_info, key_mask)
+    h = qkv.shape[1] // 3
+    out = torch.empty(n_seq * k_tokens, h, dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_attention(qkv.data_ptr(), n_seq, k_tokens, h, heads, kv_info.data_ptr(),
+                                               key_mask.data_ptr(), out.data_ptr(), _stream(dev)), "molly_attention")
+    return out
+
+
+def merge_rows_(hidden_states: Tensor, src: Tensor, seq_table: Tensor, k_tokens: int, k_cap: int) -> Tensor:
+    dev = _require_cuda(hidden_states, src, seq_table)
+    B, T, D = hidden_states.shape
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_merge_rows(src.data_ptr(), seq_table.data_ptr(), seq_table.shape[0], k_tokens,
+                                                k_cap, hidden_states.data_ptr(), _dtype_code(hidden_states), B, T, D,
+                                                error_flag(dev).data_ptr(), _stream(dev)), "molly_merge_rows")
+    return hidden_states

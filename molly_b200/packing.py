@@ -1,0 +1,159 @@
+"""Weight ingestion: ``EsmForMaskedLM.state_dict()`` + projector ``nn.Linear.state_dict()`` -> packed device tensors and
+a ``molly_encoder_t`` handle.
+
+Keys consumed (the same three modules the reference calls, omics_one.py:18-30):
+  esm.embeddings.word_embeddings.weight, [esm.embeddings.position_embeddings.weight], [esm.embeddings.layer_norm.*],
+  esm.encoder.layer.{i}.attention.{LayerNorm, self.query|key|value, output.dense}.*,
+  esm.encoder.layer.{i}.{LayerNorm, intermediate.dense, output.dense}.*, esm.encoder.emb_layer_norm_after.*;
+  projector: weight [D, h], bias [D].
+Packing done once: q/k/v stacked into one [3h, h] matrix (one GEMM instead of three), NT-v2 gate/up rows interleaved so
+one accumulator tile holds both halves of each GLU pair, matrices cast to bf16, vectors to fp32, rotary cos/sin tables
+in fp32 (the bf16 reference computes them in bf16; fp32 is closer to the fp32 oracle).
+The LM head (``lm_head.*``) is ignored: the reference discards its output (omics_one.py:91).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Mapping, Optional
+
+import torch
+
+from . import _lib
+from .config import EncoderConfig
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class PackedEncoder:
+    """Owns the packed weights of one modality (encoder + projector) and the native handle built on them."""
+
+    def __init__(self, cfg: EncoderConfig, state_dict: Mapping[str, torch.Tensor], projector: Mapping[str, torch.Tensor],
+                 project_token_num: int, device: torch.device, rope_len: int = 4096):
+        if device.type != "cuda":
+            raise RuntimeError("molly_b200 runs on CUDA devices only (no CPU fallback)")
+        self.cfg = cfg
+        self.device = device
+        self.project_token_num = int(project_token_num)
+        self.llm_hidden_size = int(projector["weight"].shape[0])
+        self._keep: List[torch.Tensor] = []
+        self._handle = C.c_void_p()
+        self._lib = _lib.load()
+        h, L, Fi = cfg.hidden_size, cfg.num_hidden_layers, cfg.intermediate_size
+        if projector["weight"].shape[1] != h:
+            raise ValueError(f"projector in_features {projector['weight'].shape[1]} != encoder hidden {h}")
+
+        def mat(t):   # bf16 matrix on device
+            o = t.detach().to(device=device, dtype=torch.float32).to(torch.bfloat16).contiguous()
+            self._keep.append(o)
+            return o
+
+        def vec(t):   # fp32 vector on device
+            o = t.detach().to(device=device, dtype=torch.float32).contiguous()
+            self._keep.append(o)
+            return o
+
+        sd = state_dict
+        w = _lib.EncoderWeights()
+        w.word_emb_dev = _ptr(mat(sd["esm.embeddings.word_embeddings.weight"]))
+        w.pos_emb_dev = None
+        if cfg.position_embedding_type == "absolute":
+            w.pos_emb_dev = _ptr(mat(sd["esm.embeddings.position_embeddings.weight"]))
+        w.emb_ln_w_dev = w.emb_ln_b_dev = None
+        if cfg.emb_layer_norm_before:
+            w.emb_ln_w_dev = _ptr(vec(sd["esm.embeddings.layer_norm.weight"]))
+            w.emb_ln_b_dev = _ptr(vec(sd["esm.embeddings.layer_norm.bias"]))
+        # rotary tables exactly as HF:81-115 builds them, in fp32
+        d = cfg.head_dim
+        self.rope_len = max(int(rope_len), int(cfg.max_position_embeddings))
+        inv_freq = 1.0 / (10000 ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))
+        freqs = torch.outer(torch.arange(self.rope_len).float(), inv_freq)
+        w.rope_cos_dev = _ptr(vec(freqs.cos()))
+        w.rope_sin_dev = _ptr(vec(freqs.sin()))
+        w.rope_len = self.rope_len
+
+        names = ["ln1_w", "ln1_b", "w_qkv", "b_qkv", "w_attn_out", "b_attn_out", "ln2_w", "ln2_b", "w_ffn1", "b_ffn1",
+                 "w_ffn2", "b_ffn2"]
+        arrays: Dict[str, List[Optional[int]]] = {n: [] for n in names}
+        for i in range(L):
+            p = f"esm.encoder.layer.{i}."
+            arrays["ln1_w"].append(_ptr(vec(sd[p + "attention.LayerNorm.weight"])))
+            arrays["ln1_b"].append(_ptr(vec(sd[p + "attention.LayerNorm.bias"])))
+            wq, wk, wv = (sd[p + f"attention.self.{n}.weight"] for n in ("query", "key", "value"))
+            bq, bk, bv = (sd[p + f"attention.self.{n}.bias"] for n in ("query", "key", "value"))
+            arrays["w_qkv"].append(_ptr(mat(torch.cat([wq, wk, wv], dim=0))))
+            arrays["b_qkv"].append(_ptr(vec(torch.cat([bq, bk, bv], dim=0))))
+            arrays["w_attn_out"].append(_ptr(mat(sd[p + "attention.output.dense.weight"])))
+            arrays["b_attn_out"].append(_ptr(vec(sd[p + "attention.output.dense.bias"])))
+            arrays["ln2_w"].append(_ptr(vec(sd[p + "LayerNorm.weight"])))
+            arrays["ln2_b"].append(_ptr(vec(sd[p + "LayerNorm.bias"])))
+            w1 = sd[p + "intermediate.dense.weight"]
+            if cfg.ffn_type == "glu":
+                if w1.shape[0] != 2 * Fi:
+                    raise ValueError(f"GLU intermediate.dense.weight must be [2F, h], got {tuple(w1.shape)}")
+                # silu(x1) * x2 with x1 = rows [0,F), x2 = rows [F,2F)  ->  interleave (x1_0, x2_0, x1_1, x2_1, ...)
+                w1 = torch.stack([w1[:Fi], w1[Fi:]], dim=1).reshape(2 * Fi, h)
+                arrays["w_ffn1"].append(_ptr(mat(w1)))
+                arrays["b_ffn1"].append(None)
+                arrays["w_ffn2"].append(_ptr(mat(sd[p + "output.dense.weight"])))
+                arrays["b_ffn2"].append(None)
+            else:
+                arrays["w_ffn1"].append(_ptr(mat(w1)))
+                arrays["b_ffn1"].append(_ptr(vec(sd[p + "intermediate.dense.bias"])))
+                arrays["w_ffn2"].append(_ptr(mat(sd[p + "output.dense.weight"])))
+                arrays["b_ffn2"].append(_ptr(vec(sd[p + "output.dense.bias"])))
+        self._ptr_arrays = {}
+        for n in names:
+            arr = (C.c_void_p * L)(*arrays[n])
+            self._ptr_arrays[n] = arr
+            setattr(w, n + "_dev", C.cast(arr, _lib.c_void_pp))
+        w.final_ln_w_dev = _ptr(vec(sd["esm.encoder.emb_layer_norm_after.weight"]))
+        w.final_ln_b_dev = _ptr(vec(sd["esm.encoder.emb_layer_norm_after.bias"]))
+        # projector buffers are refreshed in place when the nn.Linear trains (--train-mlp)
+        self.proj_w = torch.empty(self.llm_hidden_size, h, dtype=torch.bfloat16, device=device)
+        self.proj_b = torch.empty(self.llm_hidden_size, dtype=torch.float32, device=device)
+        self.load_projector(projector["weight"], projector["bias"])
+        w.w_proj_dev = _ptr(self.proj_w)
+        w.b_proj_dev = _ptr(self.proj_b)
+
+        c = _lib.EncoderConfig(
+            hidden_size=h, num_layers=L, num_heads=cfg.num_attention_heads, intermediate_size=Fi,
+            vocab_size=cfg.vocab_size, pad_token_id=cfg.pad_token_id, mask_token_id=cfg.mask_token_id,
+            position_type=_lib.POS_ABSOLUTE if cfg.position_embedding_type == "absolute" else _lib.POS_ROTARY,
+            max_positions=cfg.max_position_embeddings,
+            ffn_type=_lib.FFN_GLU if cfg.ffn_type == "glu" else _lib.FFN_GELU,
+            token_dropout=int(cfg.token_dropout), emb_layer_norm_before=int(cfg.emb_layer_norm_before),
+            layer_norm_eps=cfg.layer_norm_eps, llm_hidden_size=self.llm_hidden_size,
+            project_token_num=self.project_token_num)
+        self.c_config = c
+        self._weights_struct = w
+        with torch.cuda.device(device):
+            _lib.check(self._lib.molly_encoder_create(C.byref(c), C.byref(w), C.byref(self._handle)),
+                       "molly_encoder_create")
+
+    # ------------------------------------------------------------------
+    def load_projector(self, weight: torch.Tensor, bias: torch.Tensor) -> None:
+        """(Re)pack ``nn.Linear`` projector parameters into the buffers the kernels read."""
+        self.proj_w.copy_(weight.detach())
+        self.proj_b.copy_(bias.detach())
+
+    @property
+    def handle(self) -> C.c_void_p:
+        if not self._handle:
+            raise RuntimeError("encoder handle already destroyed")
+        return self._handle
+
+    def workspace_bytes(self, n_seq: int, k_tokens: int) -> int:
+        return int(self._lib.molly_encoder_workspace_bytes(self.handle, n_seq, k_tokens))
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None):
+            self._lib.molly_encoder_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

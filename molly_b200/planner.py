@@ -1,0 +1,103 @@
+"""Host-side planning of one ``process_omic_sequences`` call: route every (omic_ids, info) pair to its modality exactly
+like the reference's Python loop (omics_one.py:104-118), but emit ONE packed id matrix and ONE int32 sequence table per
+modality instead of one ``.to(device)`` per sequence.  Pure host logic (numpy / CPU torch), testable without a GPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+NT_TYPES = ("dna", "rna")
+
+
+@dataclass
+class ModalityPlan:
+    """Sequences of one modality, in the reference's append order (batch-major, then slot index)."""
+    b_idx: List[int]
+    slot_idx: List[int]
+    starts: List[int]
+
+    def __len__(self) -> int:
+        return len(self.b_idx)
+
+    def seq_table(self) -> torch.Tensor:
+        """int32 [n, 2] = (b, start_pos); start -1 is kept (the kernels skip it, omics_one.py:94-95)."""
+        return torch.tensor(list(zip(self.b_idx, self.starts)), dtype=torch.int32).reshape(len(self.b_idx), 2)
+
+
+def route(batch_size: int, omic_ids_list, omic_info_list) -> Tuple[ModalityPlan, ModalityPlan]:
+    """omics_one.py:104-118 -- pairs are zipped BY INDEX (shorter of the two wins, like ``zip``); 'pad' is skipped;
+    an unknown type raises ``ValueError("Unsupported omic type: ...")``."""
+    nt, pr = ModalityPlan([], [], []), ModalityPlan([], [], [])
+    for b in range(batch_size):
+        ids_b, infos_b = omic_ids_list[b], omic_info_list[b]
+        for i in range(min(len(ids_b), len(infos_b))):
+            info = infos_b[i]
+            omic_type = info["type"]
+            start_pos = info["start"]
+            if omic_type in NT_TYPES:
+                tgt = nt
+            elif omic_type == "protein":
+                tgt = pr
+            elif omic_type == "pad":
+                continue
+            else:
+                raise ValueError(f"Unsupported omic type: {omic_type}")
+            tgt.b_idx.append(b)
+            tgt.slot_idx.append(i)
+            tgt.starts.append(int(start_pos))
+    return nt, pr
+
+
+def gather_ids(omic_ids_list, plan: ModalityPlan) -> torch.Tensor:
+    """``torch.stack(omic_ids)`` (omics_one.py:69) for one modality: int64 [n, K] on the device the ids live on.
+    Ragged lengths raise ``RuntimeError`` exactly as ``torch.stack`` would."""
+    if isinstance(omic_ids_list, torch.Tensor):               # collated [B, Nmax, K]
+        bi = torch.as_tensor(plan.b_idx, dtype=torch.long, device=omic_ids_list.device)
+        si = torch.as_tensor(plan.slot_idx, dtype=torch.long, device=omic_ids_list.device)
+        ids = omic_ids_list[bi, si]
+    else:
+        ids = torch.stack([omic_ids_list[b][i] for b, i in zip(plan.b_idx, plan.slot_idx)], dim=0)
+    if ids.dim() != 2:
+        raise RuntimeError(f"omic ids must be 1-D per sequence, got stacked shape {tuple(ids.shape)}")
+    return ids.to(torch.int64).contiguous()
+
+
+def check_placement(plan: ModalityPlan, k: int, batch_size: int, seq_len: int) -> None:
+    """The reference's slice-assign (omics_one.py:97) raises ``RuntimeError`` when ``start+1+k`` runs past T."""
+    for b, start in zip(plan.b_idx, plan.starts):
+        if start == -1:
+            continue
+        if start < -1 or start + 1 + k > seq_len:
+            raise RuntimeError(
+                f"The expanded size of the tensor ({max(0, seq_len - start - 1)}) must match the existing size ({k}) "
+                f"at non-singleton dimension 0 (sample {b}: start={start}, k={k}, T={seq_len})")
+
+
+def check_vocab(ids: torch.Tensor, vocab_size: int) -> None:
+    """omics_one.py:71-72 for ids that are already on the host."""
+    bad = ids >= vocab_size
+    if bool(bad.any()):
+        raise AssertionError(f"out-of-range token: {ids[bad]}")
+
+
+def shard_samples(batch_size: int, world_size: int, rank: int) -> range:
+    """Sample-sharding of SURVEY.md 8e: rank r owns samples [r*B/W, (r+1)*B/W)."""
+    per = (batch_size + world_size - 1) // world_size
+    return range(min(batch_size, rank * per), min(batch_size, (rank + 1) * per))
+
+
+def balance_by_cost(costs: Sequence[float], world_size: int) -> List[List[int]]:
+    """Greedy longest-processing-time assignment of samples to ranks (cfg-3: cost = sum kv_len^2 + sum K)."""
+    order = sorted(range(len(costs)), key=lambda i: -costs[i])
+    loads = [0.0] * world_size
+    out: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda j: loads[j])
+        out[r].append(i)
+        loads[r] += costs[i]
+    for lst in out:
+        lst.sort()
+    return out

@@ -1,0 +1,131 @@
+"""CPU: host-side planner (routing, seq table, error conventions), config ingestion, ABI export checks."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+import torch
+
+from molly_b200 import planner
+from molly_b200.config import EncoderConfig
+from oracle import cases, synth
+
+
+def test_route_matches_reference_order_and_pairs_by_index():
+    case = cases.golden_cases()["tiny_rotary_glu"]
+    nt, pr = planner.route(4, case.batch.omic_ids, case.batch.omic_info_list)
+    # reference appends batch-major, slot order; dna/rna share one list (omics_one.py:104-118)
+    exp_nt, exp_pr = [], []
+    for b, infos in enumerate(case.batch.omic_info_list):
+        for i, info in enumerate(infos):
+            if info["type"] in ("dna", "rna"):
+                exp_nt.append((b, i, info["start"]))
+            elif info["type"] == "protein":
+                exp_pr.append((b, i, info["start"]))
+    assert list(zip(nt.b_idx, nt.slot_idx, nt.starts)) == exp_nt
+    assert list(zip(pr.b_idx, pr.slot_idx, pr.starts)) == exp_pr
+    tbl = nt.seq_table()
+    assert tbl.dtype == torch.int32 and tuple(tbl.shape) == (len(exp_nt), 2)
+    assert tbl.tolist() == [[b, s] for b, _, s in exp_nt]
+    ids = planner.gather_ids(case.batch.omic_ids, nt)
+    assert torch.equal(ids, torch.stack([case.batch.omic_ids[b, i] for b, i, _ in exp_nt]))
+    # list-of-lists input form (omics_one.py signature) gives the same matrix
+    as_lists = [[row for row in sample] for sample in case.batch.omic_ids]
+    assert torch.equal(planner.gather_ids(as_lists, nt), ids)
+
+
+def test_route_errors_and_skips():
+    ids = torch.ones(1, 3, 8, dtype=torch.int64)
+    infos = [[{"type": "pad", "start": -1}, {"type": "dna", "start": -1}, {"type": "lipid", "start": 3}]]
+    with pytest.raises(ValueError, match="Unsupported omic type: lipid"):
+        planner.route(1, ids, infos)
+    nt, pr = planner.route(1, ids, [infos[0][:2]])          # zip stops at the shorter list; 'pad' skipped
+    assert len(nt) == 1 and len(pr) == 0 and nt.starts == [-1]
+    planner.check_placement(nt, 8, 1, 10)                   # start == -1 is never checked (omics_one.py:94-95)
+
+
+def test_check_placement_and_vocab():
+    p = planner.ModalityPlan([0, 1], [0, 0], [5, 91])
+    planner.check_placement(p, 8, 2, 100)                   # 91+1+8 == 100 fits exactly
+    with pytest.raises(RuntimeError):
+        planner.check_placement(p, 9, 2, 100)
+    with pytest.raises(AssertionError, match="out-of-range token"):
+        planner.check_vocab(torch.tensor([[1, 2, 33]]), 33)
+    planner.check_vocab(torch.tensor([[1, 2, 32]]), 33)
+
+
+def test_ragged_ids_raise_like_torch_stack():
+    ids = [[torch.ones(8, dtype=torch.int64), torch.ones(9, dtype=torch.int64)]]
+    infos = [[{"type": "dna", "start": 0}, {"type": "rna", "start": 20}]]
+    nt, _ = planner.route(1, ids, infos)
+    with pytest.raises(RuntimeError):
+        planner.gather_ids(ids, nt)
+
+
+def test_sharding_helpers():
+    assert [list(planner.shard_samples(10, 4, r)) for r in range(4)] == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9]]
+    parts = planner.balance_by_cost([9, 1, 1, 1, 8, 2, 2, 2], 2)
+    assert sorted(sum(parts, [])) == list(range(8))
+    loads = [sum([9, 1, 1, 1, 8, 2, 2, 2][i] for i in p) for p in parts]
+    assert abs(loads[0] - loads[1]) <= 1
+
+
+def test_config_from_hf():
+    from transformers import EsmConfig
+    hf = EsmConfig(vocab_size=33, mask_token_id=32, pad_token_id=1, hidden_size=320, num_hidden_layers=6,
+                   num_attention_heads=20, intermediate_size=1280, max_position_embeddings=1026, layer_norm_eps=1e-5,
+                   position_embedding_type="rotary", token_dropout=True, emb_layer_norm_before=False)
+    c = EncoderConfig.from_hf_config(hf)
+    assert (c.hidden_size, c.head_dim, c.ffn_type, c.token_dropout, c.position_embedding_type) == (320, 16, "gelu", True, "rotary")
+    sd = {"esm.encoder.layer.0.intermediate.dense.weight": torch.zeros(2 * 1280, 320)}
+    assert EncoderConfig.from_hf_config(hf, sd).ffn_type == "glu"
+
+
+def test_abi_library_exports_every_declared_symbol():
+    from molly_b200 import _lib
+    declared = _lib.declared_symbols()
+    assert set(declared) == set(_lib.SIGNATURES), "ctypes table and include/molly_b200.h disagree"
+    lib = _lib.load()                                        # raises if the .so was not built
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported by libmolly_b200.so"
+    assert lib.molly_abi_version() == 1
+    assert lib.molly_kernel_launch_count() >= 0
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(declared) <= exported
+
+
+def test_abi_rejects_bad_arguments_without_a_gpu():
+    """Argument validation happens before any CUDA call, so it is testable on the CPU box."""
+    from molly_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.molly_encoder_create(None, None, ctypes.byref(h)) == _lib.ERR_INVALID
+    assert b"NULL" in lib.molly_last_error()
+    cfg = _lib.EncoderConfig(hidden_size=100, num_layers=1, num_heads=3, intermediate_size=64, vocab_size=10)
+    w = _lib.EncoderWeights()
+    assert lib.molly_encoder_create(ctypes.byref(cfg), ctypes.byref(w), ctypes.byref(h)) == _lib.ERR_INVALID
+    assert b"not divisible" in lib.molly_last_error()
+    cfg = _lib.EncoderConfig(hidden_size=96, num_layers=1, num_heads=4, intermediate_size=64, vocab_size=10,
+                             llm_hidden_size=64)
+    assert lib.molly_encoder_create(ctypes.byref(cfg), ctypes.byref(w), ctypes.byref(h)) == _lib.ERR_UNSUPPORTED
+    assert b"head_dim 24" in lib.molly_last_error()
+    assert lib.molly_encoder_workspace_bytes(None, 4, 4) == 0
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through the oracle (or any CPU fallback)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "molly_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_cpu_tensors_are_refused():
+    from molly_b200 import ops
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        ops.layernorm(torch.zeros(4, 64), torch.ones(64), torch.zeros(64), 1e-5)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.molly_b200.placeholder_scan(torch.zeros(2, 8, dtype=torch.int64), 1, 2, 3)
