@@ -168,6 +168,20 @@ int molly_merge_rows(const void* src_dev /*[n_seq*k, D]*/, const int32_t* seq_ta
                      int32_t k_tokens, int32_t k_cap, void* hidden_states_dev, int32_t dtype, int32_t B, int32_t T,
                      int32_t D, int32_t* err_flag_dev, void* stream);
 
+/* ---- per-kernel-family timing with CUDA events on the launching stream (bench.py's roofline numbers) ------------
+ * molly_profile_start() arms it; every kernel launched by this library afterwards is bracketed by two events;
+ * molly_profile_stop() synchronises them and fills MOLLY_PROFILE_FAMILIES entries.  Off by default (zero overhead). */
+#define MOLLY_PROFILE_FAMILIES 12
+typedef struct molly_profile_entry {
+    const char* name;      /* embed, layernorm, gemm_qkv, rotary, attention, gemm_attn_out, gemm_ffn1, gemm_ffn2, ... */
+    int32_t launches;
+    int32_t work_is_flops; /* 1: `work` is algorithmic FLOP; 0: algorithmic HBM bytes */
+    double total_ms;
+    double work;
+} molly_profile_entry;
+int molly_profile_start(void);
+int molly_profile_stop(molly_profile_entry* out, int32_t max_entries);
+
 const char* molly_last_error(void);
 int molly_abi_version(void);
 int molly_kernel_launch_count(void); /* kernels launched by this library since load (bench `gpu_launches`) */

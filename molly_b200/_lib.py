@@ -54,6 +54,13 @@ class EncoderWeights(C.Structure):
     ]
 
 
+class ProfileEntry(C.Structure):
+    """struct molly_profile_entry"""
+    _fields_ = [("name", C.c_char_p), ("launches", C.c_int32), ("work_is_flops", C.c_int32),
+                ("total_ms", C.c_double), ("work", C.c_double)]
+
+
+PROFILE_FAMILIES = 12
 _i32, _i64p, _vp, _sz = C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t
 
 # name -> (restype, argtypes); must list every function declared in include/molly_b200.h (tests/test_abi.py checks)
@@ -75,6 +82,8 @@ SIGNATURES = {
     "molly_rotary": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "molly_attention": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "molly_merge_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "molly_profile_start": (C.c_int, []),
+    "molly_profile_stop": (C.c_int, [C.POINTER(ProfileEntry), _i32]),
     "molly_last_error": (C.c_char_p, []),
     "molly_abi_version": (C.c_int, []),
     "molly_kernel_launch_count": (C.c_int, []),

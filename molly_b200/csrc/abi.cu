@@ -126,25 +126,30 @@ int encode(molly_encoder* e, const int64_t* ids, int n_seq, int k, void* final_o
         // --- attention block: x = x + Wo * Attn(LN(x)) + bo   (HF:386-403)
         if ((rc = layernorm_launch(x, e->ln1_w[l], e->ln1_b[l], M, h, c.layer_norm_eps, xn, DT_BF16, stream))) return rc;
         // q, k, v = Linear(LN(x)); q *= d^-1/2 BEFORE rotary (HF:329-341) -- folded into the epilogue of one fused GEMM
+        set_gemm_family(PF_GEMM_QKV);
         if ((rc = gemm_launch(p.tm_xn, e->tm_wqkv[l], M, 3 * h, h, EPI_BIAS, e->b_qkv[l], nullptr, qkv, DT_BF16, 3 * h,
                               nullptr, 0, 0, 0, 0, nullptr, stream, h, e->q_scale)))
             return rc;
         if (c.position_type == MOLLY_POS_ROTARY)
             if ((rc = rotary_launch(qkv, M, k, h, c.num_heads, e->w.rope_cos_dev, e->w.rope_sin_dev, stream))) return rc;
         if ((rc = attention_launch(p.tm_qkv, n_seq, k, h, c.num_heads, kv_info, key_mask, attn, stream))) return rc;
+        set_gemm_family(PF_GEMM_ATTN_OUT);
         if ((rc = gemm_launch(p.tm_attn, e->tm_wo[l], M, h, h, EPI_BIAS_RESID, e->b_o[l], x, x, DT_F32, h, nullptr, 0, 0,
                               0, 0, nullptr, stream)))
             return rc;
         // --- feed-forward block: x = x + W2 * act(W1 * LN(x) + b1) + b2   (HF:478-482)
         if ((rc = layernorm_launch(x, e->ln2_w[l], e->ln2_b[l], M, h, c.layer_norm_eps, xn, DT_BF16, stream))) return rc;
         const int epi1 = c.ffn_type == MOLLY_FFN_GLU ? EPI_GLU : EPI_BIAS_GELU;
+        set_gemm_family(PF_GEMM_FFN1);
         if ((rc = gemm_launch(p.tm_xn, e->tm_w1[l], M, e->ffn1_n, h, epi1, e->b_ffn1[l], nullptr, mid, DT_BF16, F,
                               nullptr, 0, 0, 0, 0, nullptr, stream)))
             return rc;
+        set_gemm_family(PF_GEMM_FFN2);
         if ((rc = gemm_launch(p.tm_mid, e->tm_w2[l], M, h, F, EPI_BIAS_RESID, e->b_ffn2[l], x, x, DT_F32, h, nullptr, 0,
                               0, 0, 0, nullptr, stream)))
             return rc;
     }
+    set_gemm_family(PF_GEMM_OTHER);
     // emb_layer_norm_after (HF:511-512) -> hidden_states[-1] (omics_one.py:91)
     return layernorm_launch(x, e->w.final_ln_w_dev, e->w.final_ln_b_dev, M, h, c.layer_norm_eps, final_out, DT_BF16, stream);
 }
@@ -156,6 +161,22 @@ extern "C" {
 const char* molly_last_error(void) { return get_last_error(); }
 int molly_abi_version(void) { return MOLLY_ABI_VERSION; }
 int molly_kernel_launch_count(void) { return launch_count(); }
+
+int molly_profile_start(void) { prof_start(); return MOLLY_OK; }
+int molly_profile_stop(molly_profile_entry* out, int32_t max_entries) {
+    static const char* names[PF_COUNT] = {"embed", "layernorm", "gemm_qkv", "rotary", "attention", "gemm_attn_out",
+                                          "gemm_ffn1", "gemm_ffn2", "gemm_proj", "gemm_other", "merge", "other"};
+    static const int is_flops[PF_COUNT] = {0, 0, 1, 0, 1, 1, 1, 1, 1, 1, 0, 0};
+    int launches[PF_COUNT]; double ms[PF_COUNT], work[PF_COUNT];
+    int rc = prof_stop(launches, ms, work);
+    MOLLY_CHECK(out != nullptr && max_entries >= PF_COUNT, MOLLY_ERR_INVALID, "molly_profile_stop: need %d entries", PF_COUNT);
+    for (int f = 0; f < PF_COUNT; ++f) {
+        out[f].name = names[f]; out[f].launches = launches[f]; out[f].total_ms = ms[f]; out[f].work = work[f];
+        out[f].work_is_flops = is_flops[f];
+    }
+    MOLLY_CHECK(rc == 0, MOLLY_ERR_CUDA, "molly_profile_stop: event timing failed");
+    return PF_COUNT == 12 ? MOLLY_OK : MOLLY_ERR_INVALID;
+}
 
 int molly_encoder_create(const molly_encoder_config* cfg, const molly_encoder_weights* w, molly_encoder_t** out) {
     MOLLY_CHECK(cfg && w && out, MOLLY_ERR_INVALID, "molly_encoder_create: NULL argument");
@@ -239,9 +260,12 @@ int molly_encode_project_merge_fwd(molly_encoder_t* enc, const int64_t* ids_dev,
     if (rc) return rc;
     // projector + merge: hidden[b, start+1+j, :] = LN_out[n*K+j, :] Wp^T + bp  for j < min(K cap, K)  (omics_one.py:91-97)
     const int k_cap = enc->cfg.project_token_num < k_tokens ? enc->cfg.project_token_num : k_tokens;
-    return gemm_launch(enc->plan.tm_final, enc->tm_wproj, n_seq * k_tokens, D, enc->cfg.hidden_size, EPI_SCATTER,
+    set_gemm_family(PF_GEMM_PROJ);
+    rc = gemm_launch(enc->plan.tm_final, enc->tm_wproj, n_seq * k_tokens, D, enc->cfg.hidden_size, EPI_SCATTER,
                        enc->w.b_proj_dev, nullptr, hidden_states_dev, hs_dtype, D, seq_table_dev, k_tokens, B, T, k_cap,
                        err_flag_dev, s);
+    set_gemm_family(PF_GEMM_OTHER);
+    return rc;
 }
 
 int molly_pool_fwd(const void* enc_out_dev, const int64_t* ids_dev, int32_t n_seq, int32_t k_tokens, int32_t h,

@@ -311,8 +311,11 @@ int launch_attention(const CUtensorMap& tm, int n_seq, int k_tokens, int h, int 
         configured = true;
     }
     dim3 grid((k_tokens + ATT_BLOCK - 1) / ATT_BLOCK, heads, n_seq);
-    kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, k_tokens, h, kv_info, key_mask,
-                                                           static_cast<__nv_bfloat16*>(out));
+    {   // dense-equivalent work 4*n*K*K*h (exact when every sequence is full length)
+        ProfScope prof(PF_ATTENTION, 4.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
+        kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, k_tokens, h, kv_info, key_mask,
+                                                               static_cast<__nv_bfloat16*>(out));
+    }
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
     return MOLLY_OK;

@@ -2,6 +2,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "kernels.h"
 
@@ -32,6 +33,48 @@ EncodeTiledFn get_encode_fn() {
 
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 const char* get_last_error() { return g_last_error.c_str(); }
+
+namespace {
+struct ProfRecord { int family; double work; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRecord> g_prof;
+thread_local int g_gemm_family = PF_GEMM_OTHER;
+}  // namespace
+
+void set_gemm_family(int f) { g_gemm_family = f; }
+int gemm_family() { return g_gemm_family; }
+
+ProfScope::ProfScope(int family, double work, cudaStream_t s) : stream(s), slot(-1) {
+    if (!g_prof_on) return;
+    ProfRecord r{family, work, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, s);
+    g_prof.push_back(r);
+    slot = static_cast<int>(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+    if (slot >= 0) cudaEventRecord(g_prof[slot].b, stream);
+}
+
+void prof_start() {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = true;
+}
+// aggregates per family: launches[f], ms[f], work[f]; returns 0 on success
+int prof_stop(int* launches, double* ms, double* work) {
+    g_prof_on = false;
+    for (int f = 0; f < PF_COUNT; ++f) { launches[f] = 0; ms[f] = 0.0; work[f] = 0.0; }
+    int rc = 0;
+    for (auto& r : g_prof) {
+        float t = 0.f;
+        if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) rc = 1;
+        launches[r.family] += 1; ms[r.family] += t; work[r.family] += r.work;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    return rc;
+}
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int launch_count() { return g_launches.load(std::memory_order_relaxed); }

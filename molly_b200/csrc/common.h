@@ -45,4 +45,7 @@ int make_tma_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols
 
 int device_sm_count();
 
+void prof_start();
+int prof_stop(int* launches, double* ms, double* work);
+
 }  // namespace molly

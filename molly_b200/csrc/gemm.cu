@@ -285,7 +285,10 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
     }
     const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
     const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-    kernel<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+    {
+        ProfScope prof(gemm_family(), 2.0 * p.M * p.N * p.K, stream);
+        kernel<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+    }
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
     return MOLLY_OK;

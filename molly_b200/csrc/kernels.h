@@ -12,6 +12,20 @@ enum { DT_BF16 = 0, DT_F32 = 1 };
 void count_launch();
 int launch_count();
 
+// ---- optional per-launch profiling (CUDA events on the launching stream; off by default) ----
+enum ProfFamily {
+    PF_EMBED = 0, PF_LAYERNORM, PF_GEMM_QKV, PF_ROTARY, PF_ATTENTION, PF_GEMM_ATTN_OUT, PF_GEMM_FFN1, PF_GEMM_FFN2,
+    PF_GEMM_PROJ, PF_GEMM_OTHER, PF_MERGE, PF_OTHER, PF_COUNT
+};
+struct ProfScope {            // brackets ONE kernel launch with two events when profiling is on
+    cudaStream_t stream;
+    int slot;
+    ProfScope(int family, double work, cudaStream_t s);
+    ~ProfScope();
+};
+void set_gemm_family(int f);  // tag for the next gemm_launch calls of this thread
+int gemm_family();
+
 // ---- gemm.cu ----
 int gemm_block_n(int N);
 int gemm_make_map_a(CUtensorMap* ta, const void* a, int lda, int M, int K);

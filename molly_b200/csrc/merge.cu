@@ -116,6 +116,7 @@ int merge_rows_launch(const void* src, const int32_t* seq_table, int n_seq, int 
     MOLLY_CHECK((static_cast<long long>(D) * eb) % 16 == 0, MOLLY_ERR_UNSUPPORTED, "merge: row bytes must be 16-B multiple");
     const int rows = n_seq * k_tokens;
     const int grid = (rows + 7) / 8;
+    ProfScope prof(PF_MERGE, static_cast<double>(rows) * D * eb * 2.0, stream);
     if (eb == 4)
         merge_rows_kernel<4><<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(src), seq_table, rows, k_tokens,
                                                        k_cap, static_cast<uint8_t*>(hidden), B, T, D, err_flag);

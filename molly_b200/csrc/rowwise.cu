@@ -279,6 +279,7 @@ int embed_launch(const int64_t* ids, int n_seq, int k_tokens, const EmbedArgs& a
     splits = max(1, min(splits, (k_tokens + 63) / 64));
     const size_t smem = a.position_type == 1 ? sizeof(int32_t) * k_tokens : 0;
     MOLLY_CHECK(smem <= 48 * 1024, MOLLY_ERR_UNSUPPORTED, "embed: k_tokens %d too long for absolute positions", k_tokens);
+    ProfScope prof(PF_EMBED, static_cast<double>(n_seq) * k_tokens * (a.hidden * 6.0 + 9.0), stream);
     embed_kernel<<<dim3(n_seq, splits), EMB_THREADS, smem, stream>>>(
         ids, k_tokens, a, static_cast<const __nv_bfloat16*>(word_emb), static_cast<const __nv_bfloat16*>(pos_emb), x,
         kv_len, key_mask, err_flag);
@@ -300,6 +301,7 @@ int layernorm_launch(const float* x, const float* w, const float* b, int rows, i
                 h, LN_MAXV * 128);
     MOLLY_CHECK(rows > 0, MOLLY_ERR_INVALID, "layernorm: rows=%d", rows);
     const int grid = (rows + LN_THREADS / 32 - 1) / (LN_THREADS / 32);
+    ProfScope prof(PF_LAYERNORM, static_cast<double>(rows) * h * (out_dtype == DT_F32 ? 8.0 : 6.0), stream);
     if (out_dtype == DT_F32)
         layernorm_kernel<float><<<grid, LN_THREADS, 0, stream>>>(x, w, b, rows, h, eps, static_cast<float*>(out));
     else
@@ -315,6 +317,7 @@ int rotary_launch(void* qkv, int rows, int k_tokens, int h, int heads, const flo
     const int d = h / heads;
     MOLLY_CHECK(d % 16 == 0, MOLLY_ERR_UNSUPPORTED, "rotary: head_dim %d must be a multiple of 16", d);
     const long long items = static_cast<long long>(rows) * 2 * heads * (d / 16);
+    ProfScope prof(PF_ROTARY, static_cast<double>(rows) * 2.0 * h * 4.0, stream);     // q,k read + write, bf16
     rotary_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, stream>>>(
         static_cast<__nv_bfloat16*>(qkv), items, k_tokens, h, heads, cos_t, sin_t);
     count_launch();

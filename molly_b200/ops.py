@@ -114,6 +114,23 @@ def kernel_launch_count() -> int:
     return int(_lib.load().molly_kernel_launch_count())
 
 
+def profile_start() -> None:
+    """Bracket every kernel the library launches from now on with CUDA events on the launching stream."""
+    _lib.check(_lib.load().molly_profile_start(), "molly_profile_start")
+
+
+def profile_stop() -> Dict[str, dict]:
+    """Per kernel family: launches, total ms, algorithmic work (FLOP or HBM bytes) since profile_start()."""
+    arr = (_lib.ProfileEntry * _lib.PROFILE_FAMILIES)()
+    _lib.check(_lib.load().molly_profile_stop(arr, _lib.PROFILE_FAMILIES), "molly_profile_stop")
+    out = {}
+    for e in arr:
+        if e.launches:
+            out[e.name.decode()] = {"launches": int(e.launches), "ms": float(e.total_ms), "work": float(e.work),
+                                    "unit": "flop" if e.work_is_flops else "byte"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # hot-path ops
 # ------------------------------------------------------------------------------------------------
