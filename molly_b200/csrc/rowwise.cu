@@ -85,7 +85,10 @@ embed_kernel(const int64_t* __restrict__ ids, int k_tokens, EmbedArgs a, const _
     for (int w = 0; w < EMB_THREADS / 32; ++w) {
         n_nonpad += s_red[0][w]; n_mask += s_red[1][w]; last = max(last, s_red[2][w]);
     }
-    if (blockIdx.y == 0 && threadIdx.x == 0) kv_len[n] = last;
+    if (blockIdx.y == 0 && threadIdx.x == 0) {      // kv_info[n] = (last non-pad index + 1, number of non-pad ids)
+        kv_len[2 * n] = last;
+        kv_len[2 * n + 1] = n_nonpad;
+    }
 
     // HF:213-222: (x * (1 - 0.15*0.8)) / (1 - n_mask / src_len)
     const float keep = 0.88f;                                      // python: 1 - 0.15 * 0.8 -> float32(0.88)

@@ -27,7 +27,7 @@ run path_golden   600 $PT tests/test_gpu_path.py -k "golden"
 run path_rest     900 $PT tests/test_gpu_path.py -k "not golden and not encoder_forward"
 run smoke         300 python __graft_entry__.py smoke
 echo "---- summary ----"; cat $OUT/summary.txt
-# failures first: print the interesting part of each failing log
+# compact failure digest (full logs stay in gpurun_out/bringup/)
 for f in $OUT/*.log; do
-  if grep -qE "failed|error|Error|rc=[1-9]" $f; then echo "=== $f"; grep -vE "^\s*$" $f | head -150; fi
-done | head -400
+  if grep -qE "failed|rror" $f; then echo "=== $f"; grep -hE "^(E  |FAILED|molly:|.*Error)" $f | cut -c1-220 | head -${DIGEST_LINES:-40}; fi
+done | head -300
