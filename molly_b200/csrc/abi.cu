@@ -26,7 +26,8 @@ struct molly_encoder {
         void* ws = nullptr;
         int n_seq = 0, k = 0;
         void* final_out = nullptr;
-        CUtensorMap tm_xn, tm_attn, tm_mid, tm_qkv, tm_final;
+        CUtensorMap tm_xn, tm_attn, tm_mid, tm_qkv, tm_final;   // A operands / attention input
+        CUtensorMap tc_qkv, tc_x, tc_mid;                       // GEMM outputs (tc_x also feeds the residual loads)
     } plan;
 };
 
@@ -84,6 +85,9 @@ int build_plan(molly_encoder* e, void* ws, int n_seq, int k, void* final_out) {
     if ((rc = gemm_make_map_a(&p.tm_mid, base + L.off_mid, F, M, F))) return rc;
     if ((rc = attention_make_map(&p.tm_qkv, base + L.off_qkv, M, h, c.num_heads))) return rc;
     if ((rc = gemm_make_map_a(&p.tm_final, final_out, h, M, h))) return rc;
+    if ((rc = gemm_make_map_c(&p.tc_qkv, base + L.off_qkv, DT_BF16, 3 * h, M, 3 * h))) return rc;
+    if ((rc = gemm_make_map_c(&p.tc_x, base + L.off_x, DT_F32, h, M, h))) return rc;
+    if ((rc = gemm_make_map_c(&p.tc_mid, base + L.off_mid, DT_BF16, F, M, F))) return rc;
     p.ws = ws; p.n_seq = n_seq; p.k = k; p.final_out = final_out;
     return MOLLY_OK;
 }
@@ -127,26 +131,26 @@ int encode(molly_encoder* e, const int64_t* ids, int n_seq, int k, void* final_o
         if ((rc = layernorm_launch(x, e->ln1_w[l], e->ln1_b[l], M, h, c.layer_norm_eps, xn, DT_BF16, stream))) return rc;
         // q, k, v = Linear(LN(x)); q *= d^-1/2 BEFORE rotary (HF:329-341) -- folded into the epilogue of one fused GEMM
         set_gemm_family(PF_GEMM_QKV);
-        if ((rc = gemm_launch(p.tm_xn, e->tm_wqkv[l], M, 3 * h, h, EPI_BIAS, e->b_qkv[l], nullptr, qkv, DT_BF16, 3 * h,
+        if ((rc = gemm_launch(p.tm_xn, e->tm_wqkv[l], &p.tc_qkv, M, 3 * h, h, EPI_BIAS, e->b_qkv[l], qkv, DT_BF16, 3 * h,
                               nullptr, 0, 0, 0, 0, nullptr, stream, h, e->q_scale)))
             return rc;
         if (c.position_type == MOLLY_POS_ROTARY)
             if ((rc = rotary_launch(qkv, M, k, h, c.num_heads, e->w.rope_cos_dev, e->w.rope_sin_dev, stream))) return rc;
         if ((rc = attention_launch(p.tm_qkv, n_seq, k, h, c.num_heads, kv_info, key_mask, attn, stream))) return rc;
         set_gemm_family(PF_GEMM_ATTN_OUT);
-        if ((rc = gemm_launch(p.tm_attn, e->tm_wo[l], M, h, h, EPI_BIAS_RESID, e->b_o[l], x, x, DT_F32, h, nullptr, 0, 0,
-                              0, 0, nullptr, stream)))
+        if ((rc = gemm_launch(p.tm_attn, e->tm_wo[l], &p.tc_x, M, h, h, EPI_BIAS_RESID, e->b_o[l], x, DT_F32, h, nullptr, 0,
+                              0, 0, 0, nullptr, stream)))
             return rc;
         // --- feed-forward block: x = x + W2 * act(W1 * LN(x) + b1) + b2   (HF:478-482)
         if ((rc = layernorm_launch(x, e->ln2_w[l], e->ln2_b[l], M, h, c.layer_norm_eps, xn, DT_BF16, stream))) return rc;
         const int epi1 = c.ffn_type == MOLLY_FFN_GLU ? EPI_GLU : EPI_BIAS_GELU;
         set_gemm_family(PF_GEMM_FFN1);
-        if ((rc = gemm_launch(p.tm_xn, e->tm_w1[l], M, e->ffn1_n, h, epi1, e->b_ffn1[l], nullptr, mid, DT_BF16, F,
+        if ((rc = gemm_launch(p.tm_xn, e->tm_w1[l], &p.tc_mid, M, e->ffn1_n, h, epi1, e->b_ffn1[l], mid, DT_BF16, F,
                               nullptr, 0, 0, 0, 0, nullptr, stream)))
             return rc;
         set_gemm_family(PF_GEMM_FFN2);
-        if ((rc = gemm_launch(p.tm_mid, e->tm_w2[l], M, h, F, EPI_BIAS_RESID, e->b_ffn2[l], x, x, DT_F32, h, nullptr, 0,
-                              0, 0, 0, nullptr, stream)))
+        if ((rc = gemm_launch(p.tm_mid, e->tm_w2[l], &p.tc_x, M, h, F, EPI_BIAS_RESID, e->b_ffn2[l], x, DT_F32, h, nullptr,
+                              0, 0, 0, 0, nullptr, stream)))
             return rc;
     }
     set_gemm_family(PF_GEMM_OTHER);
@@ -218,12 +222,13 @@ int molly_encoder_create(const molly_encoder_config* cfg, const molly_encoder_we
             rc = MOLLY_ERR_INVALID;
             break;
         }
-        if ((rc = gemm_make_map_b(&e->tm_wqkv[l], e->w_qkv[l], h, 3 * h, h))) break;
-        if ((rc = gemm_make_map_b(&e->tm_wo[l], e->w_o[l], h, h, h))) break;
-        if ((rc = gemm_make_map_b(&e->tm_w1[l], e->w_ffn1[l], h, e->ffn1_n, h))) break;
-        if ((rc = gemm_make_map_b(&e->tm_w2[l], e->w_ffn2[l], F, h, F))) break;
+        if ((rc = gemm_make_map_b(&e->tm_wqkv[l], e->w_qkv[l], h, 3 * h, h, EPI_BIAS))) break;
+        if ((rc = gemm_make_map_b(&e->tm_wo[l], e->w_o[l], h, h, h, EPI_BIAS_RESID))) break;
+        if ((rc = gemm_make_map_b(&e->tm_w1[l], e->w_ffn1[l], h, e->ffn1_n, h,
+                                  cfg->ffn_type == MOLLY_FFN_GLU ? EPI_GLU : EPI_BIAS_GELU))) break;
+        if ((rc = gemm_make_map_b(&e->tm_w2[l], e->w_ffn2[l], F, h, F, EPI_BIAS_RESID))) break;
     }
-    if (rc == 0) rc = gemm_make_map_b(&e->tm_wproj, w->w_proj_dev, h, D, h);
+    if (rc == 0) rc = gemm_make_map_b(&e->tm_wproj, w->w_proj_dev, h, D, h, EPI_SCATTER);
     if (rc) { delete e; return rc; }
     *out = e;
     return MOLLY_OK;
@@ -261,9 +266,8 @@ int molly_encode_project_merge_fwd(molly_encoder_t* enc, const int64_t* ids_dev,
     // projector + merge: hidden[b, start+1+j, :] = LN_out[n*K+j, :] Wp^T + bp  for j < min(K cap, K)  (omics_one.py:91-97)
     const int k_cap = enc->cfg.project_token_num < k_tokens ? enc->cfg.project_token_num : k_tokens;
     set_gemm_family(PF_GEMM_PROJ);
-    rc = gemm_launch(enc->plan.tm_final, enc->tm_wproj, n_seq * k_tokens, D, enc->cfg.hidden_size, EPI_SCATTER,
-                       enc->w.b_proj_dev, nullptr, hidden_states_dev, hs_dtype, D, seq_table_dev, k_tokens, B, T, k_cap,
-                       err_flag_dev, s);
+    rc = gemm_launch(enc->plan.tm_final, enc->tm_wproj, nullptr, n_seq * k_tokens, D, enc->cfg.hidden_size, EPI_SCATTER,
+                     enc->w.b_proj_dev, hidden_states_dev, hs_dtype, D, seq_table_dev, k_tokens, B, T, k_cap, err_flag_dev, s);
     set_gemm_family(PF_GEMM_OTHER);
     return rc;
 }
@@ -308,11 +312,21 @@ int molly_gemm_bf16(const void* a_dev, int32_t lda, const void* w_dev, int32_t l
                     int32_t out_dtype, int32_t ldo, const int32_t* seq_table_dev, int32_t seq_k_tokens, int32_t B,
                     int32_t T, int32_t k_cap, int32_t* err_flag_dev, int32_t scale_cols, float scale, void* stream) {
     MOLLY_CHECK(a_dev && w_dev && out_dev, MOLLY_ERR_INVALID, "molly_gemm_bf16: NULL pointer");
-    CUtensorMap ta, tb;
-    int rc = gemm_make_maps(&ta, &tb, a_dev, lda, w_dev, ldw, M, N, K);
+    auto s = static_cast<cudaStream_t>(stream);
+    CUtensorMap ta, tb, tc;
+    int rc = gemm_make_map_a(&ta, a_dev, lda, M, K);
     if (rc) return rc;
-    return gemm_launch(ta, tb, M, N, K, epilogue, bias_dev, residual_dev, out_dev, out_dtype, ldo, seq_table_dev,
-                       seq_k_tokens, B, T, k_cap, err_flag_dev, static_cast<cudaStream_t>(stream), scale_cols, scale);
+    if ((rc = gemm_make_map_b(&tb, w_dev, ldw, N, K, epilogue))) return rc;
+    if (epilogue == EPI_BIAS_RESID) {
+        MOLLY_CHECK(residual_dev != nullptr, MOLLY_ERR_INVALID, "molly_gemm_bf16: residual epilogue needs a residual");
+        if (static_cast<const void*>(residual_dev) != out_dev)       // the kernel updates the fp32 stream in place
+            MOLLY_CUDA(cudaMemcpy2DAsync(out_dev, static_cast<size_t>(ldo) * 4, residual_dev, static_cast<size_t>(ldo) * 4,
+                                         static_cast<size_t>(N) * 4, M, cudaMemcpyDeviceToDevice, s));
+    }
+    if (epilogue != EPI_SCATTER)
+        if ((rc = gemm_make_map_c(&tc, out_dev, out_dtype, ldo, M, epilogue == EPI_GLU ? N / 2 : N))) return rc;
+    return gemm_launch(ta, tb, epilogue == EPI_SCATTER ? nullptr : &tc, M, N, K, epilogue, bias_dev, out_dev, out_dtype,
+                       ldo, seq_table_dev, seq_k_tokens, B, T, k_cap, err_flag_dev, s, scale_cols, scale);
 }
 
 int molly_layernorm(const float* x_dev, const float* w_dev, const float* b_dev, int32_t rows, int32_t h, float eps,

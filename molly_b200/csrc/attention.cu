@@ -65,7 +65,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
     uint64_t* bar_s_full = bars + 5;
     uint64_t* bar_p_full = bars + 6;
     uint64_t* bar_o_full = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* bar_s_free = bars + 8;      // softmax has S(j) in registers -> S(j+1) may overwrite the TMEM columns
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * ATT_BLOCK, head = blockIdx.y, n = blockIdx.z;
@@ -92,6 +93,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
             mbar_init(bar_s_full, 1);
             mbar_init(bar_p_full, 128);
             mbar_init(bar_o_full, 1);
+            mbar_init(bar_s_free, 128);
             fence_mbar_init();
         }
         __syncwarp();
@@ -114,42 +116,44 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
                     tma_load_2d(smem + smem_off + b * Cfg::BOX_BYTES, &tma_qkv, bar, col + b * Cfg::BOX_D, row);
             };
             const int qcol = head * D, kcol = h + head * D, vcol = 2 * h + head * D;
-            mbar_arrive_expect_tx(bar_q, Cfg::TILE_BYTES);
-            load_tile(Cfg::OFF_Q, bar_q, qcol, static_cast<int>(row_base) + q0);
-            mbar_arrive_expect_tx(&bar_kv_full[0], 2 * Cfg::TILE_BYTES);
-            load_tile(Cfg::OFF_K, &bar_kv_full[0], kcol, static_cast<int>(row_base));
-            load_tile(Cfg::OFF_V, &bar_kv_full[0], vcol, static_cast<int>(row_base));
-
             constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK, ATT_BLOCK, false, false);
             constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK, D, false, true);      // B (= V) is MN-major
             const uint32_t s_q = smem_u32(smem + Cfg::OFF_Q), s_k = smem_u32(smem + Cfg::OFF_K);
             const uint32_t s_v = smem_u32(smem + Cfg::OFF_V), s_p = smem_u32(smem + Cfg::OFF_P);
-
-            for (int j = 0; j < nkv; ++j) {
-                const int st = j & 1;
-                if (j + 1 < nkv) {                                        // prefetch next K/V block
-                    const int st1 = (j + 1) & 1;
-                    if (j + 1 >= 2) mbar_wait(&bar_kv_empty[st1], (((j + 1) >> 1) - 1) & 1);
-                    mbar_arrive_expect_tx(&bar_kv_full[st1], 2 * Cfg::TILE_BYTES);
-                    load_tile(Cfg::OFF_K + st1 * Cfg::TILE_BYTES, &bar_kv_full[st1], kcol,
-                              static_cast<int>(row_base) + (j + 1) * ATT_BLOCK);
-                    load_tile(Cfg::OFF_V + st1 * Cfg::TILE_BYTES, &bar_kv_full[st1], vcol,
-                              static_cast<int>(row_base) + (j + 1) * ATT_BLOCK);
-                }
-                if (j == 0) mbar_wait(bar_q, 0);
-                mbar_wait(&bar_kv_full[st], (j >> 1) & 1);
+            auto load_kv = [&](int blk) {
+                const int stg = blk & 1;
+                mbar_arrive_expect_tx(&bar_kv_full[stg], 2 * Cfg::TILE_BYTES);
+                load_tile(Cfg::OFF_K + stg * Cfg::TILE_BYTES, &bar_kv_full[stg], kcol,
+                          static_cast<int>(row_base) + blk * ATT_BLOCK);
+                load_tile(Cfg::OFF_V + stg * Cfg::TILE_BYTES, &bar_kv_full[stg], vcol,
+                          static_cast<int>(row_base) + blk * ATT_BLOCK);
+            };
+            auto issue_s = [&](int blk) {        // S = Q K(blk)^T : K-major x K-major, D/16 k-steps
+                mbar_wait(&bar_kv_full[blk & 1], (blk >> 1) & 1);
                 tc_fence_after();
-                // S = Q K^T : K-major x K-major, D/16 k-steps
 #pragma unroll
                 for (int s = 0; s < D / 16; ++s) {
                     const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
                     const uint64_t qd = make_smem_desc(s_q + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
                     const uint64_t kd =
-                        make_smem_desc(s_k + st * Cfg::TILE_BYTES + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
+                        make_smem_desc(s_k + (blk & 1) * Cfg::TILE_BYTES + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
                     umma_bf16_ss(tmem_s, qd, kd, idesc_s, s != 0);
                 }
                 umma_commit(bar_s_full);
-                // O += P V : P K-major (two 64-key atoms), V MN-major; 8 k-steps of 16 keys
+            };
+            mbar_arrive_expect_tx(bar_q, Cfg::TILE_BYTES);
+            load_tile(Cfg::OFF_Q, bar_q, qcol, static_cast<int>(row_base) + q0);
+            load_kv(0);
+            if (nkv > 1) load_kv(1);
+            mbar_wait(bar_q, 0);
+            issue_s(0);
+            for (int j = 0; j < nkv; ++j) {
+                const int st = j & 1;
+                // (1) the moment the softmax warps hold S(j) in registers, S(j+1) is issued: it runs under softmax(j)
+                mbar_wait(bar_s_free, j & 1);
+                tc_fence_after();
+                if (j + 1 < nkv) issue_s(j + 1);
+                // (2) O += P(j) V(j) : P K-major (two 64-key atoms), V MN-major; 8 k-steps of 16 keys
                 mbar_wait(bar_p_full, j & 1);
                 tc_fence_after();
 #pragma unroll
@@ -160,8 +164,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
                                                        Cfg::BOX_BYTES, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
                     umma_bf16_ss(tmem_o, pd, vd, idesc_pv, (j | s) != 0);
                 }
-                umma_commit(&bar_kv_empty[st]);
+                umma_commit(&bar_kv_empty[st]);              // PV(j) done: stage st, the P buffer and O(j) are free
                 if (j == nkv - 1) umma_commit(bar_o_full);
+                // (3) refill stage st with block j+2 once PV(j) has drained it
+                if (j + 2 < nkv) {
+                    mbar_wait(&bar_kv_empty[st], (j >> 1) & 1);
+                    load_kv(j + 2);
+                }
             }
         }
     } else {
@@ -186,6 +195,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
 #pragma unroll
                 for (int i = 0; i < ATT_BLOCK; ++i) s[i] = __uint_as_float(raw[i]);
             }
+            tc_fence_before();
+            mbar_arrive(bar_s_free);                         // S(j) is in registers: the MMA warp may start S(j+1)
             const int j0 = j * ATT_BLOCK;
             if (interior) {
                 const uint4* mk = reinterpret_cast<const uint4*>(key_mask + row_base + j0);
@@ -220,20 +231,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
                 for (int i = 0; i < ATT_BLOCK; ++i)
                     if (i >= lim) s[i] = -CUDART_INF_F;
             }
-            float mx = s[0];
+            float mx4[4] = {s[0], s[1], s[2], s[3]};          // 4 independent chains instead of one 127-deep one
 #pragma unroll
-            for (int i = 1; i < ATT_BLOCK; ++i) mx = fmaxf(mx, s[i]);
+            for (int i = 4; i < ATT_BLOCK; i += 4) {
+                mx4[0] = fmaxf(mx4[0], s[i]); mx4[1] = fmaxf(mx4[1], s[i + 1]);
+                mx4[2] = fmaxf(mx4[2], s[i + 2]); mx4[3] = fmaxf(mx4[3], s[i + 3]);
+            }
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             const float m_new = fmaxf(m_run, mx * LOG2E);
             const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
             const float alpha = ex2(m_run - m_use);                    // m_run = -inf -> 0
-            float sum = 0.f;
+            float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < ATT_BLOCK; ++i) {
-                s[i] = ex2(fmaf(s[i], LOG2E, -m_use));
-                sum += s[i];
+            for (int i = 0; i < ATT_BLOCK; i += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    s[i + u] = ex2(fmaf(s[i + u], LOG2E, -m_use));
+                    sum4[u] += s[i + u];
+                }
             }
-            l_run = l_run * alpha + sum;
+            l_run = l_run * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
             m_run = m_new;
+            // PV(j-1) must have drained the P buffer and finished O before either is touched again
+            if (j > 0) {
+                mbar_wait(&bar_kv_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                tc_fence_after();
+            }
             // P -> smem, bf16, K-major with the 128-B swizzle: 16-B chunk c of row r lands at chunk (c ^ (r & 7))
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
@@ -248,7 +271,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
                     *reinterpret_cast<uint4*>(p_row + a * (ATT_BLOCK * 128) + ((c ^ sw) << 4)) = u;
                 }
             }
-            // rescale the running O accumulator (complete through block j-1: bar_s_full(j) was committed after PV(j-1))
+            // rescale the running O accumulator (complete through block j-1, see the wait above)
             if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll
                 for (int c = 0; c < D / 16; ++c) {

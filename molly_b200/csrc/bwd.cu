@@ -59,11 +59,12 @@ int project_bwd_launch(const void* dy_bf16, const void* x_bf16, int M, int D, in
     row_sum_kernel<<<(D + 7) / 8, 256, 0, stream>>>(dyT, D, M, Mp, d_bias);
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
-    CUtensorMap ta, tb;
-    int rc = gemm_make_maps(&ta, &tb, dyT, Mp, xT, Mp, D, h, Mp);
+    CUtensorMap ta, tb, tc;
+    int rc = gemm_make_map_a(&ta, dyT, Mp, D, Mp);
     if (rc) return rc;
-    return gemm_launch(ta, tb, D, h, Mp, EPI_BIAS, nullptr, nullptr, d_weight, DT_F32, h, nullptr, 0, 0, 0, 0, nullptr,
-                       stream);
+    if ((rc = gemm_make_map_b(&tb, xT, Mp, h, Mp, EPI_BIAS))) return rc;
+    if ((rc = gemm_make_map_c(&tc, d_weight, DT_F32, h, D, h))) return rc;
+    return gemm_launch(ta, tb, &tc, D, h, Mp, EPI_BIAS, nullptr, d_weight, DT_F32, h, nullptr, 0, 0, 0, 0, nullptr, stream);
 }
 
 }  // namespace molly

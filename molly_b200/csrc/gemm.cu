@@ -1,18 +1,22 @@
 // bf16 x bf16 -> fp32 GEMM for sm_100a:  out[M,N] = epilogue(A[M,K] * W[N,K]^T)
 //
-//   * operands move HBM -> shared memory with TMA (128-byte swizzle, 64-element K slabs), 4-6 stage mbarrier ring
+//   * operands move HBM -> shared memory with TMA (128-byte swizzle, 64-element K slabs), 3-6 stage mbarrier ring
 //   * one elected thread issues tcgen05.mma (cta_group::1, M=128, N=BLOCK_N, K=16); accumulators live in TMEM,
 //     double-buffered (2 x BLOCK_N fp32 columns) so the epilogue of tile i overlaps the main loop of tile i+1
 //   * persistent: grid = #SMs, static round-robin over (m,n) tiles, n fastest so the CTAs that are co-resident
 //     share A row-blocks through L2 while the (small) weight matrix stays L2 resident
 //   * warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM alloc/dealloc, 4..11 = epilogue
 //     (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4)
-//   * fused epilogues replace the reference's separate elementwise kernels:
-//       bias                      (HF:329-335 q/k/v Linear; omics_one.py:91 projector)
+//   * epilogue: tcgen05.ld (thread == accumulator row) -> fused math -> 128-B-swizzled smem staging (conflict free)
+//     -> TMA store, so HBM sees full coalesced rows; the fp32 residual is brought in by TMA loads that are
+//     double-buffered against the math.  Fused epilogues replace the reference's separate elementwise kernels:
+//       bias (+ q *= d^-1/2)      (HF:329-341 q/k/v Linear; omics_one.py:91 projector)
 //       bias + exact-erf GELU     (HF:406-414, 57-61)
 //       bias + residual, fp32     (HF:365-375, 417-427)
 //       gated SiLU                (NT-v2 FFN, weight rows interleaved at pack time)
 //       bias + row scatter        (omics_one.py:91-97: projector output written straight into hidden_states)
+#include <string.h>
+
 #include "common.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -27,21 +31,28 @@ constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
+constexpr int STG_BUF_BYTES = 32 * 128;          // one staging buffer: 32 rows x 128 B (SWIZZLE_128B box)
 
-template <int BLOCK_N>
+constexpr int imin(int a, int b) { return a < b ? a : b; }
+
+template <int BLOCK_N, int EPI>
 struct GemmCfg {
     static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+    static constexpr int STG_BUFS = (EPI == EPI_BIAS_RESID) ? 2 : 1;          // residual prefetch needs a second buffer
+    static constexpr int STG_BYTES = NUM_EPI_WARPS * STG_BUFS * STG_BUF_BYTES;  // 32 KB or 64 KB
+    static constexpr int STAGES = imin(6, (227 * 1024 - 1024 - STG_BYTES) / (A_STAGE_BYTES + B_STAGE_BYTES));
     static constexpr int TMEM_COLS = 2 * BLOCK_N;           // 512 or 256: powers of two
-    static constexpr int BAR_OFFSET = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-    static constexpr int SMEM_BYTES = BAR_OFFSET + 256;
+    static constexpr int STG_OFFSET = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+    static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFFSET + 512;
+    static_assert(STAGES >= 3, "not enough shared memory for a 3-stage ring");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
 
 struct GemmParams {
     int M, N, K;
     const float* bias;
-    const float* residual;
-    void* out;
+    void* out;                  // EPI_SCATTER only (direct stores); every other mode stores through tma_c
     int ldo;
     const int32_t* seq_table;   // EPI_SCATTER: [n_seq][2] = (b, start)
     int seq_k, B, T, k_cap;
@@ -50,35 +61,44 @@ struct GemmParams {
     float scale;                //           (q = (x Wq^T + bq) * d^-1/2, HF:341); scale_cols % 32 == 0
 };
 
-template <typename OutT>
-__device__ __forceinline__ void store_chunk(OutT* dst, const float (&v)[32]);
+// 16-byte chunk c of staging row `lane` under the 128-B swizzle (matches CU_TENSOR_MAP_SWIZZLE_128B)
+__device__ __forceinline__ uint4* stg_chunk(uint8_t* buf, int lane, int c) {
+    return reinterpret_cast<uint4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4));
+}
 
+template <typename OutT>
+__device__ __forceinline__ void store_direct(OutT* dst, const float* v);     // 32 values
 template <>
-__device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[32]) {
+__device__ __forceinline__ void store_direct<__nv_bfloat16>(__nv_bfloat16* dst, const float* v) {
     uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint4 u;
-        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-        u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-        u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-        d4[i] = u;
-    }
+    for (int i = 0; i < 4; ++i)
+        d4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                           pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
 }
 template <>
-__device__ __forceinline__ void store_chunk<float>(float* dst, const float (&v)[32]) {
+__device__ __forceinline__ void store_direct<float>(float* dst, const float* v) {
     float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
     for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
+__device__ __forceinline__ void add_bias32(float* v, const float* bias, int col0) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 bb = __ldg(b4 + i);
+        v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+    }
+}
+
 template <int BLOCK_N, int EPI, typename OutT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    const GemmParams p) {
-    using Cfg = GemmCfg<BLOCK_N>;
+                    const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N, EPI>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr bool kOutF32 = sizeof(OutT) == 4;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
@@ -86,7 +106,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* res_bar = tmem_empty + 2;                      // [NUM_EPI_WARPS][2] residual-load barriers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * NUM_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -98,6 +119,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
+        if constexpr (EPI != EPI_SCATTER) tma_prefetch_desc(&tma_c);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -108,6 +130,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
         }
+        for (int s = 0; s < 2 * NUM_EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -174,20 +197,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
     } else if (warp >= 4) {
         // ------------------------------ epilogue ------------------------------
+        const int ew = warp - 4;
         const int q = warp & 3;                     // TMEM lane quarter this warp may access
-        const int half = (warp - 4) >> 2;           // which half of the tile's columns
+        const int half = ew >> 2;                   // which half of the tile's columns
         constexpr int COLS_PER_WARP = BLOCK_N / 2;
-        constexpr int CHUNKS = COLS_PER_WARP / 32;
-        OutT* const out = reinterpret_cast<OutT*>(p.out);
+        uint8_t* const stg = smem + Cfg::STG_OFFSET + ew * (Cfg::STG_BUFS * STG_BUF_BYTES);
+        uint64_t* const rbar = res_bar + 2 * ew;
+        uint32_t rphase0 = 0, rphase1 = 0;
+        const uint32_t lane_tmem = static_cast<uint32_t>(q * 32) << 16;
         int local = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
             const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
-            const int row = m_blk * BLOCK_M + q * 32 + lane;
-            long long dst_row = (row < p.M) ? row : -1;
+            const int row0 = m_blk * BLOCK_M + q * 32;                   // first row of this warp's slab
+            const int colw = n_blk * BLOCK_N + half * COLS_PER_WARP;     // first column of this warp's slab
+            const uint32_t tacc = tmem_base + lane_tmem + acc * BLOCK_N + half * COLS_PER_WARP;
+
             if constexpr (EPI == EPI_SCATTER) {
-                dst_row = -1;
+                // ---- projector: rows go to hidden_states[b, start+1+j, :]; direct 16-B stores (0.3 % of the FLOPs)
+                OutT* const out = reinterpret_cast<OutT*>(p.out);
+                const int row = row0 + lane;
+                long long dst_row = -1;
                 if (row < p.M) {
                     const int n = row / p.seq_k;
                     const int j = row - n * p.seq_k;
@@ -199,64 +230,169 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         else if (p.err_flag) atomicOr(p.err_flag, 2);
                     }
                 }
-            }
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < CHUNKS; ++c) {
-                const int col_in_tile = half * COLS_PER_WARP + c * 32;
-                const int col0 = n_blk * BLOCK_N + col_in_tile;
-                if (col0 >= p.N) break;                                       // warp-uniform
-                uint32_t raw[32];
-                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + col_in_tile, raw);
-                tmem_ld_wait();
-                float v[32];
+                for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+                    const int col0 = colw + c * 32;
+                    if (col0 >= p.N) break;                                   // warp-uniform
+                    uint32_t raw[32];
+                    tmem_ld32(tacc + c * 32, raw);
+                    tmem_ld_wait();
+                    float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-                if constexpr (EPI != EPI_GLU) {
-                    if (p.bias != nullptr) {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                    if (p.bias != nullptr) add_bias32(v, p.bias, col0);
+                    if (dst_row >= 0) store_direct<OutT>(out + dst_row * p.ldo + col0, v);
+                }
+            } else if constexpr (EPI == EPI_BIAS_RESID) {
+                // ---- out(fp32) = acc + bias + residual; residual chunks (32 rows x 32 fp32) arrive by TMA, double-buffered
+                constexpr int CHUNKS = COLS_PER_WARP / 32;
+                int nchunks = 0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 bb = __ldg(b4 + i);
-                            v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
-                        }
+                for (int c = 0; c < CHUNKS; ++c) nchunks += (colw + c * 32 < p.N) ? 1 : 0;
+                if (lane == 0 && nchunks > 0) {             // chunk 0 is fetched while the main loop still runs
+                    tma_store_wait_read<0>();               // buffer 0 may still be read by an earlier store
+                    mbar_arrive_expect_tx(&rbar[0], STG_BUF_BYTES);
+                    tma_load_2d(stg, &tma_c, &rbar[0], colw, row0);
+                }
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < nchunks; ++c) {
+                    const int buf = c & 1;
+                    uint8_t* const sbuf = stg + buf * STG_BUF_BYTES;
+                    if (lane == 0 && c + 1 < nchunks) {      // prefetch the next residual chunk into the other buffer
+                        tma_store_wait_read<0>();            // ... once the store that last used it has read it out
+                        mbar_arrive_expect_tx(&rbar[buf ^ 1], STG_BUF_BYTES);
+                        tma_load_2d(stg + (buf ^ 1) * STG_BUF_BYTES, &tma_c, &rbar[buf ^ 1], colw + (c + 1) * 32, row0);
+                    }
+                    const int col0 = colw + c * 32;
+                    uint32_t raw[32];
+                    tmem_ld32(tacc + c * 32, raw);
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                    if (p.bias != nullptr) add_bias32(v, p.bias, col0);
+                    if (buf == 0) { mbar_wait(&rbar[0], rphase0); rphase0 ^= 1; }
+                    else          { mbar_wait(&rbar[1], rphase1); rphase1 ^= 1; }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        uint4* ptr = stg_chunk(sbuf, lane, i);
+                        const uint4 r = *ptr;
+                        uint4 o;
+                        o.x = __float_as_uint(v[4 * i] + __uint_as_float(r.x));
+                        o.y = __float_as_uint(v[4 * i + 1] + __uint_as_float(r.y));
+                        o.z = __float_as_uint(v[4 * i + 2] + __uint_as_float(r.z));
+                        o.w = __float_as_uint(v[4 * i + 3] + __uint_as_float(r.w));
+                        *ptr = o;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tma_c, sbuf, col0, row0);
+                        tma_store_commit();
                     }
                 }
-                if constexpr (EPI == EPI_BIAS) {
-                    if (col0 < p.scale_cols) {                                  // warp-uniform
+            } else {
+                // ---- bf16 / fp32 outputs through one staging buffer per warp
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                constexpr int ACC_PER_CHUNK = (EPI == EPI_GLU) ? 128 : (kOutF32 ? 32 : 64);   // accumulator columns / store
+                constexpr int CHUNKS = COLS_PER_WARP / ACC_PER_CHUNK;
+                static_assert(CHUNKS >= 1, "GLU epilogue needs BLOCK_N == 256");
+#pragma unroll 1
+                for (int c = 0; c < CHUNKS; ++c) {
+                    const int col0 = colw + c * ACC_PER_CHUNK;
+                    if (col0 >= p.N) break;                                   // warp-uniform
+                    if constexpr (EPI == EPI_GLU) {
+                        // 128 accumulator columns (x1_0, x2_0, x1_1, ...) -> 64 outputs silu(x1) * x2 = one 128-B row
+                        uint4 packed[8];
+                        uint32_t* pw = reinterpret_cast<uint32_t*>(packed);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] *= p.scale;
-                    }
-                }
-                if (dst_row >= 0) {
-                    if constexpr (EPI == EPI_BIAS_GELU) {
+                        for (int hh = 0; hh < 4; ++hh) {
+                            uint32_t raw[32];
+                            tmem_ld32(tacc + c * 128 + hh * 32, raw);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-                        store_chunk<OutT>(out + dst_row * p.ldo + col0, v);
-                    } else if constexpr (EPI == EPI_BIAS_RESID) {
-                        const float4* r4 = reinterpret_cast<const float4*>(p.residual + dst_row * p.ldo + col0);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 rr = r4[i];
-                            v[4 * i] += rr.x; v[4 * i + 1] += rr.y; v[4 * i + 2] += rr.z; v[4 * i + 3] += rr.w;
+                            for (int i = 0; i < 8; ++i) {
+                                const float g0 = silu(__uint_as_float(raw[4 * i])) * __uint_as_float(raw[4 * i + 1]);
+                                const float g1 = silu(__uint_as_float(raw[4 * i + 2])) * __uint_as_float(raw[4 * i + 3]);
+                                pw[hh * 8 + i] = pack_bf16x2(g0, g1);
+                            }
                         }
-                        store_chunk<OutT>(out + dst_row * p.ldo + col0, v);
-                    } else if constexpr (EPI == EPI_GLU) {
-                        uint4 u[2];
-                        uint32_t* uw = reinterpret_cast<uint32_t*>(u);
+                        if (lane == 0) tma_store_wait_read<0>();
+                        __syncwarp();
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float g0 = silu(v[4 * i]) * v[4 * i + 1];
-                            const float g1 = silu(v[4 * i + 2]) * v[4 * i + 3];
-                            uw[i] = pack_bf16x2(g0, g1);
+                        for (int i = 0; i < 8; ++i) *stg_chunk(stg, lane, i) = packed[i];
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tma_c, stg, col0 >> 1, row0);
+                            tma_store_commit();
                         }
-                        uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                                             dst_row * p.ldo + (col0 >> 1));
-                        d4[0] = u[0];
-                        d4[1] = u[1];
+                    } else if constexpr (kOutF32) {
+                        uint32_t raw[32];
+                        tmem_ld32(tacc + c * 32, raw);
+                        tmem_ld_wait();
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                        if (p.bias != nullptr) add_bias32(v, p.bias, col0);
+                        if (EPI == EPI_BIAS && col0 < p.scale_cols) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+                        }
+                        if (lane == 0) tma_store_wait_read<0>();
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            *stg_chunk(stg, lane, i) = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+                                                                  __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tma_c, stg, col0, row0);
+                            tma_store_commit();
+                        }
                     } else {
-                        store_chunk<OutT>(out + dst_row * p.ldo + col0, v);
+                        // bf16: 64 accumulator columns -> one 128-B row
+                        uint4 packed[8];
+                        uint32_t* pw = reinterpret_cast<uint32_t*>(packed);
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int colh = col0 + hh * 32;
+                            uint32_t raw[32];
+                            tmem_ld32(tacc + c * 64 + hh * 32, raw);
+                            tmem_ld_wait();
+                            float v[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                            if (colh < p.N) {                                   // N % 32 == 0: halves are all-in or all-out
+                                if (p.bias != nullptr) add_bias32(v, p.bias, colh);
+                                if (EPI == EPI_BIAS && colh < p.scale_cols) {
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+                                }
+                                if constexpr (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) pw[hh * 16 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                        }
+                        if (lane == 0) tma_store_wait_read<0>();
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) *stg_chunk(stg, lane, i) = packed[i];
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tma_c, stg, col0, row0);      // rows >= M / cols >= N are clipped by the TMA unit
+                            tma_store_commit();
+                        }
                     }
                 }
             }
@@ -264,6 +400,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (lane == 0) tma_store_wait<0>();          // all of this warp's stores are complete before the CTA retires
     }
 
     tc_fence_before();
@@ -275,8 +412,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 }
 
 template <int BLOCK_N, int EPI, typename OutT>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-    using Cfg = GemmCfg<BLOCK_N>;
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+                cudaStream_t stream) {
+    using Cfg = GemmCfg<BLOCK_N, EPI>;
     auto kernel = gemm_tcgen05_kernel<BLOCK_N, EPI, OutT>;
     static bool configured = false;
     if (!configured) {
@@ -287,7 +425,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
     const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
     {
         ProfScope prof(gemm_family(), 2.0 * p.M * p.N * p.K, stream);
-        kernel<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+        kernel<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, p);
     }
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
@@ -295,25 +433,23 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
 }
 
 template <int BLOCK_N>
-int dispatch_epilogue(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi, int out_dtype,
-                      cudaStream_t stream) {
-    const bool f32 = out_dtype == 1;
+int dispatch_epilogue(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int epi,
+                      int out_dtype, cudaStream_t stream) {
+    const bool f32 = out_dtype == DT_F32;
     switch (epi) {
         case EPI_BIAS:
-            return f32 ? launch_gemm<BLOCK_N, EPI_BIAS, float>(ta, tb, p, stream)
-                       : launch_gemm<BLOCK_N, EPI_BIAS, __nv_bfloat16>(ta, tb, p, stream);
+            return f32 ? launch_gemm<BLOCK_N, EPI_BIAS, float>(ta, tb, tc, p, stream)
+                       : launch_gemm<BLOCK_N, EPI_BIAS, __nv_bfloat16>(ta, tb, tc, p, stream);
         case EPI_BIAS_GELU:
-            MOLLY_CHECK(!f32, MOLLY_ERR_UNSUPPORTED, "gemm: GELU epilogue writes bf16 only");
-            return launch_gemm<BLOCK_N, EPI_BIAS_GELU, __nv_bfloat16>(ta, tb, p, stream);
+            return launch_gemm<BLOCK_N, EPI_BIAS_GELU, __nv_bfloat16>(ta, tb, tc, p, stream);
         case EPI_BIAS_RESID:
-            MOLLY_CHECK(f32, MOLLY_ERR_UNSUPPORTED, "gemm: residual epilogue writes the fp32 residual stream only");
-            return launch_gemm<BLOCK_N, EPI_BIAS_RESID, float>(ta, tb, p, stream);
+            return launch_gemm<BLOCK_N, EPI_BIAS_RESID, float>(ta, tb, tc, p, stream);
         case EPI_GLU:
-            MOLLY_CHECK(!f32, MOLLY_ERR_UNSUPPORTED, "gemm: GLU epilogue writes bf16 only");
-            return launch_gemm<BLOCK_N, EPI_GLU, __nv_bfloat16>(ta, tb, p, stream);
+            if constexpr (BLOCK_N == 256) return launch_gemm<256, EPI_GLU, __nv_bfloat16>(ta, tb, tc, p, stream);
+            MOLLY_CHECK(false, MOLLY_ERR_UNSUPPORTED, "gemm: GLU epilogue needs 256-wide tiles");
         case EPI_SCATTER:
-            return f32 ? launch_gemm<BLOCK_N, EPI_SCATTER, float>(ta, tb, p, stream)
-                       : launch_gemm<BLOCK_N, EPI_SCATTER, __nv_bfloat16>(ta, tb, p, stream);
+            return f32 ? launch_gemm<BLOCK_N, EPI_SCATTER, float>(ta, tb, tc, p, stream)
+                       : launch_gemm<BLOCK_N, EPI_SCATTER, __nv_bfloat16>(ta, tb, tc, p, stream);
         default:
             MOLLY_CHECK(false, MOLLY_ERR_INVALID, "gemm: unknown epilogue %d", epi);
     }
@@ -321,7 +457,8 @@ int dispatch_epilogue(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
 
 }  // namespace
 
-int gemm_block_n(int N) {
+int gemm_block_n(int N, int epi) {
+    if (epi == EPI_GLU) return 256;
     // 256-wide tiles unless the last tile would be mostly padding
     const int t256 = (N + 255) / 256 * 256, t128 = (N + 127) / 128 * 128;
     return (t256 * 10 > t128 * 11) ? 128 : 256;
@@ -334,39 +471,48 @@ int gemm_make_map_a(CUtensorMap* ta, const void* a, int lda, int M, int K) {
     return make_tma_2d(ta, a, M, K, lda, BLOCK_M, BLOCK_K, 2);
 }
 
-int gemm_make_map_b(CUtensorMap* tb, const void* w, int ldw, int N, int K) {
+int gemm_make_map_b(CUtensorMap* tb, const void* w, int ldw, int N, int K, int epi) {
     MOLLY_CHECK(K % 8 == 0 && ldw % 8 == 0, MOLLY_ERR_UNSUPPORTED,
                 "gemm: K and ldw must be multiples of 8 (16-B TMA strides); got K=%d ldw=%d", K, ldw);
     MOLLY_CHECK((reinterpret_cast<uintptr_t>(w) & 15) == 0, MOLLY_ERR_INVALID, "gemm: W must be 16-B aligned");
-    return make_tma_2d(tb, w, N, K, ldw, gemm_block_n(N), BLOCK_K, 2);
+    return make_tma_2d(tb, w, N, K, ldw, gemm_block_n(N, epi), BLOCK_K, 2);
 }
 
-int gemm_make_maps(CUtensorMap* ta, CUtensorMap* tb, const void* a, int lda, const void* w, int ldw, int M, int N,
-                   int K) {
-    int rc = gemm_make_map_a(ta, a, lda, M, K);
-    if (rc) return rc;
-    return gemm_make_map_b(tb, w, ldw, N, K);
+// Output (and residual) map: 32-row x 128-byte boxes, 128-B swizzle.  `n_out` = columns of the OUTPUT matrix.
+int gemm_make_map_c(CUtensorMap* tc, void* out, int out_dtype, int ldo, int M, int n_out) {
+    const int eb = out_dtype == DT_F32 ? 4 : 2;
+    MOLLY_CHECK((static_cast<long long>(ldo) * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                MOLLY_ERR_INVALID, "gemm: output must be 16-B aligned with a 16-B multiple pitch (ldo=%d)", ldo);
+    return make_tma_2d(tc, out, M, n_out, ldo, 32, 128 / eb, eb);
 }
 
-int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int epi, const float* bias,
-                const float* residual, void* out, int out_dtype, int ldo, const int32_t* seq_table, int seq_k, int B,
-                int T, int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols, float scale) {
+int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tc, int M, int N, int K, int epi,
+                const float* bias, void* out, int out_dtype, int ldo, const int32_t* seq_table, int seq_k, int B, int T,
+                int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols, float scale) {
     MOLLY_CHECK(M > 0 && N > 0 && K > 0, MOLLY_ERR_INVALID, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     MOLLY_CHECK(N % 32 == 0, MOLLY_ERR_UNSUPPORTED, "gemm: N must be a multiple of 32, got %d", N);
-    MOLLY_CHECK(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, MOLLY_ERR_INVALID,
-                "gemm: output must be 16-B aligned with ldo %% 8 == 0 (ldo=%d)", ldo);
     MOLLY_CHECK(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, MOLLY_ERR_INVALID,
                 "gemm: bias must be 16-B aligned");
-    if (epi == EPI_BIAS_RESID)
-        MOLLY_CHECK(residual != nullptr && (reinterpret_cast<uintptr_t>(residual) & 15) == 0, MOLLY_ERR_INVALID,
-                    "gemm: residual epilogue needs a 16-B aligned residual");
-    if (epi == EPI_SCATTER)
-        MOLLY_CHECK(seq_table != nullptr && seq_k > 0 && B > 0 && T > 0, MOLLY_ERR_INVALID,
-                    "gemm: scatter epilogue needs seq_table / k_tokens / B / T");
     MOLLY_CHECK(scale_cols % 32 == 0, MOLLY_ERR_UNSUPPORTED, "gemm: scale_cols must be a multiple of 32");
-    GemmParams p{M, N, K, bias, residual, out, ldo, seq_table, seq_k, B, T, k_cap, err_flag, scale_cols, scale};
-    if (gemm_block_n(N) == 256) return dispatch_epilogue<256>(ta, tb, p, epi, out_dtype, stream);
-    return dispatch_epilogue<128>(ta, tb, p, epi, out_dtype, stream);
+    if (epi == EPI_GLU) MOLLY_CHECK(N % 256 == 0, MOLLY_ERR_UNSUPPORTED, "gemm: GLU needs N %% 256 == 0 (N=%d)", N);
+    if (epi == EPI_BIAS_GELU || epi == EPI_GLU)
+        MOLLY_CHECK(out_dtype == DT_BF16, MOLLY_ERR_UNSUPPORTED, "gemm: GELU / GLU epilogues write bf16");
+    if (epi == EPI_BIAS_RESID)
+        MOLLY_CHECK(out_dtype == DT_F32, MOLLY_ERR_UNSUPPORTED, "gemm: the residual epilogue updates the fp32 stream");
+    CUtensorMap dummy;
+    if (epi == EPI_SCATTER) {
+        MOLLY_CHECK(seq_table != nullptr && seq_k > 0 && B > 0 && T > 0 && out != nullptr, MOLLY_ERR_INVALID,
+                    "gemm: scatter epilogue needs seq_table / k_tokens / B / T / out");
+        MOLLY_CHECK(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, MOLLY_ERR_INVALID,
+                    "gemm: scatter output must be 16-B aligned with ldo %% 8 == 0 (ldo=%d)", ldo);
+        memset(&dummy, 0, sizeof(dummy));
+        tc = &dummy;
+    } else {
+        MOLLY_CHECK(tc != nullptr, MOLLY_ERR_INVALID, "gemm: missing output tensor map");
+    }
+    GemmParams p{M, N, K, bias, out, ldo, seq_table, seq_k, B, T, k_cap, err_flag, scale_cols, scale};
+    if (gemm_block_n(N, epi) == 256) return dispatch_epilogue<256>(ta, tb, *tc, p, epi, out_dtype, stream);
+    return dispatch_epilogue<128>(ta, tb, *tc, p, epi, out_dtype, stream);
 }
 
 }  // namespace molly

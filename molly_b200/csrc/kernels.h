@@ -27,13 +27,14 @@ void set_gemm_family(int f);  // tag for the next gemm_launch calls of this thre
 int gemm_family();
 
 // ---- gemm.cu ----
-int gemm_block_n(int N);
+int gemm_block_n(int N, int epi);
 int gemm_make_map_a(CUtensorMap* ta, const void* a, int lda, int M, int K);
-int gemm_make_map_b(CUtensorMap* tb, const void* w, int ldw, int N, int K);
-int gemm_make_maps(CUtensorMap* ta, CUtensorMap* tb, const void* a, int lda, const void* w, int ldw, int M, int N, int K);
-int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int epi, const float* bias,
-                const float* residual, void* out, int out_dtype, int ldo, const int32_t* seq_table, int seq_k, int B,
-                int T, int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols = 0, float scale = 1.0f);
+int gemm_make_map_b(CUtensorMap* tb, const void* w, int ldw, int N, int K, int epi);
+int gemm_make_map_c(CUtensorMap* tc, void* out, int out_dtype, int ldo, int M, int n_out);
+// EPI_BIAS_RESID reads the residual through `tc` too: the update is in place on the fp32 stream.
+int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tc, int M, int N, int K, int epi,
+                const float* bias, void* out, int out_dtype, int ldo, const int32_t* seq_table, int seq_k, int B, int T,
+                int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols = 0, float scale = 1.0f);
 
 // ---- attention.cu ----
 int attention_make_map(CUtensorMap* tq, const void* qkv, int rows, int h, int heads);

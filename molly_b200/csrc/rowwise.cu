@@ -157,10 +157,9 @@ __global__ void mask_rows_kernel(float* __restrict__ x, const uint8_t* __restric
 // One warp per row; the row is held in registers (<= 20 float4 per lane, h <= 2560); mean, then sum of squared
 // deviations (two-pass, like torch) by warp shuffles; one HBM read + one write per element.
 // ------------------------------------------------------------------------------------------------
-constexpr int LN_MAXV = 20;
-constexpr int LN_THREADS = 256;
+constexpr int LN_THREADS = 128;                 // 4 rows per CTA: small CTAs keep many loads in flight per SM
 
-template <typename OutT>
+template <typename OutT, int VPL>               // VPL = float4 vectors per lane = ceil(h / 128)
 __global__ void __launch_bounds__(LN_THREADS)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, int rows, int h,
                  float eps, OutT* __restrict__ out) {
@@ -169,22 +168,20 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     const int lane = threadIdx.x & 31;
     const int nvec = h >> 2;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * h);
-    float4 v[LN_MAXV];
+    float4 v[VPL];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < VPL; ++i) {
         const int idx = lane + 32 * i;
-        if (idx < nvec) {
-            v[i] = xr[idx];
-            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-        }
+        v[i] = (idx < nvec) ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     const float mean = warp_sum(s) / static_cast<float>(h);
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < nvec) {
+    for (int i = 0; i < VPL; ++i) {
+        if (lane + 32 * i < nvec) {
             const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
             ss += (dx * dx + dy * dy) + (dz * dz + dw * dw);
         }
@@ -193,7 +190,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     const float4* w4 = reinterpret_cast<const float4*>(w);
     const float4* b4 = reinterpret_cast<const float4*>(b);
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < VPL; ++i) {
         const int idx = lane + 32 * i;
         if (idx < nvec) {
             const float4 ww = __ldg(w4 + idx), bb = __ldg(b4 + idx);
@@ -211,6 +208,18 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
             }
         }
     }
+}
+
+template <typename OutT>
+void launch_layernorm(const float* x, const float* w, const float* b, int rows, int h, float eps, OutT* out,
+                      cudaStream_t stream) {
+    const int grid = (rows + LN_THREADS / 32 - 1) / (LN_THREADS / 32);
+    const int vpl = (h / 4 + 31) / 32;
+#define MOLLY_LN_CASE(V) \
+    if (vpl <= V) { layernorm_kernel<OutT, V><<<grid, LN_THREADS, 0, stream>>>(x, w, b, rows, h, eps, out); return; }
+    MOLLY_LN_CASE(1) MOLLY_LN_CASE(2) MOLLY_LN_CASE(3) MOLLY_LN_CASE(4) MOLLY_LN_CASE(5) MOLLY_LN_CASE(6)
+    MOLLY_LN_CASE(8) MOLLY_LN_CASE(10) MOLLY_LN_CASE(12) MOLLY_LN_CASE(16) MOLLY_LN_CASE(20)
+#undef MOLLY_LN_CASE
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -300,16 +309,11 @@ int mask_rows_launch(float* x, const uint8_t* key_mask, int rows, int h, cudaStr
 
 int layernorm_launch(const float* x, const float* w, const float* b, int rows, int h, float eps, void* out,
                      int out_dtype, cudaStream_t stream) {
-    MOLLY_CHECK(h % 4 == 0 && h <= LN_MAXV * 128, MOLLY_ERR_UNSUPPORTED, "layernorm: h=%d unsupported (h %% 4, h <= %d)",
-                h, LN_MAXV * 128);
+    MOLLY_CHECK(h % 4 == 0 && h <= 20 * 128, MOLLY_ERR_UNSUPPORTED, "layernorm: h=%d unsupported (h %% 4, h <= 2560)", h);
     MOLLY_CHECK(rows > 0, MOLLY_ERR_INVALID, "layernorm: rows=%d", rows);
-    const int grid = (rows + LN_THREADS / 32 - 1) / (LN_THREADS / 32);
     ProfScope prof(PF_LAYERNORM, static_cast<double>(rows) * h * (out_dtype == DT_F32 ? 8.0 : 6.0), stream);
-    if (out_dtype == DT_F32)
-        layernorm_kernel<float><<<grid, LN_THREADS, 0, stream>>>(x, w, b, rows, h, eps, static_cast<float*>(out));
-    else
-        layernorm_kernel<__nv_bfloat16><<<grid, LN_THREADS, 0, stream>>>(x, w, b, rows, h, eps,
-                                                                          static_cast<__nv_bfloat16*>(out));
+    if (out_dtype == DT_F32) launch_layernorm<float>(x, w, b, rows, h, eps, static_cast<float*>(out), stream);
+    else launch_layernorm<__nv_bfloat16>(x, w, b, rows, h, eps, static_cast<__nv_bfloat16*>(out), stream);
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
     return MOLLY_OK;
