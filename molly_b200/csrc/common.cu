@@ -93,7 +93,7 @@ int make_tma_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols
                 uint32_t box_cols, uint32_t elem_bytes, bool swizzle) {
     EncodeTiledFn fn = get_encode_fn();
     MOLLY_CHECK(fn != nullptr, MOLLY_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-    MOLLY_CHECK(elem_bytes == 2, MOLLY_ERR_UNSUPPORTED, "tma: only 2-byte elements are used by this library");
+    MOLLY_CHECK(elem_bytes == 2 || elem_bytes == 4, MOLLY_ERR_UNSUPPORTED, "tma: element size must be 2 (bf16) or 4 (fp32)");
     const uint32_t inner = box_cols * elem_bytes;
     CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
     if (swizzle) {
@@ -109,7 +109,7 @@ int make_tma_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols
     cuuint64_t gstride[1] = {ld * elem_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+    CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MOLLY_CHECK(r == CUDA_SUCCESS, MOLLY_ERR_CUDA,
