@@ -76,6 +76,7 @@ typedef struct molly_encoder_weights {
     const float* rope_cos_dev;           /* fp32 [rope_len, d/2]    cos(t * 10000^(-2i/d))  (HF:81-115) */
     const float* rope_sin_dev;
     int32_t rope_len;
+    const float* rope_inv_freq_dev;      /* fp32 [d/2]  10000^(-2i/d): the QKV GEMM epilogue rotates q,k itself (d <= 64) */
     const float* const* ln1_w_dev;       /* attention.LayerNorm */
     const float* const* ln1_b_dev;
     const void* const* w_qkv_dev;        /* bf16 [3h, h] = cat(Wq, Wk, Wv)  (HF:329-335); q *= d^-1/2 happens in the epilogue */
@@ -145,14 +146,16 @@ enum molly_epilogue {
     MOLLY_EPI_BIAS_GELU = 1,     /* out = gelu_erf(A W^T + b)             (HF:57-61, 406-414) */
     MOLLY_EPI_BIAS_RESIDUAL = 2, /* out = A W^T + b + residual, fp32      (HF:365-375, 417-427) */
     MOLLY_EPI_GLU = 3,           /* out[:, j] = silu(acc[:, 2j]) * acc[:, 2j+1]   (NT-v2 gated FFN) */
-    MOLLY_EPI_SCATTER = 4        /* out[b*T + start+1+j, :] = A W^T + b   (omics_one.py:91-97 fused) */
+    MOLLY_EPI_SCATTER = 4,       /* out[b*T + start+1+j, :] = A W^T + b   (omics_one.py:91-97 fused) */
+    MOLLY_EPI_BIAS_ROPE = 5      /* BIAS + scale, then NeoX rotary on out[:, :rope_cols] per head (HF:341-344, 45-123) */
 };
 int molly_gemm_bf16(const void* a_dev, int32_t lda, const void* w_dev, int32_t ldw, int32_t M, int32_t N, int32_t K,
                     int32_t epilogue, const float* bias_dev, const float* residual_dev, void* out_dev,
                     int32_t out_dtype, int32_t ldo, const int32_t* seq_table_dev, int32_t seq_k_tokens, int32_t B,
                     int32_t T, int32_t k_cap, int32_t* err_flag_dev,
-                    int32_t scale_cols /*BIAS only: out[:, :scale_cols] *= scale after the bias (q *= d^-1/2, HF:341)*/,
-                    float scale, void* stream);
+                    int32_t scale_cols /*BIAS / BIAS_ROPE: out[:, :scale_cols] *= scale after the bias (q *= d^-1/2, HF:341)*/,
+                    float scale, const float* rope_inv_freq_dev /*BIAS_ROPE: fp32 [head_dim/2]*/, int32_t rope_cols,
+                    int32_t rope_head_dim, void* stream);
 int molly_layernorm(const float* x_dev, const float* w_dev, const float* b_dev, int32_t rows, int32_t h, float eps,
                     void* out_dev, int32_t out_dtype, void* stream);
 int molly_embed(const int64_t* ids_dev, int32_t n_seq, int32_t k_tokens, const molly_encoder_config* cfg,

@@ -20,7 +20,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, 1, 2, 3, 4
 DTYPE_BF16, DTYPE_F32 = 0, 1
 POS_ROTARY, POS_ABSOLUTE = 0, 1
 FFN_GELU, FFN_GLU = 0, 1
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_GLU, EPI_SCATTER = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_GLU, EPI_SCATTER, EPI_BIAS_ROPE = 0, 1, 2, 3, 4, 5
 ERRBIT_OOV, ERRBIT_OVERFLOW, ERRBIT_POSITION = 1, 2, 4
 
 c_void_pp = C.POINTER(C.c_void_p)
@@ -43,6 +43,7 @@ class EncoderWeights(C.Structure):
         ("word_emb_dev", C.c_void_p), ("pos_emb_dev", C.c_void_p),
         ("emb_ln_w_dev", C.c_void_p), ("emb_ln_b_dev", C.c_void_p),
         ("rope_cos_dev", C.c_void_p), ("rope_sin_dev", C.c_void_p), ("rope_len", C.c_int32),
+        ("rope_inv_freq_dev", C.c_void_p),
         ("ln1_w_dev", c_void_pp), ("ln1_b_dev", c_void_pp),
         ("w_qkv_dev", c_void_pp), ("b_qkv_dev", c_void_pp),
         ("w_attn_out_dev", c_void_pp), ("b_attn_out_dev", c_void_pp),
@@ -76,7 +77,7 @@ SIGNATURES = {
     "molly_project_bwd": (C.c_int, [C.c_void_p, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp,
                                     _sz, _vp]),
     "molly_gemm_bf16": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _i32,
-                                  _i32, _i32, _i32, _vp, _i32, C.c_float, _vp]),
+                                  _i32, _i32, _i32, _vp, _i32, C.c_float, _vp, _i32, _i32, _vp]),
     "molly_layernorm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, C.c_float, _vp, _i32, _vp]),
     "molly_embed": (C.c_int, [_vp, _i32, _i32, C.POINTER(EncoderConfig), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "molly_rotary": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),

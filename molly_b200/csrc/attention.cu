@@ -238,20 +238,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
                 mx4[2] = fmaxf(mx4[2], s[i + 2]); mx4[3] = fmaxf(mx4[3], s[i + 3]);
             }
             const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-            const float m_new = fmaxf(m_run, mx * LOG2E);
-            const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-            const float alpha = ex2(m_run - m_use);                    // m_run = -inf -> 0
-            float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+            // Lazy rescaling: the reference max only moves when the row max grew by more than 2^8; until then P is
+            // computed against the stale max (P <= 256, exact in the fp32 sum and harmless in bf16) and O / l need no
+            // correction.  The result is unchanged because O and l always share the same reference max.
+            const float m_cand = fmaxf(m_run, mx * LOG2E);
+            float alpha = 1.0f;
+            if (m_cand > m_run + 8.0f) {                               // first valid block: m_run = -inf -> alpha = 0
+                alpha = ex2(m_run - m_cand);
+                m_run = m_cand;
+            }
+            const float m_use = (m_run == -CUDART_INF_F) ? 0.f : m_run;
+            // exp2(s*log2e - m) and the row sum with packed fp32x2 FMA / ADD (FFMA2 / FADD2): half the issue slots
+            const uint64_t sc2 = pack_f32x2(LOG2E, LOG2E), nm2 = pack_f32x2(-m_use, -m_use);
+            uint64_t sum2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
 #pragma unroll
             for (int i = 0; i < ATT_BLOCK; i += 4) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    s[i + u] = ex2(fmaf(s[i + u], LOG2E, -m_use));
-                    sum4[u] += s[i + u];
+                for (int u = 0; u < 2; ++u) {
+                    float x0, x1;
+                    unpack_f32x2(fma_f32x2(pack_f32x2(s[i + 2 * u], s[i + 2 * u + 1]), sc2, nm2), x0, x1);
+                    s[i + 2 * u] = ex2(x0);
+                    s[i + 2 * u + 1] = ex2(x1);
+                    sum2[u] = add_f32x2(sum2[u], pack_f32x2(s[i + 2 * u], s[i + 2 * u + 1]));
                 }
             }
-            l_run = l_run * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
-            m_run = m_new;
+            float sa, sb, sc, sd;
+            unpack_f32x2(sum2[0], sa, sb);
+            unpack_f32x2(sum2[1], sc, sd);
+            l_run = l_run * alpha + ((sa + sb) + (sc + sd));
             // PV(j-1) must have drained the P buffer and finished O before either is touched again
             if (j > 0) {
                 mbar_wait(&bar_kv_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);

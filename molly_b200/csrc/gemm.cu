@@ -35,10 +35,10 @@ constexpr int STG_BUF_BYTES = 32 * 128;          // one staging buffer: 32 rows 
 
 constexpr int imin(int a, int b) { return a < b ? a : b; }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int STG_BUFS_>
 struct GemmCfg {
     static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-    static constexpr int STG_BUFS = (EPI == EPI_BIAS_RESID) ? 2 : 1;          // residual prefetch needs a second buffer
+    static constexpr int STG_BUFS = STG_BUFS_;      // 2: residual chunks are prefetched (short-K GEMMs); 1: deeper ring
     static constexpr int STG_BYTES = NUM_EPI_WARPS * STG_BUFS * STG_BUF_BYTES;  // 32 KB or 64 KB
     static constexpr int STAGES = imin(6, (227 * 1024 - 1024 - STG_BYTES) / (A_STAGE_BYTES + B_STAGE_BYTES));
     static constexpr int TMEM_COLS = 2 * BLOCK_N;           // 512 or 256: powers of two
@@ -57,9 +57,29 @@ struct GemmParams {
     const int32_t* seq_table;   // EPI_SCATTER: [n_seq][2] = (b, start)
     int seq_k, B, T, k_cap;
     int32_t* err_flag;
-    int scale_cols;             // EPI_BIAS: columns [0, scale_cols) are multiplied by `scale` after the bias
-    float scale;                //           (q = (x Wq^T + bq) * d^-1/2, HF:341); scale_cols % 32 == 0
+    int scale_cols;             // EPI_BIAS / EPI_BIAS_ROPE: columns [0, scale_cols) are multiplied by `scale` after the
+    float scale;                //           bias (q = (x Wq^T + bq) * d^-1/2, HF:341); scale_cols % 32 == 0
+    const float* rope_inv_freq; // EPI_BIAS_ROPE: fp32 [head_dim/2] = 10000^(-2i/d)   (HF:81-95)
+    int rope_cols;              //   columns [0, rope_cols) (= q and k) are rotated; rope_cols % 64 == 0
+    int rope_head_dim;          //   16 | 32 | 64 ; position = row % seq_k  (row index inside the padded sequence, HF:103)
 };
+
+// NeoX rotary on one 64-column chunk held by one thread (its row): x*cos + rotate_half(x)*sin per head (HF:45-54).
+// Angles are float(t) * inv_freq rounded once, like torch.outer; sincosf is the accurate (non fast-math) version.
+template <int D>
+__device__ __forceinline__ void rope_chunk64(float* v, float t, const float* __restrict__ inv_freq) {
+#pragma unroll
+    for (int i = 0; i < D / 2; ++i) {
+        float sn, cs;
+        sincosf(__fmul_rn(t, __ldg(inv_freq + i)), &sn, &cs);
+#pragma unroll
+        for (int hl = 0; hl < 64 / D; ++hl) {
+            const float x1 = v[hl * D + i], x2 = v[hl * D + i + D / 2];
+            v[hl * D + i] = x1 * cs - x2 * sn;
+            v[hl * D + i + D / 2] = x2 * cs + x1 * sn;
+        }
+    }
+}
 
 // 16-byte chunk c of staging row `lane` under the 128-B swizzle (matches CU_TENSOR_MAP_SWIZZLE_128B)
 __device__ __forceinline__ uint4* stg_chunk(uint8_t* buf, int lane, int c) {
@@ -92,11 +112,11 @@ __device__ __forceinline__ void add_bias32(float* v, const float* bias, int col0
     }
 }
 
-template <int BLOCK_N, int EPI, typename OutT>
+template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
-    using Cfg = GemmCfg<BLOCK_N, EPI>;
+    using Cfg = GemmCfg<BLOCK_N, STG_BUFS>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool kOutF32 = sizeof(OutT) == 4;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -246,7 +266,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     if (dst_row >= 0) store_direct<OutT>(out + dst_row * p.ldo + col0, v);
                 }
             } else if constexpr (EPI == EPI_BIAS_RESID) {
-                // ---- out(fp32) = acc + bias + residual; residual chunks (32 rows x 32 fp32) arrive by TMA, double-buffered
+                // ---- out(fp32) = acc + bias + residual; residual chunks (32 rows x 32 fp32) arrive by TMA.
+                // STG_BUFS == 2: chunk c+1 is prefetched while chunk c is processed (and chunk 0 under the main loop);
+                // STG_BUFS == 1: one buffer, load -> add -> store per chunk (long-K GEMMs, where the ring needs the smem).
                 constexpr int CHUNKS = COLS_PER_WARP / 32;
                 int nchunks = 0;
 #pragma unroll
@@ -260,12 +282,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 tc_fence_after();
 #pragma unroll 1
                 for (int c = 0; c < nchunks; ++c) {
-                    const int buf = c & 1;
+                    const int buf = (STG_BUFS == 2) ? (c & 1) : 0;
                     uint8_t* const sbuf = stg + buf * STG_BUF_BYTES;
-                    if (lane == 0 && c + 1 < nchunks) {      // prefetch the next residual chunk into the other buffer
-                        tma_store_wait_read<0>();            // ... once the store that last used it has read it out
-                        mbar_arrive_expect_tx(&rbar[buf ^ 1], STG_BUF_BYTES);
-                        tma_load_2d(stg + (buf ^ 1) * STG_BUF_BYTES, &tma_c, &rbar[buf ^ 1], colw + (c + 1) * 32, row0);
+                    if constexpr (STG_BUFS == 2) {
+                        if (lane == 0 && c + 1 < nchunks) {  // prefetch the next residual chunk into the other buffer
+                            tma_store_wait_read<0>();        // ... once the store that last used it has read it out
+                            mbar_arrive_expect_tx(&rbar[buf ^ 1], STG_BUF_BYTES);
+                            tma_load_2d(stg + (buf ^ 1) * STG_BUF_BYTES, &tma_c, &rbar[buf ^ 1], colw + (c + 1) * 32, row0);
+                        }
+                    } else {
+                        if (lane == 0 && c > 0) {
+                            tma_store_wait_read<0>();
+                            mbar_arrive_expect_tx(&rbar[0], STG_BUF_BYTES);
+                            tma_load_2d(stg, &tma_c, &rbar[0], colw + c * 32, row0);
+                        }
                     }
                     const int col0 = colw + c * 32;
                     uint32_t raw[32];
@@ -358,31 +388,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         }
                     } else {
                         // bf16: 64 accumulator columns -> one 128-B row
-                        uint4 packed[8];
-                        uint32_t* pw = reinterpret_cast<uint32_t*>(packed);
+                        float v[64];
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {
                             const int colh = col0 + hh * 32;
                             uint32_t raw[32];
                             tmem_ld32(tacc + c * 64 + hh * 32, raw);
                             tmem_ld_wait();
-                            float v[32];
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                            for (int i = 0; i < 32; ++i) v[hh * 32 + i] = __uint_as_float(raw[i]);
                             if (colh < p.N) {                                   // N % 32 == 0: halves are all-in or all-out
-                                if (p.bias != nullptr) add_bias32(v, p.bias, colh);
-                                if (EPI == EPI_BIAS && colh < p.scale_cols) {
+                                if (p.bias != nullptr) add_bias32(v + hh * 32, p.bias, colh);
+                                if ((EPI == EPI_BIAS || EPI == EPI_BIAS_ROPE) && colh < p.scale_cols) {
 #pragma unroll
-                                    for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+                                    for (int i = 0; i < 32; ++i) v[hh * 32 + i] *= p.scale;
                                 }
                                 if constexpr (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-                                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+                                    for (int i = 0; i < 32; ++i) v[hh * 32 + i] = gelu_erf(v[hh * 32 + i]);
                                 }
                             }
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) pw[hh * 16 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
                         }
+                        if constexpr (EPI == EPI_BIAS_ROPE) {
+                            if (col0 < p.rope_cols) {                           // warp-uniform: q and k columns only
+                                const float t = static_cast<float>((row0 + lane) % p.seq_k);
+                                if (p.rope_head_dim == 64) rope_chunk64<64>(v, t, p.rope_inv_freq);
+                                else if (p.rope_head_dim == 32) rope_chunk64<32>(v, t, p.rope_inv_freq);
+                                else rope_chunk64<16>(v, t, p.rope_inv_freq);
+                            }
+                        }
+                        uint4 packed[8];
+                        uint32_t* pw = reinterpret_cast<uint32_t*>(packed);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) pw[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
                         if (lane == 0) tma_store_wait_read<0>();
                         __syncwarp();
 #pragma unroll
@@ -411,11 +449,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
 }
 
-template <int BLOCK_N, int EPI, typename OutT>
+template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS = 1>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
                 cudaStream_t stream) {
-    using Cfg = GemmCfg<BLOCK_N, EPI>;
-    auto kernel = gemm_tcgen05_kernel<BLOCK_N, EPI, OutT>;
+    using Cfg = GemmCfg<BLOCK_N, STG_BUFS>;
+    auto kernel = gemm_tcgen05_kernel<BLOCK_N, EPI, OutT, STG_BUFS>;
     static bool configured = false;
     if (!configured) {
         MOLLY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -442,8 +480,11 @@ int dispatch_epilogue(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
                        : launch_gemm<BLOCK_N, EPI_BIAS, __nv_bfloat16>(ta, tb, tc, p, stream);
         case EPI_BIAS_GELU:
             return launch_gemm<BLOCK_N, EPI_BIAS_GELU, __nv_bfloat16>(ta, tb, tc, p, stream);
-        case EPI_BIAS_RESID:
-            return launch_gemm<BLOCK_N, EPI_BIAS_RESID, float>(ta, tb, tc, p, stream);
+        case EPI_BIAS_RESID:       // short K: the epilogue is a large share -> prefetch residual chunks; long K: deeper ring
+            return p.K >= 2048 ? launch_gemm<BLOCK_N, EPI_BIAS_RESID, float, 1>(ta, tb, tc, p, stream)
+                               : launch_gemm<BLOCK_N, EPI_BIAS_RESID, float, 2>(ta, tb, tc, p, stream);
+        case EPI_BIAS_ROPE:
+            return launch_gemm<BLOCK_N, EPI_BIAS_ROPE, __nv_bfloat16>(ta, tb, tc, p, stream);
         case EPI_GLU:
             if constexpr (BLOCK_N == 256) return launch_gemm<256, EPI_GLU, __nv_bfloat16>(ta, tb, tc, p, stream);
             MOLLY_CHECK(false, MOLLY_ERR_UNSUPPORTED, "gemm: GLU epilogue needs 256-wide tiles");
@@ -488,8 +529,16 @@ int gemm_make_map_c(CUtensorMap* tc, void* out, int out_dtype, int ldo, int M, i
 
 int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tc, int M, int N, int K, int epi,
                 const float* bias, void* out, int out_dtype, int ldo, const int32_t* seq_table, int seq_k, int B, int T,
-                int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols, float scale) {
+                int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols, float scale, const float* rope_inv_freq,
+                int rope_cols, int rope_head_dim) {
     MOLLY_CHECK(M > 0 && N > 0 && K > 0, MOLLY_ERR_INVALID, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+    if (epi == EPI_BIAS_ROPE) {
+        MOLLY_CHECK(out_dtype == DT_BF16 && rope_inv_freq != nullptr && seq_k > 0, MOLLY_ERR_INVALID,
+                    "gemm: rotary epilogue needs bf16 output, inv_freq table and k_tokens");
+        MOLLY_CHECK((rope_head_dim == 16 || rope_head_dim == 32 || rope_head_dim == 64) && rope_cols % 64 == 0,
+                    MOLLY_ERR_UNSUPPORTED, "gemm: rotary epilogue supports head_dim 16/32/64 (got %d), rope_cols %% 64 == 0",
+                    rope_head_dim);
+    }
     MOLLY_CHECK(N % 32 == 0, MOLLY_ERR_UNSUPPORTED, "gemm: N must be a multiple of 32, got %d", N);
     MOLLY_CHECK(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, MOLLY_ERR_INVALID,
                 "gemm: bias must be 16-B aligned");
@@ -510,7 +559,8 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap*
     } else {
         MOLLY_CHECK(tc != nullptr, MOLLY_ERR_INVALID, "gemm: missing output tensor map");
     }
-    GemmParams p{M, N, K, bias, out, ldo, seq_table, seq_k, B, T, k_cap, err_flag, scale_cols, scale};
+    GemmParams p{M, N, K, bias, out, ldo, seq_table, seq_k, B, T, k_cap, err_flag, scale_cols, scale,
+                 rope_inv_freq, rope_cols, rope_head_dim};
     if (gemm_block_n(N, epi) == 256) return dispatch_epilogue<256>(ta, tb, *tc, p, epi, out_dtype, stream);
     return dispatch_epilogue<128>(ta, tb, *tc, p, epi, out_dtype, stream);
 }

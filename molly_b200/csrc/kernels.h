@@ -6,7 +6,7 @@
 
 namespace molly {
 
-enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_GLU = 3, EPI_SCATTER = 4 };
+enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_GLU = 3, EPI_SCATTER = 4, EPI_BIAS_ROPE = 5 };
 enum { DT_BF16 = 0, DT_F32 = 1 };
 
 void count_launch();
@@ -34,7 +34,8 @@ int gemm_make_map_c(CUtensorMap* tc, void* out, int out_dtype, int ldo, int M, i
 // EPI_BIAS_RESID reads the residual through `tc` too: the update is in place on the fp32 stream.
 int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tc, int M, int N, int K, int epi,
                 const float* bias, void* out, int out_dtype, int ldo, const int32_t* seq_table, int seq_k, int B, int T,
-                int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols = 0, float scale = 1.0f);
+                int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols = 0, float scale = 1.0f,
+                const float* rope_inv_freq = nullptr, int rope_cols = 0, int rope_head_dim = 0);
 
 // ---- attention.cu ----
 int attention_make_map(CUtensorMap* tq, const void* qkv, int rows, int h, int heads);

@@ -72,6 +72,7 @@ class PackedEncoder:
         w.rope_cos_dev = _ptr(vec(freqs.cos()))
         w.rope_sin_dev = _ptr(vec(freqs.sin()))
         w.rope_len = self.rope_len
+        w.rope_inv_freq_dev = _ptr(vec(inv_freq))
 
         names = ["ln1_w", "ln1_b", "w_qkv", "b_qkv", "w_attn_out", "b_attn_out", "ln2_w", "ln2_b", "w_ffn1", "b_ffn1",
                  "w_ffn2", "b_ffn2"]

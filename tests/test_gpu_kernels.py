@@ -60,6 +60,29 @@ def test_gemm_nobias_and_qscale():
     assert_close("gemm_qscale", got, refq, 2e-5)
 
 
+@pytest.mark.parametrize("heads,d,k,n_seq", [(20, 64, 200, 3), (20, 16, 77, 4), (16, 32, 130, 2)])
+def test_gemm_qkv_rope_epilogue(heads, d, k, n_seq):
+    """Fused QKV GEMM: bias, q *= d^-1/2 (HF:341), then NeoX rotary on q and k with position = row inside the padded
+    sequence (HF:45-54, 81-123); v passes through."""
+    ops, L = _ops()
+    from oracle.esm_oracle import rotary_tables, rotate_half
+    h = heads * d
+    M = n_seq * k
+    a, w = bf16r(M, h, seed=70).to(DEV), bf16r(3 * h, h, scale=0.05, seed=71).to(DEV)
+    bias = torch.randn(3 * h, generator=torch.Generator().manual_seed(72)).to(DEV)
+    y = (a.float() @ w.float().t() + bias).cpu().view(n_seq, k, 3, heads, d)
+    y[:, :, 0] *= d ** -0.5
+    cos, sin = rotary_tables(k, d)
+    ref = y.clone()
+    for which in (0, 1):
+        t = y[:, :, which].permute(0, 2, 1, 3)
+        ref[:, :, which] = (t * cos + rotate_half(t) * sin).permute(0, 2, 1, 3)
+    inv_freq = (1.0 / (10000 ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))).to(DEV)
+    got = ops.gemm_bf16(a, w, L.EPI_BIAS_ROPE, bias=bias, seq_k=k, scale_cols=h, scale=d ** -0.5,
+                        rope_inv_freq=inv_freq, rope_cols=2 * h, rope_head_dim=d)
+    assert_close(f"gemm_qkv_rope d={d}", got.view(n_seq, k, 3, heads, d), ref, BF16_EPS)
+
+
 @pytest.mark.parametrize("M,N,K", [(256, 512, 128), (300, 1280, 320), (1024, 5120, 1280)])
 def test_gemm_gelu(M, N, K):
     ops, L = _ops()

@@ -19,7 +19,7 @@ run() {  # name timeout cmd...
 PT="python -m pytest -q --tb=short -rA -p no:cacheprovider"
 run simple        400 $PT tests/test_gpu_kernels.py -k "layernorm or rotary or embed or placeholder or merge_rows"
 run gemm_bias     400 $PT tests/test_gpu_kernels.py -k "gemm_bias"
-run gemm_misc     400 $PT tests/test_gpu_kernels.py -k "gemm_nobias or gemm_gelu or gemm_residual or gemm_glu or gemm_scatter"
+run gemm_misc     400 $PT tests/test_gpu_kernels.py -k "gemm_nobias or gemm_gelu or gemm_residual or gemm_glu or gemm_scatter or gemm_qkv_rope"
 run attn_d64      400 $PT tests/test_gpu_kernels.py -k "test_attention and 64-"
 run attn_other    400 $PT tests/test_gpu_kernels.py -k "test_attention and not 64-"
 run path_encoder  600 $PT tests/test_gpu_path.py -k "encoder_forward"
