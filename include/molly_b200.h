@@ -76,7 +76,8 @@ typedef struct molly_encoder_weights {
     const float* rope_cos_dev;           /* fp32 [rope_len, d/2]    cos(t * 10000^(-2i/d))  (HF:81-115) */
     const float* rope_sin_dev;
     int32_t rope_len;
-    const float* rope_inv_freq_dev;      /* fp32 [d/2]  10000^(-2i/d): the QKV GEMM epilogue rotates q,k itself (d <= 64) */
+    const float* rope_cos_t_dev;         /* fp32 [d/2, rope_len]: the same tables, frequency-major, read by the QKV GEMM */
+    const float* rope_sin_t_dev;         /*   epilogue that rotates q,k itself when head_dim <= 64 */
     const float* const* ln1_w_dev;       /* attention.LayerNorm */
     const float* const* ln1_b_dev;
     const void* const* w_qkv_dev;        /* bf16 [3h, h] = cat(Wq, Wk, Wv)  (HF:329-335); q *= d^-1/2 happens in the epilogue */
@@ -154,8 +155,8 @@ int molly_gemm_bf16(const void* a_dev, int32_t lda, const void* w_dev, int32_t l
                     int32_t out_dtype, int32_t ldo, const int32_t* seq_table_dev, int32_t seq_k_tokens, int32_t B,
                     int32_t T, int32_t k_cap, int32_t* err_flag_dev,
                     int32_t scale_cols /*BIAS / BIAS_ROPE: out[:, :scale_cols] *= scale after the bias (q *= d^-1/2, HF:341)*/,
-                    float scale, const float* rope_inv_freq_dev /*BIAS_ROPE: fp32 [head_dim/2]*/, int32_t rope_cols,
-                    int32_t rope_head_dim, void* stream);
+                    float scale, const float* rope_cos_t_dev /*BIAS_ROPE: fp32 [head_dim/2, rope_len]*/,
+                    const float* rope_sin_t_dev, int32_t rope_len, int32_t rope_cols, int32_t rope_head_dim, void* stream);
 int molly_layernorm(const float* x_dev, const float* w_dev, const float* b_dev, int32_t rows, int32_t h, float eps,
                     void* out_dev, int32_t out_dtype, void* stream);
 int molly_embed(const int64_t* ids_dev, int32_t n_seq, int32_t k_tokens, const molly_encoder_config* cfg,

@@ -43,7 +43,7 @@ class EncoderWeights(C.Structure):
         ("word_emb_dev", C.c_void_p), ("pos_emb_dev", C.c_void_p),
         ("emb_ln_w_dev", C.c_void_p), ("emb_ln_b_dev", C.c_void_p),
         ("rope_cos_dev", C.c_void_p), ("rope_sin_dev", C.c_void_p), ("rope_len", C.c_int32),
-        ("rope_inv_freq_dev", C.c_void_p),
+        ("rope_cos_t_dev", C.c_void_p), ("rope_sin_t_dev", C.c_void_p),
         ("ln1_w_dev", c_void_pp), ("ln1_b_dev", c_void_pp),
         ("w_qkv_dev", c_void_pp), ("b_qkv_dev", c_void_pp),
         ("w_attn_out_dev", c_void_pp), ("b_attn_out_dev", c_void_pp),
@@ -77,7 +77,7 @@ SIGNATURES = {
     "molly_project_bwd": (C.c_int, [C.c_void_p, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp,
                                     _sz, _vp]),
     "molly_gemm_bf16": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _i32,
-                                  _i32, _i32, _i32, _vp, _i32, C.c_float, _vp, _i32, _i32, _vp]),
+                                  _i32, _i32, _i32, _vp, _i32, C.c_float, _vp, _vp, _i32, _i32, _i32, _vp]),
     "molly_layernorm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, C.c_float, _vp, _i32, _vp]),
     "molly_embed": (C.c_int, [_vp, _i32, _i32, C.POINTER(EncoderConfig), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "molly_rotary": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),

@@ -134,10 +134,10 @@ int encode(molly_encoder* e, const int64_t* ids, int n_seq, int k, void* final_o
         // and, for head_dim <= 64, so is the rotary embedding (HF:343-344): no separate pass over q and k
         const int d = h / c.num_heads;
         const bool rope = c.position_type == MOLLY_POS_ROTARY;
-        const bool rope_fused = rope && d <= 64 && e->w.rope_inv_freq_dev != nullptr;
+        const bool rope_fused = rope && d <= 64 && e->w.rope_cos_t_dev != nullptr && e->w.rope_sin_t_dev != nullptr;
         if ((rc = gemm_launch(p.tm_xn, e->tm_wqkv[l], &p.tc_qkv, M, 3 * h, h, rope_fused ? EPI_BIAS_ROPE : EPI_BIAS,
                               e->b_qkv[l], qkv, DT_BF16, 3 * h, nullptr, k, 0, 0, 0, nullptr, stream, h, e->q_scale,
-                              e->w.rope_inv_freq_dev, 2 * h, d)))
+                              e->w.rope_cos_t_dev, e->w.rope_sin_t_dev, e->w.rope_len, 2 * h, d)))
             return rc;
         if (rope && !rope_fused)
             if ((rc = rotary_launch(qkv, M, k, h, c.num_heads, e->w.rope_cos_dev, e->w.rope_sin_dev, stream))) return rc;
@@ -316,7 +316,8 @@ int molly_gemm_bf16(const void* a_dev, int32_t lda, const void* w_dev, int32_t l
                     int32_t epilogue, const float* bias_dev, const float* residual_dev, void* out_dev,
                     int32_t out_dtype, int32_t ldo, const int32_t* seq_table_dev, int32_t seq_k_tokens, int32_t B,
                     int32_t T, int32_t k_cap, int32_t* err_flag_dev, int32_t scale_cols, float scale,
-                    const float* rope_inv_freq_dev, int32_t rope_cols, int32_t rope_head_dim, void* stream) {
+                    const float* rope_cos_t_dev, const float* rope_sin_t_dev, int32_t rope_len, int32_t rope_cols,
+                    int32_t rope_head_dim, void* stream) {
     MOLLY_CHECK(a_dev && w_dev && out_dev, MOLLY_ERR_INVALID, "molly_gemm_bf16: NULL pointer");
     auto s = static_cast<cudaStream_t>(stream);
     CUtensorMap ta, tb, tc;
@@ -332,8 +333,8 @@ int molly_gemm_bf16(const void* a_dev, int32_t lda, const void* w_dev, int32_t l
     if (epilogue != EPI_SCATTER)
         if ((rc = gemm_make_map_c(&tc, out_dev, out_dtype, ldo, M, epilogue == EPI_GLU ? N / 2 : N))) return rc;
     return gemm_launch(ta, tb, epilogue == EPI_SCATTER ? nullptr : &tc, M, N, K, epilogue, bias_dev, out_dev, out_dtype,
-                       ldo, seq_table_dev, seq_k_tokens, B, T, k_cap, err_flag_dev, s, scale_cols, scale, rope_inv_freq_dev,
-                       rope_cols, rope_head_dim);
+                       ldo, seq_table_dev, seq_k_tokens, B, T, k_cap, err_flag_dev, s, scale_cols, scale, rope_cos_t_dev,
+                       rope_sin_t_dev, rope_len, rope_cols, rope_head_dim);
 }
 
 int molly_layernorm(const float* x_dev, const float* w_dev, const float* b_dev, int32_t rows, int32_t h, float eps,

@@ -15,6 +15,7 @@
 //       bias + residual, fp32     (HF:365-375, 417-427)
 //       gated SiLU                (NT-v2 FFN, weight rows interleaved at pack time)
 //       bias + row scatter        (omics_one.py:91-97: projector output written straight into hidden_states)
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -22,6 +23,8 @@
 #include "ptx.cuh"
 
 namespace molly {
+
+bool gemm_use_pair(int N, int epi);
 
 namespace {
 
@@ -35,12 +38,14 @@ constexpr int STG_BUF_BYTES = 32 * 128;          // one staging buffer: 32 rows 
 
 constexpr int imin(int a, int b) { return a < b ? a : b; }
 
-template <int BLOCK_N, int STG_BUFS_>
+// CTA2: the tile belongs to a CTA PAIR (cluster of 2): 256 x BLOCK_N, each CTA stages its 128 A rows and HALF of the
+// B rows; one tcgen05.mma.cta_group::2 (M=256) consumes both CTAs' shared memory and fills both CTAs' TMEM.
+template <int BLOCK_N, int STG_BUFS_, bool CTA2 = false>
 struct GemmCfg {
-    static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int B_STAGE_BYTES = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
     static constexpr int STG_BUFS = STG_BUFS_;      // 2: residual chunks are prefetched (short-K GEMMs); 1: deeper ring
     static constexpr int STG_BYTES = NUM_EPI_WARPS * STG_BUFS * STG_BUF_BYTES;  // 32 KB or 64 KB
-    static constexpr int STAGES = imin(6, (227 * 1024 - 1024 - STG_BYTES) / (A_STAGE_BYTES + B_STAGE_BYTES));
+    static constexpr int STAGES = imin(8, (227 * 1024 - 1024 - STG_BYTES) / (A_STAGE_BYTES + B_STAGE_BYTES));
     static constexpr int TMEM_COLS = 2 * BLOCK_N;           // 512 or 256: powers of two
     static constexpr int STG_OFFSET = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
     static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
@@ -59,19 +64,23 @@ struct GemmParams {
     int32_t* err_flag;
     int scale_cols;             // EPI_BIAS / EPI_BIAS_ROPE: columns [0, scale_cols) are multiplied by `scale` after the
     float scale;                //           bias (q = (x Wq^T + bq) * d^-1/2, HF:341); scale_cols % 32 == 0
-    const float* rope_inv_freq; // EPI_BIAS_ROPE: fp32 [head_dim/2] = 10000^(-2i/d)   (HF:81-95)
+    const float* rope_cos_t;    // EPI_BIAS_ROPE: fp32 [head_dim/2][rope_len] cos / sin of t * 10000^(-2i/d), FREQUENCY-major
+    const float* rope_sin_t;    //   so the 32 lanes of a warp (32 consecutive positions t) read 128 contiguous bytes
+    int rope_len;
     int rope_cols;              //   columns [0, rope_cols) (= q and k) are rotated; rope_cols % 64 == 0
     int rope_head_dim;          //   16 | 32 | 64 ; position = row % seq_k  (row index inside the padded sequence, HF:103)
 };
 
 // NeoX rotary on one 64-column chunk held by one thread (its row): x*cos + rotate_half(x)*sin per head (HF:45-54).
-// Angles are float(t) * inv_freq rounded once, like torch.outer; sincosf is the accurate (non fast-math) version.
+// cos/sin come from fp32 tables built on the host exactly like HF:81-115; the tables are frequency-major so that the
+// warp's 32 positions make one coalesced 128-B load per frequency.
 template <int D>
-__device__ __forceinline__ void rope_chunk64(float* v, float t, const float* __restrict__ inv_freq) {
+__device__ __forceinline__ void rope_chunk64(float* v, int t, const float* __restrict__ cos_t,
+                                             const float* __restrict__ sin_t, int rope_len) {
 #pragma unroll
     for (int i = 0; i < D / 2; ++i) {
-        float sn, cs;
-        sincosf(__fmul_rn(t, __ldg(inv_freq + i)), &sn, &cs);
+        const float cs = __ldg(cos_t + static_cast<size_t>(i) * rope_len + t);
+        const float sn = __ldg(sin_t + static_cast<size_t>(i) * rope_len + t);
 #pragma unroll
         for (int hl = 0; hl < 64 / D; ++hl) {
             const float x1 = v[hl * D + i], x2 = v[hl * D + i + D / 2];
@@ -112,11 +121,15 @@ __device__ __forceinline__ void add_bias32(float* v, const float* bias, int col0
     }
 }
 
-template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS>
+template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
-    using Cfg = GemmCfg<BLOCK_N, STG_BUFS>;
+    using Cfg = GemmCfg<BLOCK_N, STG_BUFS, CTA2>;
+    constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
+    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs), 1 = peer
+    const int tile_first = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool kOutF32 = sizeof(OutT) == 4;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -148,22 +161,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+            mbar_init(&tmem_empty[s], CTA2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);   // pair: both CTAs' epilogues arrive
         }
         for (int s = 0; s < 2 * NUM_EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (CTA2) { tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all(); else __syncthreads();      // barriers of BOTH CTAs are initialised
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
-    const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int tiles_m = (p.M + TILE_M - 1) / TILE_M;
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
 
@@ -172,29 +185,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
                 const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+                const int a_row = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;
+                const int b_row = n_blk * BLOCK_N + (CTA2 ? static_cast<int>(cta_rank) * (BLOCK_N / 2) : 0);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
-                    tma_load_2d(sA + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-                    tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tma_b, &full_bar[stage], kb * BLOCK_K,
-                                n_blk * BLOCK_N);
+                    if constexpr (CTA2) {
+                        // both CTAs' bytes are credited to the leader's barrier; only the leader arms it
+                        if (cta_rank == 0)
+                            mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
+                        tma_load_2d_pair(sA + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], kb * BLOCK_K, a_row);
+                        tma_load_2d_pair(sB + stage * Cfg::B_STAGE_BYTES, &tma_b, &full_bar[stage], kb * BLOCK_K, b_row);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
+                        tma_load_2d(sA + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], kb * BLOCK_K, a_row);
+                        tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tma_b, &full_bar[stage], kb * BLOCK_K, b_row);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, false, false);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, false, false);
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++local) {
                 const int acc = local & 1;
                 const uint32_t acc_phase = (local >> 1) & 1;
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                if constexpr (CTA2) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+                else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -206,13 +229,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         make_smem_desc(smem_u32(sB + stage * Cfg::B_STAGE_BYTES), 16, 8 * BLOCK_K * 2, kLayoutSW128);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        umma_bf16_ss(d_tmem, desc_advance(a_desc, k * UMMA_K * 2), desc_advance(b_desc, k * UMMA_K * 2),
-                                     idesc, (kb | k) != 0);
+                        if constexpr (CTA2)
+                            umma_bf16_ss_pair(d_tmem, desc_advance(a_desc, k * UMMA_K * 2),
+                                              desc_advance(b_desc, k * UMMA_K * 2), idesc, (kb | k) != 0);
+                        else
+                            umma_bf16_ss(d_tmem, desc_advance(a_desc, k * UMMA_K * 2), desc_advance(b_desc, k * UMMA_K * 2),
+                                         idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty_bar[stage]);          // frees this smem stage once the MMAs have read it
+                    // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
+                    if constexpr (CTA2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (of both CTAs of a pair)
+                if constexpr (CTA2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
             }
         }
     } else if (warp >= 4) {
@@ -226,11 +255,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         uint32_t rphase0 = 0, rphase1 = 0;
         const uint32_t lane_tmem = static_cast<uint32_t>(q * 32) << 16;
         int local = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++local) {
             const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
-            const int row0 = m_blk * BLOCK_M + q * 32;                   // first row of this warp's slab
+            const int row0 = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + q * 32;   // first row of this warp's slab
             const int colw = n_blk * BLOCK_N + half * COLS_PER_WARP;     // first column of this warp's slab
             const uint32_t tacc = tmem_base + lane_tmem + acc * BLOCK_N + half * COLS_PER_WARP;
 
@@ -411,10 +440,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         }
                         if constexpr (EPI == EPI_BIAS_ROPE) {
                             if (col0 < p.rope_cols) {                           // warp-uniform: q and k columns only
-                                const float t = static_cast<float>((row0 + lane) % p.seq_k);
-                                if (p.rope_head_dim == 64) rope_chunk64<64>(v, t, p.rope_inv_freq);
-                                else if (p.rope_head_dim == 32) rope_chunk64<32>(v, t, p.rope_inv_freq);
-                                else rope_chunk64<16>(v, t, p.rope_inv_freq);
+                                const int t = (row0 + lane) % p.seq_k;
+                                if (p.rope_head_dim == 64) rope_chunk64<64>(v, t, p.rope_cos_t, p.rope_sin_t, p.rope_len);
+                                else if (p.rope_head_dim == 32) rope_chunk64<32>(v, t, p.rope_cos_t, p.rope_sin_t, p.rope_len);
+                                else rope_chunk64<16>(v, t, p.rope_cos_t, p.rope_sin_t, p.rope_len);
                             }
                         }
                         uint4 packed[8];
@@ -436,38 +465,74 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if constexpr (CTA2) mbar_arrive_remote(&tmem_empty[acc], 0);      // the leader owns the MMA issue
+                else mbar_arrive(&tmem_empty[acc]);
+            }
         }
         if (lane == 0) tma_store_wait<0>();          // all of this warp's stores are complete before the CTA retires
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // nobody leaves while the peer still uses its smem / TMEM
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if constexpr (CTA2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
-template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS = 1>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
-                cudaStream_t stream) {
-    using Cfg = GemmCfg<BLOCK_N, STG_BUFS>;
-    auto kernel = gemm_tcgen05_kernel<BLOCK_N, EPI, OutT, STG_BUFS>;
+template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS, bool CTA2>
+int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+                     cudaStream_t stream) {
+    using Cfg = GemmCfg<BLOCK_N, STG_BUFS, CTA2>;
+    auto kernel = gemm_tcgen05_kernel<BLOCK_N, EPI, OutT, STG_BUFS, CTA2>;
     static bool configured = false;
     if (!configured) {
         MOLLY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
-    const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+    constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
+    const int tiles = ((p.M + TILE_M - 1) / TILE_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+    const int slots = CTA2 ? device_sm_count() / 2 : device_sm_count();
+    const int grid = (tiles < slots ? tiles : slots) * (CTA2 ? 2 : 1);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     {
         ProfScope prof(gemm_family(), 2.0 * p.M * p.N * p.K, stream);
-        kernel<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, p);
+        MOLLY_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, p));
     }
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
     return MOLLY_OK;
+}
+
+bool g_pair_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOLLY_GEMM_PAIR");          // bring-up switch: MOLLY_GEMM_PAIR=0 forces single-CTA tiles
+        v = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS = 1>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+                cudaStream_t stream) {
+    if constexpr (BLOCK_N == 256 && EPI != EPI_SCATTER) {
+        if (gemm_use_pair(p.N, EPI)) return launch_gemm_impl<256, EPI, OutT, STG_BUFS, true>(ta, tb, tc, p, stream);
+    }
+    return launch_gemm_impl<BLOCK_N, EPI, OutT, STG_BUFS, false>(ta, tb, tc, p, stream);
 }
 
 template <int BLOCK_N>
@@ -498,6 +563,9 @@ int dispatch_epilogue(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
 
 }  // namespace
 
+// CTA-pair (cta_group::2) tiles: 256 x 256 per pair; used whenever N is a whole number of 256-column tiles.
+bool gemm_use_pair(int N, int epi) { return g_pair_enabled() && epi != EPI_SCATTER && N % 256 == 0; }
+
 int gemm_block_n(int N, int epi) {
     if (epi == EPI_GLU) return 256;
     // 256-wide tiles unless the last tile would be mostly padding
@@ -516,7 +584,8 @@ int gemm_make_map_b(CUtensorMap* tb, const void* w, int ldw, int N, int K, int e
     MOLLY_CHECK(K % 8 == 0 && ldw % 8 == 0, MOLLY_ERR_UNSUPPORTED,
                 "gemm: K and ldw must be multiples of 8 (16-B TMA strides); got K=%d ldw=%d", K, ldw);
     MOLLY_CHECK((reinterpret_cast<uintptr_t>(w) & 15) == 0, MOLLY_ERR_INVALID, "gemm: W must be 16-B aligned");
-    return make_tma_2d(tb, w, N, K, ldw, gemm_block_n(N, epi), BLOCK_K, 2);
+    // a CTA pair splits the 256 B rows of a tile: each CTA loads a 128-row box
+    return make_tma_2d(tb, w, N, K, ldw, gemm_use_pair(N, epi) ? 128 : gemm_block_n(N, epi), BLOCK_K, 2);
 }
 
 // Output (and residual) map: 32-row x 128-byte boxes, 128-B swizzle.  `n_out` = columns of the OUTPUT matrix.
@@ -529,12 +598,13 @@ int gemm_make_map_c(CUtensorMap* tc, void* out, int out_dtype, int ldo, int M, i
 
 int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tc, int M, int N, int K, int epi,
                 const float* bias, void* out, int out_dtype, int ldo, const int32_t* seq_table, int seq_k, int B, int T,
-                int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols, float scale, const float* rope_inv_freq,
-                int rope_cols, int rope_head_dim) {
+                int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols, float scale, const float* rope_cos_t,
+                const float* rope_sin_t, int rope_len, int rope_cols, int rope_head_dim) {
     MOLLY_CHECK(M > 0 && N > 0 && K > 0, MOLLY_ERR_INVALID, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     if (epi == EPI_BIAS_ROPE) {
-        MOLLY_CHECK(out_dtype == DT_BF16 && rope_inv_freq != nullptr && seq_k > 0, MOLLY_ERR_INVALID,
-                    "gemm: rotary epilogue needs bf16 output, inv_freq table and k_tokens");
+        MOLLY_CHECK(out_dtype == DT_BF16 && rope_cos_t != nullptr && rope_sin_t != nullptr && seq_k > 0 &&
+                        rope_len >= seq_k, MOLLY_ERR_INVALID,
+                    "gemm: rotary epilogue needs bf16 output, cos/sin tables covering k_tokens (%d >= %d)", rope_len, seq_k);
         MOLLY_CHECK((rope_head_dim == 16 || rope_head_dim == 32 || rope_head_dim == 64) && rope_cols % 64 == 0,
                     MOLLY_ERR_UNSUPPORTED, "gemm: rotary epilogue supports head_dim 16/32/64 (got %d), rope_cols %% 64 == 0",
                     rope_head_dim);
@@ -560,7 +630,7 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap*
         MOLLY_CHECK(tc != nullptr, MOLLY_ERR_INVALID, "gemm: missing output tensor map");
     }
     GemmParams p{M, N, K, bias, out, ldo, seq_table, seq_k, B, T, k_cap, err_flag, scale_cols, scale,
-                 rope_inv_freq, rope_cols, rope_head_dim};
+                 rope_cos_t, rope_sin_t, rope_len, rope_cols, rope_head_dim};
     if (gemm_block_n(N, epi) == 256) return dispatch_epilogue<256>(ta, tb, *tc, p, epi, out_dtype, stream);
     return dispatch_epilogue<128>(ta, tb, *tc, p, epi, out_dtype, stream);
 }

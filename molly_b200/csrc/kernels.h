@@ -28,6 +28,7 @@ int gemm_family();
 
 // ---- gemm.cu ----
 int gemm_block_n(int N, int epi);
+bool gemm_use_pair(int N, int epi);
 int gemm_make_map_a(CUtensorMap* ta, const void* a, int lda, int M, int K);
 int gemm_make_map_b(CUtensorMap* tb, const void* w, int ldw, int N, int K, int epi);
 int gemm_make_map_c(CUtensorMap* tc, void* out, int out_dtype, int ldo, int M, int n_out);
@@ -35,7 +36,8 @@ int gemm_make_map_c(CUtensorMap* tc, void* out, int out_dtype, int ldo, int M, i
 int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tc, int M, int N, int K, int epi,
                 const float* bias, void* out, int out_dtype, int ldo, const int32_t* seq_table, int seq_k, int B, int T,
                 int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols = 0, float scale = 1.0f,
-                const float* rope_inv_freq = nullptr, int rope_cols = 0, int rope_head_dim = 0);
+                const float* rope_cos_t = nullptr, const float* rope_sin_t = nullptr, int rope_len = 0, int rope_cols = 0,
+                int rope_head_dim = 0);
 
 // ---- attention.cu ----
 int attention_make_map(CUtensorMap* tq, const void* qkv, int rows, int h, int heads);

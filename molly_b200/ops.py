@@ -243,8 +243,8 @@ def placeholder_scan(input_ids: Tensor, pad0: int, pad1: int, pad2: int) -> Tupl
 def gemm_bf16(a: Tensor, w: Tensor, epilogue: int, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None,
               out: Optional[Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
               seq_table: Optional[Tensor] = None, seq_k: int = 0, k_cap: int = 0, scale_cols: int = 0,
-              scale: float = 1.0, rope_inv_freq: Optional[Tensor] = None, rope_cols: int = 0,
-              rope_head_dim: int = 0) -> Tensor:
+              scale: float = 1.0, rope_cos_t: Optional[Tensor] = None, rope_sin_t: Optional[Tensor] = None,
+              rope_cols: int = 0, rope_head_dim: int = 0) -> Tensor:
     dev = _require_cuda(a, w, bias, residual, out, seq_table)
     M, K = a.shape
     N = w.shape[0]
@@ -263,7 +263,8 @@ def gemm_bf16(a: Tensor, w: Tensor, epilogue: int, bias: Optional[Tensor] = None
             None if bias is None else bias.data_ptr(), None if residual is None else residual.data_ptr(),
             out.data_ptr(), _dtype_code(out), ldo, None if seq_table is None else seq_table.data_ptr(), seq_k, B, T,
             k_cap, error_flag(dev).data_ptr(), scale_cols, scale,
-            None if rope_inv_freq is None else rope_inv_freq.data_ptr(), rope_cols, rope_head_dim, _stream(dev)),
+            None if rope_cos_t is None else rope_cos_t.data_ptr(), None if rope_sin_t is None else rope_sin_t.data_ptr(),
+            0 if rope_cos_t is None else rope_cos_t.shape[1], rope_cols, rope_head_dim, _stream(dev)),
             "molly_gemm_bf16")
     return out
 

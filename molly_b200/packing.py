@@ -72,7 +72,8 @@ class PackedEncoder:
         w.rope_cos_dev = _ptr(vec(freqs.cos()))
         w.rope_sin_dev = _ptr(vec(freqs.sin()))
         w.rope_len = self.rope_len
-        w.rope_inv_freq_dev = _ptr(vec(inv_freq))
+        w.rope_cos_t_dev = _ptr(vec(freqs.cos().t()))      # frequency-major copies for the fused QKV epilogue
+        w.rope_sin_t_dev = _ptr(vec(freqs.sin().t()))
 
         names = ["ln1_w", "ln1_b", "w_qkv", "b_qkv", "w_attn_out", "b_attn_out", "ln2_w", "ln2_b", "w_ffn1", "b_ffn1",
                  "w_ffn2", "b_ffn2"]

@@ -77,9 +77,10 @@ def test_gemm_qkv_rope_epilogue(heads, d, k, n_seq):
     for which in (0, 1):
         t = y[:, :, which].permute(0, 2, 1, 3)
         ref[:, :, which] = (t * cos + rotate_half(t) * sin).permute(0, 2, 1, 3)
-    inv_freq = (1.0 / (10000 ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))).to(DEV)
+    cos_t = cos[:, :d // 2].t().contiguous().to(DEV)                  # frequency-major [d/2, k]
+    sin_t = sin[:, :d // 2].t().contiguous().to(DEV)
     got = ops.gemm_bf16(a, w, L.EPI_BIAS_ROPE, bias=bias, seq_k=k, scale_cols=h, scale=d ** -0.5,
-                        rope_inv_freq=inv_freq, rope_cols=2 * h, rope_head_dim=d)
+                        rope_cos_t=cos_t, rope_sin_t=sin_t, rope_cols=2 * h, rope_head_dim=d)
     assert_close(f"gemm_qkv_rope d={d}", got.view(n_seq, k, 3, heads, d), ref, BF16_EPS)
 
 
