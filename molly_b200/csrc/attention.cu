@@ -14,6 +14,7 @@
 //   * keys >= kv_len are never loaded (whole blocks skipped); interior pad keys use the byte mask
 // Two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "kernels.h"
@@ -337,9 +338,400 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
     }
 }
 
+// ================================================================================================
+// Persistent variant (default).  A CTA walks a static stride of work items (sequence, head, 128-query block) and
+// treats all their KV blocks as ONE stream of iterations g = 0, 1, 2, ...:
+//   * K/V ring, S / P hand-offs and barrier parities are indexed by g, so the loads for the next item's first blocks,
+//     its Q tile and its first S = QK^T are all issued while the current item's last blocks are still in softmax;
+//   * O is double-buffered in TMEM (item parity), so the write-out of item i overlaps the first PV of item i+1.
+// The per-CTA prologue (TMEM alloc, barrier init, first TMA round trip) is paid once per launch instead of once per
+// 128-query block, which was ~25 % of the non-persistent kernel at K = 1024.
+// ================================================================================================
+struct AttnCursor {              // position in the flattened (item, kv-block) stream of this CTA
+    int item;                    // global work-item index (n, head, qb); >= total -> stream exhausted
+    int it;                      // local item counter of this CTA (0, 1, 2, ...)
+    int j;                       // kv block inside the item
+    int g;                       // global iteration counter
+    int nkv, kvl, n, head, q0;
+};
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_CTAS)
+attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int heads, int k_tokens, int h,
+                            const int32_t* __restrict__ kv_info, const uint8_t* __restrict__ key_mask,
+                            __nv_bfloat16* __restrict__ out) {
+    using Cfg = AttnCfg<D>;
+    constexpr int TMEM_COLS = (D == 128) ? 512 : 256;            // S: 128 columns, O: 2 x D columns
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+    uint64_t* bar_q = bars + 0;
+    uint64_t* bar_kv_full = bars + 1;     // [2]
+    uint64_t* bar_kv_empty = bars + 3;    // [2]  PV(g) complete
+    uint64_t* bar_s_full = bars + 5;
+    uint64_t* bar_p_full = bars + 6;
+    uint64_t* bar_s_free = bars + 7;
+    uint64_t* bar_o_full = bars + 8;      // [2]  last PV of an item complete
+    uint64_t* bar_o_free = bars + 10;     // [2]  softmax warps have read O[buf] out
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nqb = (k_tokens + ATT_BLOCK - 1) / ATT_BLOCK;
+    const int total = n_seq * heads * nqb;
+
+    // cursor helpers (every role walks the same stream; items whose sequence is all padding are skipped)
+    auto load_item = [&](AttnCursor& c) {
+        while (c.item < total) {
+            const int qb = c.item % nqb, t = c.item / nqb;
+            c.head = t % heads;
+            c.n = t / heads;
+            c.q0 = qb * ATT_BLOCK;
+            c.kvl = __ldg(kv_info + 2 * c.n);
+            c.nkv = (c.kvl + ATT_BLOCK - 1) / ATT_BLOCK;
+            if (c.nkv > 0) return;
+            c.item += gridDim.x;              // all-pad sequence: no stream entries (softmax role zero-fills its rows)
+        }
+    };
+    auto advance = [&](AttnCursor& c) {
+        ++c.g;
+        if (++c.j == c.nkv) {
+            c.j = 0;
+            ++c.it;
+            c.item += gridDim.x;
+            load_item(c);
+        }
+    };
+    auto first = [&]() {
+        AttnCursor c;
+        c.item = blockIdx.x; c.it = 0; c.j = 0; c.g = 0; c.nkv = 0; c.kvl = 0; c.n = 0; c.head = 0; c.q0 = 0;
+        load_item(c);
+        return c;
+    };
+
+    if (warp == 4) {
+        if (lane == 0) {
+            if ((smem_u32(smem) & 1023u) != 0) { printf("molly attention: smem base not 1024-B aligned\n"); __trap(); }
+            tma_prefetch_desc(&tma_qkv);
+            mbar_init(bar_q, 1);
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&bar_kv_full[i], 1);
+                mbar_init(&bar_kv_empty[i], 1);
+                mbar_init(&bar_o_full[i], 1);
+                mbar_init(&bar_o_free[i], 128);
+            }
+            mbar_init(bar_s_full, 1);
+            mbar_init(bar_p_full, 128);
+            mbar_init(bar_s_free, 128);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_s = tmem_base;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // ---------------- control thread: TMA producer + MMA issuer ----------------
+            constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK, ATT_BLOCK, false, false);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK, D, false, true);      // B (= V) is MN-major
+            const uint32_t s_q = smem_u32(smem + Cfg::OFF_Q), s_k = smem_u32(smem + Cfg::OFF_K);
+            const uint32_t s_v = smem_u32(smem + Cfg::OFF_V), s_p = smem_u32(smem + Cfg::OFF_P);
+            auto load_tile = [&](int smem_off, uint64_t* bar, int col, int row) {
+#pragma unroll
+                for (int b = 0; b < Cfg::NBOX; ++b)
+                    tma_load_2d(smem + smem_off + b * Cfg::BOX_BYTES, &tma_qkv, bar, col + b * Cfg::BOX_D, row);
+            };
+            auto load_q = [&](const AttnCursor& c) {
+                mbar_arrive_expect_tx(bar_q, Cfg::TILE_BYTES);
+                load_tile(Cfg::OFF_Q, bar_q, c.head * D, c.n * k_tokens + c.q0);
+            };
+            auto load_kv = [&](const AttnCursor& c) {
+                const int stg = c.g & 1;
+                const int row = c.n * k_tokens + c.j * ATT_BLOCK;
+                mbar_arrive_expect_tx(&bar_kv_full[stg], 2 * Cfg::TILE_BYTES);
+                load_tile(Cfg::OFF_K + stg * Cfg::TILE_BYTES, &bar_kv_full[stg], h + c.head * D, row);
+                load_tile(Cfg::OFF_V + stg * Cfg::TILE_BYTES, &bar_kv_full[stg], 2 * h + c.head * D, row);
+            };
+            auto issue_s = [&](const AttnCursor& c) {       // S = Q K^T : K-major x K-major, D/16 k-steps
+                mbar_wait(&bar_kv_full[c.g & 1], (c.g >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < D / 16; ++s) {
+                    const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
+                    const uint64_t qd = make_smem_desc(s_q + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
+                    const uint64_t kd =
+                        make_smem_desc(s_k + (c.g & 1) * Cfg::TILE_BYTES + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
+                    umma_bf16_ss(tmem_s, qd, kd, idesc_s, s != 0);
+                }
+                umma_commit(bar_s_full);
+            };
+
+            AttnCursor cl = first(), cs = cl, cp = cl;      // load / S-issue / PV cursors
+            if (cp.item < total) {
+                load_q(cl);
+                load_kv(cl); advance(cl);
+                if (cl.item < total) { load_kv(cl); advance(cl); }
+                mbar_wait(bar_q, 0);
+                issue_s(cs); advance(cs);
+                while (cp.item < total) {
+                    const int g = cp.g, st = g & 1;
+                    // (1) softmax holds S(g) in registers -> S(g+1) runs under softmax(g); a new item first gets its Q
+                    mbar_wait(bar_s_free, g & 1);
+                    tc_fence_after();
+                    if (cs.item < total) {
+                        if (cs.j == 0) {                    // S(g) was the last user of the Q tile: reload it
+                            load_q(cs);
+                            mbar_wait(bar_q, cs.it & 1);
+                        }
+                        issue_s(cs);
+                        advance(cs);
+                    }
+                    // (2) O[it & 1] (+)= P(g) V(g) : P K-major (two 64-key atoms), V MN-major; 8 k-steps of 16 keys
+                    mbar_wait(bar_p_full, g & 1);
+                    if (cp.j == 0 && cp.it >= 2) mbar_wait(&bar_o_free[cp.it & 1], ((cp.it >> 1) - 1) & 1);
+                    tc_fence_after();
+                    const uint32_t tmem_o = tmem_base + 128 + (cp.it & 1) * D;
+#pragma unroll
+                    for (int s = 0; s < ATT_BLOCK / 16; ++s) {
+                        const uint64_t pd = make_smem_desc(s_p + (s >> 2) * (ATT_BLOCK * 128) + (s & 3) * 32, 16, 1024,
+                                                           kLayoutSW128);
+                        const uint64_t vd = make_smem_desc(s_v + st * Cfg::TILE_BYTES + s * 16 * Cfg::ROW_BYTES,
+                                                           Cfg::BOX_BYTES, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
+                        umma_bf16_ss(tmem_o, pd, vd, idesc_pv, (cp.j | s) != 0);
+                    }
+                    umma_commit(&bar_kv_empty[st]);          // PV(g) done: stage st and the P buffer are free
+                    if (cp.j == cp.nkv - 1) umma_commit(&bar_o_full[cp.it & 1]);
+                    // (3) refill stage st with stream entry g+2 once PV(g) has drained it
+                    if (cl.item < total) {
+                        mbar_wait(&bar_kv_empty[st], (g >> 1) & 1);
+                        load_kv(cl);
+                        advance(cl);
+                    }
+                    advance(cp);
+                }
+            }
+        }
+    } else {
+        // ---------------- softmax warps: thread r owns query row r ----------------
+        const int r = threadIdx.x;
+        const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+        uint8_t* p_row = smem + Cfg::OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
+        const int sw = r & 7;
+        int g = 0, it = 0;                                    // stream position, identical to the control thread's
+        for (int item = blockIdx.x; item < total; item += gridDim.x) {
+            const int qb = item % nqb, tq = item / nqb;
+            const int head = tq % heads, n = tq / heads;
+            const int q0 = qb * ATT_BLOCK;
+            const int kvl = __ldg(kv_info + 2 * n);
+            const int nkv = (kvl + ATT_BLOCK - 1) / ATT_BLOCK;
+            const long long row_base = static_cast<long long>(n) * k_tokens;
+            if (nkv == 0) {          // all-pad sequence: not in the stream; zero-fill (the reference never encodes one)
+                if (q0 + r < k_tokens) {
+                    uint4* o = reinterpret_cast<uint4*>(out + (row_base + q0 + r) * h + head * D);
+                    for (int i = 0; i < D / 8; ++i) o[i] = make_uint4(0, 0, 0, 0);
+                }
+                continue;
+            }
+            const bool interior = __ldg(kv_info + 2 * n + 1) != kvl;       // pad ids before the last real token
+            const uint32_t tmem_o = tmem_base + 128 + (it & 1) * D;
+            float m_run = -CUDART_INF_F;      // running reference max, log2 domain
+            float l_run = 0.f;
+            for (int j = 0; j < nkv; ++j, ++g) {
+                mbar_wait(bar_s_full, g & 1);
+                tc_fence_after();
+                float s[ATT_BLOCK];
+                {
+                    uint32_t raw[ATT_BLOCK];
+                    tmem_ld32(tmem_s + lane_addr + 0, raw);
+                    tmem_ld32(tmem_s + lane_addr + 32, raw + 32);
+                    tmem_ld32(tmem_s + lane_addr + 64, raw + 64);
+                    tmem_ld32(tmem_s + lane_addr + 96, raw + 96);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < ATT_BLOCK; ++i) s[i] = __uint_as_float(raw[i]);
+                }
+                tc_fence_before();
+                mbar_arrive(bar_s_free);                     // S(g) is in registers: the MMA warp may start S(g+1)
+                const int j0 = j * ATT_BLOCK;
+                if (interior) {
+                    const uint4* mk = reinterpret_cast<const uint4*>(key_mask + row_base + j0);
+                    const bool vec_ok = ((row_base + j0) & 15) == 0 && j0 + ATT_BLOCK <= k_tokens;
+#pragma unroll
+                    for (int gq = 0; gq < 8; ++gq) {
+                        uint32_t w[4];
+                        if (vec_ok) {
+                            const uint4 u = __ldg(mk + gq);
+                            w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                w[i] = 0;
+#pragma unroll
+                                for (int b = 0; b < 4; ++b) {
+                                    const int cc = j0 + gq * 16 + i * 4 + b;
+                                    const uint32_t v = (cc < k_tokens) ? key_mask[row_base + cc] : 0;
+                                    w[i] |= (v & 0xffu) << (8 * b);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const bool ok = ((w[i >> 2] >> (8 * (i & 3))) & 0xffu) != 0 && (j0 + gq * 16 + i < kvl);
+                            if (!ok) s[gq * 16 + i] = -CUDART_INF_F;
+                        }
+                    }
+                } else if (j0 + ATT_BLOCK > kvl) {
+                    const int lim = kvl - j0;
+#pragma unroll
+                    for (int i = 0; i < ATT_BLOCK; ++i)
+                        if (i >= lim) s[i] = -CUDART_INF_F;
+                }
+                float mx4[4] = {s[0], s[1], s[2], s[3]};
+#pragma unroll
+                for (int i = 4; i < ATT_BLOCK; i += 4) {
+                    mx4[0] = fmaxf(mx4[0], s[i]); mx4[1] = fmaxf(mx4[1], s[i + 1]);
+                    mx4[2] = fmaxf(mx4[2], s[i + 2]); mx4[3] = fmaxf(mx4[3], s[i + 3]);
+                }
+                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+                // lazy rescaling (see the non-persistent kernel): move the reference max only when it grew by > 2^8
+                const float m_cand = fmaxf(m_run, mx * LOG2E);
+                float alpha = 1.0f;
+                if (m_cand > m_run + 8.0f) {
+                    alpha = ex2(m_run - m_cand);
+                    m_run = m_cand;
+                }
+                const float m_use = (m_run == -CUDART_INF_F) ? 0.f : m_run;
+                const uint64_t sc2 = pack_f32x2(LOG2E, LOG2E), nm2 = pack_f32x2(-m_use, -m_use);
+                uint64_t sum2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
+#pragma unroll
+                for (int i = 0; i < ATT_BLOCK; i += 4) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        float x0, x1;
+                        unpack_f32x2(fma_f32x2(pack_f32x2(s[i + 2 * u], s[i + 2 * u + 1]), sc2, nm2), x0, x1);
+                        s[i + 2 * u] = ex2(x0);
+                        s[i + 2 * u + 1] = ex2(x1);
+                        sum2[u] = add_f32x2(sum2[u], pack_f32x2(s[i + 2 * u], s[i + 2 * u + 1]));
+                    }
+                }
+                float sa, sb, sc, sd;
+                unpack_f32x2(sum2[0], sa, sb);
+                unpack_f32x2(sum2[1], sc, sd);
+                l_run = l_run * alpha + ((sa + sb) + (sc + sd));
+                // PV(g-1) must have drained the P buffer (and, inside an item, finished O) before either is touched
+                if (g > 0) {
+                    mbar_wait(&bar_kv_empty[(g - 1) & 1], ((g - 1) >> 1) & 1);
+                    tc_fence_after();
+                }
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) {
+                        const int e = a * 64 + cc * 8;
+                        uint4 u;
+                        u.x = pack_bf16x2(s[e + 0], s[e + 1]);
+                        u.y = pack_bf16x2(s[e + 2], s[e + 3]);
+                        u.z = pack_bf16x2(s[e + 4], s[e + 5]);
+                        u.w = pack_bf16x2(s[e + 6], s[e + 7]);
+                        *reinterpret_cast<uint4*>(p_row + a * (ATT_BLOCK * 128) + ((cc ^ sw) << 4)) = u;
+                    }
+                }
+                if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+                    for (int cc = 0; cc < D / 16; ++cc) {
+                        uint32_t o[16];
+                        tmem_ld16(tmem_o + lane_addr + cc * 16, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st16(tmem_o + lane_addr + cc * 16, o);
+                    }
+                    tmem_st_wait();
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(bar_p_full);
+            }
+            // item epilogue: O[it & 1] / l -> bf16 -> HBM, then hand the O buffer back
+            mbar_wait(&bar_o_full[it & 1], (it >> 1) & 1);
+            tc_fence_after();
+            const float inv_l = 1.0f / l_run;
+            const bool row_ok = q0 + r < k_tokens;
+            __nv_bfloat16* orow = out + (row_base + q0 + r) * h + head * D;
+#pragma unroll
+            for (int cc = 0; cc < D / 16; ++cc) {
+                uint32_t o[16];
+                tmem_ld16(tmem_o + lane_addr + cc * 16, o);
+                tmem_ld_wait();
+                if (row_ok) {
+                    uint4 u0, u1;
+                    u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l);
+                    u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l);
+                    u0.z = pack_bf16x2(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l);
+                    u0.w = pack_bf16x2(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l);
+                    u1.x = pack_bf16x2(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l);
+                    u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l);
+                    u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l);
+                    u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l);
+                    reinterpret_cast<uint4*>(orow + cc * 16)[0] = u0;
+                    reinterpret_cast<uint4*>(orow + cc * 16)[1] = u1;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bar_o_free[it & 1]);
+            ++it;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+bool attention_persistent_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOLLY_ATTN_PERSISTENT");     // bring-up switch: 0 selects the one-item-per-CTA kernel
+        v = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+template <int D>
+int launch_attention_persistent(const CUtensorMap& tm, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
+                                const uint8_t* key_mask, void* out, cudaStream_t stream) {
+    using Cfg = AttnCfg<D>;
+    auto kernel = attention_persistent_kernel<D>;
+    static bool configured = false;
+    if (!configured) {
+        MOLLY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int total = n_seq * heads * ((k_tokens + ATT_BLOCK - 1) / ATT_BLOCK);
+    const int slots = device_sm_count() * Cfg::MIN_CTAS;
+    const int grid = total < slots ? total : slots;
+    {   // dense-equivalent work 4*n*K*K*h (exact when every sequence is full length)
+        ProfScope prof(PF_ATTENTION, 4.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
+        kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, n_seq, heads, k_tokens, h, kv_info, key_mask,
+                                                               static_cast<__nv_bfloat16*>(out));
+    }
+    count_launch();
+    MOLLY_CUDA(cudaGetLastError());
+    return MOLLY_OK;
+}
+
 template <int D>
 int launch_attention(const CUtensorMap& tm, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
                      const uint8_t* key_mask, void* out, cudaStream_t stream) {
+    if (attention_persistent_enabled())
+        return launch_attention_persistent<D>(tm, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
     using Cfg = AttnCfg<D>;
     auto kernel = attention_kernel<D>;
     static bool configured = false;
