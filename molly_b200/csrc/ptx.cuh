@@ -39,26 +39,29 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// try_wait with a suspend-time hint: the waiting thread is parked by the hardware (and woken by the completing
+// arrive) instead of spinning through the issue slots of the SM sub-partition it shares with the math warps.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)      // up to 1 ms parked per try
         : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 #ifndef MOLLY_MBAR_TIMEOUT_CYCLES
-#define MOLLY_MBAR_TIMEOUT_CYCLES 4000000000ll   // ~2 s at 1.9 GHz
+#define MOLLY_MBAR_TIMEOUT_CYCLES 6000000000ll   // ~3-4 s of SM clocks; checked every 32 failed tries only
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > MOLLY_MBAR_TIMEOUT_CYCLES) {
+        if ((++spins & 31u) == 0 && clock64() - t0 > MOLLY_MBAR_TIMEOUT_CYCLES) {
             printf("molly: mbarrier timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
                    blockIdx.z, threadIdx.x, smem_u32(bar), parity);
             __trap();
@@ -198,18 +201,19 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
         : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait_cluster(bar, parity)) return;
     const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait_cluster(bar, parity)) {
-        if (clock64() - t0 > MOLLY_MBAR_TIMEOUT_CYCLES) {
+        if ((++spins & 31u) == 0 && clock64() - t0 > MOLLY_MBAR_TIMEOUT_CYCLES) {
             printf("molly: cluster mbarrier timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x,
                    blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
             __trap();

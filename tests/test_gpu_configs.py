@@ -18,6 +18,9 @@ DEV = "cuda"
 
 
 def test_cfg3_molly4b_varlen_full_encoders():
+    import psutil
+    if psutil.virtual_memory().available < 24 * 2 ** 30:
+        pytest.skip("fp32 CPU oracle of ESM-2 650M + NT-v2 500M needs ~12 GB of host memory")
     case = cases.build_case("cfg3_molly4b", "nt_v2_500m", "esm2_t33_650m", D=2560, K=2048, T=4400, seed=3000,
                             samples=[[("dna", 2048), ("protein", 701)], [("rna", 97)]], mask_tokens=False)
     ref = case.batch.hidden_states.clone()
@@ -33,6 +36,9 @@ def test_cfg3_molly4b_varlen_full_encoders():
 
 
 def test_cfg4_molly8b_nt_v1_2p5b():
+    import psutil
+    if psutil.virtual_memory().available < 48 * 2 ** 30:
+        pytest.skip("fp32 CPU oracle of NT-2.5B needs ~25 GB of host memory")
     case = cases.build_case("cfg4_molly8b", "nt_v1_2p5b", "tiny_esm2", D=4096, K=256, T=600, seed=4000,
                             samples=[[("dna", 171), ("dna", 171)]], mask_tokens=False)
     ref = case.batch.hidden_states.clone()
