@@ -456,16 +456,21 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                 load_tile(Cfg::OFF_K + stg * Cfg::TILE_BYTES, &bar_kv_full[stg], h + c.head * D, row);
                 load_tile(Cfg::OFF_V + stg * Cfg::TILE_BYTES, &bar_kv_full[stg], 2 * h + c.head * D, row);
             };
+            // Base descriptors are built once; per MMA only the 14-bit start-address field moves (one 32-bit add),
+            // so the single issuing thread spends a handful of instructions per tcgen05.mma instead of ~15.
+            const uint64_t qd0 = make_smem_desc(s_q, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
+            const uint64_t kd0 = make_smem_desc(s_k, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
+            const uint64_t pd0 = make_smem_desc(s_p, 16, 1024, kLayoutSW128);
+            const uint64_t vd0 = make_smem_desc(s_v, Cfg::BOX_BYTES, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
             auto issue_s = [&](const AttnCursor& c) {       // S = Q K^T : K-major x K-major, D/16 k-steps
                 mbar_wait(&bar_kv_full[c.g & 1], (c.g >> 1) & 1);
                 tc_fence_after();
+                const uint64_t kd = desc_advance(kd0, (c.g & 1) * Cfg::TILE_BYTES);
 #pragma unroll
                 for (int s = 0; s < D / 16; ++s) {
+                    constexpr int dummy = 0; (void)dummy;
                     const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
-                    const uint64_t qd = make_smem_desc(s_q + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
-                    const uint64_t kd =
-                        make_smem_desc(s_k + (c.g & 1) * Cfg::TILE_BYTES + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
-                    umma_bf16_ss(tmem_s, qd, kd, idesc_s, s != 0);
+                    umma_bf16_ss(tmem_s, desc_advance(qd0, off), desc_advance(kd, off), idesc_s, s != 0);
                 }
                 umma_commit(bar_s_full);
             };
@@ -495,13 +500,11 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                     if (cp.j == 0 && cp.it >= 2) mbar_wait(&bar_o_free[cp.it & 1], ((cp.it >> 1) - 1) & 1);
                     tc_fence_after();
                     const uint32_t tmem_o = tmem_base + 128 + (cp.it & 1) * D;
+                    const uint64_t vd = desc_advance(vd0, st * Cfg::TILE_BYTES);
 #pragma unroll
                     for (int s = 0; s < ATT_BLOCK / 16; ++s) {
-                        const uint64_t pd = make_smem_desc(s_p + (s >> 2) * (ATT_BLOCK * 128) + (s & 3) * 32, 16, 1024,
-                                                           kLayoutSW128);
-                        const uint64_t vd = make_smem_desc(s_v + st * Cfg::TILE_BYTES + s * 16 * Cfg::ROW_BYTES,
-                                                           Cfg::BOX_BYTES, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
-                        umma_bf16_ss(tmem_o, pd, vd, idesc_pv, (cp.j | s) != 0);
+                        umma_bf16_ss(tmem_o, desc_advance(pd0, (s >> 2) * (ATT_BLOCK * 128) + (s & 3) * 32),
+                                     desc_advance(vd, s * 16 * Cfg::ROW_BYTES), idesc_pv, (cp.j | s) != 0);
                     }
                     umma_commit(&bar_kv_empty[st]);          // PV(g) done: stage st and the P buffer are free
                     if (cp.j == cp.nkv - 1) umma_commit(&bar_o_full[cp.it & 1]);
@@ -607,15 +610,20 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                 const float m_use = (m_run == -CUDART_INF_F) ? 0.f : m_run;
                 const uint64_t sc2 = pack_f32x2(LOG2E, LOG2E), nm2 = pack_f32x2(-m_use, -m_use);
                 uint64_t sum2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
+                // The warp issues in order: an add placed right behind its two MUFU producers stalls for the MUFU latency
+                // and idles the XU pipe.  The row sum therefore trails the exponentials by SUM_LAG pairs.
+                constexpr int SUM_LAG = 6;
 #pragma unroll
-                for (int i = 0; i < ATT_BLOCK; i += 4) {
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
+                for (int i = 0; i < ATT_BLOCK / 2 + SUM_LAG; ++i) {
+                    if (i < ATT_BLOCK / 2) {
                         float x0, x1;
-                        unpack_f32x2(fma_f32x2(pack_f32x2(s[i + 2 * u], s[i + 2 * u + 1]), sc2, nm2), x0, x1);
-                        s[i + 2 * u] = ex2(x0);
-                        s[i + 2 * u + 1] = ex2(x1);
-                        sum2[u] = add_f32x2(sum2[u], pack_f32x2(s[i + 2 * u], s[i + 2 * u + 1]));
+                        unpack_f32x2(fma_f32x2(pack_f32x2(s[2 * i], s[2 * i + 1]), sc2, nm2), x0, x1);
+                        s[2 * i] = ex2(x0);
+                        s[2 * i + 1] = ex2(x1);
+                    }
+                    if (i >= SUM_LAG) {
+                        const int k = i - SUM_LAG;
+                        sum2[k & 1] = add_f32x2(sum2[k & 1], pack_f32x2(s[2 * k], s[2 * k + 1]));
                     }
                 }
                 float sa, sb, sc, sd;

@@ -151,7 +151,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;
 }
 // Advance the start-address field by `bytes` (stays inside the same 1024-B swizzle atom or moves whole atoms).
-__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) {
+    // only the low word (start address, 16-B units) moves; the sum never carries out of the 14-bit field
+    return (desc & 0xFFFFFFFF00000000ull) | static_cast<uint32_t>(static_cast<uint32_t>(desc) + (bytes >> 4));
+}
 
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32:
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt (1 = bf16)  [15] A major (0 = K, 1 = MN)
