@@ -342,10 +342,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
 // Persistent variant (default).  A CTA walks a static stride of work items (sequence, head, 128-query block) and
 // treats all their KV blocks as ONE stream of iterations g = 0, 1, 2, ...:
 //   * K/V ring, S / P hand-offs and barrier parities are indexed by g, so the loads for the next item's first blocks,
-//     its Q tile and its first S = QK^T are all issued while the current item's last blocks are still in softmax;
-//   * O is double-buffered in TMEM (item parity), so the write-out of item i overlaps the first PV of item i+1.
-// The per-CTA prologue (TMEM alloc, barrier init, first TMA round trip) is paid once per launch instead of once per
-// 128-query block, which was ~25 % of the non-persistent kernel at K = 1024.
+//     its Q tile (double-buffered) and its first S = QK^T are issued while the current item is still in softmax;
+//   * P never touches shared memory: the softmax warps write it as packed bf16 into TMEM (tcgen05.st) and O += P V
+//     takes its A operand from TMEM (tcgen05.mma ..., [a_tmem], b_desc).  At head_dim 64 the smem-P form spent
+//     ~45 % of the shared-memory bandwidth of a KV block on writing P and reading it back, and shared memory
+//     (UMMA operand reads + TMA fills), not the tensor pipe, is what bounds this kernel.
+// TMEM columns: S [0,128) fp32 | P [128,192) bf16x2 | O [192, 192+D) fp32.
 // ================================================================================================
 struct AttnCursor {              // position in the flattened (item, kv-block) stream of this CTA
     int item;                    // global work-item index (n, head, qb); >= total -> stream exhausted
@@ -356,23 +358,36 @@ struct AttnCursor {              // position in the flattened (item, kv-block) s
 };
 
 template <int D>
-__global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_CTAS)
+struct AttnPCfg {                // shared memory of the persistent kernel: Q x2 | K x2 | V x2 | barriers
+    using B = AttnCfg<D>;
+    static constexpr int OFF_Q = 0;
+    static constexpr int OFF_K = 2 * B::TILE_BYTES;
+    static constexpr int OFF_V = 4 * B::TILE_BYTES;
+    static constexpr int OFF_BAR = 6 * B::TILE_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 128;
+    static constexpr int TMEM_COLS = (D == 128) ? 512 : 256;
+    static constexpr int MIN_CTAS = SMEM_BYTES <= 113000 ? 2 : 1;
+    static constexpr int TM_S = 0, TM_P = 128, TM_O = 192;
+};
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS, AttnPCfg<D>::MIN_CTAS)
 attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int heads, int k_tokens, int h,
                             const int32_t* __restrict__ kv_info, const uint8_t* __restrict__ key_mask,
                             __nv_bfloat16* __restrict__ out) {
     using Cfg = AttnCfg<D>;
-    constexpr int TMEM_COLS = (D == 128) ? 512 : 256;            // S: 128 columns, O: 2 x D columns
+    using PC = AttnPCfg<D>;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-    uint64_t* bar_q = bars + 0;
-    uint64_t* bar_kv_full = bars + 1;     // [2]
-    uint64_t* bar_kv_empty = bars + 3;    // [2]  PV(g) complete
-    uint64_t* bar_s_full = bars + 5;
-    uint64_t* bar_p_full = bars + 6;
-    uint64_t* bar_s_free = bars + 7;
-    uint64_t* bar_o_full = bars + 8;      // [2]  last PV of an item complete
-    uint64_t* bar_o_free = bars + 10;     // [2]  softmax warps have read O[buf] out
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PC::OFF_BAR);
+    uint64_t* bar_q = bars + 0;           // [2]  Q tile of item it landed in buffer it & 1
+    uint64_t* bar_kv_full = bars + 2;     // [2]
+    uint64_t* bar_kv_empty = bars + 4;    // [2]  PV(g) complete: K/V stage g & 1 and P are free
+    uint64_t* bar_s_full = bars + 6;
+    uint64_t* bar_p_full = bars + 7;
+    uint64_t* bar_s_free = bars + 8;
+    uint64_t* bar_o_full = bars + 9;      // last PV of an item complete
+    uint64_t* bar_o_free = bars + 10;     // softmax warps have read O out
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nqb = (k_tokens + ATT_BLOCK - 1) / ATT_BLOCK;
@@ -400,6 +415,11 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
             load_item(c);
         }
     };
+    auto next_item = [&](AttnCursor& c) {     // item-granular step (Q prefetch cursor)
+        ++c.it;
+        c.item += gridDim.x;
+        load_item(c);
+    };
     auto first = [&]() {
         AttnCursor c;
         c.item = blockIdx.x; c.it = 0; c.j = 0; c.g = 0; c.nkv = 0; c.kvl = 0; c.n = 0; c.head = 0; c.q0 = 0;
@@ -411,103 +431,102 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
         if (lane == 0) {
             if ((smem_u32(smem) & 1023u) != 0) { printf("molly attention: smem base not 1024-B aligned\n"); __trap(); }
             tma_prefetch_desc(&tma_qkv);
-            mbar_init(bar_q, 1);
             for (int i = 0; i < 2; ++i) {
+                mbar_init(&bar_q[i], 1);
                 mbar_init(&bar_kv_full[i], 1);
                 mbar_init(&bar_kv_empty[i], 1);
-                mbar_init(&bar_o_full[i], 1);
-                mbar_init(&bar_o_free[i], 128);
             }
             mbar_init(bar_s_full, 1);
             mbar_init(bar_p_full, 128);
             mbar_init(bar_s_free, 128);
+            mbar_init(bar_o_full, 1);
+            mbar_init(bar_o_free, 128);
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_alloc(tmem_slot, PC::TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_s = tmem_base;
+    const uint32_t tmem_s = tmem_base + PC::TM_S;
+    const uint32_t tmem_p = tmem_base + PC::TM_P;
+    const uint32_t tmem_o = tmem_base + PC::TM_O;
 
     if (warp == 4) {
         if (lane == 0) {
             // ---------------- control thread: TMA producer + MMA issuer ----------------
             constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK, ATT_BLOCK, false, false);
             constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK, D, false, true);      // B (= V) is MN-major
-            const uint32_t s_q = smem_u32(smem + Cfg::OFF_Q), s_k = smem_u32(smem + Cfg::OFF_K);
-            const uint32_t s_v = smem_u32(smem + Cfg::OFF_V), s_p = smem_u32(smem + Cfg::OFF_P);
+            const uint32_t s_q = smem_u32(smem + PC::OFF_Q), s_k = smem_u32(smem + PC::OFF_K);
+            const uint32_t s_v = smem_u32(smem + PC::OFF_V);
             auto load_tile = [&](int smem_off, uint64_t* bar, int col, int row) {
 #pragma unroll
                 for (int b = 0; b < Cfg::NBOX; ++b)
                     tma_load_2d(smem + smem_off + b * Cfg::BOX_BYTES, &tma_qkv, bar, col + b * Cfg::BOX_D, row);
             };
             auto load_q = [&](const AttnCursor& c) {
-                mbar_arrive_expect_tx(bar_q, Cfg::TILE_BYTES);
-                load_tile(Cfg::OFF_Q, bar_q, c.head * D, c.n * k_tokens + c.q0);
+                mbar_arrive_expect_tx(&bar_q[c.it & 1], Cfg::TILE_BYTES);
+                load_tile(PC::OFF_Q + (c.it & 1) * Cfg::TILE_BYTES, &bar_q[c.it & 1], c.head * D, c.n * k_tokens + c.q0);
             };
             auto load_kv = [&](const AttnCursor& c) {
                 const int stg = c.g & 1;
                 const int row = c.n * k_tokens + c.j * ATT_BLOCK;
                 mbar_arrive_expect_tx(&bar_kv_full[stg], 2 * Cfg::TILE_BYTES);
-                load_tile(Cfg::OFF_K + stg * Cfg::TILE_BYTES, &bar_kv_full[stg], h + c.head * D, row);
-                load_tile(Cfg::OFF_V + stg * Cfg::TILE_BYTES, &bar_kv_full[stg], 2 * h + c.head * D, row);
+                load_tile(PC::OFF_K + stg * Cfg::TILE_BYTES, &bar_kv_full[stg], h + c.head * D, row);
+                load_tile(PC::OFF_V + stg * Cfg::TILE_BYTES, &bar_kv_full[stg], 2 * h + c.head * D, row);
             };
-            // Base descriptors are built once; per MMA only the 14-bit start-address field moves (one 32-bit add),
-            // so the single issuing thread spends a handful of instructions per tcgen05.mma instead of ~15.
+            // Base descriptors are built once; per MMA only the start-address field moves (one 32-bit add).
             const uint64_t qd0 = make_smem_desc(s_q, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
             const uint64_t kd0 = make_smem_desc(s_k, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
-            const uint64_t pd0 = make_smem_desc(s_p, 16, 1024, kLayoutSW128);
             const uint64_t vd0 = make_smem_desc(s_v, Cfg::BOX_BYTES, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
             auto issue_s = [&](const AttnCursor& c) {       // S = Q K^T : K-major x K-major, D/16 k-steps
+                if (c.j == 0) mbar_wait(&bar_q[c.it & 1], (c.it >> 1) & 1);
                 mbar_wait(&bar_kv_full[c.g & 1], (c.g >> 1) & 1);
                 tc_fence_after();
+                const uint64_t qd = desc_advance(qd0, (c.it & 1) * Cfg::TILE_BYTES);
                 const uint64_t kd = desc_advance(kd0, (c.g & 1) * Cfg::TILE_BYTES);
 #pragma unroll
                 for (int s = 0; s < D / 16; ++s) {
-                    constexpr int dummy = 0; (void)dummy;
                     const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
-                    umma_bf16_ss(tmem_s, desc_advance(qd0, off), desc_advance(kd, off), idesc_s, s != 0);
+                    umma_bf16_ss(tmem_s, desc_advance(qd, off), desc_advance(kd, off), idesc_s, s != 0);
                 }
                 umma_commit(bar_s_full);
             };
 
-            AttnCursor cl = first(), cs = cl, cp = cl;      // load / S-issue / PV cursors
+            AttnCursor cl = first(), cs = cl, cp = cl, cq = cl;      // KV-load / S-issue / PV / Q-load cursors
             if (cp.item < total) {
-                load_q(cl);
+                load_q(cq); next_item(cq);
                 load_kv(cl); advance(cl);
                 if (cl.item < total) { load_kv(cl); advance(cl); }
-                mbar_wait(bar_q, 0);
+                if (cq.item < total) { load_q(cq); next_item(cq); }           // second Q buffer
                 issue_s(cs); advance(cs);
                 while (cp.item < total) {
                     const int g = cp.g, st = g & 1;
-                    // (1) softmax holds S(g) in registers -> S(g+1) runs under softmax(g); a new item first gets its Q
+                    // (1) softmax holds S(g) in registers -> S(g+1) runs under softmax(g)
                     mbar_wait(bar_s_free, g & 1);
                     tc_fence_after();
                     if (cs.item < total) {
-                        if (cs.j == 0) {                    // S(g) was the last user of the Q tile: reload it
-                            load_q(cs);
-                            mbar_wait(bar_q, cs.it & 1);
-                        }
+                        // S(g) was the last user of the previous item's Q buffer when cs starts a new item:
+                        // refill that buffer with the Q tile of the item after cs
+                        const bool new_item = cs.j == 0;
                         issue_s(cs);
+                        if (new_item && cq.item < total && cq.it == cs.it + 1) { load_q(cq); next_item(cq); }
                         advance(cs);
                     }
-                    // (2) O[it & 1] (+)= P(g) V(g) : P K-major (two 64-key atoms), V MN-major; 8 k-steps of 16 keys
+                    // (2) O (+)= P(g) V(g) : P from TMEM (64 packed columns), V MN-major from smem; 8 k-steps of 16 keys
                     mbar_wait(bar_p_full, g & 1);
-                    if (cp.j == 0 && cp.it >= 2) mbar_wait(&bar_o_free[cp.it & 1], ((cp.it >> 1) - 1) & 1);
+                    if (cp.j == 0 && cp.it >= 1) mbar_wait(bar_o_free, (cp.it - 1) & 1);   // previous item's O was read out
                     tc_fence_after();
-                    const uint32_t tmem_o = tmem_base + 128 + (cp.it & 1) * D;
                     const uint64_t vd = desc_advance(vd0, st * Cfg::TILE_BYTES);
 #pragma unroll
-                    for (int s = 0; s < ATT_BLOCK / 16; ++s) {
-                        umma_bf16_ss(tmem_o, desc_advance(pd0, (s >> 2) * (ATT_BLOCK * 128) + (s & 3) * 32),
-                                     desc_advance(vd, s * 16 * Cfg::ROW_BYTES), idesc_pv, (cp.j | s) != 0);
-                    }
-                    umma_commit(&bar_kv_empty[st]);          // PV(g) done: stage st and the P buffer are free
-                    if (cp.j == cp.nkv - 1) umma_commit(&bar_o_full[cp.it & 1]);
+                    for (int s = 0; s < ATT_BLOCK / 16; ++s)
+                        umma_bf16_ts(tmem_o, tmem_p + s * 8, desc_advance(vd, s * 16 * Cfg::ROW_BYTES), idesc_pv,
+                                     (cp.j | s) != 0);
+                    umma_commit(&bar_kv_empty[st]);          // PV(g) done: stage st and P are free
+                    if (cp.j == cp.nkv - 1) umma_commit(bar_o_full);
                     // (3) refill stage st with stream entry g+2 once PV(g) has drained it
                     if (cl.item < total) {
                         mbar_wait(&bar_kv_empty[st], (g >> 1) & 1);
@@ -522,8 +541,6 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
         // ---------------- softmax warps: thread r owns query row r ----------------
         const int r = threadIdx.x;
         const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-        uint8_t* p_row = smem + Cfg::OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
-        const int sw = r & 7;
         int g = 0, it = 0;                                    // stream position, identical to the control thread's
         for (int item = blockIdx.x; item < total; item += gridDim.x) {
             const int qb = item % nqb, tq = item / nqb;
@@ -540,7 +557,6 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                 continue;
             }
             const bool interior = __ldg(kv_info + 2 * n + 1) != kvl;       // pad ids before the last real token
-            const uint32_t tmem_o = tmem_base + 128 + (it & 1) * D;
             float m_run = -CUDART_INF_F;      // running reference max, log2 domain
             float l_run = 0.f;
             for (int j = 0; j < nkv; ++j, ++g) {
@@ -630,23 +646,18 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                 unpack_f32x2(sum2[0], sa, sb);
                 unpack_f32x2(sum2[1], sc, sd);
                 l_run = l_run * alpha + ((sa + sb) + (sc + sd));
-                // PV(g-1) must have drained the P buffer (and, inside an item, finished O) before either is touched
+                // PV(g-1) must have consumed P (and, inside an item, finished O) before either is touched again
                 if (g > 0) {
                     mbar_wait(&bar_kv_empty[(g - 1) & 1], ((g - 1) >> 1) & 1);
                     tc_fence_after();
                 }
+                // P -> TMEM as packed bf16 pairs: column c of lane r holds keys (2c, 2c+1) of query row r
 #pragma unroll
-                for (int a = 0; a < 2; ++a) {
+                for (int hh = 0; hh < 4; ++hh) {             // 16 packed columns at a time keeps the register peak low
+                    uint32_t pk[16];
 #pragma unroll
-                    for (int cc = 0; cc < 8; ++cc) {
-                        const int e = a * 64 + cc * 8;
-                        uint4 u;
-                        u.x = pack_bf16x2(s[e + 0], s[e + 1]);
-                        u.y = pack_bf16x2(s[e + 2], s[e + 3]);
-                        u.z = pack_bf16x2(s[e + 4], s[e + 5]);
-                        u.w = pack_bf16x2(s[e + 6], s[e + 7]);
-                        *reinterpret_cast<uint4*>(p_row + a * (ATT_BLOCK * 128) + ((cc ^ sw) << 4)) = u;
-                    }
+                    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(s[hh * 32 + 2 * i], s[hh * 32 + 2 * i + 1]);
+                    tmem_st16(tmem_p + lane_addr + hh * 16, pk);
                 }
                 if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll
@@ -658,14 +669,13 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                         for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
                         tmem_st16(tmem_o + lane_addr + cc * 16, o);
                     }
-                    tmem_st_wait();
                 }
-                fence_proxy_async_smem();
+                tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(bar_p_full);
             }
-            // item epilogue: O[it & 1] / l -> bf16 -> HBM, then hand the O buffer back
-            mbar_wait(&bar_o_full[it & 1], (it >> 1) & 1);
+            // item epilogue: O / l -> bf16 -> HBM, then hand O back to the MMA thread
+            mbar_wait(bar_o_full, it & 1);
             tc_fence_after();
             const float inv_l = 1.0f / l_run;
             const bool row_ok = q0 + r < k_tokens;
@@ -690,7 +700,7 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                 }
             }
             tc_fence_before();
-            mbar_arrive(&bar_o_free[it & 1]);
+            mbar_arrive(bar_o_free);
             ++it;
         }
     }
@@ -699,7 +709,7 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc(tmem_base, PC::TMEM_COLS);
     }
 }
 
@@ -715,7 +725,7 @@ bool attention_persistent_enabled() {
 template <int D>
 int launch_attention_persistent(const CUtensorMap& tm, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
                                 const uint8_t* key_mask, void* out, cudaStream_t stream) {
-    using Cfg = AttnCfg<D>;
+    using Cfg = AttnPCfg<D>;
     auto kernel = attention_persistent_kernel<D>;
     static bool configured = false;
     if (!configured) {
