@@ -358,22 +358,24 @@ struct AttnCursor {              // position in the flattened (item, kv-block) s
 };
 
 template <int D>
-struct AttnPCfg {                // shared memory of the persistent kernel: Q x2 | K x2 | V x2 | barriers
+struct AttnPCfg {                // shared memory of the persistent kernel: Q x2 | K x3 | V x2 | barriers
     using B = AttnCfg<D>;
+    // K and V have SEPARATE rings.  S(g+1) = Q K(g+1)^T is issued at the start of softmax(g), a whole block-time before
+    // V(g+1) is needed, so a shared K/V stage (freed only by PV) made every K tile arrive one TMA latency late -- that
+    // latency, not MUFU or shared memory, set the ~2000 cycles per KV block of the earlier versions.
+    static constexpr int KST = 3, VST = 2;
     static constexpr int OFF_Q = 0;
     static constexpr int OFF_K = 2 * B::TILE_BYTES;
-    static constexpr int OFF_V = 4 * B::TILE_BYTES;
-    static constexpr int OFF_BAR = 6 * B::TILE_BYTES;
-    static constexpr int OFF_X = OFF_BAR + 128;                 // row-max / row-sum exchange between the two half-row warps
-    static constexpr int SMEM_BYTES = OFF_X + (2 * 2 + 2) * 128 * 4;
-    static constexpr int THREADS = 8 * 32 + 32;                 // 8 softmax warps (two per TMEM lane quarter) + control
+    static constexpr int OFF_V = (2 + KST) * B::TILE_BYTES;
+    static constexpr int OFF_BAR = (2 + KST + VST) * B::TILE_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256;
     static constexpr int TMEM_COLS = (D == 128) ? 512 : 256;
-    static constexpr int MIN_CTAS = SMEM_BYTES <= 113000 ? 2 : 1;
+    static constexpr int MIN_CTAS = SMEM_BYTES <= 115712 ? 2 : 1;       // (228 KB - 2 x 1 KB reserved) / 2
     static constexpr int TM_S = 0, TM_P = 128, TM_O = 192;
 };
 
 template <int D>
-__global__ void __launch_bounds__(AttnPCfg<D>::THREADS, AttnPCfg<D>::MIN_CTAS)
+__global__ void __launch_bounds__(ATT_THREADS, AttnPCfg<D>::MIN_CTAS)
 attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int heads, int k_tokens, int h,
                             const int32_t* __restrict__ kv_info, const uint8_t* __restrict__ key_mask,
                             __nv_bfloat16* __restrict__ out) {
@@ -382,14 +384,16 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PC::OFF_BAR);
     uint64_t* bar_q = bars + 0;           // [2]  Q tile of item it landed in buffer it & 1
-    uint64_t* bar_kv_full = bars + 2;     // [2]
-    uint64_t* bar_kv_empty = bars + 4;    // [2]  PV(g) complete: K/V stage g & 1 and P are free
-    uint64_t* bar_s_full = bars + 6;
-    uint64_t* bar_p_full = bars + 7;
-    uint64_t* bar_s_free = bars + 8;
-    uint64_t* bar_o_full = bars + 9;      // last PV of an item complete
-    uint64_t* bar_o_free = bars + 10;     // softmax warps have read O out
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+    uint64_t* bar_k_full = bars + 2;      // [3]
+    uint64_t* bar_k_empty = bars + 5;     // [3]  S(g) complete: K stage g % 3 is free
+    uint64_t* bar_v_full = bars + 8;      // [2]
+    uint64_t* bar_v_empty = bars + 10;    // [2]  PV(g) complete: V stage g & 1 and P are free
+    uint64_t* bar_s_full = bars + 12;
+    uint64_t* bar_p_full = bars + 13;
+    uint64_t* bar_s_free = bars + 14;
+    uint64_t* bar_o_full = bars + 15;     // last PV of an item complete
+    uint64_t* bar_o_free = bars + 16;     // softmax warps have read O out
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nqb = (k_tokens + ATT_BLOCK - 1) / ATT_BLOCK;
@@ -429,20 +433,24 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
         return c;
     };
 
-    if (warp == 8) {
+    if (warp == 4) {
         if (lane == 0) {
             if ((smem_u32(smem) & 1023u) != 0) { printf("molly attention: smem base not 1024-B aligned\n"); __trap(); }
             tma_prefetch_desc(&tma_qkv);
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&bar_q[i], 1);
-                mbar_init(&bar_kv_full[i], 1);
-                mbar_init(&bar_kv_empty[i], 1);
+                mbar_init(&bar_v_full[i], 1);
+                mbar_init(&bar_v_empty[i], 1);
+            }
+            for (int i = 0; i < PC::KST; ++i) {
+                mbar_init(&bar_k_full[i], 1);
+                mbar_init(&bar_k_empty[i], 1);
             }
             mbar_init(bar_s_full, 1);
-            mbar_init(bar_p_full, 256);
-            mbar_init(bar_s_free, 256);
+            mbar_init(bar_p_full, 128);
+            mbar_init(bar_s_free, 128);
             mbar_init(bar_o_full, 1);
-            mbar_init(bar_o_free, 256);
+            mbar_init(bar_o_free, 128);
             fence_mbar_init();
         }
         __syncwarp();
@@ -457,7 +465,7 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
     const uint32_t tmem_p = tmem_base + PC::TM_P;
     const uint32_t tmem_o = tmem_base + PC::TM_O;
 
-    if (warp == 8) {
+    if (warp == 4) {
         if (lane == 0) {
             // ---------------- control thread: TMA producer + MMA issuer ----------------
             constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK, ATT_BLOCK, false, false);
@@ -473,12 +481,19 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                 mbar_arrive_expect_tx(&bar_q[c.it & 1], Cfg::TILE_BYTES);
                 load_tile(PC::OFF_Q + (c.it & 1) * Cfg::TILE_BYTES, &bar_q[c.it & 1], c.head * D, c.n * k_tokens + c.q0);
             };
-            auto load_kv = [&](const AttnCursor& c) {
+            auto load_k = [&](const AttnCursor& c) {      // K(g) -> stage g % 3, once S(g-3) has released it
+                const int stg = c.g % PC::KST;
+                if (c.g >= PC::KST) mbar_wait(&bar_k_empty[stg], ((c.g / PC::KST) - 1) & 1);
+                mbar_arrive_expect_tx(&bar_k_full[stg], Cfg::TILE_BYTES);
+                load_tile(PC::OFF_K + stg * Cfg::TILE_BYTES, &bar_k_full[stg], h + c.head * D,
+                          c.n * k_tokens + c.j * ATT_BLOCK);
+            };
+            auto load_v = [&](const AttnCursor& c) {      // V(g) -> stage g & 1, once PV(g-2) has released it
                 const int stg = c.g & 1;
-                const int row = c.n * k_tokens + c.j * ATT_BLOCK;
-                mbar_arrive_expect_tx(&bar_kv_full[stg], 2 * Cfg::TILE_BYTES);
-                load_tile(PC::OFF_K + stg * Cfg::TILE_BYTES, &bar_kv_full[stg], h + c.head * D, row);
-                load_tile(PC::OFF_V + stg * Cfg::TILE_BYTES, &bar_kv_full[stg], 2 * h + c.head * D, row);
+                if (c.g >= 2) mbar_wait(&bar_v_empty[stg], ((c.g >> 1) - 1) & 1);
+                mbar_arrive_expect_tx(&bar_v_full[stg], Cfg::TILE_BYTES);
+                load_tile(PC::OFF_V + stg * Cfg::TILE_BYTES, &bar_v_full[stg], 2 * h + c.head * D,
+                          c.n * k_tokens + c.j * ATT_BLOCK);
             };
             // Base descriptors are built once; per MMA only the start-address field moves (one 32-bit add).
             const uint64_t qd0 = make_smem_desc(s_q, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
@@ -486,23 +501,25 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
             const uint64_t vd0 = make_smem_desc(s_v, Cfg::BOX_BYTES, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
             auto issue_s = [&](const AttnCursor& c) {       // S = Q K^T : K-major x K-major, D/16 k-steps
                 if (c.j == 0) mbar_wait(&bar_q[c.it & 1], (c.it >> 1) & 1);
-                mbar_wait(&bar_kv_full[c.g & 1], (c.g >> 1) & 1);
+                const int kst = c.g % PC::KST;
+                mbar_wait(&bar_k_full[kst], (c.g / PC::KST) & 1);
                 tc_fence_after();
                 const uint64_t qd = desc_advance(qd0, (c.it & 1) * Cfg::TILE_BYTES);
-                const uint64_t kd = desc_advance(kd0, (c.g & 1) * Cfg::TILE_BYTES);
+                const uint64_t kd = desc_advance(kd0, kst * Cfg::TILE_BYTES);
 #pragma unroll
                 for (int s = 0; s < D / 16; ++s) {
                     const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
                     umma_bf16_ss(tmem_s, desc_advance(qd, off), desc_advance(kd, off), idesc_s, s != 0);
                 }
                 umma_commit(bar_s_full);
+                umma_commit(&bar_k_empty[kst]);              // the same completion also releases the K stage
             };
 
-            AttnCursor cl = first(), cs = cl, cp = cl, cq = cl;      // KV-load / S-issue / PV / Q-load cursors
+            AttnCursor ck = first(), cv = ck, cs = ck, cp = ck, cq = ck;   // K-load / V-load / S-issue / PV / Q-load cursors
             if (cp.item < total) {
                 load_q(cq); next_item(cq);
-                load_kv(cl); advance(cl);
-                if (cl.item < total) { load_kv(cl); advance(cl); }
+                for (int i = 0; i < PC::KST && ck.item < total; ++i) { load_k(ck); advance(ck); }
+                for (int i = 0; i < PC::VST && cv.item < total; ++i) { load_v(cv); advance(cv); }
                 if (cq.item < total) { load_q(cq); next_item(cq); }           // second Q buffer
                 issue_s(cs); advance(cs);
                 while (cp.item < total) {
@@ -518,39 +535,31 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                         if (new_item && cq.item < total && cq.it == cs.it + 1) { load_q(cq); next_item(cq); }
                         advance(cs);
                     }
+                    // S(g) is complete (the softmax warps have read it), so its K stage is free: fetch K(g+3) now,
+                    // two block-times before S(g+3) is issued
+                    if (ck.item < total) { load_k(ck); advance(ck); }
                     // (2) O (+)= P(g) V(g) : P from TMEM (64 packed columns), V MN-major from smem; 8 k-steps of 16 keys
                     mbar_wait(bar_p_full, g & 1);
                     if (cp.j == 0 && cp.it >= 1) mbar_wait(bar_o_free, (cp.it - 1) & 1);   // previous item's O was read out
+                    mbar_wait(&bar_v_full[st], (g >> 1) & 1);
                     tc_fence_after();
                     const uint64_t vd = desc_advance(vd0, st * Cfg::TILE_BYTES);
 #pragma unroll
                     for (int s = 0; s < ATT_BLOCK / 16; ++s)
                         umma_bf16_ts(tmem_o, tmem_p + s * 8, desc_advance(vd, s * 16 * Cfg::ROW_BYTES), idesc_pv,
                                      (cp.j | s) != 0);
-                    umma_commit(&bar_kv_empty[st]);          // PV(g) done: stage st and P are free
+                    umma_commit(&bar_v_empty[st]);           // PV(g) done: V stage st and P are free
                     if (cp.j == cp.nkv - 1) umma_commit(bar_o_full);
-                    // (3) refill stage st with stream entry g+2 once PV(g) has drained it
-                    if (cl.item < total) {
-                        mbar_wait(&bar_kv_empty[st], (g >> 1) & 1);
-                        load_kv(cl);
-                        advance(cl);
-                    }
+                    // (3) refill V stage st with V(g+2) once PV(g) has drained it (needed two block-times from now)
+                    if (cv.item < total) { load_v(cv); advance(cv); }
                     advance(cp);
                 }
             }
         }
     } else {
-        // ---------------- softmax warps: TWO threads per query row r, each owns 64 of the 128 key columns --------
-        // (warps w and w+4 share TMEM lane quarter w; twice the warps in flight hides the MUFU / TMEM latencies that a
-        //  single warp per scheduler could not, and halves the per-thread register footprint)
-        const int r = threadIdx.x & 127;
-        const int half = threadIdx.x >> 7;
-        const int quarter = warp & 3;
-        const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-        float* const xmax = reinterpret_cast<float*>(smem + PC::OFF_X);            // [2 (g parity)][2 (half)][128]
-        float* const xsum = xmax + 2 * 2 * 128;                                    // [2 (half)][128]
-        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory"); };
-        constexpr int HC = ATT_BLOCK / 2;                                          // key columns per thread
+        // ---------------- softmax warps: thread r owns query row r ----------------
+        const int r = threadIdx.x;
+        const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
         int g = 0, it = 0;                                    // stream position, identical to the control thread's
         for (int item = blockIdx.x; item < total; item += gridDim.x) {
             const int qb = item % nqb, tq = item / nqb;
@@ -560,37 +569,37 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
             const int nkv = (kvl + ATT_BLOCK - 1) / ATT_BLOCK;
             const long long row_base = static_cast<long long>(n) * k_tokens;
             if (nkv == 0) {          // all-pad sequence: not in the stream; zero-fill (the reference never encodes one)
-                if (half == 0 && q0 + r < k_tokens) {
+                if (q0 + r < k_tokens) {
                     uint4* o = reinterpret_cast<uint4*>(out + (row_base + q0 + r) * h + head * D);
                     for (int i = 0; i < D / 8; ++i) o[i] = make_uint4(0, 0, 0, 0);
                 }
                 continue;
             }
             const bool interior = __ldg(kv_info + 2 * n + 1) != kvl;       // pad ids before the last real token
-            float m_run = -CUDART_INF_F;      // running reference max, log2 domain (identical in both threads of a row)
-            float l_run = 0.f;                // row sum over THIS thread's columns; the halves are added in the epilogue
-            constexpr int OC = D >= 32 ? D / 2 : D;                    // O columns this thread rescales / writes out
-            const int o_col0 = D >= 32 ? half * OC : 0;
+            float m_run = -CUDART_INF_F;      // running reference max, log2 domain
+            float l_run = 0.f;
             for (int j = 0; j < nkv; ++j, ++g) {
                 mbar_wait(bar_s_full, g & 1);
                 tc_fence_after();
-                float s[HC];
+                float s[ATT_BLOCK];
                 {
-                    uint32_t raw[HC];
-                    tmem_ld32(tmem_s + lane_addr + half * HC, raw);
-                    tmem_ld32(tmem_s + lane_addr + half * HC + 32, raw + 32);
+                    uint32_t raw[ATT_BLOCK];
+                    tmem_ld32(tmem_s + lane_addr + 0, raw);
+                    tmem_ld32(tmem_s + lane_addr + 32, raw + 32);
+                    tmem_ld32(tmem_s + lane_addr + 64, raw + 64);
+                    tmem_ld32(tmem_s + lane_addr + 96, raw + 96);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < HC; ++i) s[i] = __uint_as_float(raw[i]);
+                    for (int i = 0; i < ATT_BLOCK; ++i) s[i] = __uint_as_float(raw[i]);
                 }
                 tc_fence_before();
                 mbar_arrive(bar_s_free);                     // S(g) is in registers: the MMA warp may start S(g+1)
-                const int j0 = j * ATT_BLOCK + half * HC;             // first key column of this thread
+                const int j0 = j * ATT_BLOCK;
                 if (interior) {
                     const uint4* mk = reinterpret_cast<const uint4*>(key_mask + row_base + j0);
-                    const bool vec_ok = ((row_base + j0) & 15) == 0 && j0 + HC <= k_tokens;
+                    const bool vec_ok = ((row_base + j0) & 15) == 0 && j0 + ATT_BLOCK <= k_tokens;
 #pragma unroll
-                    for (int gq = 0; gq < HC / 16; ++gq) {
+                    for (int gq = 0; gq < 8; ++gq) {
                         uint32_t w[4];
                         if (vec_ok) {
                             const uint4 u = __ldg(mk + gq);
@@ -613,23 +622,19 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                             if (!ok) s[gq * 16 + i] = -CUDART_INF_F;
                         }
                     }
-                } else if (j0 + HC > kvl) {
+                } else if (j0 + ATT_BLOCK > kvl) {
                     const int lim = kvl - j0;
 #pragma unroll
-                    for (int i = 0; i < HC; ++i)
+                    for (int i = 0; i < ATT_BLOCK; ++i)
                         if (i >= lim) s[i] = -CUDART_INF_F;
                 }
                 float mx4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-                for (int i = 4; i < HC; i += 4) {
+                for (int i = 4; i < ATT_BLOCK; i += 4) {
                     mx4[0] = fmaxf(mx4[0], s[i]); mx4[1] = fmaxf(mx4[1], s[i + 1]);
                     mx4[2] = fmaxf(mx4[2], s[i + 2]); mx4[3] = fmaxf(mx4[3], s[i + 3]);
                 }
-                float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-                // the row max needs the other half's 64 columns: one float through smem, 64-thread named barrier
-                xmax[((g & 1) * 2 + half) * 128 + r] = mx;
-                pair_sync();
-                mx = fmaxf(mx, xmax[((g & 1) * 2 + (half ^ 1)) * 128 + r]);
+                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
                 // lazy rescaling (see the non-persistent kernel): move the reference max only when it grew by > 2^8
                 const float m_cand = fmaxf(m_run, mx * LOG2E);
                 float alpha = 1.0f;
@@ -642,10 +647,10 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                 uint64_t sum2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
                 // The warp issues in order: an add placed right behind its two MUFU producers stalls for the MUFU latency
                 // and idles the XU pipe.  The row sum therefore trails the exponentials by SUM_LAG pairs.
-                constexpr int SUM_LAG = 3;
+                constexpr int SUM_LAG = 6;
 #pragma unroll
-                for (int i = 0; i < HC / 2 + SUM_LAG; ++i) {
-                    if (i < HC / 2) {
+                for (int i = 0; i < ATT_BLOCK / 2 + SUM_LAG; ++i) {
+                    if (i < ATT_BLOCK / 2) {
                         float x0, x1;
                         unpack_f32x2(fma_f32x2(pack_f32x2(s[2 * i], s[2 * i + 1]), sc2, nm2), x0, x1);
                         s[2 * i] = ex2(x0);
@@ -662,27 +667,26 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                 l_run = l_run * alpha + ((sa + sb) + (sc + sd));
                 // PV(g-1) must have consumed P (and, inside an item, finished O) before either is touched again
                 if (g > 0) {
-                    mbar_wait(&bar_kv_empty[(g - 1) & 1], ((g - 1) >> 1) & 1);
+                    mbar_wait(&bar_v_empty[(g - 1) & 1], ((g - 1) >> 1) & 1);
                     tc_fence_after();
                 }
                 // P -> TMEM as packed bf16 pairs: column c of lane r holds keys (2c, 2c+1) of query row r
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {             // this thread's 64 keys = 32 packed columns
+                for (int hh = 0; hh < 4; ++hh) {             // 16 packed columns at a time keeps the register peak low
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(s[hh * 32 + 2 * i], s[hh * 32 + 2 * i + 1]);
-                    tmem_st16(tmem_p + lane_addr + half * 32 + hh * 16, pk);
+                    tmem_st16(tmem_p + lane_addr + hh * 16, pk);
                 }
-                // O rescale: the two threads of a row split the D accumulator columns (D >= 32), else half 0 does it
-                if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f) && (D >= 32 || half == 0)) {
+                if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll
-                    for (int cc = 0; cc < OC / 16; ++cc) {
+                    for (int cc = 0; cc < D / 16; ++cc) {
                         uint32_t o[16];
-                        tmem_ld16(tmem_o + lane_addr + o_col0 + cc * 16, o);
+                        tmem_ld16(tmem_o + lane_addr + cc * 16, o);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st16(tmem_o + lane_addr + o_col0 + cc * 16, o);
+                        tmem_st16(tmem_o + lane_addr + cc * 16, o);
                     }
                 }
                 tmem_st_wait();
@@ -690,32 +694,28 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                 mbar_arrive(bar_p_full);
             }
             // item epilogue: O / l -> bf16 -> HBM, then hand O back to the MMA thread
-            xsum[half * 128 + r] = l_run;
-            pair_sync();
-            const float inv_l = 1.0f / (l_run + xsum[(half ^ 1) * 128 + r]);
             mbar_wait(bar_o_full, it & 1);
             tc_fence_after();
-            const bool row_ok = q0 + r < k_tokens && (D >= 32 || half == 0);
-            __nv_bfloat16* orow = out + (row_base + q0 + r) * h + head * D + o_col0;
-            if (D >= 32 || half == 0) {
+            const float inv_l = 1.0f / l_run;
+            const bool row_ok = q0 + r < k_tokens;
+            __nv_bfloat16* orow = out + (row_base + q0 + r) * h + head * D;
 #pragma unroll
-                for (int cc = 0; cc < OC / 16; ++cc) {
-                    uint32_t o[16];
-                    tmem_ld16(tmem_o + lane_addr + o_col0 + cc * 16, o);
-                    tmem_ld_wait();
-                    if (row_ok) {
-                        uint4 u0, u1;
-                        u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l);
-                        u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l);
-                        u0.z = pack_bf16x2(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l);
-                        u0.w = pack_bf16x2(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l);
-                        u1.x = pack_bf16x2(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l);
-                        u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l);
-                        u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l);
-                        u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l);
-                        reinterpret_cast<uint4*>(orow + cc * 16)[0] = u0;
-                        reinterpret_cast<uint4*>(orow + cc * 16)[1] = u1;
-                    }
+            for (int cc = 0; cc < D / 16; ++cc) {
+                uint32_t o[16];
+                tmem_ld16(tmem_o + lane_addr + cc * 16, o);
+                tmem_ld_wait();
+                if (row_ok) {
+                    uint4 u0, u1;
+                    u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l);
+                    u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l);
+                    u0.z = pack_bf16x2(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l);
+                    u0.w = pack_bf16x2(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l);
+                    u1.x = pack_bf16x2(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l);
+                    u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l);
+                    u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l);
+                    u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l);
+                    reinterpret_cast<uint4*>(orow + cc * 16)[0] = u0;
+                    reinterpret_cast<uint4*>(orow + cc * 16)[1] = u1;
                 }
             }
             tc_fence_before();
@@ -726,7 +726,7 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 4) {
         tc_fence_after();
         tmem_dealloc(tmem_base, PC::TMEM_COLS);
     }
@@ -756,7 +756,7 @@ int launch_attention_persistent(const CUtensorMap& tm, int n_seq, int k_tokens, 
     const int grid = total < slots ? total : slots;
     {   // dense-equivalent work 4*n*K*K*h (exact when every sequence is full length)
         ProfScope prof(PF_ATTENTION, 4.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
-        kernel<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm, n_seq, heads, k_tokens, h, kv_info, key_mask,
+        kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, n_seq, heads, k_tokens, h, kv_info, key_mask,
                                                                static_cast<__nv_bfloat16*>(out));
     }
     count_launch();

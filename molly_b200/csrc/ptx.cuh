@@ -40,16 +40,16 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-// try_wait with a suspend-time hint: the waiting thread is parked by the hardware (and woken by the completing
-// arrive) instead of spinning through the issue slots of the SM sub-partition it shares with the math warps.
+// try_wait parks the thread for a hardware-chosen interval; an explicit long suspend-time hint (NANOSLEEP.SYNCS) was
+// measured to ADD wake-up latency on the attention hand-offs (run r01f), so the default is kept.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)      // up to 1 ms parked per try
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     return ok != 0;
 }
@@ -216,10 +216,10 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     return ok != 0;
 }
