@@ -168,6 +168,9 @@ int molly_rotary(void* qkv_dev /*bf16 [rows, 3h] in place on q and k*/, int32_t 
 int molly_attention(const void* qkv_dev /*bf16 [n_seq*k, 3h]*/, int32_t n_seq, int32_t k_tokens, int32_t h,
                     int32_t heads, const int32_t* kv_info_dev /*[n_seq,2] from molly_embed*/,
                     const uint8_t* key_mask_dev, void* out_dev /*bf16 [n_seq*k, h]*/, void* stream);
+/* bring-up aid: when non-NULL, CTA 0 of the attention kernel records clock64() stamps into timeline_dev
+ * (int64 [2 roles][64 iterations][8 slots]); NULL (default) disables it */
+int molly_attention_debug(long long* timeline_dev);
 int molly_merge_rows(const void* src_dev /*[n_seq*k, D]*/, const int32_t* seq_table_dev, int32_t n_seq,
                      int32_t k_tokens, int32_t k_cap, void* hidden_states_dev, int32_t dtype, int32_t B, int32_t T,
                      int32_t D, int32_t* err_flag_dev, void* stream);

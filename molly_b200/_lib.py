@@ -82,6 +82,7 @@ SIGNATURES = {
     "molly_embed": (C.c_int, [_vp, _i32, _i32, C.POINTER(EncoderConfig), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "molly_rotary": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "molly_attention": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "molly_attention_debug": (C.c_int, [_vp]),
     "molly_merge_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "molly_profile_start": (C.c_int, []),
     "molly_profile_stop": (C.c_int, [C.POINTER(ProfileEntry), _i32]),

@@ -370,6 +370,11 @@ int molly_attention(const void* qkv_dev, int32_t n_seq, int32_t k_tokens, int32_
                             static_cast<cudaStream_t>(stream));
 }
 
+int molly_attention_debug(long long* timeline_dev) {
+    attention_set_debug(timeline_dev);
+    return MOLLY_OK;
+}
+
 int molly_merge_rows(const void* src_dev, const int32_t* seq_table_dev, int32_t n_seq, int32_t k_tokens, int32_t k_cap,
                      void* hidden_states_dev, int32_t dtype, int32_t B, int32_t T, int32_t D, int32_t* err_flag_dev,
                      void* stream) {

@@ -378,9 +378,14 @@ template <int D>
 __global__ void __launch_bounds__(ATT_THREADS, AttnPCfg<D>::MIN_CTAS)
 attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int heads, int k_tokens, int h,
                             const int32_t* __restrict__ kv_info, const uint8_t* __restrict__ key_mask,
-                            __nv_bfloat16* __restrict__ out) {
+                            __nv_bfloat16* __restrict__ out, long long* __restrict__ dbg) {
     using Cfg = AttnCfg<D>;
     using PC = AttnPCfg<D>;
+    // optional timeline of CTA 0 (tools/attn_timeline.py): dbg[role][iteration][slot] = clock64()
+#define MOLLY_DBG(role, iter, slot)                                                             \
+    do {                                                                                        \
+        if (dbg != nullptr && blockIdx.x == 0 && (iter) < 64) dbg[((role) * 64 + (iter)) * 8 + (slot)] = clock64(); \
+    } while (0)
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PC::OFF_BAR);
     uint64_t* bar_q = bars + 0;           // [2]  Q tile of item it landed in buffer it & 1
@@ -525,7 +530,9 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                 while (cp.item < total) {
                     const int g = cp.g, st = g & 1;
                     // (1) softmax holds S(g) in registers -> S(g+1) runs under softmax(g)
+                    MOLLY_DBG(0, g, 0);
                     mbar_wait(bar_s_free, g & 1);
+                    MOLLY_DBG(0, g, 1);
                     tc_fence_after();
                     if (cs.item < total) {
                         // S(g) was the last user of the previous item's Q buffer when cs starts a new item:
@@ -538,9 +545,11 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                     // S(g) is complete (the softmax warps have read it), so its K stage is free: fetch K(g+3) now,
                     // two block-times before S(g+3) is issued
                     if (ck.item < total) { load_k(ck); advance(ck); }
+                    MOLLY_DBG(0, g, 2);
                     // (2) O (+)= P(g) V(g) : P from TMEM (64 packed columns), V MN-major from smem; 8 k-steps of 16 keys
                     mbar_wait(bar_p_full, g & 1);
                     if (cp.j == 0 && cp.it >= 1) mbar_wait(bar_o_free, (cp.it - 1) & 1);   // previous item's O was read out
+                    MOLLY_DBG(0, g, 3);
                     mbar_wait(&bar_v_full[st], (g >> 1) & 1);
                     tc_fence_after();
                     const uint64_t vd = desc_advance(vd0, st * Cfg::TILE_BYTES);
@@ -550,8 +559,10 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                                      (cp.j | s) != 0);
                     umma_commit(&bar_v_empty[st]);           // PV(g) done: V stage st and P are free
                     if (cp.j == cp.nkv - 1) umma_commit(bar_o_full);
+                    MOLLY_DBG(0, g, 4);
                     // (3) refill V stage st with V(g+2) once PV(g) has drained it (needed two block-times from now)
                     if (cv.item < total) { load_v(cv); advance(cv); }
+                    MOLLY_DBG(0, g, 5);
                     advance(cp);
                 }
             }
@@ -579,7 +590,9 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
             float m_run = -CUDART_INF_F;      // running reference max, log2 domain
             float l_run = 0.f;
             for (int j = 0; j < nkv; ++j, ++g) {
+                if (threadIdx.x == 0) MOLLY_DBG(1, g, 0);
                 mbar_wait(bar_s_full, g & 1);
+                if (threadIdx.x == 0) MOLLY_DBG(1, g, 1);
                 tc_fence_after();
                 float s[ATT_BLOCK];
                 {
@@ -594,6 +607,7 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                 }
                 tc_fence_before();
                 mbar_arrive(bar_s_free);                     // S(g) is in registers: the MMA warp may start S(g+1)
+                if (threadIdx.x == 0) MOLLY_DBG(1, g, 2);
                 const int j0 = j * ATT_BLOCK;
                 if (interior) {
                     const uint4* mk = reinterpret_cast<const uint4*>(key_mask + row_base + j0);
@@ -665,6 +679,7 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                 unpack_f32x2(sum2[0], sa, sb);
                 unpack_f32x2(sum2[1], sc, sd);
                 l_run = l_run * alpha + ((sa + sb) + (sc + sd));
+                if (threadIdx.x == 0) MOLLY_DBG(1, g, 3);
                 // PV(g-1) must have consumed P (and, inside an item, finished O) before either is touched again
                 if (g > 0) {
                     mbar_wait(&bar_v_empty[(g - 1) & 1], ((g - 1) >> 1) & 1);
@@ -689,9 +704,11 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                         tmem_st16(tmem_o + lane_addr + cc * 16, o);
                     }
                 }
+                if (threadIdx.x == 0) MOLLY_DBG(1, g, 4);
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(bar_p_full);
+                if (threadIdx.x == 0) MOLLY_DBG(1, g, 5);
             }
             // item epilogue: O / l -> bf16 -> HBM, then hand O back to the MMA thread
             mbar_wait(bar_o_full, it & 1);
@@ -732,6 +749,8 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
     }
 }
 
+long long* g_attn_debug = nullptr;     // set through molly_attention_debug(); nullptr in production
+
 bool attention_persistent_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -757,7 +776,7 @@ int launch_attention_persistent(const CUtensorMap& tm, int n_seq, int k_tokens, 
     {   // dense-equivalent work 4*n*K*K*h (exact when every sequence is full length)
         ProfScope prof(PF_ATTENTION, 4.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
         kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, n_seq, heads, k_tokens, h, kv_info, key_mask,
-                                                               static_cast<__nv_bfloat16*>(out));
+                                                               static_cast<__nv_bfloat16*>(out), g_attn_debug);
     }
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
@@ -788,6 +807,8 @@ int launch_attention(const CUtensorMap& tm, int n_seq, int k_tokens, int h, int 
 }
 
 }  // namespace
+
+void attention_set_debug(long long* buf) { g_attn_debug = buf; }
 
 int attention_make_map(CUtensorMap* tq, const void* qkv, int rows, int h, int heads) {
     const int d = h / heads;

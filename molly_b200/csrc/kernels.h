@@ -40,6 +40,7 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap*
                 int rope_head_dim = 0);
 
 // ---- attention.cu ----
+void attention_set_debug(long long* buf);
 int attention_make_map(CUtensorMap* tq, const void* qkv, int rows, int h, int heads);
 int attention_launch(const CUtensorMap& tqkv, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_len,
                      const uint8_t* key_mask, void* out, cudaStream_t stream);
