@@ -690,7 +690,7 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                 for (int hh = 0; hh < 4; ++hh) {             // 16 packed columns at a time keeps the register peak low
                     uint32_t pk[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(s[hh * 32 + 2 * i], s[hh * 32 + 2 * i + 1]);
+                    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2_alu(s[hh * 32 + 2 * i], s[hh * 32 + 2 * i + 1]);
                     tmem_st16(tmem_p + lane_addr + hh * 16, pk);
                 }
                 if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
