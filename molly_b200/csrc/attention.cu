@@ -754,8 +754,11 @@ long long* g_attn_debug = nullptr;     // set through molly_attention_debug(); n
 bool attention_persistent_enabled() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("MOLLY_ATTN_PERSISTENT");     // bring-up switch: 0 selects the one-item-per-CTA kernel
-        v = (e == nullptr || e[0] != '0') ? 1 : 0;
+        // Measured (tools/attn_bench.py, ESM-650M layer shape): one item per CTA with P staged in shared memory 579 us,
+        // persistent + smem P 586 us, persistent + P in TMEM 666 us -> the simple kernel is the default;
+        // MOLLY_ATTN_PERSISTENT=1 selects the streamed, P-in-TMEM variant.
+        const char* e = getenv("MOLLY_ATTN_PERSISTENT");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
     }
     return v == 1;
 }

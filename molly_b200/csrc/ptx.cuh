@@ -322,9 +322,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 // ----------------------------------------------------------------------------------------------
 // small math / packing helpers
 // ----------------------------------------------------------------------------------------------
-// fp32 pair -> packed bf16x2 on the INTEGER pipe: add half an ulp (round half up) and splice the two high halves with one
-// PRMT.  cvt.rn.bf16x2.f32 (F2FP) issues on the quarter-rate XU pipe that the softmax's MUFU.EX2 already saturates: in
-// the attention kernel the 64 packs per row cost half as many XU cycles as the 128 exponentials themselves.
+// fp32 pair -> packed bf16x2 on the integer pipe (round half up + PRMT).  Tried as a replacement for F2FP in the softmax
+// (hypothesis: F2FP competes with MUFU.EX2 for the XU pipe); measured SLOWER than F2FP in the one-item-per-CTA kernel
+// (600 vs 579 us, tools/attn_bench.py), so only the P-in-TMEM variant, where it removed spills, still uses it.
 __device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
     return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
 }
