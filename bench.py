@@ -363,9 +363,20 @@ def main() -> None:
     g_fl = sum(v["work"] for k, v in prof.items() if k.startswith("gemm"))
     g_n = sum(v["launches"] for k, v in prof.items() if k.startswith("gemm"))
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    traffic, traffic_src = None, None        # DRAM bytes per GEMM launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            tj = json.load(open(tpath))
+            vals = [l["dram_bytes"] for l in tj.get("launches", []) if "gemm" in l["kernel"]]
+            if vals:
+                traffic, traffic_src = sum(vals) / len(vals), tj.get("source")
+        except Exception:
+            pass
     roofline = {"kernel": "gemm_tcgen05_kernel (all encoder + projector GEMMs)", "bound": "tensor",
                 "achieved": round(achieved, 1), "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": round(achieved / peaks["tflops_sustained"], 4), "traffic": None,
+                "frac": round(achieved / peaks["tflops_sustained"], 4), "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches": g_n, "avg_launch_ms": round(g_ms / max(g_n, 1), 4), "share_of_step": round(g_ms / tot_ms, 4),
                 "frac_of_burst": round(achieved / peaks["tflops_burst"], 4)}

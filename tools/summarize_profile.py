@@ -77,6 +77,26 @@ def ncu_md(rep: str) -> str:
     return "\n".join(out)
 
 
+def traffic_json(rep: str) -> dict:
+    """dram__bytes_read.sum + dram__bytes_write.sum per captured launch (bench.py's roofline.traffic)."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    if len(rows) < 3:
+        return {}
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    out = []
+    for r in rows[2:]:
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r[idx[k]].replace(",", "")) * scale.get(units[idx[k]], 1.0)
+        out.append({"kernel": short(r[idx["Kernel Name"]]), "dram_bytes": tot,
+                    "duration_us": float(r[idx["gpu__time_duration.sum"]].replace(",", "")) *
+                    {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[idx["gpu__time_duration.sum"]], 1.0)})
+    return {"launches": out}
+
+
 def main():
     tag = sys.argv[1]
     src = os.path.join(ROOT, "gpurun_out", f"measure_{tag}")
@@ -101,6 +121,11 @@ def main():
             parts.append(f"## {name}.ncu-rep (`ncu --set full --clock-control none --import-source on`)\n\n" + ncu_md(rep))
     if parts:
         open(os.path.join(dst, f"{tag}_ncu.md"), "w").write(f"# ncu --set full summary `{tag}`\n\n" + "\n".join(parts))
+    rep = os.path.join(src, "prof_gemm.ncu-rep")
+    if os.path.isfile(rep):
+        tj = traffic_json(rep)
+        tj["source"] = f"profiles/{tag}_ncu.md (ncu --set full, one NT-v2-500M encoder layer: QKV, attn-out, FFN1, FFN2)"
+        json.dump(tj, open(os.path.join(dst, "ncu_traffic.json"), "w"), indent=1)
     print("wrote", sorted(f for f in os.listdir(dst) if f.startswith(tag)))
 
 
