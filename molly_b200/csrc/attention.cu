@@ -27,6 +27,7 @@ namespace {
 constexpr int ATT_BLOCK = 128;                 // query rows per CTA == keys per KV block
 constexpr int ATT_THREADS = 160;               // 4 softmax warps + 1 control warp
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr int ATTN_POLY_DEFAULT = 0;           // set from the A/B measurement (tools/attn_bench.py)
 
 template <int D>
 struct AttnCfg {
@@ -53,7 +54,27 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-template <int D>
+// exp2 on the FMA pipe (FlashAttention-4 style) for POLY out of every 4 element pairs: the softmax is bound by the
+// 16-per-clock MUFU.EX2 unit, while the FMA pipe is ~80 % idle.  2^x = 2^n * p(r), n = round(x), r = x - n in [-0.5, 0.5],
+// p = cubic with max relative error 1.0e-4 (P is rounded to bf16 right after: 3.9e-3), 2^n spliced into the exponent field.
+__device__ __forceinline__ void exp2_poly_pair(float& x0, float& x1) {
+    const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);            // 1.5 * 2^23: low mantissa bits = round(x)
+    const uint64_t x2 = pack_f32x2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));     // keep 2^n a normal number
+    const uint64_t t2 = add_f32x2(x2, magic);
+    const uint64_t n2 = add_f32x2(t2, pack_f32x2(-12582912.0f, -12582912.0f));
+    const uint64_t r2 = fma_f32x2(n2, pack_f32x2(-1.0f, -1.0f), x2);
+    uint64_t p2 = fma_f32x2(pack_f32x2(0.05583828315138817f, 0.05583828315138817f), r2,
+                            pack_f32x2(0.2426394820213318f, 0.2426394820213318f));
+    p2 = fma_f32x2(p2, r2, pack_f32x2(0.6931367516517639f, 0.6931367516517639f));
+    p2 = fma_f32x2(p2, r2, pack_f32x2(0.9999245405197144f, 0.9999245405197144f));
+    float p0, p1, t0, t1;
+    unpack_f32x2(p2, p0, p1);
+    unpack_f32x2(t2, t0, t1);
+    x0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+    x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+template <int D, int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_CTAS)
 attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int h, const int32_t* __restrict__ kv_info,
                  const uint8_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out) {
@@ -258,8 +279,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
                 for (int u = 0; u < 2; ++u) {
                     float x0, x1;
                     unpack_f32x2(fma_f32x2(pack_f32x2(s[i + 2 * u], s[i + 2 * u + 1]), sc2, nm2), x0, x1);
-                    s[i + 2 * u] = ex2(x0);
-                    s[i + 2 * u + 1] = ex2(x1);
+                    if (((i >> 1) + u) % 4 < POLY) {          // this pair goes to the FMA pipe
+                        exp2_poly_pair(x0, x1);
+                        s[i + 2 * u] = x0;
+                        s[i + 2 * u + 1] = x1;
+                    } else {                                  // this pair goes to the MUFU
+                        s[i + 2 * u] = ex2(x0);
+                        s[i + 2 * u + 1] = ex2(x1);
+                    }
                     sum2[u] = add_f32x2(sum2[u], pack_f32x2(s[i + 2 * u], s[i + 2 * u + 1]));
                 }
             }
@@ -792,10 +819,17 @@ int launch_attention(const CUtensorMap& tm, int n_seq, int k_tokens, int h, int 
     if (attention_persistent_enabled())
         return launch_attention_persistent<D>(tm, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
     using Cfg = AttnCfg<D>;
-    auto kernel = attention_kernel<D>;
+    static int poly = -1;             // pairs out of 4 whose exp2 runs on the FMA pipe (MOLLY_ATTN_POLY = 0 | 1 | 2)
+    if (poly < 0) {
+        const char* e = getenv("MOLLY_ATTN_POLY");
+        poly = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : ATTN_POLY_DEFAULT;
+    }
+    auto kernel = poly == 0 ? attention_kernel<D, 0> : (poly == 1 ? attention_kernel<D, 1> : attention_kernel<D, 2>);
     static bool configured = false;
     if (!configured) {
-        MOLLY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MOLLY_CUDA(cudaFuncSetAttribute(attention_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MOLLY_CUDA(cudaFuncSetAttribute(attention_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MOLLY_CUDA(cudaFuncSetAttribute(attention_kernel<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
     dim3 grid((k_tokens + ATT_BLOCK - 1) / ATT_BLOCK, heads, n_seq);
