@@ -155,6 +155,26 @@ def make_inputs(wl: dict, seed: int = 1234):
     return omic_ids, infos
 
 
+LLM_VOCAB = 151936                                         # Qwen3 embedding rows (config.json vocab_size)
+PLACEHOLDER_BASE = 151669                                  # first id after Qwen3's own specials: the 9 added omics tags
+PAD_TOKEN_IDS = (PLACEHOLDER_BASE + 1, PLACEHOLDER_BASE + 4, PLACEHOLDER_BASE + 7)
+
+
+def build_input_ids(wl: dict, infos, seed: int = 7):
+    """Text tokens + ``x_start, x_pad * K, x_end`` at every info["start"] (the dataset's layout, omics_dataset.py:270-288)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, 150000, (wl["B"], wl["T"]), generator=g)
+    base = {"dna": 0, "rna": 3, "protein": 6}
+    for b, row in enumerate(infos):
+        for info in row:
+            s, o = info["start"], PLACEHOLDER_BASE + base[info["type"]]
+            ids[b, s] = o
+            ids[b, s + 1:s + 1 + wl["K"]] = o + 1
+            ids[b, s + 1 + wl["K"]] = o + 2
+    return ids
+
+
 def gpu_state_dict(e: dict, device, seed: int):
     """Random-init weights of the named architecture with EsmForMaskedLM.state_dict() key names, built on the GPU."""
     import torch
@@ -347,6 +367,35 @@ def main() -> None:
     e2e_value = world * tokens_per_step * args.steps / (e2e_ms / 1e3)
     path.strict = False
 
+    # ---- embed_tokens(input_ids) fused with the path (run scan on the device is the index source)
+    input_ids = build_input_ids(wl, infos).to(dev)
+    table = (torch.randn(LLM_VOCAB, wl["D"], device=dev) * 0.02).to(torch.bfloat16)
+    two_step = lambda: path.process_omic_sequences(torch.nn.functional.embedding(input_ids, table), omic_ids_dev, infos, dev)
+    fused = lambda: path.embed_and_process(input_ids, table, omic_ids_dev, infos, PAD_TOKEN_IDS)
+    for _ in range(2):
+        a, b = two_step(), fused()
+    n1_equal = bool(torch.equal(a, b))
+    del a, b
+    two_ms = timed(two_step, args.steps) / args.steps
+    fused_ms = timed(fused, args.steps) / args.steps
+    text_rows = wl["B"] * (wl["T"] - 2 * wl["K"])
+    # the lookup alone (the step-level difference is below run-to-run noise): torch's gather vs scan + skipping gather
+    slots = torch.full((wl["B"],), 2, dtype=torch.int32, device=dev)
+
+    def ours_lookup():
+        runs = ops.placeholder_runs(input_ids, PAD_TOKEN_IDS, slots, 2)
+        return ops.embed_tokens_skip(input_ids, runs[4], PAD_TOKEN_IDS, wl["K"], wl["K"], table)
+
+    lookup_torch_ms = timed(lambda: torch.nn.functional.embedding(input_ids, table), 20) / 20
+    lookup_ours_ms = timed(ours_lookup, 20) / 20
+    input_fusion = {"two_step_ms": round(two_ms, 3), "fused_ms": round(fused_ms, 3), "bit_identical": n1_equal,
+                    "tokens_per_s_fused": round(world * tokens_per_step / (fused_ms * 1e-3), 1),
+                    "lookup_ms_torch": round(lookup_torch_ms, 4), "lookup_ms_fused": round(lookup_ours_ms, 4),
+                    "lookup_bytes_torch": 2 * wl["B"] * wl["T"] * wl["D"] * 2,
+                    "lookup_bytes_fused": 2 * text_rows * wl["D"] * 2,
+                    "lookup_gbs_fused": round(2 * text_rows * wl["D"] * 2 / (lookup_ours_ms * 1e-3) / 1e9, 1)}
+    del table
+
     # ---- one profiled step: per-launch CUDA events on the launching stream -> roofline of the dominant kernel
     peaks = measured_peaks()
     ops.profile_start()
@@ -398,6 +447,7 @@ def main() -> None:
         "gpu_launches": launches,
         "roofline": roofline,
         "model_tflops_per_gpu": round(model_flops / (step_ms * 1e-3) / 1e12, 1),
+        "input_fusion": input_fusion,
         "kernels": kernels,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -42,7 +42,9 @@ enum molly_ffn_type { MOLLY_FFN_GELU = 0, MOLLY_FFN_GLU = 1 };
 enum molly_err_bits {
     MOLLY_ERRBIT_OOV = 1,        /* token id outside [0, vocab)           -> reference AssertionError, omics_one.py:71-72 */
     MOLLY_ERRBIT_OVERFLOW = 2,   /* start+1+k > T or bad batch index       -> reference RuntimeError (slice shape mismatch) */
-    MOLLY_ERRBIT_POSITION = 4    /* absolute position id >= max_positions  -> reference IndexError inside the encoder */
+    MOLLY_ERRBIT_POSITION = 4,   /* absolute position id >= max_positions  -> reference IndexError inside the encoder */
+    MOLLY_ERRBIT_LAYOUT = 8,     /* placeholder runs in input_ids do not match the omic_ids slots (fused-input path only) */
+    MOLLY_ERRBIT_TOKEN = 16      /* input_ids entry outside the LLM embedding table -> reference IndexError (nn.Embedding) */
 };
 
 /* Mirrors the fields of transformers.EsmConfig the reference reads (HF:161-186, 285-316) + the two OmicsOne fields
@@ -130,6 +132,26 @@ int molly_pool_fwd(const void* enc_out_dev, const int64_t* ids_dev, int32_t n_se
  * out_kind_dev int32 [B, T]: 0 dna, 1 rna, 2 protein for each listed position                                     */
 int molly_placeholder_scan(const int64_t* input_ids_dev, int32_t B, int32_t T, const int64_t pad_token_ids[3],
                            int32_t* out_pos_dev, int32_t* out_kind_dev, int32_t* out_counts_dev, void* stream);
+
+/* ---- the input producer on the device -------------------------------------------------------
+ * molly_placeholder_runs: per sample the runs of *_pad tokens in text order (first position, kind 0/1/2, length) and
+ *   pos_j[b,t] = index of position t inside its run (-1 for non-placeholder tokens and for runs beyond the sample's
+ *   n_slots, which the reference's zip never reaches)                                       (omics_dataset.py:270-288)
+ * molly_build_seq_table: seq_table[n] = (b, run_start[b][slot]-1): exactly info["start"] of the reference, paired with the
+ *   omic_ids slots BY INDEX like the reference's zip (omics_one.py:105); mismatches OR MOLLY_ERRBIT_LAYOUT
+ * molly_embed_tokens_skip: inputs_embeds = embed_tokens(input_ids) (omics_one.py:164, :209) for every row the omics path
+ *   will not overwrite (j >= K cap or not a placeholder) -- the overwritten rows are never read or written            */
+int molly_placeholder_runs(const int64_t* input_ids_dev, int32_t B, int32_t T, const int64_t pad_token_ids[3],
+                           const int32_t* n_slots_dev /*[B] omic_ids slots per sample, or NULL*/, int32_t max_runs, int32_t* run_start_dev /*[B,max_runs]*/, int32_t* run_kind_dev,
+                           int32_t* run_len_dev, int32_t* n_runs_dev /*[B]*/, int32_t* pos_j_dev /*[B,T]*/, void* stream);
+int molly_build_seq_table(const int32_t* b_idx_dev, const int32_t* slot_idx_dev, int32_t n, const int32_t* run_start_dev,
+                          const int32_t* run_kind_dev, const int32_t* run_len_dev, const int32_t* n_runs_dev,
+                          int32_t max_runs, int32_t expect_protein, int32_t k_need, int32_t* seq_table_dev /*[n,2]*/,
+                          int32_t* err_flag_dev, void* stream);
+int molly_embed_tokens_skip(const int64_t* input_ids_dev, const int32_t* pos_j_dev, const int64_t pad_token_ids[3],
+                            int32_t cap_dna_rna, int32_t cap_protein, const void* table_dev /*[vocab,D]*/, int32_t dtype,
+                            int32_t vocab, int32_t D, void* out_dev /*[B,T,D]*/, int32_t B, int32_t T,
+                            int32_t* err_flag_dev, void* stream);
 
 /* ---- projector backward (training, --train-mlp): grads of `nn.Linear` projector through the slice-assign ----------
  * d_hidden_dev  [B,T,D] grad wrt merged hidden_states (bf16|fp32).  Rows written by the forward are gathered:

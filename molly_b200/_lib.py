@@ -21,7 +21,7 @@ DTYPE_BF16, DTYPE_F32 = 0, 1
 POS_ROTARY, POS_ABSOLUTE = 0, 1
 FFN_GELU, FFN_GLU = 0, 1
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_GLU, EPI_SCATTER, EPI_BIAS_ROPE = 0, 1, 2, 3, 4, 5
-ERRBIT_OOV, ERRBIT_OVERFLOW, ERRBIT_POSITION = 1, 2, 4
+ERRBIT_OOV, ERRBIT_OVERFLOW, ERRBIT_POSITION, ERRBIT_LAYOUT, ERRBIT_TOKEN = 1, 2, 4, 8, 16
 
 c_void_pp = C.POINTER(C.c_void_p)
 
@@ -82,6 +82,10 @@ SIGNATURES = {
     "molly_embed": (C.c_int, [_vp, _i32, _i32, C.POINTER(EncoderConfig), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "molly_rotary": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "molly_attention": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "molly_placeholder_runs": (C.c_int, [_vp, _i32, _i32, C.POINTER(C.c_int64), _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "molly_build_seq_table": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "molly_embed_tokens_skip": (C.c_int, [_vp, _vp, C.POINTER(C.c_int64), _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i32,
+                                          _i32, _vp, _vp]),
     "molly_attention_debug": (C.c_int, [_vp]),
     "molly_merge_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "molly_profile_start": (C.c_int, []),

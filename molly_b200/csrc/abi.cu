@@ -370,6 +370,38 @@ int molly_attention(const void* qkv_dev, int32_t n_seq, int32_t k_tokens, int32_
                             static_cast<cudaStream_t>(stream));
 }
 
+int molly_placeholder_runs(const int64_t* input_ids_dev, int32_t B, int32_t T, const int64_t pad_token_ids[3],
+                           const int32_t* n_slots_dev, int32_t max_runs, int32_t* run_start_dev, int32_t* run_kind_dev, int32_t* run_len_dev,
+                           int32_t* n_runs_dev, int32_t* pos_j_dev, void* stream) {
+    MOLLY_CHECK(input_ids_dev && pad_token_ids && run_start_dev && run_kind_dev && run_len_dev && n_runs_dev && pos_j_dev,
+                MOLLY_ERR_INVALID, "molly_placeholder_runs: NULL pointer");
+    return placeholder_runs_launch(input_ids_dev, B, T, pad_token_ids[0], pad_token_ids[1], pad_token_ids[2], n_slots_dev,
+                                   max_runs, run_start_dev, run_kind_dev, run_len_dev, n_runs_dev, pos_j_dev,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int molly_embed_tokens_skip(const int64_t* input_ids_dev, const int32_t* pos_j_dev, const int64_t pad_token_ids[3],
+                            int32_t cap_dna_rna, int32_t cap_protein, const void* table_dev, int32_t dtype,
+                            int32_t vocab, int32_t D, void* out_dev, int32_t B, int32_t T, int32_t* err_flag_dev,
+                            void* stream) {
+    MOLLY_CHECK(input_ids_dev && pos_j_dev && pad_token_ids && table_dev && out_dev, MOLLY_ERR_INVALID,
+                "molly_embed_tokens_skip: NULL pointer");
+    return embed_tokens_skip_launch(input_ids_dev, pos_j_dev, pad_token_ids[0], pad_token_ids[1], cap_dna_rna, cap_protein,
+                                    table_dev, dtype, vocab, D, out_dev, B, T, err_flag_dev,
+                                    static_cast<cudaStream_t>(stream));
+}
+
+int molly_build_seq_table(const int32_t* b_idx_dev, const int32_t* slot_idx_dev, int32_t n, const int32_t* run_start_dev,
+                          const int32_t* run_kind_dev, const int32_t* run_len_dev, const int32_t* n_runs_dev,
+                          int32_t max_runs, int32_t expect_protein, int32_t k_need, int32_t* seq_table_dev,
+                          int32_t* err_flag_dev, void* stream) {
+    MOLLY_CHECK(b_idx_dev && slot_idx_dev && run_start_dev && run_kind_dev && run_len_dev && n_runs_dev && seq_table_dev,
+                MOLLY_ERR_INVALID, "molly_build_seq_table: NULL pointer");
+    return build_seq_table_launch(b_idx_dev, slot_idx_dev, n, run_start_dev, run_kind_dev, run_len_dev, n_runs_dev,
+                                  max_runs, expect_protein, k_need, seq_table_dev, err_flag_dev,
+                                  static_cast<cudaStream_t>(stream));
+}
+
 int molly_attention_debug(long long* timeline_dev) {
     attention_set_debug(timeline_dev);
     return MOLLY_OK;

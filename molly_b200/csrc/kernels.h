@@ -69,6 +69,16 @@ int merge_rows_launch(const void* src, const int32_t* seq_table, int n_seq, int 
 int gather_grad_rows_launch(void* d_hidden, int dtype, const int32_t* seq_table, int n_seq, int k_tokens, int k_cap,
                             int B, int T, int D, void* dy_bf16, int zero_rows, cudaStream_t stream);
 
+int placeholder_runs_launch(const int64_t* input_ids, int B, int T, int64_t pad0, int64_t pad1, int64_t pad2,
+                            const int32_t* n_slots, int max_runs, int32_t* run_start, int32_t* run_kind, int32_t* run_len, int32_t* n_runs,
+                            int32_t* pos_j, cudaStream_t stream);
+int embed_tokens_skip_launch(const int64_t* input_ids, const int32_t* pos_j, int64_t pad0, int64_t pad1, int cap_nt,
+                             int cap_pr, const void* table, int dtype, int vocab, int D, void* out, int B, int T,
+                             int32_t* err_flag, cudaStream_t stream);
+int build_seq_table_launch(const int32_t* b_idx, const int32_t* slot_idx, int n, const int32_t* run_start,
+                           const int32_t* run_kind, const int32_t* run_len, const int32_t* n_runs, int max_runs,
+                           int expect_protein, int k_need, int32_t* seq_table, int32_t* err_flag, cudaStream_t stream);
+
 // ---- bwd.cu ----
 int project_bwd_launch(const void* dy_bf16, const void* x_bf16, int M, int D, int h, float* d_weight, float* d_bias,
                        void* workspace, size_t workspace_bytes, cudaStream_t stream);

@@ -155,6 +155,61 @@ class FastOmicsPath:
         if target is not hidden_states:
             hidden_states.copy_(target)
 
+    # ------------------------------------------------------------------ the input producer, fused
+    @torch.no_grad()
+    def embed_and_process(self, input_ids: torch.Tensor, embed_weight: torch.Tensor, omic_ids_list,
+                          omic_info_list: List[List[dict]], pad_token_ids) -> torch.Tensor:
+        """``process_omic_sequences(embed_tokens(input_ids), omic_ids, omic_info_list)`` (omics_one.py:164-170 and
+        :209-215) in one pass, forward only (eval / ``generate``).  The placeholder runs found in ``input_ids`` ON THE DEVICE
+        are the index source: only ``info["type"]`` is read, ``info["start"]`` is what the run scan reproduces
+        (omics_dataset.py:270-288).  The LLM embedding lookup never touches the rows the projector is about to overwrite.
+        ``pad_token_ids`` = (dna_pad, rna_pad, protein_pad) token ids.  A layout that does not pair with the ids raises
+        ``RuntimeError`` in strict mode (MOLLY_ERRBIT_LAYOUT)."""
+        if input_ids.dim() != 2 or embed_weight.dim() != 2:
+            raise ValueError("input_ids must be [B, T] and embed_weight [vocab, D]")
+        dev = embed_weight.device
+        input_ids = input_ids.to(dev, torch.int64, non_blocking=True).contiguous()
+        B, T = input_ids.shape
+        for i in range(len(omic_ids_list)):                                                  # omics_one.py:166-170
+            assert len(omic_ids_list[i]) == len(omic_info_list[i]), f"Mismatch in omic count vs info count at index {i}"
+        nt_plan, pr_plan = planner.route(B, omic_ids_list, omic_info_list)                   # may raise ValueError
+        n_slots = [0] * B
+        for plan in (nt_plan, pr_plan):
+            for b, r in zip(plan.b_idx, plan.run_idx):
+                n_slots[b] = max(n_slots[b], r + 1)
+        caps = {}
+        for name, plan in (("dna_rna", nt_plan), ("protein", pr_plan)):
+            caps[name] = 0
+            if len(plan):
+                if name not in self._ids:
+                    raise RuntimeError(f"Error processing omic sequences: no {name} encoder is loaded")
+                enc = ops.get_encoder(self._ids[name])
+                k_ids = omic_ids_list.shape[-1] if isinstance(omic_ids_list, torch.Tensor) else \
+                    omic_ids_list[plan.b_idx[0]][plan.slot_idx[0]].shape[-1]
+                caps[name] = min(enc.project_token_num, int(k_ids))
+        slots_dev = torch.tensor(n_slots, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+        runs = ops.placeholder_runs(input_ids, tuple(pad_token_ids), slots_dev, max(1, max(n_slots)))
+        hidden = ops.embed_tokens_skip(input_ids, runs[4], tuple(pad_token_ids), caps["dna_rna"], caps["protein"],
+                                       embed_weight)
+        for name, plan in (("dna_rna", nt_plan), ("protein", pr_plan)):
+            if len(plan) == 0:
+                continue
+            enc_id = self._ids[name]
+            enc = ops.get_encoder(enc_id)
+            ids = planner.gather_ids(omic_ids_list, plan)
+            if not ids.is_cuda:
+                planner.check_vocab(ids, enc.cfg.vocab_size)
+                ids = ids.pin_memory().to(dev, non_blocking=True)
+            idx = torch.tensor([plan.b_idx, plan.run_idx], dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+            seq_table = ops.build_seq_table(idx[0], idx[1], runs, expect_protein=(name == "protein"))
+            proj = self._proj_modules.get(name)
+            if proj is not None:
+                self._refresh_projector(name, enc, proj)
+            ops.encode_project_merge(hidden, ids, seq_table, enc_id, False)
+        if self.strict:
+            ops.check_device_errors(dev, "embed_and_process")
+        return hidden
+
     def _refresh_projector(self, name: str, enc: PackedEncoder, proj) -> None:
         ver = (proj.weight._version, proj.bias._version, proj.weight.data_ptr())
         if self._proj_versions.get(name) != ver:

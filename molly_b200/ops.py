@@ -107,6 +107,10 @@ def check_device_errors(dev: torch.device, what: str = "process_omic_sequences")
         raise RuntimeError(f"{what}: omics placeholder run exceeds the text sequence length")       # slice shape mismatch
     if bits & _lib.ERRBIT_POSITION:
         raise RuntimeError(f"Error processing omic sequences: position id exceeds max_position_embeddings")  # :89-90
+    if bits & _lib.ERRBIT_TOKEN:
+        raise IndexError(f"{what}: index out of range in self (input_ids entry outside the LLM embedding table)")
+    if bits & _lib.ERRBIT_LAYOUT:
+        raise RuntimeError(f"{what}: placeholder runs in input_ids do not pair with the omic_ids slots")
     raise RuntimeError(f"{what}: device error flag {bits}")
 
 
@@ -235,6 +239,59 @@ def placeholder_scan(input_ids: Tensor, pad0: int, pad1: int, pad2: int) -> Tupl
         _lib.check(_lib.load().molly_placeholder_scan(input_ids.data_ptr(), B, T, pads, pos.data_ptr(), kind.data_ptr(),
                                                       cnt.data_ptr(), _stream(dev)), "molly_placeholder_scan")
     return pos, kind, cnt
+
+
+def placeholder_runs(input_ids: Tensor, pad_ids: Tuple[int, int, int], n_slots: Optional[Tensor], max_runs: int):
+    """Runs of *_pad tokens per sample in text order -> (run_start, run_kind, run_len) [B, max_runs], n_runs [B] and
+    pos_j [B, T] (index inside the run, -1 for text / unpaired runs).  SURVEY.md 8f row N1."""
+    dev = _require_cuda(input_ids)
+    if input_ids.dtype != torch.int64 or input_ids.dim() != 2 or not input_ids.is_contiguous():
+        raise ValueError("input_ids must be contiguous int64 [B, T]")
+    B, T = input_ids.shape
+    run_start = torch.full((B, max_runs), -1, dtype=torch.int32, device=dev)
+    run_kind = torch.full((B, max_runs), -1, dtype=torch.int32, device=dev)
+    run_len = torch.empty(B, max_runs, dtype=torch.int32, device=dev)
+    n_runs = torch.empty(B, dtype=torch.int32, device=dev)
+    pos_j = torch.empty(B, T, dtype=torch.int32, device=dev)
+    pads = (C.c_int64 * 3)(*[int(p) for p in pad_ids])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_placeholder_runs(
+            input_ids.data_ptr(), B, T, pads, n_slots.data_ptr() if n_slots is not None else None, max_runs,
+            run_start.data_ptr(), run_kind.data_ptr(), run_len.data_ptr(), n_runs.data_ptr(), pos_j.data_ptr(),
+            _stream(dev)), "molly_placeholder_runs")
+    return run_start, run_kind, run_len, n_runs, pos_j
+
+
+def build_seq_table(b_idx: Tensor, run_idx: Tensor, runs, expect_protein: bool, k_need: int = 1) -> Tensor:
+    """seq_table [n, 2] = (b, x_start position) from the device-side runs: the reference's info["start"]."""
+    dev = _require_cuda(b_idx, run_idx)
+    run_start, run_kind, run_len, n_runs, _ = runs
+    n = b_idx.numel()
+    table = torch.empty(n, 2, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_build_seq_table(
+            b_idx.data_ptr(), run_idx.data_ptr(), n, run_start.data_ptr(), run_kind.data_ptr(), run_len.data_ptr(),
+            n_runs.data_ptr(), run_start.shape[1], int(expect_protein), k_need, table.data_ptr(),
+            error_flag(dev).data_ptr(), _stream(dev)), "molly_build_seq_table")
+    return table
+
+
+def embed_tokens_skip(input_ids: Tensor, pos_j: Tensor, pad_ids: Tuple[int, int, int], cap_dna_rna: int, cap_protein: int,
+                      table: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """``embed_tokens(input_ids)`` (omics_one.py:164, :209) except the rows the omics path is about to overwrite."""
+    dev = _require_cuda(input_ids, pos_j, table)
+    B, T = input_ids.shape
+    vocab, D = table.shape
+    if not table.is_contiguous():
+        raise ValueError("embedding table must be contiguous")
+    if out is None:
+        out = torch.empty(B, T, D, dtype=table.dtype, device=dev)
+    pads = (C.c_int64 * 3)(*[int(p) for p in pad_ids])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_embed_tokens_skip(
+            input_ids.data_ptr(), pos_j.data_ptr(), pads, cap_dna_rna, cap_protein, table.data_ptr(), _dtype_code(table),
+            vocab, D, out.data_ptr(), B, T, error_flag(dev).data_ptr(), _stream(dev)), "molly_embed_tokens_skip")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

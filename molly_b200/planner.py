@@ -4,7 +4,7 @@ modality instead of one ``.to(device)`` per sequence.  Pure host logic (numpy / 
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -18,6 +18,7 @@ class ModalityPlan:
     b_idx: List[int]
     slot_idx: List[int]
     starts: List[int]
+    run_idx: List[int] = field(default_factory=list)    # index among the sample's non-'pad' slots == placeholder run index
 
     def __len__(self) -> int:
         return len(self.b_idx)
@@ -33,6 +34,7 @@ def route(batch_size: int, omic_ids_list, omic_info_list) -> Tuple[ModalityPlan,
     nt, pr = ModalityPlan([], [], []), ModalityPlan([], [], [])
     for b in range(batch_size):
         ids_b, infos_b = omic_ids_list[b], omic_info_list[b]
+        run = 0
         for i in range(min(len(ids_b), len(infos_b))):
             info = infos_b[i]
             omic_type = info["type"]
@@ -48,6 +50,8 @@ def route(batch_size: int, omic_ids_list, omic_info_list) -> Tuple[ModalityPlan,
             tgt.b_idx.append(b)
             tgt.slot_idx.append(i)
             tgt.starts.append(int(start_pos))
+            tgt.run_idx.append(run)
+            run += 1
     return nt, pr
 
 

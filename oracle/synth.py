@@ -117,3 +117,31 @@ def expected_rows(omic_info_list: List[List[dict]], K: int, k_cap_nt: int, k_cap
             for j in range(k):
                 rows[(b, info["start"] + 1 + j)] = (b, i, j)
     return rows
+
+
+def placeholder_runs(input_ids: torch.Tensor, pad_ids: Sequence[int]) -> List[List[Tuple[int, int, int]]]:
+    """Per sample, the maximal runs of *_pad tokens in text order as ``(first_pad_position, kind, length)``.
+    ``first_pad_position - 1`` is the x_start token, i.e. ``info["start"]`` as the dataset records it
+    (REF/src/dataset/omics_dataset.py:270-288; Test-mode left padding shifts it, :387-391).  Plain Python loop."""
+    pad_ids = [int(p) for p in pad_ids]
+    out = []
+    for row in input_ids.tolist():
+        runs, t, T = [], 0, len(row)
+        while t < T:
+            if row[t] in pad_ids:
+                s = t
+                while t < T and row[t] in pad_ids:
+                    t += 1
+                runs.append((s, pad_ids.index(row[s]), t - s))
+            else:
+                t += 1
+        out.append(runs)
+    return out
+
+
+def embed_then_process(input_ids: torch.Tensor, embed_weight: torch.Tensor, omic_ids_list, omic_info_list, nt, pr):
+    """``inputs_embeds = embed_tokens(input_ids)`` followed by ``process_omic_sequences`` (REF/src/model/omics_one.py:164-170
+    in ``forward`` and :209-215 in ``generate``)."""
+    from .esm_oracle import process_omic_sequences
+    hidden = embed_weight[input_ids]
+    return process_omic_sequences(hidden, omic_ids_list, omic_info_list, nt, pr)

@@ -129,3 +129,23 @@ def test_cpu_tensors_are_refused():
         ops.layernorm(torch.zeros(4, 64), torch.ones(64), torch.zeros(64), 1e-5)
     with pytest.raises((RuntimeError, NotImplementedError)):
         torch.ops.molly_b200.placeholder_scan(torch.zeros(2, 8, dtype=torch.int64), 1, 2, 3)
+
+
+def test_route_run_index_skips_pad_slots():
+    """Run index = rank among the sample's non-'pad' slots, whatever the slot's position."""
+    infos = [[{"type": "dna", "start": 3}, {"type": "pad", "start": -1}, {"type": "protein", "start": 50}],
+             [{"type": "protein", "start": 1}, {"type": "rna", "start": 9}, {"type": "pad", "start": -1}]]
+    ids = [[torch.zeros(4, dtype=torch.long)] * 3] * 2
+    nt, pr = planner.route(2, ids, infos)
+    assert (nt.b_idx, nt.slot_idx, nt.run_idx) == ([0, 1], [0, 1], [0, 1])
+    assert (pr.b_idx, pr.slot_idx, pr.run_idx) == ([0, 1], [2, 0], [1, 0])
+
+
+def test_oracle_placeholder_runs_reproduce_dataset_starts():
+    from oracle import cases, synth
+    for case in cases.golden_cases().values():
+        runs = synth.placeholder_runs(case.batch.input_ids, synth.PAD_TOKEN_IDS)
+        for rr, infos in zip(runs, case.batch.omic_info_list):
+            real = [i for i in infos if i["type"] != "pad"]
+            assert [r[0] - 1 for r in rr] == [i["start"] for i in real]
+            assert [("dna", "rna", "protein")[r[1]] for r in rr] == [i["type"] for i in real]
