@@ -26,7 +26,8 @@ struct molly_encoder {
         void* ws = nullptr;
         int n_seq = 0, k = 0;
         void* final_out = nullptr;
-        CUtensorMap tm_xn, tm_attn, tm_mid, tm_qkv, tm_final;   // A operands / attention input
+        CUtensorMap tm_xn, tm_attn, tm_mid, tm_final;   // A operands
+        AttnMaps tm_qkv;                                // attention input
         CUtensorMap tc_qkv, tc_x, tc_mid;                       // GEMM outputs (tc_x also feeds the residual loads)
     } plan;
 };
@@ -363,7 +364,7 @@ int molly_rotary(void* qkv_dev, int32_t rows, int32_t k_tokens, int32_t h, int32
 int molly_attention(const void* qkv_dev, int32_t n_seq, int32_t k_tokens, int32_t h, int32_t heads,
                     const int32_t* kv_info_dev, const uint8_t* key_mask_dev, void* out_dev, void* stream) {
     MOLLY_CHECK(qkv_dev && kv_info_dev && key_mask_dev && out_dev, MOLLY_ERR_INVALID, "molly_attention: NULL pointer");
-    CUtensorMap tm;
+    AttnMaps tm;
     int rc = attention_make_map(&tm, qkv_dev, n_seq * k_tokens, h, heads);
     if (rc) return rc;
     return attention_launch(tm, n_seq, k_tokens, h, heads, kv_info_dev, key_mask_dev, out_dev,

@@ -4,8 +4,8 @@
 // Input is the packed bf16 QKV activation [n_seq*k_tokens, 3h] written by the fused QKV GEMM (q already scaled by
 // d^-1/2 through the packed weights, rotary already applied); output is bf16 [n_seq*k_tokens, h].
 //
-// One CTA = 128 query rows of one (sequence, head):
-//   * TMA brings Q once and K/V tiles (128 keys) through a 2-stage mbarrier ring
+// attention_kernel: a CTA streams work items = 128 query rows of one (sequence, head); two CTAs per SM:
+//   * TMA brings Q once per item and K/V tiles (128 keys) through a 2-stage mbarrier ring that runs across items
 //   * S = Q K^T  : tcgen05.mma, both operands K-major from swizzled smem, fp32 accumulator in TMEM (128 columns)
 //   * softmax    : 4 warps, thread r owns row r (tcgen05.ld 32x32b: TMEM lane == row, so row max / row sum need no
 //                  shuffles); exp2 with the running max in the log2 domain; P written to smem as the bf16 K-major
@@ -13,6 +13,8 @@
 //   * O += P V   : tcgen05.mma, B operand = V tile straight from TMA ([key][d] row-major == MN-major B), fp32 in TMEM
 //   * keys >= kv_len are never loaded (whole blocks skipped); interior pad keys use the byte mask
 // Two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+// Variants kept for A/B timing (tests/test_gpu_variants.py): 64-key blocks / three CTAs per SM (MOLLY_ATTN_KVB=64), one CTA per
+// item (MOLLY_ATTN_STREAM=0), exp2 partly on the FMA pipe (MOLLY_ATTN_POLY), two-tile ping-pong CTA (MOLLY_ATTN_PP=1).
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -24,28 +26,53 @@ namespace molly {
 
 namespace {
 
+// Bring-up aid: -DATT_ABLATE=n builds a deliberately WRONG kernel with one piece removed, to time what that piece costs
+// (tools/attn_ablate.sh), a bit mask: 1 no exp2, 2 no P pack/store, 4 PV MMA one k-step, 8 no row max, 16 S MMA one k-step,
+// 32 no K/V TMA after the first two blocks.
+#ifndef ATT_ABLATE
+#define ATT_ABLATE 0
+#endif
+
+// -DATT_TIMELINE: clock64 timeline of the first 2048 CTAs of the default kernel (tools/attn_timeline2.py), 72 slots each.
+#ifdef ATT_TIMELINE
+__device__ long long* d_attn_tl = nullptr;
+#define TL(slot)                                                                                               \
+    do {                                                                                                       \
+        if (d_attn_tl != nullptr && tl_id < 2048 && (slot) < 72) d_attn_tl[tl_id * 72 + (slot)] = clock64();   \
+    } while (0)
+#else
+#define TL(slot) do { } while (0)
+#endif
+
 constexpr int ATT_BLOCK = 128;                 // query rows per CTA == keys per KV block
 constexpr int ATT_THREADS = 160;               // 4 softmax warps + 1 control warp
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int ATTN_POLY_DEFAULT = 0;           // set from the A/B measurement (tools/attn_bench.py)
+constexpr bool ATTN_PP_DEFAULT = false;        // two-tile ping-pong kernel at head_dim <= 64 (set from the A/B measurement)
+constexpr bool ATTN_KVB64_DEFAULT = false;     // 64-key KV blocks (3 CTAs / SM) at head_dim <= 64
 
-template <int D>
+template <int D, int KVB = 128>       // KVB = keys per KV block (128, or 64 to fit three CTAs per SM at head_dim <= 64)
 struct AttnCfg {
     static constexpr int BOX_D = D < 64 ? D : 64;
     static constexpr int NBOX = D / BOX_D;
     static constexpr int ROW_BYTES = BOX_D * 2;                       // 32 / 64 / 128
     static constexpr uint32_t LAYOUT = ROW_BYTES == 128 ? kLayoutSW128 : (ROW_BYTES == 64 ? kLayoutSW64 : kLayoutSW32);
-    static constexpr int BOX_BYTES = ATT_BLOCK * ROW_BYTES;
-    static constexpr int TILE_BYTES = NBOX * BOX_BYTES;               // one Q / K / V tile
-    static constexpr int P_BYTES = ATT_BLOCK * ATT_BLOCK * 2;         // two 128x64 bf16 swizzle atoms
+    static constexpr int BOX_BYTES = ATT_BLOCK * ROW_BYTES;           // one TMA box of the Q tile
+    static constexpr int TILE_BYTES = NBOX * BOX_BYTES;               // the Q tile
+    static constexpr int KV_BOX_BYTES = KVB * ROW_BYTES;
+    static constexpr int KV_TILE_BYTES = NBOX * KV_BOX_BYTES;         // one K / V tile
+    static constexpr int P_BYTES = ATT_BLOCK * KVB * 2;               // KVB/64 bf16 swizzle atoms of 128 x 64
     static constexpr int OFF_Q = 0;
     static constexpr int OFF_K = TILE_BYTES;
-    static constexpr int OFF_V = 3 * TILE_BYTES;
-    static constexpr int OFF_P = 5 * TILE_BYTES;
+    static constexpr int OFF_V = OFF_K + 2 * KV_TILE_BYTES;
+    static constexpr int OFF_P = OFF_V + 2 * KV_TILE_BYTES;
     static constexpr int OFF_BAR = OFF_P + P_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 128;
-    static constexpr int TMEM_COLS = 256;                             // S: 128, O: D (<= 128)
-    static constexpr int MIN_CTAS = SMEM_BYTES <= 115000 ? 2 : 1;
+    static constexpr int TMEM_COLS = (KVB + D) <= 128 ? 128 : 256;    // S: KVB columns, O: D columns
+    static constexpr int BY_SMEM = (227 * 1024) / (SMEM_BYTES + 1024);
+    static constexpr int BY_TMEM = 512 / TMEM_COLS;
+    static constexpr int MIN_CTAS_RAW = BY_SMEM < BY_TMEM ? BY_SMEM : BY_TMEM;
+    static constexpr int MIN_CTAS = MIN_CTAS_RAW > 3 ? 3 : (MIN_CTAS_RAW < 1 ? 1 : MIN_CTAS_RAW);
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -74,11 +101,166 @@ __device__ __forceinline__ void exp2_poly_pair(float& x0, float& x1) {
     x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
-template <int D, int POLY>
-__global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_CTAS)
-attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int h, const int32_t* __restrict__ kv_info,
+// One KV block of the online softmax for the 128 threads of a softmax group (thread = query row): S(g) from TMEM ->
+// mask -> running max (lazy rescale) -> P = exp2(S*log2e - m) as the bf16 K-major A operand in smem -> hand-off.
+template <int D, int KVB, int POLY, bool PINGPONG>
+__device__ __forceinline__ void softmax_block(uint64_t* bar_s_full, uint32_t s_parity, uint64_t* bar_s_free,
+                                              uint64_t* bar_pv_done, uint32_t pv_parity, uint64_t* bar_p_full,
+                                              uint32_t tmem_s, uint32_t tmem_o, uint32_t lane_addr, uint8_t* p_row,
+                                              int sw, bool interior, const uint8_t* __restrict__ key_mask,
+                                              long long row_base, int j0, int kvl, int k_tokens, bool first,
+                                              float& m_run, float& l_run, int my_bar, int other_bar, bool tl_on,
+                                              int tl_id, int tl_base) {
+    (void)tl_on; (void)tl_id; (void)tl_base; (void)my_bar; (void)other_bar;
+    mbar_wait(bar_s_full, s_parity);
+    if (tl_on) TL(tl_base + 0);
+    tc_fence_after();
+    float s[KVB];
+    {
+        uint32_t raw[KVB];
+#pragma unroll
+        for (int c = 0; c < KVB / 32; ++c) tmem_ld32(tmem_s + lane_addr + c * 32, raw + c * 32);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < KVB; ++i) s[i] = __uint_as_float(raw[i]);
+    }
+    tc_fence_before();
+    mbar_arrive(bar_s_free);                         // S(j) is in registers: the MMA warp may start S(j+1)
+    if (tl_on) TL(tl_base + 1);
+    if (interior) {
+        const uint4* mk = reinterpret_cast<const uint4*>(key_mask + row_base + j0);
+        const bool vec_ok = ((row_base + j0) & 15) == 0 && j0 + KVB <= k_tokens;
+#pragma unroll
+        for (int g = 0; g < KVB / 16; ++g) {
+            uint32_t w[4];
+            if (vec_ok) {
+                const uint4 u = __ldg(mk + g);
+                w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    w[i] = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int c = j0 + g * 16 + i * 4 + b;
+                        const uint32_t v = (c < k_tokens) ? key_mask[row_base + c] : 0;
+                        w[i] |= (v & 0xffu) << (8 * b);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const bool ok = ((w[i >> 2] >> (8 * (i & 3))) & 0xffu) != 0 && (j0 + g * 16 + i < kvl);
+                if (!ok) s[g * 16 + i] = -CUDART_INF_F;
+            }
+        }
+    } else if (j0 + KVB > kvl) {
+        const int lim = kvl - j0;
+#pragma unroll
+        for (int i = 0; i < KVB; ++i)
+            if (i >= lim) s[i] = -CUDART_INF_F;
+    }
+    float mx4[4] = {s[0], s[1], s[2], s[3]};          // 4 independent chains instead of one 127-deep one
+#pragma unroll
+    for (int i = 4; i < KVB; i += 4) {
+        mx4[0] = fmaxf(mx4[0], s[i]); mx4[1] = fmaxf(mx4[1], s[i + 1]);
+        mx4[2] = fmaxf(mx4[2], s[i + 2]); mx4[3] = fmaxf(mx4[3], s[i + 3]);
+    }
+#if ATT_ABLATE & 8
+    const float mx = fmaxf(s[0], s[KVB - 1]);
+#else
+    const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+#endif
+    // Lazy rescaling: the reference max only moves when the row max grew by more than 2^8; until then P is
+    // computed against the stale max (P <= 256, exact in the fp32 sum and harmless in bf16) and O / l need no
+    // correction.  The result is unchanged because O and l always share the same reference max.
+    const float m_cand = fmaxf(m_run, mx * LOG2E);
+    float alpha = 1.0f;
+    if (m_cand > m_run + 8.0f) {                               // first valid block: m_run = -inf -> alpha = 0
+        alpha = ex2(m_run - m_cand);
+        m_run = m_cand;
+    }
+    const float m_use = (m_run == -CUDART_INF_F) ? 0.f : m_run;
+    // exp2(s*log2e - m) and the row sum with packed fp32x2 FMA / ADD (FFMA2 / FADD2): half the issue slots
+    if (PINGPONG) named_bar_sync(my_bar, 256);            // my turn on the MUFU (see attention_pp_kernel)
+    if (tl_on) TL(tl_base + 2);
+    const uint64_t sc2 = pack_f32x2(LOG2E, LOG2E), nm2 = pack_f32x2(-m_use, -m_use);
+    uint64_t sum2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
+#pragma unroll
+    for (int i = 0; i < KVB; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            float x0, x1;
+            unpack_f32x2(fma_f32x2(pack_f32x2(s[i + 2 * u], s[i + 2 * u + 1]), sc2, nm2), x0, x1);
+            if (((i >> 1) + u) % 4 < POLY) {          // this pair goes to the FMA pipe
+                exp2_poly_pair(x0, x1);
+                s[i + 2 * u] = x0;
+                s[i + 2 * u + 1] = x1;
+            } else {                                  // this pair goes to the MUFU
+#if ATT_ABLATE & 1
+                s[i + 2 * u] = x0;
+                s[i + 2 * u + 1] = x1;
+#else
+                s[i + 2 * u] = ex2(x0);
+                s[i + 2 * u + 1] = ex2(x1);
+#endif
+            }
+            sum2[u] = add_f32x2(sum2[u], pack_f32x2(s[i + 2 * u], s[i + 2 * u + 1]));
+        }
+    }
+    if (PINGPONG) named_bar_arrive(other_bar, 256);       // hand the MUFU to the other softmax group
+    float sa, sb, sc, sd;
+    unpack_f32x2(sum2[0], sa, sb);
+    unpack_f32x2(sum2[1], sc, sd);
+    l_run = l_run * alpha + ((sa + sb) + (sc + sd));
+    if (tl_on) TL(tl_base + 3);
+    // PV(j-1) must have drained the P buffer and finished O before either is touched again
+    if (!first) {                                     // (first block: covered by the previous item's bar_o_full)
+        mbar_wait(bar_pv_done, pv_parity);
+        tc_fence_after();
+    }
+    // P -> smem, bf16, K-major with the 128-B swizzle: 16-B chunk c of row r lands at chunk (c ^ (r & 7))
+#if ATT_ABLATE & 2
+    if (l_run == 123.456f)
+#endif
+#pragma unroll
+    for (int a = 0; a < KVB / 64; ++a) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int e = a * 64 + c * 8;
+            uint4 u;
+            u.x = pack_bf16x2(s[e + 0], s[e + 1]);
+            u.y = pack_bf16x2(s[e + 2], s[e + 3]);
+            u.z = pack_bf16x2(s[e + 4], s[e + 5]);
+            u.w = pack_bf16x2(s[e + 6], s[e + 7]);
+            *reinterpret_cast<uint4*>(p_row + a * (ATT_BLOCK * 128) + ((c ^ sw) << 4)) = u;
+        }
+    }
+    // rescale the running O accumulator (complete through block j-1, see the wait above)
+    if (!first && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+        for (int c = 0; c < D / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tmem_o + lane_addr + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_o + lane_addr + c * 16, o);
+        }
+        tmem_st_wait();
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(bar_p_full);
+    if (tl_on) TL(tl_base + 4);
+}
+
+template <int D, int KVB, int POLY>
+__global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D, KVB>::MIN_CTAS)
+attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_kv, int n_seq,
+                 int heads, int k_tokens, int h, const int32_t* __restrict__ kv_info,
                  const uint8_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out) {
-    using Cfg = AttnCfg<D>;
+    using Cfg = AttnCfg<D, KVB>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
     uint64_t* bar_q = bars + 0;
@@ -91,24 +273,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * ATT_BLOCK, head = blockIdx.y, n = blockIdx.z;
-    const int kvl = kv_info[2 * n], n_nonpad = kv_info[2 * n + 1];
-    const bool interior = n_nonpad != kvl;                  // pad ids before the last real token
-    const int nkv = (kvl + ATT_BLOCK - 1) / ATT_BLOCK;
-    const long long row_base = static_cast<long long>(n) * k_tokens;
-
-    if (nkv == 0) {                                         // all-pad sequence: the reference never encodes one
-        if (warp < 4 && q0 + threadIdx.x < k_tokens) {
-            uint4* o = reinterpret_cast<uint4*>(out + (row_base + q0 + threadIdx.x) * h + head * D);
-            for (int i = 0; i < D / 8; ++i) o[i] = make_uint4(0, 0, 0, 0);
-        }
-        return;
-    }
+    // Work items = (sequence, head, 128-query block), query block fastest so that the CTAs running side by side share one
+    // (sequence, head)'s K/V in L2.  A CTA walks items blockIdx.x, blockIdx.x + gridDim.x, ...; all their KV blocks form ONE
+    // stream g = 0, 1, 2, ... that indexes the K/V ring and every barrier parity, so the next item's Q / K / V loads and its
+    // first S = QK^T are in flight while the softmax warps still normalise and store the current item's O.
+    const int nqb = (k_tokens + ATT_BLOCK - 1) / ATT_BLOCK;
+    const int total = n_seq * heads * nqb;
+    struct Item { int n, head, q0, kvl, nkv, n_nonpad; };
+    auto decode = [&](int item) {
+        Item w;
+        w.q0 = (item % nqb) * ATT_BLOCK;
+        w.head = (item / nqb) % heads;
+        w.n = item / (nqb * heads);
+        w.kvl = kv_info[2 * w.n];
+        w.n_nonpad = kv_info[2 * w.n + 1];
+        w.nkv = (w.kvl + KVB - 1) / KVB;
+        return w;
+    };
+    int tl_id = blockIdx.x;
+    (void)tl_id;
+    if (threadIdx.x == 0) TL(0);
 
     if (warp == 4) {
         if (lane == 0) {
             if ((smem_u32(smem) & 1023u) != 0) { printf("molly attention: smem base not 1024-B aligned\n"); __trap(); }
             tma_prefetch_desc(&tma_qkv);
+            tma_prefetch_desc(&tma_kv);
             mbar_init(bar_q, 1);
             mbar_init(&bar_kv_full[0], 1); mbar_init(&bar_kv_full[1], 1);
             mbar_init(&bar_kv_empty[0], 1); mbar_init(&bar_kv_empty[1], 1);
@@ -126,73 +316,121 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TL(1);
     const uint32_t tmem_s = tmem_base;
-    const uint32_t tmem_o = tmem_base + 128;
+    const uint32_t tmem_o = tmem_base + KVB;
 
     if (warp == 4) {
         if (lane == 0) {
             // ---------------- control thread: TMA producer + MMA issuer ----------------
-            auto load_tile = [&](int smem_off, uint64_t* bar, int col, int row) {
-#pragma unroll
-                for (int b = 0; b < Cfg::NBOX; ++b)
-                    tma_load_2d(smem + smem_off + b * Cfg::BOX_BYTES, &tma_qkv, bar, col + b * Cfg::BOX_D, row);
-            };
-            const int qcol = head * D, kcol = h + head * D, vcol = 2 * h + head * D;
-            constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK, ATT_BLOCK, false, false);
+            constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK, KVB, false, false);
             constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK, D, false, true);      // B (= V) is MN-major
             const uint32_t s_q = smem_u32(smem + Cfg::OFF_Q), s_k = smem_u32(smem + Cfg::OFF_K);
             const uint32_t s_v = smem_u32(smem + Cfg::OFF_V), s_p = smem_u32(smem + Cfg::OFF_P);
-            auto load_kv = [&](int blk) {
-                const int stg = blk & 1;
-                mbar_arrive_expect_tx(&bar_kv_full[stg], 2 * Cfg::TILE_BYTES);
-                load_tile(Cfg::OFF_K + stg * Cfg::TILE_BYTES, &bar_kv_full[stg], kcol,
-                          static_cast<int>(row_base) + blk * ATT_BLOCK);
-                load_tile(Cfg::OFF_V + stg * Cfg::TILE_BYTES, &bar_kv_full[stg], vcol,
-                          static_cast<int>(row_base) + blk * ATT_BLOCK);
+            auto next_item = [&](int item) {                 // first item >= `item` of this CTA that has keys
+                while (item < total && kv_info[2 * (item / (nqb * heads))] <= 0) item += gridDim.x;
+                return item;
             };
-            auto issue_s = [&](int blk) {        // S = Q K(blk)^T : K-major x K-major, D/16 k-steps
-                mbar_wait(&bar_kv_full[blk & 1], (blk >> 1) & 1);
+            auto load_q = [&](const Item& w) {               // Q: 128-row boxes
+                mbar_arrive_expect_tx(bar_q, Cfg::TILE_BYTES);
+#pragma unroll
+                for (int b = 0; b < Cfg::NBOX; ++b)
+                    tma_load_2d(smem + Cfg::OFF_Q + b * Cfg::BOX_BYTES, &tma_qkv, bar_q, w.head * D + b * Cfg::BOX_D,
+                                w.n * k_tokens + w.q0);
+            };
+            // load cursor: runs two KV blocks ahead of the compute cursor, across item boundaries
+            int l_item = next_item(blockIdx.x), l_j = 0, g_load = 0;
+            Item lw = decode(l_item < total ? l_item : 0);
+            auto load_next_kv = [&]() {                      // K / V: KVB-row boxes into stage g_load & 1
+                if (l_item >= total) return;
+                if ((ATT_ABLATE & 32) && g_load >= 2) {
+                    mbar_arrive(&bar_kv_full[g_load & 1]);
+                } else {
+                    const int stg = g_load & 1, row = lw.n * k_tokens + l_j * KVB;
+                    mbar_arrive_expect_tx(&bar_kv_full[stg], 2 * Cfg::KV_TILE_BYTES);
+#pragma unroll
+                    for (int b = 0; b < Cfg::NBOX; ++b) {
+                        tma_load_2d(smem + Cfg::OFF_K + stg * Cfg::KV_TILE_BYTES + b * Cfg::KV_BOX_BYTES, &tma_kv,
+                                    &bar_kv_full[stg], h + lw.head * D + b * Cfg::BOX_D, row);
+                        tma_load_2d(smem + Cfg::OFF_V + stg * Cfg::KV_TILE_BYTES + b * Cfg::KV_BOX_BYTES, &tma_kv,
+                                    &bar_kv_full[stg], 2 * h + lw.head * D + b * Cfg::BOX_D, row);
+                    }
+                }
+                ++g_load;
+                if (++l_j == lw.nkv) {
+                    l_item = next_item(l_item + gridDim.x);
+                    l_j = 0;
+                    if (l_item < total) lw = decode(l_item);
+                }
+            };
+            auto issue_s = [&](int g) {          // S = Q K(g)^T : K-major x K-major, D/16 k-steps
+                mbar_wait(&bar_kv_full[g & 1], (g >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
-                for (int s = 0; s < D / 16; ++s) {
+                for (int s = 0; s < ((ATT_ABLATE & 16) ? 1 : D / 16); ++s) {
                     const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
+                    const uint32_t koff = ((s * 16) / Cfg::BOX_D) * Cfg::KV_BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
                     const uint64_t qd = make_smem_desc(s_q + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
-                    const uint64_t kd =
-                        make_smem_desc(s_k + (blk & 1) * Cfg::TILE_BYTES + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
+                    const uint64_t kd = make_smem_desc(s_k + (g & 1) * Cfg::KV_TILE_BYTES + koff, 16, 8 * Cfg::ROW_BYTES,
+                                                       Cfg::LAYOUT);
                     umma_bf16_ss(tmem_s, qd, kd, idesc_s, s != 0);
                 }
                 umma_commit(bar_s_full);
             };
-            mbar_arrive_expect_tx(bar_q, Cfg::TILE_BYTES);
-            load_tile(Cfg::OFF_Q, bar_q, qcol, static_cast<int>(row_base) + q0);
-            load_kv(0);
-            if (nkv > 1) load_kv(1);
-            mbar_wait(bar_q, 0);
-            issue_s(0);
-            for (int j = 0; j < nkv; ++j) {
-                const int st = j & 1;
-                // (1) the moment the softmax warps hold S(j) in registers, S(j+1) is issued: it runs under softmax(j)
-                mbar_wait(bar_s_free, j & 1);
-                tc_fence_after();
-                if (j + 1 < nkv) issue_s(j + 1);
-                // (2) O += P(j) V(j) : P K-major (two 64-key atoms), V MN-major; 8 k-steps of 16 keys
-                mbar_wait(bar_p_full, j & 1);
-                tc_fence_after();
+            int c_item = l_item, it = 0, g = 0;
+            if (c_item < total) {
+                load_q(lw);
+                load_next_kv();
+                load_next_kv();
+                TL(40);
+                mbar_wait(bar_q, 0);
+                TL(41);
+                issue_s(0);
+                TL(42);
+            }
+            while (c_item < total) {
+                const Item w = decode(c_item);
+                const int nxt = next_item(c_item + gridDim.x);
+                tl_id = c_item;
+                for (int j = 0; j < w.nkv; ++j, ++g) {
+                    const int st = g & 1;
+                    const bool last = j == w.nkv - 1;
+                    // (1) the moment the softmax warps hold S(g) in registers, S(g+1) is issued: it runs under softmax(g).
+                    //     On an item's last block Q is dead instead: the next item's Q is fetched into the same buffer.
+                    mbar_wait(bar_s_free, g & 1);
+                    TL(43 + 3 * j);
+                    tc_fence_after();
+                    if (!last) issue_s(g + 1);
+                    else if (nxt < total) load_q(decode(nxt));
+                    // (2) O += P(g) V(g) : P K-major (64-key atoms), V MN-major; KVB/16 k-steps of 16 keys
+                    mbar_wait(bar_p_full, g & 1);
+                    TL(44 + 3 * j);
+                    tc_fence_after();
 #pragma unroll
-                for (int s = 0; s < ATT_BLOCK / 16; ++s) {
-                    const uint64_t pd = make_smem_desc(s_p + (s >> 2) * (ATT_BLOCK * 128) + (s & 3) * 32, 16, 1024,
-                                                       kLayoutSW128);
-                    const uint64_t vd = make_smem_desc(s_v + st * Cfg::TILE_BYTES + s * 16 * Cfg::ROW_BYTES,
-                                                       Cfg::BOX_BYTES, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
-                    umma_bf16_ss(tmem_o, pd, vd, idesc_pv, (j | s) != 0);
+                    for (int s = 0; s < ((ATT_ABLATE & 4) ? 1 : KVB / 16); ++s) {
+                        const uint64_t pd = make_smem_desc(s_p + (s >> 2) * (ATT_BLOCK * 128) + (s & 3) * 32, 16, 1024,
+                                                           kLayoutSW128);
+                        const uint64_t vd = make_smem_desc(s_v + st * Cfg::KV_TILE_BYTES + s * 16 * Cfg::ROW_BYTES,
+                                                           Cfg::KV_BOX_BYTES, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
+                        umma_bf16_ss(tmem_o, pd, vd, idesc_pv, (j | s) != 0);
+                    }
+                    umma_commit(&bar_kv_empty[st]);          // PV(g) done: stage st, the P buffer and O are free
+                    if (last) {
+                        umma_commit(bar_o_full);
+                        if (nxt < total) {                   // first S of the next item, under this item's epilogue
+                            mbar_wait(bar_q, (it + 1) & 1);
+                            issue_s(g + 1);
+                        }
+                    }
+                    // (3) refill stage st with stream block g+2 once PV(g) has drained it
+                    if (l_item < total) {
+                        mbar_wait(&bar_kv_empty[st], (g >> 1) & 1);
+                        TL(45 + 3 * j);
+                        load_next_kv();
+                    }
                 }
-                umma_commit(&bar_kv_empty[st]);              // PV(j) done: stage st, the P buffer and O(j) are free
-                if (j == nkv - 1) umma_commit(bar_o_full);
-                // (3) refill stage st with block j+2 once PV(j) has drained it
-                if (j + 2 < nkv) {
-                    mbar_wait(&bar_kv_empty[st], (j >> 1) & 1);
-                    load_kv(j + 2);
-                }
+                ++it;
+                c_item = nxt;
             }
         }
     } else {
@@ -201,137 +439,31 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
         const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
         uint8_t* p_row = smem + Cfg::OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
         const int sw = r & 7;
+        int it = 0, g = 0;
+        for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const Item w = decode(item);
+        const int kvl = w.kvl, nkv = w.nkv, q0 = w.q0, head = w.head;
+        const bool interior = w.n_nonpad != w.kvl;            // pad ids before the last real token
+        const long long row_base = static_cast<long long>(w.n) * k_tokens;
+        tl_id = item;
+        if (nkv == 0) {                                       // all-pad sequence: the reference never encodes one
+            if (q0 + r < k_tokens) {
+                uint4* o = reinterpret_cast<uint4*>(out + (row_base + q0 + r) * h + head * D);
+                for (int i = 0; i < D / 8; ++i) o[i] = make_uint4(0, 0, 0, 0);
+            }
+            continue;
+        }
         float m_run = -CUDART_INF_F;      // running max, log2 domain
         float l_run = 0.f;
-        for (int j = 0; j < nkv; ++j) {
-            mbar_wait(bar_s_full, j & 1);
-            tc_fence_after();
-            float s[ATT_BLOCK];
-            {
-                uint32_t raw[ATT_BLOCK];
-                tmem_ld32(tmem_s + lane_addr + 0, raw);
-                tmem_ld32(tmem_s + lane_addr + 32, raw + 32);
-                tmem_ld32(tmem_s + lane_addr + 64, raw + 64);
-                tmem_ld32(tmem_s + lane_addr + 96, raw + 96);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < ATT_BLOCK; ++i) s[i] = __uint_as_float(raw[i]);
-            }
-            tc_fence_before();
-            mbar_arrive(bar_s_free);                         // S(j) is in registers: the MMA warp may start S(j+1)
-            const int j0 = j * ATT_BLOCK;
-            if (interior) {
-                const uint4* mk = reinterpret_cast<const uint4*>(key_mask + row_base + j0);
-                const bool vec_ok = ((row_base + j0) & 15) == 0 && j0 + ATT_BLOCK <= k_tokens;
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    uint32_t w[4];
-                    if (vec_ok) {
-                        const uint4 u = __ldg(mk + g);
-                        w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            w[i] = 0;
-#pragma unroll
-                            for (int b = 0; b < 4; ++b) {
-                                const int c = j0 + g * 16 + i * 4 + b;
-                                const uint32_t v = (c < k_tokens) ? key_mask[row_base + c] : 0;
-                                w[i] |= (v & 0xffu) << (8 * b);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const bool ok = ((w[i >> 2] >> (8 * (i & 3))) & 0xffu) != 0 && (j0 + g * 16 + i < kvl);
-                        if (!ok) s[g * 16 + i] = -CUDART_INF_F;
-                    }
-                }
-            } else if (j0 + ATT_BLOCK > kvl) {
-                const int lim = kvl - j0;
-#pragma unroll
-                for (int i = 0; i < ATT_BLOCK; ++i)
-                    if (i >= lim) s[i] = -CUDART_INF_F;
-            }
-            float mx4[4] = {s[0], s[1], s[2], s[3]};          // 4 independent chains instead of one 127-deep one
-#pragma unroll
-            for (int i = 4; i < ATT_BLOCK; i += 4) {
-                mx4[0] = fmaxf(mx4[0], s[i]); mx4[1] = fmaxf(mx4[1], s[i + 1]);
-                mx4[2] = fmaxf(mx4[2], s[i + 2]); mx4[3] = fmaxf(mx4[3], s[i + 3]);
-            }
-            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-            // Lazy rescaling: the reference max only moves when the row max grew by more than 2^8; until then P is
-            // computed against the stale max (P <= 256, exact in the fp32 sum and harmless in bf16) and O / l need no
-            // correction.  The result is unchanged because O and l always share the same reference max.
-            const float m_cand = fmaxf(m_run, mx * LOG2E);
-            float alpha = 1.0f;
-            if (m_cand > m_run + 8.0f) {                               // first valid block: m_run = -inf -> alpha = 0
-                alpha = ex2(m_run - m_cand);
-                m_run = m_cand;
-            }
-            const float m_use = (m_run == -CUDART_INF_F) ? 0.f : m_run;
-            // exp2(s*log2e - m) and the row sum with packed fp32x2 FMA / ADD (FFMA2 / FADD2): half the issue slots
-            const uint64_t sc2 = pack_f32x2(LOG2E, LOG2E), nm2 = pack_f32x2(-m_use, -m_use);
-            uint64_t sum2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
-#pragma unroll
-            for (int i = 0; i < ATT_BLOCK; i += 4) {
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    float x0, x1;
-                    unpack_f32x2(fma_f32x2(pack_f32x2(s[i + 2 * u], s[i + 2 * u + 1]), sc2, nm2), x0, x1);
-                    if (((i >> 1) + u) % 4 < POLY) {          // this pair goes to the FMA pipe
-                        exp2_poly_pair(x0, x1);
-                        s[i + 2 * u] = x0;
-                        s[i + 2 * u + 1] = x1;
-                    } else {                                  // this pair goes to the MUFU
-                        s[i + 2 * u] = ex2(x0);
-                        s[i + 2 * u + 1] = ex2(x1);
-                    }
-                    sum2[u] = add_f32x2(sum2[u], pack_f32x2(s[i + 2 * u], s[i + 2 * u + 1]));
-                }
-            }
-            float sa, sb, sc, sd;
-            unpack_f32x2(sum2[0], sa, sb);
-            unpack_f32x2(sum2[1], sc, sd);
-            l_run = l_run * alpha + ((sa + sb) + (sc + sd));
-            // PV(j-1) must have drained the P buffer and finished O before either is touched again
-            if (j > 0) {
-                mbar_wait(&bar_kv_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
-                tc_fence_after();
-            }
-            // P -> smem, bf16, K-major with the 128-B swizzle: 16-B chunk c of row r lands at chunk (c ^ (r & 7))
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int e = a * 64 + c * 8;
-                    uint4 u;
-                    u.x = pack_bf16x2(s[e + 0], s[e + 1]);
-                    u.y = pack_bf16x2(s[e + 2], s[e + 3]);
-                    u.z = pack_bf16x2(s[e + 4], s[e + 5]);
-                    u.w = pack_bf16x2(s[e + 6], s[e + 7]);
-                    *reinterpret_cast<uint4*>(p_row + a * (ATT_BLOCK * 128) + ((c ^ sw) << 4)) = u;
-                }
-            }
-            // rescale the running O accumulator (complete through block j-1, see the wait above)
-            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll
-                for (int c = 0; c < D / 16; ++c) {
-                    uint32_t o[16];
-                    tmem_ld16(tmem_o + lane_addr + c * 16, o);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    tmem_st16(tmem_o + lane_addr + c * 16, o);
-                }
-                tmem_st_wait();
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(bar_p_full);
-        }
+        for (int j = 0; j < nkv; ++j, ++g)
+            softmax_block<D, KVB, POLY, false>(bar_s_full, g & 1, bar_s_free, &bar_kv_empty[(g - 1) & 1],
+                                               ((g - 1) >> 1) & 1, bar_p_full, tmem_s, tmem_o, lane_addr, p_row, sw,
+                                               interior, key_mask, row_base, j * KVB, kvl, k_tokens, j == 0, m_run, l_run,
+                                               0, 0, r == 0 && j < 6, tl_id, 2 + 5 * j);
         // epilogue: O / l -> bf16 -> HBM
-        mbar_wait(bar_o_full, 0);
+        mbar_wait(bar_o_full, it & 1);
+        ++it;
+        if (r == 0) TL(34);
         tc_fence_after();
         const float inv_l = 1.0f / l_run;
         const bool row_ok = q0 + r < k_tokens;
@@ -355,398 +487,242 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, int k_tokens, int 
                 reinterpret_cast<uint4*>(orow + c * 16)[1] = u1;
             }
         }
+        tc_fence_before();                                    // O is read: the next item's PV may overwrite it
+        }   // item loop
     }
 
+    if (threadIdx.x == 0) TL(35);
     tc_fence_before();
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
+#ifdef ATT_TIMELINE
+    if (threadIdx.x == 0) {
+        TL(36);
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (d_attn_tl != nullptr && blockIdx.x < 2048) d_attn_tl[blockIdx.x * 72 + 37] = smid;
+    }
+#endif
 }
 
 // ================================================================================================
-// Persistent variant (default).  A CTA walks a static stride of work items (sequence, head, 128-query block) and
-// treats all their KV blocks as ONE stream of iterations g = 0, 1, 2, ...:
-//   * K/V ring, S / P hand-offs and barrier parities are indexed by g, so the loads for the next item's first blocks,
-//     its Q tile (double-buffered) and its first S = QK^T are issued while the current item is still in softmax;
-//   * P never touches shared memory: the softmax warps write it as packed bf16 into TMEM (tcgen05.st) and O += P V
-//     takes its A operand from TMEM (tcgen05.mma ..., [a_tmem], b_desc).  At head_dim 64 the smem-P form spent
-//     ~45 % of the shared-memory bandwidth of a KV block on writing P and reading it back, and shared memory
-//     (UMMA operand reads + TMA fills), not the tensor pipe, is what bounds this kernel.
-// TMEM columns: S [0,128) fp32 | P [128,192) bf16x2 | O [192, 192+D) fp32.
+// Ping-pong kernel (head_dim <= 64).  One CTA per SM works on TWO 128-query tiles of one (sequence, head) at a time:
+//   warps 0-3  softmax group A (Q rows q0 .. q0+127)      warp 8   TMA producer (Q_A, Q_B, shared K/V ring)
+//   warps 4-7  softmax group B (Q rows q0+128 .. q0+255)  warp 9   MMA issuer of group A (S_A = Q_A K^T, O_A += P_A V)
+//                                                          warp 10  MMA issuer of group B
+// Why: with two independent CTAs per SM, each SM sub-partition holds one softmax warp of each CTA and the two drift into
+// running their exp2 phases at the same time -- both then get half of the 4-lane MUFU -- and their TMEM-load / row-max /
+// P-store phases at the same time, when the MUFU idles (measured: MUFU 65 % busy, nothing else above 62 %, and removing any
+// single piece of work barely moved the time).  Here the two groups share the SM *cooperatively*: a token (two named
+// barriers) lets exactly one group run its exp2 phase while the other loads S, finds its row max, stores P and hands over,
+// so the MUFU never sees two warps on one sub-partition and never idles.  K/V tiles are loaded once for both query tiles.
+// Items (sequence, head, query-tile pair) are streamed per CTA as in attention_kernel.  A tile past k_tokens (odd tile count)
+// is computed on whatever rows follow and never stored.
+// TMEM columns: S_A [0,128) | S_B [128,256) | O_A [256,256+D) | O_B [384,384+D).
 // ================================================================================================
-struct AttnCursor {              // position in the flattened (item, kv-block) stream of this CTA
-    int item;                    // global work-item index (n, head, qb); >= total -> stream exhausted
-    int it;                      // local item counter of this CTA (0, 1, 2, ...)
-    int j;                       // kv block inside the item
-    int g;                       // global iteration counter
-    int nkv, kvl, n, head, q0;
-};
+constexpr int PP_THREADS = 352;
+constexpr int PP_BAR_A = 1, PP_BAR_B = 2;      // named barriers: "group A / B may start its exp2 phase"
 
 template <int D>
-struct AttnPCfg {                // shared memory of the persistent kernel: Q x2 | K x3 | V x2 | barriers
-    using B = AttnCfg<D>;
-    // K and V have SEPARATE rings.  S(g+1) = Q K(g+1)^T is issued at the start of softmax(g), a whole block-time before
-    // V(g+1) is needed, so a shared K/V stage (freed only by PV) made every K tile arrive one TMA latency late -- that
-    // latency, not MUFU or shared memory, set the ~2000 cycles per KV block of the earlier versions.
-    static constexpr int KST = 3, VST = 2;
-    static constexpr int OFF_Q = 0;
+struct AttnPPCfg {
+    using B = AttnCfg<D, 128>;
+    static constexpr int NST = 3;                                   // shared K/V ring
+    static constexpr int OFF_Q = 0;                                 // Q_A | Q_B
     static constexpr int OFF_K = 2 * B::TILE_BYTES;
-    static constexpr int OFF_V = (2 + KST) * B::TILE_BYTES;
-    static constexpr int OFF_BAR = (2 + KST + VST) * B::TILE_BYTES;
+    static constexpr int OFF_V = OFF_K + NST * B::KV_TILE_BYTES;
+    static constexpr int OFF_P = OFF_V + NST * B::KV_TILE_BYTES;    // P_A | P_B
+    static constexpr int OFF_BAR = OFF_P + 2 * B::P_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 256;
-    static constexpr int TMEM_COLS = (D == 128) ? 512 : 256;
-    static constexpr int MIN_CTAS = SMEM_BYTES <= 115712 ? 2 : 1;       // (228 KB - 2 x 1 KB reserved) / 2
-    static constexpr int TM_S = 0, TM_P = 128, TM_O = 192;
 };
 
 template <int D>
-__global__ void __launch_bounds__(ATT_THREADS, AttnPCfg<D>::MIN_CTAS)
-attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int heads, int k_tokens, int h,
-                            const int32_t* __restrict__ kv_info, const uint8_t* __restrict__ key_mask,
-                            __nv_bfloat16* __restrict__ out, long long* __restrict__ dbg) {
-    using Cfg = AttnCfg<D>;
-    using PC = AttnPCfg<D>;
-    // optional timeline of CTA 0 (tools/attn_timeline.py): dbg[role][iteration][slot] = clock64()
-#define MOLLY_DBG(role, iter, slot)                                                             \
-    do {                                                                                        \
-        if (dbg != nullptr && blockIdx.x == 0 && (iter) < 64) dbg[((role) * 64 + (iter)) * 8 + (slot)] = clock64(); \
-    } while (0)
+__global__ void __launch_bounds__(PP_THREADS, 1)
+attention_pp_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int heads, int k_tokens, int h,
+                    const int32_t* __restrict__ kv_info, const uint8_t* __restrict__ key_mask,
+                    __nv_bfloat16* __restrict__ out) {
+    using Cfg = AttnPPCfg<D>;
+    using B = typename Cfg::B;
+    constexpr int NST = Cfg::NST;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PC::OFF_BAR);
-    uint64_t* bar_q = bars + 0;           // [2]  Q tile of item it landed in buffer it & 1
-    uint64_t* bar_k_full = bars + 2;      // [3]
-    uint64_t* bar_k_empty = bars + 5;     // [3]  S(g) complete: K stage g % 3 is free
-    uint64_t* bar_v_full = bars + 8;      // [2]
-    uint64_t* bar_v_empty = bars + 10;    // [2]  PV(g) complete: V stage g & 1 and P are free
-    uint64_t* bar_s_full = bars + 12;
-    uint64_t* bar_p_full = bars + 13;
-    uint64_t* bar_s_free = bars + 14;
-    uint64_t* bar_o_full = bars + 15;     // last PV of an item complete
-    uint64_t* bar_o_free = bars + 16;     // softmax warps have read O out
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+    uint64_t* bar_q_full = bars + 0;        // [2]  Q_X landed                       (tx)
+    uint64_t* bar_q_free = bars + 2;        // [2]  every S of the item has been consumed: Q_X may be overwritten
+    uint64_t* bar_kv_full = bars + 4;       // [NST]                                 (tx)
+    uint64_t* bar_kv_empty = bars + 4 + NST;        // [NST] both groups' PV(g) drained the stage (2 commits)
+    uint64_t* bar_s_full = bars + 4 + 2 * NST;      // [2]
+    uint64_t* bar_s_free = bars + 6 + 2 * NST;      // [2]  128 arrivals
+    uint64_t* bar_p_full = bars + 8 + 2 * NST;      // [2]  128 arrivals
+    uint64_t* bar_pv_done = bars + 10 + 2 * NST;    // [2]  PV_X(g) complete: P_X and O_X may be touched
+    uint64_t* bar_o_full = bars + 12 + 2 * NST;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14 + 2 * NST);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nqb = (k_tokens + ATT_BLOCK - 1) / ATT_BLOCK;
-    const int total = n_seq * heads * nqb;
-
-    // cursor helpers (every role walks the same stream; items whose sequence is all padding are skipped)
-    auto load_item = [&](AttnCursor& c) {
-        while (c.item < total) {
-            const int qb = c.item % nqb, t = c.item / nqb;
-            c.head = t % heads;
-            c.n = t / heads;
-            c.q0 = qb * ATT_BLOCK;
-            c.kvl = __ldg(kv_info + 2 * c.n);
-            c.nkv = (c.kvl + ATT_BLOCK - 1) / ATT_BLOCK;
-            if (c.nkv > 0) return;
-            c.item += gridDim.x;              // all-pad sequence: no stream entries (softmax role zero-fills its rows)
-        }
-    };
-    auto advance = [&](AttnCursor& c) {
-        ++c.g;
-        if (++c.j == c.nkv) {
-            c.j = 0;
-            ++c.it;
-            c.item += gridDim.x;
-            load_item(c);
-        }
-    };
-    auto next_item = [&](AttnCursor& c) {     // item-granular step (Q prefetch cursor)
-        ++c.it;
-        c.item += gridDim.x;
-        load_item(c);
-    };
-    auto first = [&]() {
-        AttnCursor c;
-        c.item = blockIdx.x; c.it = 0; c.j = 0; c.g = 0; c.nkv = 0; c.kvl = 0; c.n = 0; c.head = 0; c.q0 = 0;
-        load_item(c);
-        return c;
+    const int nqb = (k_tokens + ATT_BLOCK - 1) / ATT_BLOCK, npair = (nqb + 1) / 2;
+    const int total = n_seq * heads * npair;
+    struct Item { int n, head, q0, kvl, nkv, n_nonpad; };
+    auto decode = [&](int item) {
+        Item w;
+        w.q0 = (item % npair) * 2 * ATT_BLOCK;
+        w.head = (item / npair) % heads;
+        w.n = item / (npair * heads);
+        w.kvl = kv_info[2 * w.n];
+        w.n_nonpad = kv_info[2 * w.n + 1];
+        w.nkv = (w.kvl + ATT_BLOCK - 1) / ATT_BLOCK;
+        return w;
     };
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             if ((smem_u32(smem) & 1023u) != 0) { printf("molly attention: smem base not 1024-B aligned\n"); __trap(); }
             tma_prefetch_desc(&tma_qkv);
-            for (int i = 0; i < 2; ++i) {
-                mbar_init(&bar_q[i], 1);
-                mbar_init(&bar_v_full[i], 1);
-                mbar_init(&bar_v_empty[i], 1);
+            for (int x = 0; x < 2; ++x) {
+                mbar_init(&bar_q_full[x], 1);
+                mbar_init(&bar_q_free[x], 1);
+                mbar_init(&bar_s_full[x], 1);
+                mbar_init(&bar_s_free[x], 128);
+                mbar_init(&bar_p_full[x], 128);
+                mbar_init(&bar_pv_done[x], 1);
+                mbar_init(&bar_o_full[x], 1);
             }
-            for (int i = 0; i < PC::KST; ++i) {
-                mbar_init(&bar_k_full[i], 1);
-                mbar_init(&bar_k_empty[i], 1);
+            for (int st = 0; st < NST; ++st) {
+                mbar_init(&bar_kv_full[st], 1);
+                mbar_init(&bar_kv_empty[st], 2);
             }
-            mbar_init(bar_s_full, 1);
-            mbar_init(bar_p_full, 128);
-            mbar_init(bar_s_free, 128);
-            mbar_init(bar_o_full, 1);
-            mbar_init(bar_o_free, 128);
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, PC::TMEM_COLS);
+        tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_s = tmem_base + PC::TM_S;
-    const uint32_t tmem_p = tmem_base + PC::TM_P;
-    const uint32_t tmem_o = tmem_base + PC::TM_O;
 
-    if (warp == 4) {
+    if (warp == 8) {
+        // ---------------- TMA producer ----------------
         if (lane == 0) {
-            // ---------------- control thread: TMA producer + MMA issuer ----------------
+            int t = 0, g = 0;
+            for (int item = blockIdx.x; item < total; item += gridDim.x) {
+                const Item w = decode(item);
+                if (w.nkv == 0) continue;
+                for (int x = 0; x < 2; ++x) {
+                    if (t > 0) mbar_wait(&bar_q_free[x], (t - 1) & 1);
+                    mbar_arrive_expect_tx(&bar_q_full[x], B::TILE_BYTES);
+#pragma unroll
+                    for (int b = 0; b < B::NBOX; ++b)
+                        tma_load_2d(smem + Cfg::OFF_Q + x * B::TILE_BYTES + b * B::BOX_BYTES, &tma_qkv, &bar_q_full[x],
+                                    w.head * D + b * B::BOX_D, w.n * k_tokens + w.q0 + x * ATT_BLOCK);
+                }
+                for (int j = 0; j < w.nkv; ++j, ++g) {
+                    const int st = g % NST;
+                    if (g >= NST) mbar_wait(&bar_kv_empty[st], (g / NST - 1) & 1);
+                    mbar_arrive_expect_tx(&bar_kv_full[st], 2 * B::KV_TILE_BYTES);
+                    const int row = w.n * k_tokens + j * ATT_BLOCK;
+#pragma unroll
+                    for (int b = 0; b < B::NBOX; ++b) {
+                        tma_load_2d(smem + Cfg::OFF_K + st * B::KV_TILE_BYTES + b * B::KV_BOX_BYTES, &tma_qkv,
+                                    &bar_kv_full[st], h + w.head * D + b * B::BOX_D, row);
+                        tma_load_2d(smem + Cfg::OFF_V + st * B::KV_TILE_BYTES + b * B::KV_BOX_BYTES, &tma_qkv,
+                                    &bar_kv_full[st], 2 * h + w.head * D + b * B::BOX_D, row);
+                    }
+                }
+                ++t;
+            }
+        }
+    } else if (warp >= 9) {
+        // ---------------- MMA issuer of group x ----------------
+        if (lane == 0) {
+            const int x = warp - 9;
             constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK, ATT_BLOCK, false, false);
             constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK, D, false, true);      // B (= V) is MN-major
-            const uint32_t s_q = smem_u32(smem + PC::OFF_Q), s_k = smem_u32(smem + PC::OFF_K);
-            const uint32_t s_v = smem_u32(smem + PC::OFF_V);
-            auto load_tile = [&](int smem_off, uint64_t* bar, int col, int row) {
-#pragma unroll
-                for (int b = 0; b < Cfg::NBOX; ++b)
-                    tma_load_2d(smem + smem_off + b * Cfg::BOX_BYTES, &tma_qkv, bar, col + b * Cfg::BOX_D, row);
-            };
-            auto load_q = [&](const AttnCursor& c) {
-                mbar_arrive_expect_tx(&bar_q[c.it & 1], Cfg::TILE_BYTES);
-                load_tile(PC::OFF_Q + (c.it & 1) * Cfg::TILE_BYTES, &bar_q[c.it & 1], c.head * D, c.n * k_tokens + c.q0);
-            };
-            auto load_k = [&](const AttnCursor& c) {      // K(g) -> stage g % 3, once S(g-3) has released it
-                const int stg = c.g % PC::KST;
-                if (c.g >= PC::KST) mbar_wait(&bar_k_empty[stg], ((c.g / PC::KST) - 1) & 1);
-                mbar_arrive_expect_tx(&bar_k_full[stg], Cfg::TILE_BYTES);
-                load_tile(PC::OFF_K + stg * Cfg::TILE_BYTES, &bar_k_full[stg], h + c.head * D,
-                          c.n * k_tokens + c.j * ATT_BLOCK);
-            };
-            auto load_v = [&](const AttnCursor& c) {      // V(g) -> stage g & 1, once PV(g-2) has released it
-                const int stg = c.g & 1;
-                if (c.g >= 2) mbar_wait(&bar_v_empty[stg], ((c.g >> 1) - 1) & 1);
-                mbar_arrive_expect_tx(&bar_v_full[stg], Cfg::TILE_BYTES);
-                load_tile(PC::OFF_V + stg * Cfg::TILE_BYTES, &bar_v_full[stg], 2 * h + c.head * D,
-                          c.n * k_tokens + c.j * ATT_BLOCK);
-            };
-            // Base descriptors are built once; per MMA only the start-address field moves (one 32-bit add).
-            const uint64_t qd0 = make_smem_desc(s_q, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
-            const uint64_t kd0 = make_smem_desc(s_k, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
-            const uint64_t vd0 = make_smem_desc(s_v, Cfg::BOX_BYTES, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
-            auto issue_s = [&](const AttnCursor& c) {       // S = Q K^T : K-major x K-major, D/16 k-steps
-                if (c.j == 0) mbar_wait(&bar_q[c.it & 1], (c.it >> 1) & 1);
-                const int kst = c.g % PC::KST;
-                mbar_wait(&bar_k_full[kst], (c.g / PC::KST) & 1);
+            const uint32_t s_q = smem_u32(smem + Cfg::OFF_Q + x * B::TILE_BYTES), s_k = smem_u32(smem + Cfg::OFF_K);
+            const uint32_t s_v = smem_u32(smem + Cfg::OFF_V), s_p = smem_u32(smem + Cfg::OFF_P + x * B::P_BYTES);
+            const uint32_t tmem_s = tmem_base + x * 128, tmem_o = tmem_base + 256 + x * 128;
+            auto issue_s = [&](int g) {
+                const int st = g % NST;
+                mbar_wait(&bar_kv_full[st], (g / NST) & 1);
                 tc_fence_after();
-                const uint64_t qd = desc_advance(qd0, (c.it & 1) * Cfg::TILE_BYTES);
-                const uint64_t kd = desc_advance(kd0, kst * Cfg::TILE_BYTES);
 #pragma unroll
                 for (int s = 0; s < D / 16; ++s) {
-                    const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
-                    umma_bf16_ss(tmem_s, desc_advance(qd, off), desc_advance(kd, off), idesc_s, s != 0);
+                    const uint32_t off = ((s * 16) / B::BOX_D) * B::BOX_BYTES + ((s * 16) % B::BOX_D) * 2;
+                    const uint64_t qd = make_smem_desc(s_q + off, 16, 8 * B::ROW_BYTES, B::LAYOUT);
+                    const uint64_t kd = make_smem_desc(s_k + st * B::KV_TILE_BYTES + off, 16, 8 * B::ROW_BYTES, B::LAYOUT);
+                    umma_bf16_ss(tmem_s, qd, kd, idesc_s, s != 0);
                 }
-                umma_commit(bar_s_full);
-                umma_commit(&bar_k_empty[kst]);              // the same completion also releases the K stage
+                umma_commit(&bar_s_full[x]);
             };
-
-            AttnCursor ck = first(), cv = ck, cs = ck, cp = ck, cq = ck;   // K-load / V-load / S-issue / PV / Q-load cursors
-            if (cp.item < total) {
-                load_q(cq); next_item(cq);
-                for (int i = 0; i < PC::KST && ck.item < total; ++i) { load_k(ck); advance(ck); }
-                for (int i = 0; i < PC::VST && cv.item < total; ++i) { load_v(cv); advance(cv); }
-                if (cq.item < total) { load_q(cq); next_item(cq); }           // second Q buffer
-                issue_s(cs); advance(cs);
-                while (cp.item < total) {
-                    const int g = cp.g, st = g & 1;
-                    // (1) softmax holds S(g) in registers -> S(g+1) runs under softmax(g)
-                    MOLLY_DBG(0, g, 0);
-                    mbar_wait(bar_s_free, g & 1);
-                    MOLLY_DBG(0, g, 1);
+            int t = 0, g = 0;
+            for (int item = blockIdx.x; item < total; item += gridDim.x) {
+                const Item w = decode(item);
+                if (w.nkv == 0) continue;
+                mbar_wait(&bar_q_full[x], t & 1);
+                issue_s(g);
+                for (int j = 0; j < w.nkv; ++j, ++g) {
+                    const int st = g % NST;
+                    const bool last = j == w.nkv - 1;
+                    mbar_wait(&bar_s_free[x], g & 1);        // S_X(g) is in registers
                     tc_fence_after();
-                    if (cs.item < total) {
-                        // S(g) was the last user of the previous item's Q buffer when cs starts a new item:
-                        // refill that buffer with the Q tile of the item after cs
-                        const bool new_item = cs.j == 0;
-                        issue_s(cs);
-                        if (new_item && cq.item < total && cq.it == cs.it + 1) { load_q(cq); next_item(cq); }
-                        advance(cs);
-                    }
-                    // S(g) is complete (the softmax warps have read it), so its K stage is free: fetch K(g+3) now,
-                    // two block-times before S(g+3) is issued
-                    if (ck.item < total) { load_k(ck); advance(ck); }
-                    MOLLY_DBG(0, g, 2);
-                    // (2) O (+)= P(g) V(g) : P from TMEM (64 packed columns), V MN-major from smem; 8 k-steps of 16 keys
-                    mbar_wait(bar_p_full, g & 1);
-                    if (cp.j == 0 && cp.it >= 1) mbar_wait(bar_o_free, (cp.it - 1) & 1);   // previous item's O was read out
-                    MOLLY_DBG(0, g, 3);
-                    mbar_wait(&bar_v_full[st], (g >> 1) & 1);
+                    if (!last) issue_s(g + 1);               // runs under softmax_X(g)
+                    else mbar_arrive(&bar_q_free[x]);        // every S of this item is consumed
+                    mbar_wait(&bar_p_full[x], g & 1);
                     tc_fence_after();
-                    const uint64_t vd = desc_advance(vd0, st * Cfg::TILE_BYTES);
 #pragma unroll
-                    for (int s = 0; s < ATT_BLOCK / 16; ++s)
-                        umma_bf16_ts(tmem_o, tmem_p + s * 8, desc_advance(vd, s * 16 * Cfg::ROW_BYTES), idesc_pv,
-                                     (cp.j | s) != 0);
-                    umma_commit(&bar_v_empty[st]);           // PV(g) done: V stage st and P are free
-                    if (cp.j == cp.nkv - 1) umma_commit(bar_o_full);
-                    MOLLY_DBG(0, g, 4);
-                    // (3) refill V stage st with V(g+2) once PV(g) has drained it (needed two block-times from now)
-                    if (cv.item < total) { load_v(cv); advance(cv); }
-                    MOLLY_DBG(0, g, 5);
-                    advance(cp);
+                    for (int s = 0; s < ATT_BLOCK / 16; ++s) {
+                        const uint64_t pd = make_smem_desc(s_p + (s >> 2) * (ATT_BLOCK * 128) + (s & 3) * 32, 16, 1024,
+                                                           kLayoutSW128);
+                        const uint64_t vd = make_smem_desc(s_v + st * B::KV_TILE_BYTES + s * 16 * B::ROW_BYTES,
+                                                           B::KV_BOX_BYTES, 8 * B::ROW_BYTES, B::LAYOUT);
+                        umma_bf16_ss(tmem_o, pd, vd, idesc_pv, (j | s) != 0);
+                    }
+                    umma_commit(&bar_pv_done[x]);
+                    umma_commit(&bar_kv_empty[st]);
+                    if (last) umma_commit(&bar_o_full[x]);
                 }
+                ++t;
             }
         }
     } else {
-        // ---------------- softmax warps: thread r owns query row r ----------------
-        const int r = threadIdx.x;
-        const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-        int g = 0, it = 0;                                    // stream position, identical to the control thread's
+        // ---------------- softmax groups: thread r of group x owns query row q0 + 128 x + r ----------------
+        const int x = warp >> 2, r = threadIdx.x & 127;
+        const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const uint32_t tmem_s = tmem_base + x * 128, tmem_o = tmem_base + 256 + x * 128;
+        uint8_t* p_row = smem + Cfg::OFF_P + x * B::P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+        const int sw = r & 7;
+        const int my_bar = x == 0 ? PP_BAR_A : PP_BAR_B, other_bar = x == 0 ? PP_BAR_B : PP_BAR_A;
+        if (x == 1) named_bar_arrive(PP_BAR_A, 256);          // group A takes the first turn
+        int t = 0, g = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x) {
-            const int qb = item % nqb, tq = item / nqb;
-            const int head = tq % heads, n = tq / heads;
-            const int q0 = qb * ATT_BLOCK;
-            const int kvl = __ldg(kv_info + 2 * n);
-            const int nkv = (kvl + ATT_BLOCK - 1) / ATT_BLOCK;
-            const long long row_base = static_cast<long long>(n) * k_tokens;
-            if (nkv == 0) {          // all-pad sequence: not in the stream; zero-fill (the reference never encodes one)
-                if (q0 + r < k_tokens) {
-                    uint4* o = reinterpret_cast<uint4*>(out + (row_base + q0 + r) * h + head * D);
-                    for (int i = 0; i < D / 8; ++i) o[i] = make_uint4(0, 0, 0, 0);
-                }
+            const Item w = decode(item);
+            const int q0 = w.q0 + x * ATT_BLOCK;
+            const bool interior = w.n_nonpad != w.kvl;
+            const long long row_base = static_cast<long long>(w.n) * k_tokens;
+            const bool row_ok = q0 + r < k_tokens;
+            __nv_bfloat16* orow = out + (row_base + q0 + r) * h + w.head * D;
+            if (w.nkv == 0) {                                 // all-pad sequence: the reference never encodes one
+                if (row_ok)
+                    for (int i = 0; i < D / 8; ++i) reinterpret_cast<uint4*>(orow)[i] = make_uint4(0, 0, 0, 0);
                 continue;
             }
-            const bool interior = __ldg(kv_info + 2 * n + 1) != kvl;       // pad ids before the last real token
-            float m_run = -CUDART_INF_F;      // running reference max, log2 domain
-            float l_run = 0.f;
-            for (int j = 0; j < nkv; ++j, ++g) {
-                if (threadIdx.x == 0) MOLLY_DBG(1, g, 0);
-                mbar_wait(bar_s_full, g & 1);
-                if (threadIdx.x == 0) MOLLY_DBG(1, g, 1);
-                tc_fence_after();
-                float s[ATT_BLOCK];
-                {
-                    uint32_t raw[ATT_BLOCK];
-                    tmem_ld32(tmem_s + lane_addr + 0, raw);
-                    tmem_ld32(tmem_s + lane_addr + 32, raw + 32);
-                    tmem_ld32(tmem_s + lane_addr + 64, raw + 64);
-                    tmem_ld32(tmem_s + lane_addr + 96, raw + 96);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < ATT_BLOCK; ++i) s[i] = __uint_as_float(raw[i]);
-                }
-                tc_fence_before();
-                mbar_arrive(bar_s_free);                     // S(g) is in registers: the MMA warp may start S(g+1)
-                if (threadIdx.x == 0) MOLLY_DBG(1, g, 2);
-                const int j0 = j * ATT_BLOCK;
-                if (interior) {
-                    const uint4* mk = reinterpret_cast<const uint4*>(key_mask + row_base + j0);
-                    const bool vec_ok = ((row_base + j0) & 15) == 0 && j0 + ATT_BLOCK <= k_tokens;
-#pragma unroll
-                    for (int gq = 0; gq < 8; ++gq) {
-                        uint32_t w[4];
-                        if (vec_ok) {
-                            const uint4 u = __ldg(mk + gq);
-                            w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w;
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                w[i] = 0;
-#pragma unroll
-                                for (int b = 0; b < 4; ++b) {
-                                    const int cc = j0 + gq * 16 + i * 4 + b;
-                                    const uint32_t v = (cc < k_tokens) ? key_mask[row_base + cc] : 0;
-                                    w[i] |= (v & 0xffu) << (8 * b);
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const bool ok = ((w[i >> 2] >> (8 * (i & 3))) & 0xffu) != 0 && (j0 + gq * 16 + i < kvl);
-                            if (!ok) s[gq * 16 + i] = -CUDART_INF_F;
-                        }
-                    }
-                } else if (j0 + ATT_BLOCK > kvl) {
-                    const int lim = kvl - j0;
-#pragma unroll
-                    for (int i = 0; i < ATT_BLOCK; ++i)
-                        if (i >= lim) s[i] = -CUDART_INF_F;
-                }
-                float mx4[4] = {s[0], s[1], s[2], s[3]};
-#pragma unroll
-                for (int i = 4; i < ATT_BLOCK; i += 4) {
-                    mx4[0] = fmaxf(mx4[0], s[i]); mx4[1] = fmaxf(mx4[1], s[i + 1]);
-                    mx4[2] = fmaxf(mx4[2], s[i + 2]); mx4[3] = fmaxf(mx4[3], s[i + 3]);
-                }
-                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-                // lazy rescaling (see the non-persistent kernel): move the reference max only when it grew by > 2^8
-                const float m_cand = fmaxf(m_run, mx * LOG2E);
-                float alpha = 1.0f;
-                if (m_cand > m_run + 8.0f) {
-                    alpha = ex2(m_run - m_cand);
-                    m_run = m_cand;
-                }
-                const float m_use = (m_run == -CUDART_INF_F) ? 0.f : m_run;
-                const uint64_t sc2 = pack_f32x2(LOG2E, LOG2E), nm2 = pack_f32x2(-m_use, -m_use);
-                uint64_t sum2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
-                // The warp issues in order: an add placed right behind its two MUFU producers stalls for the MUFU latency
-                // and idles the XU pipe.  The row sum therefore trails the exponentials by SUM_LAG pairs.
-                constexpr int SUM_LAG = 6;
-#pragma unroll
-                for (int i = 0; i < ATT_BLOCK / 2 + SUM_LAG; ++i) {
-                    if (i < ATT_BLOCK / 2) {
-                        float x0, x1;
-                        unpack_f32x2(fma_f32x2(pack_f32x2(s[2 * i], s[2 * i + 1]), sc2, nm2), x0, x1);
-                        s[2 * i] = ex2(x0);
-                        s[2 * i + 1] = ex2(x1);
-                    }
-                    if (i >= SUM_LAG) {
-                        const int k = i - SUM_LAG;
-                        sum2[k & 1] = add_f32x2(sum2[k & 1], pack_f32x2(s[2 * k], s[2 * k + 1]));
-                    }
-                }
-                float sa, sb, sc, sd;
-                unpack_f32x2(sum2[0], sa, sb);
-                unpack_f32x2(sum2[1], sc, sd);
-                l_run = l_run * alpha + ((sa + sb) + (sc + sd));
-                if (threadIdx.x == 0) MOLLY_DBG(1, g, 3);
-                // PV(g-1) must have consumed P (and, inside an item, finished O) before either is touched again
-                if (g > 0) {
-                    mbar_wait(&bar_v_empty[(g - 1) & 1], ((g - 1) >> 1) & 1);
-                    tc_fence_after();
-                }
-                // P -> TMEM as packed bf16 pairs: column c of lane r holds keys (2c, 2c+1) of query row r
-#pragma unroll
-                for (int hh = 0; hh < 4; ++hh) {             // 16 packed columns at a time keeps the register peak low
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2_alu(s[hh * 32 + 2 * i], s[hh * 32 + 2 * i + 1]);
-                    tmem_st16(tmem_p + lane_addr + hh * 16, pk);
-                }
-                if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll
-                    for (int cc = 0; cc < D / 16; ++cc) {
-                        uint32_t o[16];
-                        tmem_ld16(tmem_o + lane_addr + cc * 16, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st16(tmem_o + lane_addr + cc * 16, o);
-                    }
-                }
-                if (threadIdx.x == 0) MOLLY_DBG(1, g, 4);
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(bar_p_full);
-                if (threadIdx.x == 0) MOLLY_DBG(1, g, 5);
-            }
-            // item epilogue: O / l -> bf16 -> HBM, then hand O back to the MMA thread
-            mbar_wait(bar_o_full, it & 1);
+            float m_run = -CUDART_INF_F, l_run = 0.f;
+            for (int j = 0; j < w.nkv; ++j, ++g)
+                softmax_block<D, ATT_BLOCK, 0, true>(&bar_s_full[x], g & 1, &bar_s_free[x], &bar_pv_done[x], (g - 1) & 1,
+                                                     &bar_p_full[x], tmem_s, tmem_o, lane_addr, p_row, sw, interior,
+                                                     key_mask, row_base, j * ATT_BLOCK, w.kvl, k_tokens, j == 0, m_run,
+                                                     l_run, my_bar, other_bar, r == 0 && j < 7 && item < 2048, item,
+                                                     36 * x + 5 * j);
+            // epilogue: O / l -> bf16 -> HBM
+            mbar_wait(&bar_o_full[x], t & 1);
+            ++t;
             tc_fence_after();
             const float inv_l = 1.0f / l_run;
-            const bool row_ok = q0 + r < k_tokens;
-            __nv_bfloat16* orow = out + (row_base + q0 + r) * h + head * D;
 #pragma unroll
-            for (int cc = 0; cc < D / 16; ++cc) {
+            for (int c = 0; c < D / 16; ++c) {
                 uint32_t o[16];
-                tmem_ld16(tmem_o + lane_addr + cc * 16, o);
+                tmem_ld16(tmem_o + lane_addr + c * 16, o);
                 tmem_ld_wait();
                 if (row_ok) {
                     uint4 u0, u1;
@@ -758,84 +734,130 @@ attention_persistent_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_s
                     u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l);
                     u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l);
                     u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l);
-                    reinterpret_cast<uint4*>(orow + cc * 16)[0] = u0;
-                    reinterpret_cast<uint4*>(orow + cc * 16)[1] = u1;
+                    reinterpret_cast<uint4*>(orow + c * 16)[0] = u0;
+                    reinterpret_cast<uint4*>(orow + c * 16)[1] = u1;
                 }
             }
-            tc_fence_before();
-            mbar_arrive(bar_o_free);
-            ++it;
+            tc_fence_before();                                // O_X is read: the next item's PV may overwrite it
         }
+        if (x == 0) named_bar_sync(PP_BAR_A, 256);            // consume group B's last hand-over
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, PC::TMEM_COLS);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
-long long* g_attn_debug = nullptr;     // set through molly_attention_debug(); nullptr in production
+long long* g_attn_debug = nullptr;     // timeline buffer of -DATT_TIMELINE builds (molly_attention_debug); nullptr in production
 
-bool attention_persistent_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        // Measured (tools/attn_bench.py, ESM-650M layer shape): one item per CTA with P staged in shared memory 579 us,
-        // persistent + smem P 586 us, persistent + P in TMEM 666 us -> the simple kernel is the default;
-        // MOLLY_ATTN_PERSISTENT=1 selects the streamed, P-in-TMEM variant.
-        const char* e = getenv("MOLLY_ATTN_PERSISTENT");
-        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+// Grid of the item-streaming kernel: one CTA per resident slot (MOLLY_ATTN_STREAM=0: one CTA per item, for A/B timing).
+int attention_grid(int total_items, int ctas_per_sm) {
+    static int stream_items = -1;
+    if (stream_items < 0) {
+        const char* e = getenv("MOLLY_ATTN_STREAM");
+        stream_items = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
-    return v == 1;
+    const int slots = device_sm_count() * ctas_per_sm;
+    return (stream_items && total_items > slots) ? slots : total_items;
 }
 
-template <int D>
-int launch_attention_persistent(const CUtensorMap& tm, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
-                                const uint8_t* key_mask, void* out, cudaStream_t stream) {
-    using Cfg = AttnPCfg<D>;
-    auto kernel = attention_persistent_kernel<D>;
+template <int D, int KVB>
+int launch_attention_kvb(const AttnMaps& maps, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
+                         const uint8_t* key_mask, void* out, cudaStream_t stream) {
+    using Cfg = AttnCfg<D, KVB>;
+    auto kernel = attention_kernel<D, KVB, 0>;
     static bool configured = false;
     if (!configured) {
         MOLLY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    const int total = n_seq * heads * ((k_tokens + ATT_BLOCK - 1) / ATT_BLOCK);
-    const int slots = device_sm_count() * Cfg::MIN_CTAS;
-    const int grid = total < slots ? total : slots;
-    {   // dense-equivalent work 4*n*K*K*h (exact when every sequence is full length)
+    const int grid = attention_grid(n_seq * heads * ((k_tokens + ATT_BLOCK - 1) / ATT_BLOCK), Cfg::MIN_CTAS);
+    {
         ProfScope prof(PF_ATTENTION, 4.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
-        kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, n_seq, heads, k_tokens, h, kv_info, key_mask,
-                                                               static_cast<__nv_bfloat16*>(out), g_attn_debug);
+        kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(maps.q, maps.kv64, n_seq, heads, k_tokens, h, kv_info,
+                                                               key_mask, static_cast<__nv_bfloat16*>(out));
     }
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
     return MOLLY_OK;
 }
 
+// keys per KV block: 64 puts three CTAs on an SM at head_dim <= 64 (MOLLY_ATTN_KVB = 64 | 128 overrides)
+int attention_kvb(int d) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("MOLLY_ATTN_KVB");
+        forced = e == nullptr ? 0 : atoi(e);
+    }
+    if (forced == 64 && d <= 64) return 64;
+    if (forced == 128) return 128;
+    return (ATTN_KVB64_DEFAULT && d <= 64) ? 64 : 128;
+}
+
 template <int D>
-int launch_attention(const CUtensorMap& tm, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
+int launch_attention_pp(const AttnMaps& maps, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
+                        const uint8_t* key_mask, void* out, cudaStream_t stream) {
+    using Cfg = AttnPPCfg<D>;
+    auto kernel = attention_pp_kernel<D>;
+    static bool configured = false;
+    if (!configured) {
+        MOLLY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int nqb = (k_tokens + ATT_BLOCK - 1) / ATT_BLOCK;
+    const int total = n_seq * heads * ((nqb + 1) / 2);
+    const int grid = total < device_sm_count() ? total : device_sm_count();
+    {
+        ProfScope prof(PF_ATTENTION, 4.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
+        kernel<<<grid, PP_THREADS, Cfg::SMEM_BYTES, stream>>>(maps.q, n_seq, heads, k_tokens, h, kv_info, key_mask,
+                                                              static_cast<__nv_bfloat16*>(out));
+    }
+    count_launch();
+    MOLLY_CUDA(cudaGetLastError());
+    return MOLLY_OK;
+}
+
+bool attention_pp_enabled() {           // MOLLY_ATTN_PP = 0 | 1 overrides the default
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOLLY_ATTN_PP");
+        v = e == nullptr ? (ATTN_PP_DEFAULT ? 1 : 0) : (e[0] != '0');
+    }
+    return v == 1;
+}
+
+template <int D>
+int launch_attention(const AttnMaps& maps, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
                      const uint8_t* key_mask, void* out, cudaStream_t stream) {
-    if (attention_persistent_enabled())
-        return launch_attention_persistent<D>(tm, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
+    const CUtensorMap& tm = maps.q;
+    if constexpr (D <= 64) {
+        if (attention_pp_enabled() && k_tokens > ATT_BLOCK)
+            return launch_attention_pp<D>(maps, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
+        if (attention_kvb(D) == 64)
+            return launch_attention_kvb<D, 64>(maps, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
+    }
     using Cfg = AttnCfg<D>;
     static int poly = -1;             // pairs out of 4 whose exp2 runs on the FMA pipe (MOLLY_ATTN_POLY = 0 | 1 | 2)
     if (poly < 0) {
         const char* e = getenv("MOLLY_ATTN_POLY");
         poly = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : ATTN_POLY_DEFAULT;
     }
-    auto kernel = poly == 0 ? attention_kernel<D, 0> : (poly == 1 ? attention_kernel<D, 1> : attention_kernel<D, 2>);
+    auto kernel = poly == 0 ? attention_kernel<D, 128, 0>
+                            : (poly == 1 ? attention_kernel<D, 128, 1> : attention_kernel<D, 128, 2>);
     static bool configured = false;
     if (!configured) {
-        MOLLY_CUDA(cudaFuncSetAttribute(attention_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        MOLLY_CUDA(cudaFuncSetAttribute(attention_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        MOLLY_CUDA(cudaFuncSetAttribute(attention_kernel<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MOLLY_CUDA(cudaFuncSetAttribute(attention_kernel<D, 128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MOLLY_CUDA(cudaFuncSetAttribute(attention_kernel<D, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MOLLY_CUDA(cudaFuncSetAttribute(attention_kernel<D, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    dim3 grid((k_tokens + ATT_BLOCK - 1) / ATT_BLOCK, heads, n_seq);
+    const int grid = attention_grid(n_seq * heads * ((k_tokens + ATT_BLOCK - 1) / ATT_BLOCK), Cfg::MIN_CTAS);
     {   // dense-equivalent work 4*n*K*K*h (exact when every sequence is full length)
         ProfScope prof(PF_ATTENTION, 4.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
-        kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, k_tokens, h, kv_info, key_mask,
+        kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, tm, n_seq, heads, k_tokens, h, kv_info, key_mask,
                                                                static_cast<__nv_bfloat16*>(out));
     }
     count_launch();
@@ -845,17 +867,24 @@ int launch_attention(const CUtensorMap& tm, int n_seq, int k_tokens, int h, int 
 
 }  // namespace
 
-void attention_set_debug(long long* buf) { g_attn_debug = buf; }
+void attention_set_debug(long long* buf) {
+    g_attn_debug = buf;
+#ifdef ATT_TIMELINE
+    cudaMemcpyToSymbol(d_attn_tl, &buf, sizeof(buf));
+#endif
+}
 
-int attention_make_map(CUtensorMap* tq, const void* qkv, int rows, int h, int heads) {
+int attention_make_map(AttnMaps* maps, const void* qkv, int rows, int h, int heads) {
     const int d = h / heads;
     MOLLY_CHECK(d == 16 || d == 32 || d == 64 || d == 128, MOLLY_ERR_UNSUPPORTED,
                 "attention: head_dim %d not in {16,32,64,128}", d);
     const int box_d = d < 64 ? d : 64;
-    return make_tma_2d(tq, qkv, rows, 3 * h, 3 * h, ATT_BLOCK, box_d, 2);
+    int rc = make_tma_2d(&maps->q, qkv, rows, 3 * h, 3 * h, ATT_BLOCK, box_d, 2);
+    if (rc) return rc;
+    return make_tma_2d(&maps->kv64, qkv, rows, 3 * h, 3 * h, 64, box_d, 2);
 }
 
-int attention_launch(const CUtensorMap& tqkv, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
+int attention_launch(const AttnMaps& tqkv, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
                      const uint8_t* key_mask, void* out, cudaStream_t stream) {
     MOLLY_CHECK(n_seq > 0 && k_tokens > 0 && heads > 0 && h % heads == 0, MOLLY_ERR_INVALID,
                 "attention: bad shape n_seq=%d k=%d h=%d heads=%d", n_seq, k_tokens, h, heads);

@@ -41,8 +41,12 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap*
 
 // ---- attention.cu ----
 void attention_set_debug(long long* buf);
-int attention_make_map(CUtensorMap* tq, const void* qkv, int rows, int h, int heads);
-int attention_launch(const CUtensorMap& tqkv, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_len,
+struct AttnMaps {          // views of the packed [rows, 3h] QKV activation
+    CUtensorMap q;         // 128-row boxes (Q tiles; K/V tiles of the 128-key kernels)
+    CUtensorMap kv64;      // 64-row boxes (K/V tiles of the 64-key kernel)
+};
+int attention_make_map(AttnMaps* maps, const void* qkv, int rows, int h, int heads);
+int attention_launch(const AttnMaps& tqkv, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_len,
                      const uint8_t* key_mask, void* out, cudaStream_t stream);
 
 // ---- rowwise.cu ----

@@ -53,11 +53,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {      // non-blocking probe
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 #ifndef MOLLY_MBAR_TIMEOUT_CYCLES
 #define MOLLY_MBAR_TIMEOUT_CYCLES 6000000000ll   // ~3-4 s of SM clocks; checked every 32 failed tries only
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef MOLLY_MBAR_TEST_FIRST
+    if (mbar_test_wait(bar, parity)) return;
+#endif
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     uint32_t spins = 0;
@@ -68,6 +82,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             __trap();
         }
     }
+}
+
+// named barriers (ids 1..15; 0 is __syncthreads): `count` threads in total execute sync or arrive on the same id
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 // ----------------------------------------------------------------------------------------------

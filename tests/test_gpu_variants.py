@@ -22,11 +22,26 @@ def test_single_cta_gemm_tiles():
     _run({"MOLLY_GEMM_PAIR": "0"}, "gemm")
 
 
-def test_persistent_attention_p_in_tmem():
-    """MOLLY_ATTN_PERSISTENT=1: streamed work items, P kept in TMEM (A operand from tensor memory), K/V rings."""
-    _run({"MOLLY_ATTN_PERSISTENT": "1"}, "attention")
+def test_one_cta_per_item_attention():
+    """MOLLY_ATTN_STREAM=0: grid = number of work items (no item streaming inside a CTA)."""
+    _run({"MOLLY_ATTN_STREAM": "0"}, "attention")
+
+
+def test_ping_pong_attention():
+    """MOLLY_ATTN_PP=1: one CTA per SM, two query tiles, the two softmax groups take turns on the MUFU."""
+    _run({"MOLLY_ATTN_PP": "1"}, "attention")
 
 
 def test_polynomial_exp2_attention():
     """MOLLY_ATTN_POLY=1|2: a quarter / half of the softmax exponentials evaluated on the FMA pipe (cubic, 1e-4 rel)."""
     _run({"MOLLY_ATTN_POLY": "2"}, "attention")
+
+
+def test_64_key_blocks_attention():
+    """MOLLY_ATTN_KVB=64: 64-key KV blocks (128 TMEM columns, 64 KB smem: three CTAs per SM at head_dim <= 64)."""
+    _run({"MOLLY_ATTN_KVB": "64"}, "attention")
+
+
+def test_128_key_blocks_attention():
+    """MOLLY_ATTN_KVB=128: the 128-key kernel, whichever is the default."""
+    _run({"MOLLY_ATTN_KVB": "128"}, "attention")

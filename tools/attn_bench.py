@@ -26,6 +26,6 @@ def run(heads, d, k, n_seq, tag):
     fl = 4.0 * n_seq * k * k * h
     print(f"{tag}: {t*1e3:.1f} us  {fl/t/1e9:.1f} TFLOP/s")
 
-print("lib", _lib.LIB_PATH, "persistent", os.environ.get("MOLLY_ATTN_PERSISTENT", "1"))
+print("lib", _lib.LIB_PATH, {k: v for k, v in os.environ.items() if k.startswith("MOLLY_ATTN")})
 run(20, 64, 1024, 64, "ESM-650M layer (20 heads x 64, K=1024, 64 seqs)")
 run(16, 64, 1024, 64, "NT-v2-500M layer (16 heads x 64, K=1024, 64 seqs)")
