@@ -169,46 +169,67 @@ class FastOmicsPath:
             raise ValueError("input_ids must be [B, T] and embed_weight [vocab, D]")
         dev = embed_weight.device
         input_ids = input_ids.to(dev, torch.int64, non_blocking=True).contiguous()
-        B, T = input_ids.shape
-        for i in range(len(omic_ids_list)):                                                  # omics_one.py:166-170
-            assert len(omic_ids_list[i]) == len(omic_info_list[i]), f"Mismatch in omic count vs info count at index {i}"
-        nt_plan, pr_plan = planner.route(B, omic_ids_list, omic_info_list)                   # may raise ValueError
-        n_slots = [0] * B
-        for plan in (nt_plan, pr_plan):
-            for b, r in zip(plan.b_idx, plan.run_idx):
-                n_slots[b] = max(n_slots[b], r + 1)
-        caps = {}
-        for name, plan in (("dna_rna", nt_plan), ("protein", pr_plan)):
-            caps[name] = 0
-            if len(plan):
-                if name not in self._ids:
-                    raise RuntimeError(f"Error processing omic sequences: no {name} encoder is loaded")
-                enc = ops.get_encoder(self._ids[name])
-                k_ids = omic_ids_list.shape[-1] if isinstance(omic_ids_list, torch.Tensor) else \
-                    omic_ids_list[plan.b_idx[0]][plan.slot_idx[0]].shape[-1]
-                caps[name] = min(enc.project_token_num, int(k_ids))
-        slots_dev = torch.tensor(n_slots, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
-        runs = ops.placeholder_runs(input_ids, tuple(pad_token_ids), slots_dev, max(1, max(n_slots)))
-        hidden = ops.embed_tokens_skip(input_ids, runs[4], tuple(pad_token_ids), caps["dna_rna"], caps["protein"],
-                                       embed_weight)
-        for name, plan in (("dna_rna", nt_plan), ("protein", pr_plan)):
-            if len(plan) == 0:
-                continue
-            enc_id = self._ids[name]
-            enc = ops.get_encoder(enc_id)
-            ids = planner.gather_ids(omic_ids_list, plan)
-            if not ids.is_cuda:
-                planner.check_vocab(ids, enc.cfg.vocab_size)
-                ids = ids.pin_memory().to(dev, non_blocking=True)
-            idx = torch.tensor([plan.b_idx, plan.run_idx], dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
-            seq_table = ops.build_seq_table(idx[0], idx[1], runs, expect_protein=(name == "protein"))
-            proj = self._proj_modules.get(name)
-            if proj is not None:
-                self._refresh_projector(name, enc, proj)
-            ops.encode_project_merge(hidden, ids, seq_table, enc_id, False)
+        meta = self._fused_meta(input_ids.shape[0], omic_ids_list, omic_info_list, dev)
+        ids = {}
+        for name, plan in meta["plans"].items():
+            t = planner.gather_ids(omic_ids_list, plan)
+            if not t.is_cuda:
+                planner.check_vocab(t, ops.get_encoder(self._ids[name]).cfg.vocab_size)
+                t = t.pin_memory().to(dev, non_blocking=True)
+            ids[name] = t
+        hidden = self._fused_run(input_ids, embed_weight, ids, meta, tuple(pad_token_ids))
         if self.strict:
             ops.check_device_errors(dev, "embed_and_process")
         return hidden
+
+    def _fused_meta(self, batch_size: int, omic_ids_list, omic_info_list, dev) -> dict:
+        """Host-side routing of one batch layout -> device index tables (constant for a CUDA-graph bucket)."""
+        for i in range(len(omic_ids_list)):                                                  # omics_one.py:166-170
+            assert len(omic_ids_list[i]) == len(omic_info_list[i]), f"Mismatch in omic count vs info count at index {i}"
+        nt_plan, pr_plan = planner.route(batch_size, omic_ids_list, omic_info_list)         # may raise ValueError
+        n_slots = [0] * batch_size
+        plans, caps, idx = {}, {"dna_rna": 0, "protein": 0}, {}
+        for name, plan in (("dna_rna", nt_plan), ("protein", pr_plan)):
+            if len(plan) == 0:
+                continue
+            if name not in self._ids:
+                raise RuntimeError(f"Error processing omic sequences: no {name} encoder is loaded")
+            for b, r in zip(plan.b_idx, plan.run_idx):
+                n_slots[b] = max(n_slots[b], r + 1)
+            k_ids = omic_ids_list.shape[-1] if isinstance(omic_ids_list, torch.Tensor) else \
+                omic_ids_list[plan.b_idx[0]][plan.slot_idx[0]].shape[-1]
+            caps[name] = min(ops.get_encoder(self._ids[name]).project_token_num, int(k_ids))
+            plans[name] = plan
+            idx[name] = torch.tensor([plan.b_idx, plan.run_idx, plan.slot_idx], dtype=torch.int32).pin_memory().to(
+                dev, non_blocking=True)
+        slots_dev = torch.tensor(n_slots, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+        return {"plans": plans, "caps": caps, "idx": idx, "slots": slots_dev, "max_runs": max(1, max(n_slots))}
+
+    def _fused_run(self, input_ids, embed_weight, ids: dict, meta: dict, pad_token_ids) -> torch.Tensor:
+        """Device-only part (capturable): run scan -> skipping embedding lookup -> per modality seq_table + encode/merge."""
+        runs = ops.placeholder_runs(input_ids, pad_token_ids, meta["slots"], meta["max_runs"])
+        hidden = ops.embed_tokens_skip(input_ids, runs[4], pad_token_ids, meta["caps"]["dna_rna"], meta["caps"]["protein"],
+                                       embed_weight)
+        for name in ("dna_rna", "protein"):                                                  # reference order, :120-134
+            if name not in meta["plans"]:
+                continue
+            enc_id = self._ids[name]
+            idx = meta["idx"][name]
+            seq_table = ops.build_seq_table(idx[0], idx[1], runs, expect_protein=(name == "protein"))
+            proj = self._proj_modules.get(name)
+            if proj is not None:
+                self._refresh_projector(name, ops.get_encoder(enc_id), proj)
+            ops.encode_project_merge(hidden, ids[name], seq_table, enc_id, False)
+        return hidden
+
+    # ------------------------------------------------------------------ SURVEY 8f row N2: one CUDA graph per bucket
+    def graphed(self, embed_weight: torch.Tensor, batch_size: int, seq_len: int, omic_types: List[List[str]], k_tokens: int,
+                pad_token_ids) -> "GraphedOmicsCall":
+        """Capture ``embed_and_process`` for one fixed bucket -- (B, T), the per-sample modality layout ``omic_types`` and K --
+        into a CUDA graph (``generate`` runs the path once per batch right before a long decode, omics_one.py:187-233: at
+        small B the ~200-450 launches, not the math, set the latency).  The returned callable copies the new ``input_ids``
+        and ``omic_ids`` into its static buffers, replays, and returns its static ``inputs_embeds`` buffer."""
+        return GraphedOmicsCall(self, embed_weight, batch_size, seq_len, omic_types, k_tokens, tuple(pad_token_ids))
 
     def _refresh_projector(self, name: str, enc: PackedEncoder, proj) -> None:
         ver = (proj.weight._version, proj.bias._version, proj.weight.data_ptr())
@@ -225,3 +246,50 @@ class FastOmicsPath:
         """Masked mean-pool (embed_text.py:112-129) or CLS read-out (baselines/model.py:104-120), fp32 [n, h]."""
         ids = ids.to(torch.int64).contiguous()
         return ops.pool(self.encode(name, ids), ids, 0 if mode == "mean" else 1)
+
+
+class GraphedOmicsCall:
+    """One captured bucket of ``FastOmicsPath.embed_and_process`` (see ``FastOmicsPath.graphed``)."""
+
+    def __init__(self, path: FastOmicsPath, embed_weight: torch.Tensor, batch_size: int, seq_len: int,
+                 omic_types: List[List[str]], k_tokens: int, pad_token_ids):
+        dev = embed_weight.device
+        self.path, self.embed_weight, self.pad_token_ids = path, embed_weight, pad_token_ids
+        infos = [[{"type": t, "start": -1} for t in row] for row in omic_types]
+        n_max = max(1, max(len(r) for r in omic_types))
+        for row in infos:                                                       # collate-style padding (omics_dataset.py:480-492)
+            row.extend({"type": "pad", "start": -1} for _ in range(n_max - len(row)))
+        self.input_ids = torch.zeros(batch_size, seq_len, dtype=torch.int64, device=dev)
+        self.omic_ids = torch.ones(batch_size, n_max, k_tokens, dtype=torch.int64, device=dev)
+        self.meta = path._fused_meta(batch_size, self.omic_ids, infos, dev)
+        self.gather = {name: (idx[0].long(), idx[2].long()) for name, idx in self.meta["idx"].items()}
+        need = 0
+        for name, plan in self.meta["plans"].items():
+            need = max(need, ops.get_encoder(path._ids[name]).workspace_bytes(len(plan), k_tokens))
+        self.workspace = torch.empty(need + 8192, dtype=torch.uint8, device=dev)
+        with ops.use_workspace(self.workspace):
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                                       # warm-up: lazy attribute setting, plan caches
+                self._run()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            ops.error_flag(dev).zero_()              # the all-zero warm-up input has no placeholder runs: ERRBIT_LAYOUT
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self._run()
+
+    @torch.no_grad()
+    def _run(self) -> torch.Tensor:
+        ids = {name: self.omic_ids[bi, si].contiguous() for name, (bi, si) in self.gather.items()}
+        return self.path._fused_run(self.input_ids, self.embed_weight, ids, self.meta, self.pad_token_ids)
+
+    def __call__(self, input_ids: torch.Tensor, omic_ids: torch.Tensor) -> torch.Tensor:
+        """``input_ids`` [B, T] and collated ``omic_ids`` [B, Nmax, K] of this bucket (host or device) -> inputs_embeds
+        (the call's static output buffer: consume or clone it before the next call)."""
+        self.input_ids.copy_(input_ids, non_blocking=True)
+        self.omic_ids.copy_(omic_ids, non_blocking=True)
+        self.graph.replay()
+        if self.path.strict:
+            ops.check_device_errors(self.out.device, "GraphedOmicsCall")
+        return self.out

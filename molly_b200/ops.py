@@ -65,8 +65,36 @@ def _dtype_code(t: Tensor) -> int:
     raise ValueError(f"unsupported dtype {t.dtype}: the path writes bf16 or fp32 hidden_states")
 
 
+_WS_PINNED: Dict[int, Tensor] = {}      # device index -> caller-owned workspace (CUDA-graph capture)
+
+
+class use_workspace:
+    """``with use_workspace(ws):`` every op on ``ws.device`` scratches in ``ws`` (a uint8 tensor that outlives the block's
+    kernels).  CUDA-graph capture needs it: the workspace must be allocated outside the capture and keep its address."""
+
+    def __init__(self, ws: Tensor):
+        self.ws, self.idx = ws, ws.device.index if ws.device.index is not None else torch.cuda.current_device()
+
+    def __enter__(self):
+        self.prev = _WS_PINNED.get(self.idx)
+        _WS_PINNED[self.idx] = self.ws
+        return self.ws
+
+    def __exit__(self, *exc):
+        if self.prev is None:
+            _WS_PINNED.pop(self.idx, None)
+        else:
+            _WS_PINNED[self.idx] = self.prev
+        return False
+
+
 def workspace(dev: torch.device, nbytes: int) -> Tensor:
     """Grow-only scratch buffer per (device, stream); stable pointers keep the library's TMA-descriptor plan cached."""
+    pinned = _WS_PINNED.get(dev.index if dev.index is not None else torch.cuda.current_device())
+    if pinned is not None:
+        if pinned.numel() < nbytes + 1024:
+            raise RuntimeError(f"pinned workspace too small: {pinned.numel()} < {nbytes + 1024} bytes")
+        return pinned
     key = (dev.index if dev.index is not None else torch.cuda.current_device(),
            torch.cuda.current_stream(dev).cuda_stream)
     ws = _WORKSPACES.get(key)
