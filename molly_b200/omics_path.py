@@ -237,6 +237,52 @@ class FastOmicsPath:
             enc.load_projector(proj.weight, proj.bias)
             self._proj_versions[name] = ver
 
+    # ------------------------------------------------------------------ projector checkpoints
+    PROJECTOR_FILES = {"dna_rna": "dna_rna_projector.bin", "protein": "protein_projector.bin"}
+
+    def save_projectors(self, output_dir: str) -> List[str]:
+        """Write ``dna_rna_projector.bin`` / ``protein_projector.bin`` exactly as ``OmicsTrainer.save_model`` does
+        (src/trainer/omics_trainer.py:92-103): ``torch.save`` of the ``nn.Linear`` state dict {"weight" [D, h], "bias" [D]}.
+        Live ``nn.Linear`` modules (``from_omics_one``) are the source when present, else the packed device copies."""
+        import os
+        os.makedirs(output_dir, exist_ok=True)
+        written = []
+        for name, fname in self.PROJECTOR_FILES.items():
+            if name not in self._ids:
+                continue
+            proj = self._proj_modules.get(name)
+            if proj is not None:
+                sd = {k: v.detach().cpu() for k, v in proj.state_dict().items()}
+            else:
+                enc = ops.get_encoder(self._ids[name])
+                sd = {"weight": enc.proj_w.detach().cpu().clone(), "bias": enc.proj_b.detach().cpu().clone()}
+            torch.save(sd, os.path.join(output_dir, fname))
+            written.append(os.path.join(output_dir, fname))
+        return written
+
+    def load_projectors(self, trained_model_path: str) -> List[str]:
+        """Load the two ``*.bin`` projector state dicts if present (src/inference_lora.py:218-234: missing files are
+        skipped silently) into the live modules and the packed kernel buffers."""
+        import os
+        loaded = []
+        for name, fname in self.PROJECTOR_FILES.items():
+            fpath = os.path.join(trained_model_path, fname)
+            if name not in self._ids or not os.path.exists(fpath):
+                continue
+            sd = torch.load(fpath, map_location="cpu")
+            enc = ops.get_encoder(self._ids[name])
+            if tuple(sd["weight"].shape) != tuple(enc.proj_w.shape) or tuple(sd["bias"].shape) != tuple(enc.proj_b.shape):
+                raise RuntimeError(f"size mismatch for {fname}: weight {tuple(sd['weight'].shape)} vs "
+                                   f"{tuple(enc.proj_w.shape)}")                 # what load_state_dict raises
+            proj = self._proj_modules.get(name)
+            if proj is not None:
+                proj.load_state_dict(sd)
+                self._refresh_projector(name, enc, proj)
+            else:
+                enc.load_projector(sd["weight"].to(enc.proj_w.device), sd["bias"].to(enc.proj_b.device))
+            loaded.append(fpath)
+        return loaded
+
     # ------------------------------------------------------------------ other consumers of the encoder (SURVEY 8f N3)
     def encode(self, name: str, ids: torch.Tensor) -> torch.Tensor:
         """``hidden_states[-1]`` of the named encoder for ``ids`` [n, K] -> bf16 [n, K, h]."""

@@ -255,3 +255,30 @@ def test_pooled_heads():
         assert_close("cls", path.pooled("protein", ids.to(DEV), "cls"), last[:, 0], TOL)
     finally:
         path.close()
+
+
+def test_projector_checkpoint_round_trip(tmp_path):
+    """``dna_rna_projector.bin`` / ``protein_projector.bin`` in the reference's format (omics_trainer.py:92-103 writes them,
+    inference_lora.py:218-234 reads them): an ``nn.Linear`` state dict that loads into a fresh path and gives the same rows."""
+    case = cases.golden_cases()["tiny_rotary_glu"]
+    a = build_path(case)
+    b = build_path(case)
+    try:
+        files = a.save_projectors(str(tmp_path))
+        assert sorted(os.path.basename(f) for f in files) == ["dna_rna_projector.bin", "protein_projector.bin"]
+        sd = torch.load(files[0], map_location="cpu")
+        lin = torch.nn.Linear(sd["weight"].shape[1], sd["weight"].shape[0])
+        lin.load_state_dict(sd)                                          # the reference's load path accepts it
+        for enc in (b.dna_rna, b.protein):                               # scramble b's projectors, then restore from disk
+            enc.load_projector(torch.zeros_like(enc.proj_w), torch.ones_like(enc.proj_b))
+        hs = case.batch.hidden_states.to(DEV)
+        want = a.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
+        off = b.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
+        assert not torch.equal(off, want)
+        assert len(b.load_projectors(str(tmp_path))) == 2
+        got = b.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
+        assert torch.equal(got, want)
+        assert b.load_projectors(str(tmp_path / "nowhere")) == []        # missing files are skipped like the reference
+    finally:
+        a.close()
+        b.close()
