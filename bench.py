@@ -63,6 +63,10 @@ WORKLOADS = {
     # BASELINE.json configs[0] -- the reference's own CPU-runnable case (parity config; selectable for quick runs)
     "molly_mini": dict(desc="Molly-mini: ESM-2 t6-8M + NT-v2-50M -> Qwen3-0.6B merge (D=1024)",
                        nt="nt_v2_50m", pr="esm2_t6_8m", D=1024, B=4, K=512, T=2048, valid=512),
+    # BASELINE.json configs[4] -- the path's share of one training step (--train-mlp): forward with the encoder output kept,
+    # projector backward (dW, db of both modalities) from a given d(inputs_embeds), one flat grad all-reduce (mean)
+    "train_1p7b": dict(desc="Molly-1.7B train step, path only: fwd + projector bwd + grad all-reduce (B=8/GPU)",
+                       nt="nt_v2_500m", pr="esm2_t33_650m", D=2048, B=8, K=1024, T=3072, valid=1024, train=True),
 }
 
 
@@ -282,6 +286,83 @@ def run_reference_arm(args, wl: dict, rank: int, world: int) -> None:
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def run_train_step(args, wl: dict, dev, rank: int, world: int, warmup: int) -> None:
+    """cfg-5: what the path contributes to one training step.  The LLM's own forward/backward is out of
+    scope; its product, d(loss)/d(inputs_embeds), is a fixed synthetic bf16 tensor."""
+    import torch
+    import torch.distributed as dist
+    from molly_b200 import ops
+    from molly_b200.dist import FlatGradBucket
+    path = build_path(wl, dev, strict=False)
+    projs = {}
+    for name, enc in (("dna_rna", path.dna_rna), ("protein", path.protein)):     # live nn.Linear modules, as in OmicsOne
+        lin = torch.nn.Linear(enc.proj_w.shape[1], enc.proj_w.shape[0], device=dev, dtype=torch.bfloat16)
+        with torch.no_grad():
+            lin.weight.copy_(enc.proj_w)
+            lin.bias.copy_(enc.proj_b)
+        projs[name] = lin
+    path._proj_modules = projs
+    params = [p for lin in projs.values() for p in lin.parameters()]
+    bucket = FlatGradBucket(params) if world > 1 else None
+    omic_ids, infos = make_inputs(wl, seed=1234 + rank)
+    omic_ids_dev = omic_ids.to(dev)
+    base = (torch.randn(wl["B"], wl["T"], wl["D"], device=dev) * 0.02).to(torch.bfloat16)
+    d_out = (torch.randn(wl["B"], wl["T"], wl["D"], device=dev) * 1e-3).to(torch.bfloat16)
+    tokens_per_step = wl["B"] * 2 * wl["K"]
+
+    def step():
+        for p in params:
+            p.grad = None
+        hs = base.clone()
+        out = path.process_omic_sequences(hs, omic_ids_dev, infos, dev)
+        out.backward(d_out)
+        if bucket is not None:
+            bucket.launch()
+            bucket.finish()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    assert all(p.grad is not None and torch.isfinite(p.grad.float()).all() for p in params)
+    props = torch.cuda.get_device_properties(dev)
+    sampler = ClockSampler("GPU-" + str(props.uuid))
+    l0 = ops.kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    launches = ops.kernel_launch_count() - l0
+    ops.profile_start()
+    step()
+    torch.cuda.synchronize()
+    prof = ops.profile_stop()
+    kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in prof.items()}
+    grad_elems = sum(p.numel() for p in params)
+    line = {"metric": METRIC, "value": world * tokens_per_step * args.steps / (total_ms / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl["desc"], "B_per_gpu": wl["B"], "K": wl["K"], "T": wl["T"], "D": wl["D"],
+                       "parallelism": f"sample-sharded x{world}, flat grad bucket all-reduce ({grad_elems} elements)",
+                       "trainable": "both projectors (weight + bias); encoders frozen"},
+            "clocks": clocks, "gpu_launches": launches, "kernels": kernels}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    path.close()
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -312,6 +393,11 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
 
+    if wl.get("train"):
+        run_train_step(args, wl, dev, rank, world, warmup)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     path = build_path(wl, dev, strict=False)
     omic_ids, infos = make_inputs(wl, seed=1234 + rank)
     omic_ids_dev = omic_ids.to(dev)
