@@ -65,6 +65,14 @@ WORKLOADS = {
                        nt="nt_v2_50m", pr="esm2_t6_8m", D=1024, B=4, K=512, T=2048, valid=512),
     # BASELINE.json configs[4] -- the path's share of one training step (--train-mlp): forward with the encoder output kept,
     # projector backward (dW, db of both modalities) from a given d(inputs_embeds), one flat grad all-reduce (mean)
+    # BASELINE.json configs[2] -- variable lengths: one sequence per sample, kind uniform in {dna, rna, protein}, length
+    # log-uniform in [64, 2048], K = 2048 (pad rows are computed and written like the reference; keys beyond the length are not)
+    "molly_4b": dict(desc="Molly-4B: ESM-2 650M + NT-v2 500M -> Qwen3-4B merge (D=2560), mixed kinds, log-uniform lengths",
+                     nt="nt_v2_500m", pr="esm2_t33_650m", D=2560, B=64, K=2048, T=4096, valid=2048, layout="mixed_varlen"),
+    # BASELINE.json configs[3] -- the biggest GEMMs: NT-v1 2.5B (h=2560, F=10240, head_dim 128, learned positions), 1000-bp
+    # DNA windows = 171 tokens in K=256 slots; the protein encoder is loaded but idle
+    "molly_8b": dict(desc="Molly-8B: NT-v1 2.5B multispecies -> Qwen3-8B merge (D=4096), 256 x 1000-bp DNA windows",
+                     nt="nt_v1_2p5b", pr="esm2_t6_8m", D=4096, B=256, K=256, T=512, valid=171, layout="dna_only"),
     "train_1p7b": dict(desc="Molly-1.7B train step, path only: fwd + projector bwd + grad all-reduce (B=8/GPU)",
                        nt="nt_v2_500m", pr="esm2_t33_650m", D=2048, B=8, K=1024, T=3072, valid=1024, train=True),
 }
@@ -139,24 +147,62 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------------------------
 def make_inputs(wl: dict, seed: int = 1234):
-    """Host-side synthetic batch shaped like the reference's dataset + collate."""
+    """Host-side synthetic batch shaped like the reference's dataset + collate: collated
+    ``omic_ids [B, Nmax, K]`` (pad id 1) and ``omic_info_list`` with the dataset's ``start`` positions."""
+    import math
     import torch
     g = torch.Generator().manual_seed(seed)
     B, K, T, valid = wl["B"], wl["K"], wl["T"], wl["valid"]
     nt_vocab = ENC[wl["nt"]]["vocab_size"]
-    omic_ids = torch.ones(B, 2, K, dtype=torch.int64)
-    omic_ids[:, 0, :valid] = torch.randint(6, nt_vocab - 5, (B, valid), generator=g)       # DNA k-mers, <cls>=3
-    omic_ids[:, 0, 0] = 3
-    omic_ids[:, 1, :valid] = torch.randint(4, 24, (B, valid), generator=g)                 # residues, <cls>=0 <eos>=2
-    omic_ids[:, 1, 0] = 0
-    omic_ids[:, 1, valid - 1] = 2
-    infos = []
+    layout = wl.get("layout", "pair")
+
+    def nt_seq(n):
+        row = torch.ones(K, dtype=torch.int64)
+        row[:n] = torch.randint(6, nt_vocab - 5, (n,), generator=g)             # k-mers, <cls>=3
+        row[0] = 3
+        return row
+
+    def pr_seq(n):
+        row = torch.ones(K, dtype=torch.int64)
+        row[:n] = torch.randint(4, 24, (n,), generator=g)                       # residues, <cls>=0 <eos>=2
+        row[0] = 0
+        row[n - 1] = 2
+        return row
+
+    rows, infos = [], []
     for b in range(B):
-        s0 = 20 + (b % 7)                                   # text prefix, then DNA run, 30 text tokens, protein run
-        s1 = s0 + K + 2 + 30
-        assert s1 + K + 2 <= T
-        infos.append([{"type": "dna", "start": s0}, {"type": "protein", "start": s1}])
-    return omic_ids, infos
+        s0 = 20 + (b % 7)                                                       # text prefix before the first run
+        if layout == "pair":                                                    # DNA run, 30 text tokens, protein run
+            s1 = s0 + K + 2 + 30
+            assert s1 + K + 2 <= T
+            rows.append(torch.stack([nt_seq(valid), pr_seq(valid)]))
+            infos.append([{"type": "dna", "start": s0}, {"type": "protein", "start": s1}])
+        elif layout == "mixed_varlen":
+            kind = ("dna", "rna", "protein")[int(torch.randint(0, 3, (1,), generator=g))]
+            n = int(round(math.exp(float(torch.rand(1, generator=g)) * math.log(valid / 64.0)) * 64))
+            rows.append(torch.stack([pr_seq(n) if kind == "protein" else nt_seq(n)]))
+            infos.append([{"type": kind, "start": s0}])
+        elif layout == "dna_only":
+            rows.append(torch.stack([nt_seq(valid)]))
+            infos.append([{"type": "dna", "start": s0}])
+        else:
+            raise ValueError(layout)
+        assert infos[-1][-1]["start"] + K + 2 <= T
+    return torch.stack(rows), infos
+
+
+def batch_stats(wl: dict, omic_ids, infos):
+    """(omics rows per step, valid tokens per step, model FLOP per step) of one rank's batch."""
+    rows = valid = 0
+    flops = 0.0
+    for b, row in enumerate(infos):
+        for i, info in enumerate(row):
+            e = ENC[wl["pr"] if info["type"] == "protein" else wl["nt"]]
+            n = int((omic_ids[b, i] != 1).sum())
+            rows += wl["K"]
+            valid += n
+            flops += wl["K"] * flops_per_token(e, n, wl["D"])
+    return rows, valid, flops
 
 
 LLM_VOCAB = 151936                                         # Qwen3 embedding rows (config.json vocab_size)
@@ -247,6 +293,7 @@ def cpu_reference_run(wl: dict, steps: int, warmup: int, budget_s: float):
     def one(k_tokens: int) -> float:
         sub = dict(wl, B=1, K=k_tokens, valid=min(wl["valid"], k_tokens), T=2 * k_tokens + 128)
         ids, infos = make_inputs(sub)
+        one.n_seq = sum(len(r) for r in infos)
         hs = torch.zeros(1, sub["T"], D)
         nt.project_token_num = pr.project_token_num = k_tokens
         t0 = time.perf_counter()
@@ -264,8 +311,8 @@ def cpu_reference_run(wl: dict, steps: int, warmup: int, budget_s: float):
         one(k_tokens)
     times = [one(k_tokens) for _ in range(steps)]
     total = sum(times)
-    tokens = 2 * k_tokens * steps
-    sample = (f"{steps} step(s) x 1 sample (1 DNA + 1 protein sequence x {k_tokens} tokens) of {wl['desc']}; fp32 CPU oracle, "
+    tokens = one.n_seq * k_tokens * steps
+    sample = (f"{steps} step(s) x 1 sample ({one.n_seq} sequence(s) x {k_tokens} tokens) of {wl['desc']}; fp32 CPU oracle, "
               f"{cores} torch threads")
     return tokens / total, 1e3 * total / steps, sample, cores
 
@@ -403,7 +450,8 @@ def main() -> None:
     omic_ids_dev = omic_ids.to(dev)
     omic_ids_pinned = omic_ids.pin_memory()
     hs = (torch.randn(wl["B"], wl["T"], wl["D"], device=dev) * 0.02).to(torch.bfloat16)
-    tokens_per_step = wl["B"] * 2 * wl["K"]
+    tokens_per_step, valid_per_step, model_flops = batch_stats(wl, omic_ids, infos)
+    n_seqs = sum(len(r) for r in infos)
 
     def barrier():
         if world > 1:
@@ -440,7 +488,7 @@ def main() -> None:
     # ---- end-to-end arm: ids from pinned host memory, strict errors, one merged row read back per step
     path.strict = True
     b0, t0 = 0, infos[0][0]["start"] + 1
-    h2d = omic_ids.numel() * 8 + 2 * wl["B"] * 2 * 4                 # ids + two (b, start) tables
+    h2d = omic_ids.numel() * 8 + n_seqs * 2 * 4                      # ids + the (b, start) tables
     d2h = wl["D"] * 2 + 2 * 4                                        # one merged row + error flag reads
 
     def step_e2e():
@@ -464,12 +512,13 @@ def main() -> None:
     del a, b
     two_ms = timed(two_step, args.steps) / args.steps
     fused_ms = timed(fused, args.steps) / args.steps
-    text_rows = wl["B"] * (wl["T"] - 2 * wl["K"])
+    text_rows = wl["B"] * wl["T"] - tokens_per_step
     # the lookup alone (the step-level difference is below run-to-run noise): torch's gather vs scan + skipping gather
-    slots = torch.full((wl["B"],), 2, dtype=torch.int32, device=dev)
+    slots = torch.tensor([len(r) for r in infos], dtype=torch.int32, device=dev)
+    max_runs = max(len(r) for r in infos)
 
     def ours_lookup():
-        runs = ops.placeholder_runs(input_ids, PAD_TOKEN_IDS, slots, 2)
+        runs = ops.placeholder_runs(input_ids, PAD_TOKEN_IDS, slots, max_runs)
         return ops.embed_tokens_skip(input_ids, runs[4], PAD_TOKEN_IDS, wl["K"], wl["K"], table)
 
     lookup_torch_ms = timed(lambda: torch.nn.functional.embedding(input_ids, table), 20) / 20
@@ -515,16 +564,15 @@ def main() -> None:
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches": g_n, "avg_launch_ms": round(g_ms / max(g_n, 1), 4), "share_of_step": round(g_ms / tot_ms, 4),
                 "frac_of_burst": round(achieved / peaks["tflops_burst"], 4)}
-    model_flops = tokens_per_step / 2 * (flops_per_token(ENC[wl["nt"]], wl["valid"], wl["D"]) +
-                                         flops_per_token(ENC[wl["pr"]], wl["valid"], wl["D"]))
     step_ms = total_ms / args.steps
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": wl["desc"], "B_per_gpu": wl["B"], "seqs_per_sample": "1 dna + 1 protein", "K": wl["K"],
-                   "valid_len": wl["valid"], "T": wl["T"], "D": wl["D"], "parallelism": f"sample-sharded x{world}",
+        "config": {"workload": wl["desc"], "B_per_gpu": wl["B"], "layout": wl.get("layout", "pair: 1 dna + 1 protein per sample"),
+                   "seqs_per_gpu": n_seqs, "K": wl["K"], "valid_tokens_per_gpu": valid_per_step, "T": wl["T"], "D": wl["D"],
+                   "parallelism": f"sample-sharded x{world}",
                    "l2": "working set per step (>2 GB activations + weights) is far larger than the 126 MB L2; no flush needed",
                    "residual_stream": "fp32", "pad_rows": "computed and written (reference-exact)"},
         "clocks": clocks,
@@ -533,6 +581,7 @@ def main() -> None:
         "gpu_launches": launches,
         "roofline": roofline,
         "model_tflops_per_gpu": round(model_flops / (step_ms * 1e-3) / 1e12, 1),
+        "valid_tokens_per_s": round(world * valid_per_step / (step_ms * 1e-3), 1),
         "input_fusion": input_fusion,
         "kernels": kernels,
     }

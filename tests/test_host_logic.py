@@ -149,3 +149,24 @@ def test_oracle_placeholder_runs_reproduce_dataset_starts():
             real = [i for i in infos if i["type"] != "pad"]
             assert [r[0] - 1 for r in rr] == [i["start"] for i in real]
             assert [("dna", "rna", "protein")[r[1]] for r in rr] == [i["type"] for i in real]
+
+
+def test_bench_workloads_build_valid_batches():
+    """Every bench workload's synthetic batch obeys the dataset's layout (start, K pads, end) and the collate shapes."""
+    import bench
+    for name, wl in bench.WORKLOADS.items():
+        small = dict(wl, B=min(wl["B"], 6))
+        omic_ids, infos = bench.make_inputs(small, seed=5)
+        assert omic_ids.shape[0] == small["B"] and omic_ids.shape[2] == small["K"] and omic_ids.dtype == torch.int64
+        rows, valid, flops = bench.batch_stats(small, omic_ids, infos)
+        assert rows == small["K"] * sum(len(r) for r in infos) and 0 < valid <= rows and flops > 0
+        ids = bench.build_input_ids(small, infos)
+        runs = synth.placeholder_runs(ids, bench.PAD_TOKEN_IDS)
+        for rr, row in zip(runs, infos):
+            assert [r[0] - 1 for r in rr] == [i["start"] for i in row], name
+            assert all(r[2] == small["K"] for r in rr)
+        nt, pr = planner.route(small["B"], omic_ids, infos)
+        for plan, vocab in ((nt, bench.ENC[wl["nt"]]["vocab_size"]), (pr, bench.ENC[wl["pr"]]["vocab_size"])):
+            if len(plan):
+                planner.check_vocab(planner.gather_ids(omic_ids, plan), vocab)
+                planner.check_placement(plan, small["K"], small["B"], small["T"])
