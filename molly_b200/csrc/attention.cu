@@ -14,7 +14,7 @@
 //   * keys >= kv_len are never loaded (whole blocks skipped); interior pad keys use the byte mask
 // Two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
 // Variants kept for A/B timing (tests/test_gpu_variants.py): 64-key blocks / three CTAs per SM (MOLLY_ATTN_KVB=64), one CTA per
-// item (MOLLY_ATTN_STREAM=0), exp2 partly on the FMA pipe (MOLLY_ATTN_POLY), two-tile ping-pong CTA (MOLLY_ATTN_PP=1).
+// item (MOLLY_ATTN_STREAM=0), exp2 partly on the FMA pipe (MOLLY_ATTN_POLY), register-pipelined 64-key kernel (MOLLY_ATTN_PIPE=1).
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -48,7 +48,7 @@ constexpr int ATT_BLOCK = 128;                 // query rows per CTA == keys per
 constexpr int ATT_THREADS = 160;               // 4 softmax warps + 1 control warp
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int ATTN_POLY_DEFAULT = 0;           // set from the A/B measurement (tools/attn_bench.py)
-constexpr bool ATTN_PP_DEFAULT = false;        // two-tile ping-pong kernel at head_dim <= 64 (set from the A/B measurement)
+constexpr bool ATTN_PIPE_DEFAULT = false;      // register-pipelined 64-key kernel at head_dim <= 64 (set from the A/B measurement)
 constexpr bool ATTN_KVB64_DEFAULT = false;     // 64-key KV blocks (3 CTAs / SM) at head_dim <= 64
 
 template <int D, int KVB = 128>       // KVB = keys per KV block (128, or 64 to fit three CTAs per SM at head_dim <= 64)
@@ -103,15 +103,14 @@ __device__ __forceinline__ void exp2_poly_pair(float& x0, float& x1) {
 
 // One KV block of the online softmax for the 128 threads of a softmax group (thread = query row): S(g) from TMEM ->
 // mask -> running max (lazy rescale) -> P = exp2(S*log2e - m) as the bf16 K-major A operand in smem -> hand-off.
-template <int D, int KVB, int POLY, bool PINGPONG>
+template <int D, int KVB, int POLY>
 __device__ __forceinline__ void softmax_block(uint64_t* bar_s_full, uint32_t s_parity, uint64_t* bar_s_free,
                                               uint64_t* bar_pv_done, uint32_t pv_parity, uint64_t* bar_p_full,
                                               uint32_t tmem_s, uint32_t tmem_o, uint32_t lane_addr, uint8_t* p_row,
                                               int sw, bool interior, const uint8_t* __restrict__ key_mask,
                                               long long row_base, int j0, int kvl, int k_tokens, bool first,
-                                              float& m_run, float& l_run, int my_bar, int other_bar, bool tl_on,
-                                              int tl_id, int tl_base) {
-    (void)tl_on; (void)tl_id; (void)tl_base; (void)my_bar; (void)other_bar;
+                                              float& m_run, float& l_run, bool tl_on, int tl_id, int tl_base) {
+    (void)tl_on; (void)tl_id; (void)tl_base;
     mbar_wait(bar_s_full, s_parity);
     if (tl_on) TL(tl_base + 0);
     tc_fence_after();
@@ -182,7 +181,6 @@ __device__ __forceinline__ void softmax_block(uint64_t* bar_s_full, uint32_t s_p
     }
     const float m_use = (m_run == -CUDART_INF_F) ? 0.f : m_run;
     // exp2(s*log2e - m) and the row sum with packed fp32x2 FMA / ADD (FFMA2 / FADD2): half the issue slots
-    if (PINGPONG) named_bar_sync(my_bar, 256);            // my turn on the MUFU (see attention_pp_kernel)
     if (tl_on) TL(tl_base + 2);
     const uint64_t sc2 = pack_f32x2(LOG2E, LOG2E), nm2 = pack_f32x2(-m_use, -m_use);
     uint64_t sum2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
@@ -208,7 +206,6 @@ __device__ __forceinline__ void softmax_block(uint64_t* bar_s_full, uint32_t s_p
             sum2[u] = add_f32x2(sum2[u], pack_f32x2(s[i + 2 * u], s[i + 2 * u + 1]));
         }
     }
-    if (PINGPONG) named_bar_arrive(other_bar, 256);       // hand the MUFU to the other softmax group
     float sa, sb, sc, sd;
     unpack_f32x2(sum2[0], sa, sb);
     unpack_f32x2(sum2[1], sc, sd);
@@ -456,10 +453,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
         float m_run = -CUDART_INF_F;      // running max, log2 domain
         float l_run = 0.f;
         for (int j = 0; j < nkv; ++j, ++g)
-            softmax_block<D, KVB, POLY, false>(bar_s_full, g & 1, bar_s_free, &bar_kv_empty[(g - 1) & 1],
+            softmax_block<D, KVB, POLY>(bar_s_full, g & 1, bar_s_free, &bar_kv_empty[(g - 1) & 1],
                                                ((g - 1) >> 1) & 1, bar_p_full, tmem_s, tmem_o, lane_addr, p_row, sw,
                                                interior, key_mask, row_base, j * KVB, kvl, k_tokens, j == 0, m_run, l_run,
-                                               0, 0, r == 0 && j < 6, tl_id, 2 + 5 * j);
+                                        r == 0 && j < 6, tl_id, 2 + 5 * j);
         // epilogue: O / l -> bf16 -> HBM
         mbar_wait(bar_o_full, it & 1);
         ++it;
@@ -509,139 +506,181 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
 }
 
 // ================================================================================================
-// Ping-pong kernel (head_dim <= 64).  One CTA per SM works on TWO 128-query tiles of one (sequence, head) at a time:
-//   warps 0-3  softmax group A (Q rows q0 .. q0+127)      warp 8   TMA producer (Q_A, Q_B, shared K/V ring)
-//   warps 4-7  softmax group B (Q rows q0+128 .. q0+255)  warp 9   MMA issuer of group A (S_A = Q_A K^T, O_A += P_A V)
-//                                                          warp 10  MMA issuer of group B
-// Why: with two independent CTAs per SM, each SM sub-partition holds one softmax warp of each CTA and the two drift into
-// running their exp2 phases at the same time -- both then get half of the 4-lane MUFU -- and their TMEM-load / row-max /
-// P-store phases at the same time, when the MUFU idles (measured: MUFU 65 % busy, nothing else above 62 %, and removing any
-// single piece of work barely moved the time).  Here the two groups share the SM *cooperatively*: a token (two named
-// barriers) lets exactly one group run its exp2 phase while the other loads S, finds its row max, stores P and hands over,
-// so the MUFU never sees two warps on one sub-partition and never idles.  K/V tiles are loaded once for both query tiles.
-// Items (sequence, head, query-tile pair) are streamed per CTA as in attention_kernel.  A tile past k_tokens (odd tile count)
-// is computed on whatever rows follow and never stored.
-// TMEM columns: S_A [0,128) | S_B [128,256) | O_A [256,256+D) | O_B [384,384+D).
+// Register-pipelined kernel (head_dim <= 64, 64-key blocks).  The bound of attention_kernel is not a pipe but the serial
+// chain of ONE softmax warp per scheduler: wait S -> tcgen05.ld (~300 cycles) -> row max -> exp2 -> pack/store P -> fence ->
+// arrive (tools/attn_ablate.sh, -DATT_TIMELINE).  Here a thread keeps TWO 64-key blocks of its row in registers: while the
+// exp2 phase of block g runs, the tcgen05.ld of S(g+1) is in flight, and its mask + row max are taken off the chain too
+// (they run after P(g) is handed over, while the tensor core does O += P(g) V(g)).  What stays serial per 64 keys is
+// exp2 + pack/store + hand-off.  The control thread issues S one block ahead of the PV it is waiting for
+// (arrival order: s_free(g+1), p_full(g), s_free(g+2), ...), over a 4-stage K/V ring that runs across work items.
+// TMEM: S [0,64) | O [64, 64+D).  Two CTAs per SM (registers), 96 KB smem each.
 // ================================================================================================
-constexpr int PP_THREADS = 352;
-constexpr int PP_BAR_A = 1, PP_BAR_B = 2;      // named barriers: "group A / B may start its exp2 phase"
+constexpr int PIPE_KVB = 64;
+constexpr int PIPE_NST = 4;
 
 template <int D>
-struct AttnPPCfg {
-    using B = AttnCfg<D, 128>;
-    static constexpr int NST = 3;                                   // shared K/V ring
-    static constexpr int OFF_Q = 0;                                 // Q_A | Q_B
-    static constexpr int OFF_K = 2 * B::TILE_BYTES;
-    static constexpr int OFF_V = OFF_K + NST * B::KV_TILE_BYTES;
-    static constexpr int OFF_P = OFF_V + NST * B::KV_TILE_BYTES;    // P_A | P_B
-    static constexpr int OFF_BAR = OFF_P + 2 * B::P_BYTES;
+struct AttnPipeCfg {
+    using B = AttnCfg<D, PIPE_KVB>;
+    static constexpr int OFF_Q = 0;
+    static constexpr int OFF_K = B::TILE_BYTES;
+    static constexpr int OFF_V = OFF_K + PIPE_NST * B::KV_TILE_BYTES;
+    static constexpr int OFF_P = OFF_V + PIPE_NST * B::KV_TILE_BYTES;
+    static constexpr int OFF_BAR = OFF_P + B::P_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 256;
+    static constexpr int TMEM_COLS = 128;
 };
 
-template <int D>
-__global__ void __launch_bounds__(PP_THREADS, 1)
-attention_pp_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int heads, int k_tokens, int h,
-                    const int32_t* __restrict__ kv_info, const uint8_t* __restrict__ key_mask,
-                    __nv_bfloat16* __restrict__ out) {
-    using Cfg = AttnPPCfg<D>;
+// mask the keys of one 64-key block (suffix padding by kv_len, interior pad ids by the byte mask) and return the row max
+__device__ __forceinline__ float pipe_mask_max(float (&s)[PIPE_KVB], bool interior, const uint8_t* __restrict__ key_mask,
+                                               long long row_base, int j0, int kvl, int k_tokens) {
+    if (interior) {
+        const uint4* mk = reinterpret_cast<const uint4*>(key_mask + row_base + j0);
+        const bool vec_ok = ((row_base + j0) & 15) == 0 && j0 + PIPE_KVB <= k_tokens;
+#pragma unroll
+        for (int g = 0; g < PIPE_KVB / 16; ++g) {
+            uint32_t w[4];
+            if (vec_ok) {
+                const uint4 u = __ldg(mk + g);
+                w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    w[i] = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int c = j0 + g * 16 + i * 4 + b;
+                        const uint32_t v = (c < k_tokens) ? key_mask[row_base + c] : 0;
+                        w[i] |= (v & 0xffu) << (8 * b);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const bool ok = ((w[i >> 2] >> (8 * (i & 3))) & 0xffu) != 0 && (j0 + g * 16 + i < kvl);
+                if (!ok) s[g * 16 + i] = -CUDART_INF_F;
+            }
+        }
+    } else if (j0 + PIPE_KVB > kvl) {
+        const int lim = kvl - j0;
+#pragma unroll
+        for (int i = 0; i < PIPE_KVB; ++i)
+            if (i >= lim) s[i] = -CUDART_INF_F;
+    }
+    float mx4[4] = {s[0], s[1], s[2], s[3]};
+#pragma unroll
+    for (int i = 4; i < PIPE_KVB; i += 4) {
+        mx4[0] = fmaxf(mx4[0], s[i]); mx4[1] = fmaxf(mx4[1], s[i + 1]);
+        mx4[2] = fmaxf(mx4[2], s[i + 2]); mx4[3] = fmaxf(mx4[3], s[i + 3]);
+    }
+    return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+}
+
+// lazy rescaling (see softmax_block): returns alpha for this block and moves m_run only when the row max grew by > 2^8
+__device__ __forceinline__ float pipe_update_max(float mx, float& m_run) {
+    const float m_cand = fmaxf(m_run, mx * LOG2E);
+    float alpha = 1.0f;
+    if (m_cand > m_run + 8.0f) {
+        alpha = ex2(m_run - m_cand);
+        m_run = m_cand;
+    }
+    return alpha;
+}
+
+template <int D, int POLY>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_kv, int n_seq,
+                      int heads, int k_tokens, int h, const int32_t* __restrict__ kv_info,
+                      const uint8_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out) {
+    using Cfg = AttnPipeCfg<D>;
     using B = typename Cfg::B;
-    constexpr int NST = Cfg::NST;
+    constexpr int KVB = PIPE_KVB, NST = PIPE_NST;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-    uint64_t* bar_q_full = bars + 0;        // [2]  Q_X landed                       (tx)
-    uint64_t* bar_q_free = bars + 2;        // [2]  every S of the item has been consumed: Q_X may be overwritten
-    uint64_t* bar_kv_full = bars + 4;       // [NST]                                 (tx)
-    uint64_t* bar_kv_empty = bars + 4 + NST;        // [NST] both groups' PV(g) drained the stage (2 commits)
-    uint64_t* bar_s_full = bars + 4 + 2 * NST;      // [2]
-    uint64_t* bar_s_free = bars + 6 + 2 * NST;      // [2]  128 arrivals
-    uint64_t* bar_p_full = bars + 8 + 2 * NST;      // [2]  128 arrivals
-    uint64_t* bar_pv_done = bars + 10 + 2 * NST;    // [2]  PV_X(g) complete: P_X and O_X may be touched
-    uint64_t* bar_o_full = bars + 12 + 2 * NST;     // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14 + 2 * NST);
+    uint64_t* bar_q = bars + 0;
+    uint64_t* bar_kv_full = bars + 1;               // [NST]
+    uint64_t* bar_kv_empty = bars + 1 + NST;        // [NST]  PV(g) complete: stage g % NST, the P buffer and O are free
+    uint64_t* bar_s_full = bars + 1 + 2 * NST;
+    uint64_t* bar_s_free = bars + 2 + 2 * NST;      // 128 arrivals: S(g) is in registers
+    uint64_t* bar_p_full = bars + 3 + 2 * NST;      // 128 arrivals
+    uint64_t* bar_o_full = bars + 4 + 2 * NST;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * NST);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nqb = (k_tokens + ATT_BLOCK - 1) / ATT_BLOCK, npair = (nqb + 1) / 2;
-    const int total = n_seq * heads * npair;
+    const int nqb = (k_tokens + ATT_BLOCK - 1) / ATT_BLOCK;
+    const int total = n_seq * heads * nqb;
     struct Item { int n, head, q0, kvl, nkv, n_nonpad; };
     auto decode = [&](int item) {
         Item w;
-        w.q0 = (item % npair) * 2 * ATT_BLOCK;
-        w.head = (item / npair) % heads;
-        w.n = item / (npair * heads);
+        w.q0 = (item % nqb) * ATT_BLOCK;
+        w.head = (item / nqb) % heads;
+        w.n = item / (nqb * heads);
         w.kvl = kv_info[2 * w.n];
         w.n_nonpad = kv_info[2 * w.n + 1];
-        w.nkv = (w.kvl + ATT_BLOCK - 1) / ATT_BLOCK;
+        w.nkv = (w.kvl + KVB - 1) / KVB;
         return w;
     };
 
-    if (warp == 8) {
+    if (warp == 4) {
         if (lane == 0) {
             if ((smem_u32(smem) & 1023u) != 0) { printf("molly attention: smem base not 1024-B aligned\n"); __trap(); }
             tma_prefetch_desc(&tma_qkv);
-            for (int x = 0; x < 2; ++x) {
-                mbar_init(&bar_q_full[x], 1);
-                mbar_init(&bar_q_free[x], 1);
-                mbar_init(&bar_s_full[x], 1);
-                mbar_init(&bar_s_free[x], 128);
-                mbar_init(&bar_p_full[x], 128);
-                mbar_init(&bar_pv_done[x], 1);
-                mbar_init(&bar_o_full[x], 1);
-            }
-            for (int st = 0; st < NST; ++st) {
-                mbar_init(&bar_kv_full[st], 1);
-                mbar_init(&bar_kv_empty[st], 2);
-            }
+            tma_prefetch_desc(&tma_kv);
+            mbar_init(bar_q, 1);
+            for (int st = 0; st < NST; ++st) { mbar_init(&bar_kv_full[st], 1); mbar_init(&bar_kv_empty[st], 1); }
+            mbar_init(bar_s_full, 1);
+            mbar_init(bar_s_free, 128);
+            mbar_init(bar_p_full, 128);
+            mbar_init(bar_o_full, 1);
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + KVB;
 
-    if (warp == 8) {
-        // ---------------- TMA producer ----------------
+    if (warp == 4) {
         if (lane == 0) {
-            int t = 0, g = 0;
-            for (int item = blockIdx.x; item < total; item += gridDim.x) {
-                const Item w = decode(item);
-                if (w.nkv == 0) continue;
-                for (int x = 0; x < 2; ++x) {
-                    if (t > 0) mbar_wait(&bar_q_free[x], (t - 1) & 1);
-                    mbar_arrive_expect_tx(&bar_q_full[x], B::TILE_BYTES);
-#pragma unroll
-                    for (int b = 0; b < B::NBOX; ++b)
-                        tma_load_2d(smem + Cfg::OFF_Q + x * B::TILE_BYTES + b * B::BOX_BYTES, &tma_qkv, &bar_q_full[x],
-                                    w.head * D + b * B::BOX_D, w.n * k_tokens + w.q0 + x * ATT_BLOCK);
-                }
-                for (int j = 0; j < w.nkv; ++j, ++g) {
-                    const int st = g % NST;
-                    if (g >= NST) mbar_wait(&bar_kv_empty[st], (g / NST - 1) & 1);
-                    mbar_arrive_expect_tx(&bar_kv_full[st], 2 * B::KV_TILE_BYTES);
-                    const int row = w.n * k_tokens + j * ATT_BLOCK;
-#pragma unroll
-                    for (int b = 0; b < B::NBOX; ++b) {
-                        tma_load_2d(smem + Cfg::OFF_K + st * B::KV_TILE_BYTES + b * B::KV_BOX_BYTES, &tma_qkv,
-                                    &bar_kv_full[st], h + w.head * D + b * B::BOX_D, row);
-                        tma_load_2d(smem + Cfg::OFF_V + st * B::KV_TILE_BYTES + b * B::KV_BOX_BYTES, &tma_qkv,
-                                    &bar_kv_full[st], 2 * h + w.head * D + b * B::BOX_D, row);
-                    }
-                }
-                ++t;
-            }
-        }
-    } else if (warp >= 9) {
-        // ---------------- MMA issuer of group x ----------------
-        if (lane == 0) {
-            const int x = warp - 9;
-            constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK, ATT_BLOCK, false, false);
+            // ---------------- control thread: TMA producer + MMA issuer ----------------
+            constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK, KVB, false, false);
             constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK, D, false, true);      // B (= V) is MN-major
-            const uint32_t s_q = smem_u32(smem + Cfg::OFF_Q + x * B::TILE_BYTES), s_k = smem_u32(smem + Cfg::OFF_K);
-            const uint32_t s_v = smem_u32(smem + Cfg::OFF_V), s_p = smem_u32(smem + Cfg::OFF_P + x * B::P_BYTES);
-            const uint32_t tmem_s = tmem_base + x * 128, tmem_o = tmem_base + 256 + x * 128;
+            const uint32_t s_q = smem_u32(smem + Cfg::OFF_Q), s_k = smem_u32(smem + Cfg::OFF_K);
+            const uint32_t s_v = smem_u32(smem + Cfg::OFF_V), s_p = smem_u32(smem + Cfg::OFF_P);
+            auto next_item = [&](int item) {
+                while (item < total && kv_info[2 * (item / (nqb * heads))] <= 0) item += gridDim.x;
+                return item;
+            };
+            auto load_q = [&](const Item& w) {
+                mbar_arrive_expect_tx(bar_q, B::TILE_BYTES);
+#pragma unroll
+                for (int b = 0; b < B::NBOX; ++b)
+                    tma_load_2d(smem + Cfg::OFF_Q + b * B::BOX_BYTES, &tma_qkv, bar_q, w.head * D + b * B::BOX_D,
+                                w.n * k_tokens + w.q0);
+            };
+            int l_item = next_item(blockIdx.x), l_j = 0, g_load = 0;
+            Item lw = decode(l_item < total ? l_item : 0);
+            auto load_next_kv = [&]() {                      // stream block g_load -> stage g_load % NST (caller: stage is free)
+                if (l_item >= total) return;
+                const int stg = g_load % NST, row = lw.n * k_tokens + l_j * KVB;
+                mbar_arrive_expect_tx(&bar_kv_full[stg], 2 * B::KV_TILE_BYTES);
+#pragma unroll
+                for (int b = 0; b < B::NBOX; ++b) {
+                    tma_load_2d(smem + Cfg::OFF_K + stg * B::KV_TILE_BYTES + b * B::KV_BOX_BYTES, &tma_kv, &bar_kv_full[stg],
+                                h + lw.head * D + b * B::BOX_D, row);
+                    tma_load_2d(smem + Cfg::OFF_V + stg * B::KV_TILE_BYTES + b * B::KV_BOX_BYTES, &tma_kv, &bar_kv_full[stg],
+                                2 * h + lw.head * D + b * B::BOX_D, row);
+                }
+                ++g_load;
+                if (++l_j == lw.nkv) {
+                    l_item = next_item(l_item + gridDim.x);
+                    l_j = 0;
+                    if (l_item < total) lw = decode(l_item);
+                }
+            };
             auto issue_s = [&](int g) {
                 const int st = g % NST;
                 mbar_wait(&bar_kv_full[st], (g / NST) & 1);
@@ -649,74 +688,183 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int 
 #pragma unroll
                 for (int s = 0; s < D / 16; ++s) {
                     const uint32_t off = ((s * 16) / B::BOX_D) * B::BOX_BYTES + ((s * 16) % B::BOX_D) * 2;
+                    const uint32_t koff = ((s * 16) / B::BOX_D) * B::KV_BOX_BYTES + ((s * 16) % B::BOX_D) * 2;
                     const uint64_t qd = make_smem_desc(s_q + off, 16, 8 * B::ROW_BYTES, B::LAYOUT);
-                    const uint64_t kd = make_smem_desc(s_k + st * B::KV_TILE_BYTES + off, 16, 8 * B::ROW_BYTES, B::LAYOUT);
+                    const uint64_t kd = make_smem_desc(s_k + st * B::KV_TILE_BYTES + koff, 16, 8 * B::ROW_BYTES, B::LAYOUT);
                     umma_bf16_ss(tmem_s, qd, kd, idesc_s, s != 0);
                 }
-                umma_commit(&bar_s_full[x]);
+                umma_commit(bar_s_full);
             };
-            int t = 0, g = 0;
-            for (int item = blockIdx.x; item < total; item += gridDim.x) {
-                const Item w = decode(item);
-                if (w.nkv == 0) continue;
-                mbar_wait(&bar_q_full[x], t & 1);
-                issue_s(g);
+            int c_item = l_item, it = 0, g = 0;
+            if (c_item < total) {
+                load_q(lw);
+                for (int i = 0; i < NST; ++i) load_next_kv();
+                mbar_wait(bar_q, 0);
+                issue_s(0);
+            }
+            while (c_item < total) {
+                const Item w = decode(c_item);
+                const int nxt = next_item(c_item + gridDim.x);
+                // S(g) of this item's first block is already issued.  The softmax prologue puts it in registers:
+                mbar_wait(bar_s_free, g & 1);
+                tc_fence_after();
+                if (w.nkv > 1) issue_s(g + 1);
+                else if (nxt < total) load_q(decode(nxt));   // Q is dead once the item's last S is consumed
                 for (int j = 0; j < w.nkv; ++j, ++g) {
                     const int st = g % NST;
-                    const bool last = j == w.nkv - 1;
-                    mbar_wait(&bar_s_free[x], g & 1);        // S_X(g) is in registers
-                    tc_fence_after();
-                    if (!last) issue_s(g + 1);               // runs under softmax_X(g)
-                    else mbar_arrive(&bar_q_free[x]);        // every S of this item is consumed
-                    mbar_wait(&bar_p_full[x], g & 1);
+                    // (1) S runs one block ahead of PV: s_free(g+1) arrives in the middle of the softmax step of block g
+                    if (j + 1 < w.nkv) {
+                        mbar_wait(bar_s_free, (g + 1) & 1);
+                        tc_fence_after();
+                        if (j + 2 < w.nkv) issue_s(g + 2);
+                        else if (nxt < total) load_q(decode(nxt));
+                    }
+                    // (2) O += P(g) V(g)
+                    mbar_wait(bar_p_full, g & 1);
                     tc_fence_after();
 #pragma unroll
-                    for (int s = 0; s < ATT_BLOCK / 16; ++s) {
-                        const uint64_t pd = make_smem_desc(s_p + (s >> 2) * (ATT_BLOCK * 128) + (s & 3) * 32, 16, 1024,
-                                                           kLayoutSW128);
+                    for (int s = 0; s < KVB / 16; ++s) {
+                        const uint64_t pd = make_smem_desc(s_p + (s & 3) * 32, 16, 1024, kLayoutSW128);
                         const uint64_t vd = make_smem_desc(s_v + st * B::KV_TILE_BYTES + s * 16 * B::ROW_BYTES,
                                                            B::KV_BOX_BYTES, 8 * B::ROW_BYTES, B::LAYOUT);
                         umma_bf16_ss(tmem_o, pd, vd, idesc_pv, (j | s) != 0);
                     }
-                    umma_commit(&bar_pv_done[x]);
                     umma_commit(&bar_kv_empty[st]);
-                    if (last) umma_commit(&bar_o_full[x]);
+                    if (j == w.nkv - 1) {
+                        umma_commit(bar_o_full);
+                        if (nxt < total) {                   // first S of the next item, under this item's epilogue
+                            mbar_wait(bar_q, (it + 1) & 1);
+                            issue_s(g + 1);
+                        }
+                    }
+                    // (3) refill the stage with stream block g + NST once PV(g) has drained it
+                    if (l_item < total) {
+                        mbar_wait(&bar_kv_empty[st], (g / NST) & 1);
+                        load_next_kv();
+                    }
                 }
-                ++t;
+                ++it;
+                c_item = nxt;
             }
         }
     } else {
-        // ---------------- softmax groups: thread r of group x owns query row q0 + 128 x + r ----------------
-        const int x = warp >> 2, r = threadIdx.x & 127;
-        const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-        const uint32_t tmem_s = tmem_base + x * 128, tmem_o = tmem_base + 256 + x * 128;
-        uint8_t* p_row = smem + Cfg::OFF_P + x * B::P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+        // ---------------- softmax warps: thread r owns query row r; two 64-key blocks live in registers ----------------
+        const int r = threadIdx.x;
+        const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+        uint8_t* p_row = smem + Cfg::OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
         const int sw = r & 7;
-        const int my_bar = x == 0 ? PP_BAR_A : PP_BAR_B, other_bar = x == 0 ? PP_BAR_B : PP_BAR_A;
-        if (x == 1) named_bar_arrive(PP_BAR_A, 256);          // group A takes the first turn
-        int t = 0, g = 0;
+        int it = 0, g = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x) {
             const Item w = decode(item);
-            const int q0 = w.q0 + x * ATT_BLOCK;
             const bool interior = w.n_nonpad != w.kvl;
             const long long row_base = static_cast<long long>(w.n) * k_tokens;
-            const bool row_ok = q0 + r < k_tokens;
-            __nv_bfloat16* orow = out + (row_base + q0 + r) * h + w.head * D;
+            const bool row_ok = w.q0 + r < k_tokens;
+            __nv_bfloat16* orow = out + (row_base + w.q0 + r) * h + w.head * D;
             if (w.nkv == 0) {                                 // all-pad sequence: the reference never encodes one
                 if (row_ok)
                     for (int i = 0; i < D / 8; ++i) reinterpret_cast<uint4*>(orow)[i] = make_uint4(0, 0, 0, 0);
                 continue;
             }
             float m_run = -CUDART_INF_F, l_run = 0.f;
-            for (int j = 0; j < w.nkv; ++j, ++g)
-                softmax_block<D, ATT_BLOCK, 0, true>(&bar_s_full[x], g & 1, &bar_s_free[x], &bar_pv_done[x], (g - 1) & 1,
-                                                     &bar_p_full[x], tmem_s, tmem_o, lane_addr, p_row, sw, interior,
-                                                     key_mask, row_base, j * ATT_BLOCK, w.kvl, k_tokens, j == 0, m_run,
-                                                     l_run, my_bar, other_bar, r == 0 && j < 7 && item < 2048, item,
-                                                     36 * x + 5 * j);
+            float a[KVB], b[KVB];                             // S / P of the current and of the next block
+
+            // one pipeline step: `cur` holds S(g) (masked, max already folded into m_run / alpha); `nxt` receives S(g+1)
+            auto step = [&](float (&cur)[KVB], float (&nxt)[KVB], int j, float alpha) -> float {
+                const bool has_next = j + 1 < w.nkv;
+                uint32_t* nraw = reinterpret_cast<uint32_t*>(nxt);
+                if (has_next) {                               // S(g+1): tcgen05.ld in flight under the exp2 phase
+                    mbar_wait(bar_s_full, (g + 1) & 1);
+                    tc_fence_after();
+                    tmem_ld32(tmem_s + lane_addr, nraw);
+                    tmem_ld32(tmem_s + lane_addr + 32, nraw + 32);
+                }
+                const float m_use = (m_run == -CUDART_INF_F) ? 0.f : m_run;
+                const uint64_t sc2 = pack_f32x2(LOG2E, LOG2E), nm2 = pack_f32x2(-m_use, -m_use);
+                uint64_t sum2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
+#pragma unroll
+                for (int i = 0; i < KVB; i += 4) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        float x0, x1;
+                        unpack_f32x2(fma_f32x2(pack_f32x2(cur[i + 2 * u], cur[i + 2 * u + 1]), sc2, nm2), x0, x1);
+                        if (((i >> 1) + u) % 4 < POLY) {
+                            exp2_poly_pair(x0, x1);
+                            cur[i + 2 * u] = x0;
+                            cur[i + 2 * u + 1] = x1;
+                        } else {
+                            cur[i + 2 * u] = ex2(x0);
+                            cur[i + 2 * u + 1] = ex2(x1);
+                        }
+                        sum2[u] = add_f32x2(sum2[u], pack_f32x2(cur[i + 2 * u], cur[i + 2 * u + 1]));
+                    }
+                }
+                float sa, sb, sc, sd;
+                unpack_f32x2(sum2[0], sa, sb);
+                unpack_f32x2(sum2[1], sc, sd);
+                l_run = l_run * alpha + ((sa + sb) + (sc + sd));
+                if (has_next) {                               // S(g+1) is in registers: the control thread may issue S(g+2)
+                    tmem_ld_wait_regs32(nraw);
+                    tmem_ld_wait_regs32(nraw + 32);
+                    tc_fence_before();
+                    mbar_arrive(bar_s_free);
+                }
+                if (j > 0) {                                  // PV(g-1) drained the P buffer and finished O
+                    mbar_wait(&bar_kv_empty[(g - 1) % NST], ((g - 1) / NST) & 1);
+                    tc_fence_after();
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {                 // P -> smem, bf16, K-major, 128-B swizzle
+                    uint4 u;
+                    u.x = pack_bf16x2(cur[c * 8 + 0], cur[c * 8 + 1]);
+                    u.y = pack_bf16x2(cur[c * 8 + 2], cur[c * 8 + 3]);
+                    u.z = pack_bf16x2(cur[c * 8 + 4], cur[c * 8 + 5]);
+                    u.w = pack_bf16x2(cur[c * 8 + 6], cur[c * 8 + 7]);
+                    *reinterpret_cast<uint4*>(p_row + ((c ^ sw) << 4)) = u;
+                }
+                if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+                    for (int c = 0; c < D / 16; ++c) {
+                        uint32_t o[16];
+                        tmem_ld16(tmem_o + lane_addr + c * 16, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st16(tmem_o + lane_addr + c * 16, o);
+                    }
+                    tmem_st_wait();
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(bar_p_full);
+                ++g;
+                // off the chain: mask + row max of the next block, while the tensor core runs O += P V
+                float alpha_next = 1.0f;
+                if (has_next)
+                    alpha_next = pipe_update_max(
+                        pipe_mask_max(nxt, interior, key_mask, row_base, (j + 1) * KVB, w.kvl, k_tokens), m_run);
+                return alpha_next;
+            };
+
+            // prologue: S of the item's first block
+            mbar_wait(bar_s_full, g & 1);
+            tc_fence_after();
+            {
+                uint32_t* raw = reinterpret_cast<uint32_t*>(a);
+                tmem_ld32(tmem_s + lane_addr, raw);
+                tmem_ld32(tmem_s + lane_addr + 32, raw + 32);
+                tmem_ld_wait_regs32(raw);
+                tmem_ld_wait_regs32(raw + 32);
+            }
+            tc_fence_before();
+            mbar_arrive(bar_s_free);
+            float alpha = pipe_update_max(pipe_mask_max(a, interior, key_mask, row_base, 0, w.kvl, k_tokens), m_run);
+            for (int j = 0; j < w.nkv; j += 2) {
+                alpha = step(a, b, j, alpha);
+                if (j + 1 < w.nkv) alpha = step(b, a, j + 1, alpha);
+            }
             // epilogue: O / l -> bf16 -> HBM
-            mbar_wait(&bar_o_full[x], t & 1);
-            ++t;
+            mbar_wait(bar_o_full, it & 1);
+            ++it;
             tc_fence_after();
             const float inv_l = 1.0f / l_run;
 #pragma unroll
@@ -738,16 +886,15 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int 
                     reinterpret_cast<uint4*>(orow + c * 16)[1] = u1;
                 }
             }
-            tc_fence_before();                                // O_X is read: the next item's PV may overwrite it
+            tc_fence_before();                                // O is read: the next item's PV may overwrite it
         }
-        if (x == 0) named_bar_sync(PP_BAR_A, 256);            // consume group B's last hand-over
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 4) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -798,33 +945,39 @@ int attention_kvb(int d) {
 }
 
 template <int D>
-int launch_attention_pp(const AttnMaps& maps, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
-                        const uint8_t* key_mask, void* out, cudaStream_t stream) {
-    using Cfg = AttnPPCfg<D>;
-    auto kernel = attention_pp_kernel<D>;
+int launch_attention_pipe(const AttnMaps& maps, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
+                          const uint8_t* key_mask, void* out, cudaStream_t stream) {
+    using Cfg = AttnPipeCfg<D>;
+    static int poly = -1;
+    if (poly < 0) {
+        const char* e = getenv("MOLLY_ATTN_POLY");
+        poly = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : ATTN_POLY_DEFAULT;
+    }
+    auto kernel = poly == 0 ? attention_pipe_kernel<D, 0>
+                            : (poly == 1 ? attention_pipe_kernel<D, 1> : attention_pipe_kernel<D, 2>);
     static bool configured = false;
     if (!configured) {
-        MOLLY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MOLLY_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MOLLY_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MOLLY_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    const int nqb = (k_tokens + ATT_BLOCK - 1) / ATT_BLOCK;
-    const int total = n_seq * heads * ((nqb + 1) / 2);
-    const int grid = total < device_sm_count() ? total : device_sm_count();
+    const int grid = attention_grid(n_seq * heads * ((k_tokens + ATT_BLOCK - 1) / ATT_BLOCK), 2);
     {
         ProfScope prof(PF_ATTENTION, 4.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
-        kernel<<<grid, PP_THREADS, Cfg::SMEM_BYTES, stream>>>(maps.q, n_seq, heads, k_tokens, h, kv_info, key_mask,
-                                                              static_cast<__nv_bfloat16*>(out));
+        kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(maps.q, maps.kv64, n_seq, heads, k_tokens, h, kv_info,
+                                                               key_mask, static_cast<__nv_bfloat16*>(out));
     }
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
     return MOLLY_OK;
 }
 
-bool attention_pp_enabled() {           // MOLLY_ATTN_PP = 0 | 1 overrides the default
+bool attention_pipe_enabled() {         // MOLLY_ATTN_PIPE = 0 | 1 overrides the default
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("MOLLY_ATTN_PP");
-        v = e == nullptr ? (ATTN_PP_DEFAULT ? 1 : 0) : (e[0] != '0');
+        const char* e = getenv("MOLLY_ATTN_PIPE");
+        v = e == nullptr ? (ATTN_PIPE_DEFAULT ? 1 : 0) : (e[0] != '0');
     }
     return v == 1;
 }
@@ -834,8 +987,8 @@ int launch_attention(const AttnMaps& maps, int n_seq, int k_tokens, int h, int h
                      const uint8_t* key_mask, void* out, cudaStream_t stream) {
     const CUtensorMap& tm = maps.q;
     if constexpr (D <= 64) {
-        if (attention_pp_enabled() && k_tokens > ATT_BLOCK)
-            return launch_attention_pp<D>(maps, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
+        if (attention_pipe_enabled())
+            return launch_attention_pipe<D>(maps, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
         if (attention_kvb(D) == 64)
             return launch_attention_kvb<D, 64>(maps, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
     }

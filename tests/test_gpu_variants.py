@@ -27,9 +27,9 @@ def test_one_cta_per_item_attention():
     _run({"MOLLY_ATTN_STREAM": "0"}, "attention")
 
 
-def test_ping_pong_attention():
-    """MOLLY_ATTN_PP=1: one CTA per SM, two query tiles, the two softmax groups take turns on the MUFU."""
-    _run({"MOLLY_ATTN_PP": "1"}, "attention")
+def test_register_pipelined_attention():
+    """MOLLY_ATTN_PIPE=1: 64-key blocks, S(g+1) loaded from TMEM under the exp2 phase of block g, S issued a block ahead."""
+    _run({"MOLLY_ATTN_PIPE": "1"}, "attention")
 
 
 def test_polynomial_exp2_attention():
