@@ -392,6 +392,7 @@ def run_train_step(args, wl: dict, dev, rank: int, world: int, warmup: int) -> N
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     launches = ops.kernel_launch_count() - l0
+    path.concurrent = False                                       # per-launch events need one stream
     ops.profile_start()
     step()
     torch.cuda.synchronize()
@@ -533,6 +534,7 @@ def main() -> None:
 
     # ---- one profiled step: per-launch CUDA events on the launching stream -> roofline of the dominant kernel
     peaks = measured_peaks()
+    path.concurrent = False                                       # per-launch events need one stream
     ops.profile_start()
     step_dev()
     torch.cuda.synchronize()

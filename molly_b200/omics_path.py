@@ -14,6 +14,7 @@ pairing-by-index quirk and exception types, while the work underneath is the sm_
 """
 from __future__ import annotations
 
+import os
 import types
 from typing import Any, List, Mapping, Optional
 
@@ -64,6 +65,14 @@ class FastOmicsPath:
             if enc is not None:
                 self._ids[name] = ops.register_encoder(enc)
         self.strict = strict                # True: synchronise and raise device-side errors inside the call
+        # Run the two modalities' encoders on two streams when their written rows are disjoint (always, for dataset-built
+        # batches; checked per call) and the batch is small enough to leave SMs idle: -33 % latency at B=1, -9 % at B=4,
+        # nothing at the power-capped headline batch (profiles/r01n_graph.md), hence the row threshold.
+        # MOLLY_CONCURRENT_MODALITIES=0 restores strictly sequential launches, =2 lifts the threshold.
+        mode = os.environ.get("MOLLY_CONCURRENT_MODALITIES", "1")
+        self.concurrent = mode != "0"
+        self.concurrent_max_rows = (1 << 62) if mode == "2" else 32768
+        self._side_streams = {}
         self._proj_modules = {}             # name -> nn.Linear (live parameters, for --train-mlp)
         self._proj_versions = {}
 
@@ -120,13 +129,37 @@ class FastOmicsPath:
         batch_size = hidden_states.shape[0]
         nt_plan, pr_plan = planner.route(batch_size, omic_ids_list, omic_info_list)          # may raise ValueError
         # reference order: all DNA/RNA sequences, then all protein sequences (omics_one.py:120-134)
-        for name, plan in (("dna_rna", nt_plan), ("protein", pr_plan)):
-            if len(plan) == 0:                                                               # :67-68
-                continue
-            self._inject(name, plan, hidden_states, omic_ids_list, dev)
+        work = [(name, plan) for name, plan in (("dna_rna", nt_plan), ("protein", pr_plan)) if len(plan)]  # :67-68
+        if (self.concurrent and len(work) == 2 and hidden_states.is_contiguous()
+                and max(len(nt_plan), len(pr_plan)) * self._k_ids(omic_ids_list, work[0][1]) <= self.concurrent_max_rows
+                and not (torch.is_grad_enabled() and self._proj_modules)
+                and planner.ranges_disjoint(nt_plan, self._k_rows("dna_rna", omic_ids_list, nt_plan),
+                                            pr_plan, self._k_rows("protein", omic_ids_list, pr_plan))):
+            cur = torch.cuda.current_stream(dev)
+            side = self._side_streams.setdefault(dev.index, torch.cuda.Stream(dev))
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._inject(work[1][0], work[1][1], hidden_states, omic_ids_list, dev)
+            self._inject(work[0][0], work[0][1], hidden_states, omic_ids_list, dev)
+            cur.wait_stream(side)
+        else:
+            for name, plan in work:
+                self._inject(name, plan, hidden_states, omic_ids_list, dev)
         if self.strict:
             ops.check_device_errors(dev)
         return hidden_states
+
+    @staticmethod
+    def _k_ids(omic_ids_list, plan: planner.ModalityPlan) -> int:
+        return int(omic_ids_list.shape[-1] if isinstance(omic_ids_list, torch.Tensor) else
+                   omic_ids_list[plan.b_idx[0]][plan.slot_idx[0]].shape[-1])
+
+    def _k_rows(self, name: str, omic_ids_list, plan: planner.ModalityPlan) -> int:
+        """Rows written per sequence: min(project_token_num, K) (omics_one.py:96)."""
+        k_ids = self._k_ids(omic_ids_list, plan)
+        enc_id = self._ids.get(name)
+        cap = ops.get_encoder(enc_id).project_token_num if enc_id is not None else int(k_ids)
+        return min(cap, int(k_ids))
 
     def _inject(self, name: str, plan: planner.ModalityPlan, hidden_states: torch.Tensor, omic_ids_list, dev) -> None:
         enc_id = self._ids.get(name)
@@ -210,16 +243,37 @@ class FastOmicsPath:
         runs = ops.placeholder_runs(input_ids, pad_token_ids, meta["slots"], meta["max_runs"])
         hidden = ops.embed_tokens_skip(input_ids, runs[4], pad_token_ids, meta["caps"]["dna_rna"], meta["caps"]["protein"],
                                        embed_weight)
-        for name in ("dna_rna", "protein"):                                                  # reference order, :120-134
-            if name not in meta["plans"]:
-                continue
+
+        def one(name):
             enc_id = self._ids[name]
             idx = meta["idx"][name]
-            seq_table = ops.build_seq_table(idx[0], idx[1], runs, expect_protein=(name == "protein"))
+            seq_table = ops.build_seq_table(idx[0], idx[1], runs, expect_protein=(name == "protein"),
+                                            k_need=max(1, meta["caps"][name]))    # shorter run = text rows overwritten
             proj = self._proj_modules.get(name)
             if proj is not None:
                 self._refresh_projector(name, ops.get_encoder(enc_id), proj)
             ops.encode_project_merge(hidden, ids[name], seq_table, enc_id, False)
+
+        names = [n for n in ("dna_rna", "protein") if n in meta["plans"]]                   # reference order, :120-134
+        side_ws = meta.get("side_workspace")
+        small = max(ids[n].shape[0] * ids[n].shape[1] for n in names) <= self.concurrent_max_rows if names else False
+        if (self.concurrent and small and len(names) == 2
+                and (side_ws is not None or not ops.workspace_is_pinned(hidden.device))):
+            dev = hidden.device                        # two branches (also inside a CUDA-graph capture): disjoint rows
+            cur = torch.cuda.current_stream(dev)
+            side = self._side_streams.setdefault(dev.index, torch.cuda.Stream(dev))
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                if side_ws is not None:
+                    with ops.use_workspace(side_ws):
+                        one(names[1])
+                else:
+                    one(names[1])
+            one(names[0])
+            cur.wait_stream(side)
+        else:
+            for name in names:
+                one(name)
         return hidden
 
     # ------------------------------------------------------------------ one CUDA graph per bucket
@@ -313,6 +367,9 @@ class GraphedOmicsCall:
         for name, plan in self.meta["plans"].items():
             need = max(need, ops.get_encoder(path._ids[name]).workspace_bytes(len(plan), k_tokens))
         self.workspace = torch.empty(need + 8192, dtype=torch.uint8, device=dev)
+        if (path.concurrent and len(self.meta["plans"]) == 2
+                and max(len(p) for p in self.meta["plans"].values()) * k_tokens <= path.concurrent_max_rows):   # 2nd branch
+            self.meta["side_workspace"] = torch.empty(need + 8192, dtype=torch.uint8, device=dev)
         with ops.use_workspace(self.workspace):
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))

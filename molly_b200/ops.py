@@ -88,6 +88,10 @@ class use_workspace:
         return False
 
 
+def workspace_is_pinned(dev: torch.device) -> bool:
+    return (dev.index if dev.index is not None else torch.cuda.current_device()) in _WS_PINNED
+
+
 def workspace(dev: torch.device, nbytes: int) -> Tensor:
     """Grow-only scratch buffer per (device, stream); stable pointers keep the library's TMA-descriptor plan cached."""
     pinned = _WS_PINNED.get(dev.index if dev.index is not None else torch.cuda.current_device())

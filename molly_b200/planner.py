@@ -80,6 +80,24 @@ def check_placement(plan: ModalityPlan, k: int, batch_size: int, seq_len: int) -
                 f"at non-singleton dimension 0 (sample {b}: start={start}, k={k}, T={seq_len})")
 
 
+def ranges_disjoint(nt: ModalityPlan, k_nt: int, pr: ModalityPlan, k_pr: int) -> bool:
+    """True when no DNA/RNA row range ``[start+1, start+1+k)`` intersects a protein one in the same sample -- always the
+    case for dataset-built batches (omics_dataset.py:270-288).  If they did intersect, the reference's order (DNA/RNA first,
+    protein second, omics_one.py:120-134) decides who wins, so the two modalities must then run one after the other."""
+    by_sample = {}
+    for b, s0 in zip(nt.b_idx, nt.starts):
+        if s0 != -1:
+            by_sample.setdefault(b, []).append((s0 + 1, s0 + 1 + k_nt))
+    for b, s0 in zip(pr.b_idx, pr.starts):
+        if s0 == -1:
+            continue
+        lo, hi = s0 + 1, s0 + 1 + k_pr
+        for a_lo, a_hi in by_sample.get(b, ()):
+            if lo < a_hi and a_lo < hi:
+                return False
+    return True
+
+
 def check_vocab(ids: torch.Tensor, vocab_size: int) -> None:
     """omics_one.py:71-72 for ids that are already on the host."""
     bad = ids >= vocab_size

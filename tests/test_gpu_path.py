@@ -282,3 +282,28 @@ def test_projector_checkpoint_round_trip(tmp_path):
     finally:
         a.close()
         b.close()
+
+
+def test_overlapping_ranges_keep_reference_order():
+    """Not produced by the dataset, but legal at the boundary: a protein range that overlaps a DNA range in the same sample.
+    The reference writes DNA/RNA first and protein second (omics_one.py:120-134), so the protein rows win; the two-stream
+    schedule must notice the overlap and fall back to that order."""
+    case = cases.golden_cases()["tiny_rotary_glu"]
+    infos = [[dict(i) for i in row] for row in case.batch.omic_info_list]
+    dna = next(i for i in infos[0] if i["type"] == "dna")
+    pro = next(i for i in infos[0] if i["type"] == "protein")
+    pro["start"] = dna["start"] + 7                                  # rows [s+8, s+48) overlap the DNA rows [s+1, s+41)
+    ref = case.batch.hidden_states.clone()
+    with torch.no_grad():
+        oracle_process(ref, case.batch.omic_ids, infos, case.nt, case.pr)
+    path = build_path(case)
+    try:
+        assert path.concurrent and case.K * 4 <= path.concurrent_max_rows
+        hs = case.batch.hidden_states.to(DEV)
+        for _ in range(3):                                           # a race would not lose every time
+            out = path.process_omic_sequences(hs.clone(), case.batch.omic_ids, infos, hs.device)
+            assert_close("overlapping ranges", out.float().cpu(), ref, TOL)
+            lo = pro["start"] + 1
+            assert_close("protein rows win", out[0, lo:lo + case.K].float().cpu(), ref[0, lo:lo + case.K], TOL)
+    finally:
+        path.close()

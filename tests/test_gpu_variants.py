@@ -10,9 +10,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(env_extra, select):
+def _run(env_extra, select, files=("tests/test_gpu_kernels.py",)):
     env = dict(os.environ, **env_extra)
-    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_kernels.py", "-q", "-x", "-k", select,
+    r = subprocess.run([sys.executable, "-m", "pytest", *files, "-q", "-x", "-k", select,
                         "-p", "no:cacheprovider"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
@@ -45,3 +45,10 @@ def test_64_key_blocks_attention():
 def test_128_key_blocks_attention():
     """MOLLY_ATTN_KVB=128: the 128-key kernel, whichever is the default."""
     _run({"MOLLY_ATTN_KVB": "128"}, "attention")
+
+
+def test_concurrent_modalities():
+    """MOLLY_CONCURRENT_MODALITIES=1: the DNA/RNA and the protein encoder run on two streams (two branches of the CUDA
+    graph in the captured form); results must not change."""
+    _run({"MOLLY_CONCURRENT_MODALITIES": "1"}, "golden or graph or embed_and_process or ids_on_device",
+         files=("tests/test_gpu_path.py", "tests/test_gpu_graph.py", "tests/test_gpu_inputs.py"))

@@ -170,3 +170,12 @@ def test_bench_workloads_build_valid_batches():
             if len(plan):
                 planner.check_vocab(planner.gather_ids(omic_ids, plan), vocab)
                 planner.check_placement(plan, small["K"], small["B"], small["T"])
+
+
+def test_ranges_disjoint_decides_concurrency():
+    nt = planner.ModalityPlan([0, 1], [0, 0], [10, 5])
+    pr = planner.ModalityPlan([0, 1], [1, 1], [60, -1])
+    assert planner.ranges_disjoint(nt, 40, pr, 40)              # [11,51) vs [61,101); start -1 is skipped
+    assert not planner.ranges_disjoint(nt, 40, planner.ModalityPlan([0], [1], [49]), 40)   # [11,51) vs [50,90)
+    assert planner.ranges_disjoint(nt, 40, planner.ModalityPlan([1], [1], [10]), 40) is False   # sample 1: [6,46) vs [11,51)
+    assert planner.ranges_disjoint(nt, 40, planner.ModalityPlan([], [], []), 40)
