@@ -75,6 +75,8 @@ class FastOmicsPath:
         self._side_streams = {}
         self._proj_modules = {}             # name -> nn.Linear (live parameters, for --train-mlp)
         self._proj_versions = {}
+        self._enc_modules = {}              # name -> EsmForMaskedLM (live parameters: --train-bio, late checkpoint loads)
+        self._enc_versions = {}
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -103,6 +105,10 @@ class FastOmicsPath:
         self = cls(one(om.dna_rna_model, om.dna_rna_projector, om.dna_rna_project_token_num),
                    one(om.protein_model, om.protein_projector, om.protein_project_token_num), strict=strict)
         self._proj_modules = {"dna_rna": om.dna_rna_projector, "protein": om.protein_projector}
+        self._enc_modules = {k: m for k, m in (("dna_rna", om.dna_rna_model), ("protein", om.protein_model))
+                             if m is not None}
+        for name, m in self._enc_modules.items():
+            self._enc_versions[name] = self._module_version(m)
         return self
 
     def install(self, om) -> None:
@@ -127,6 +133,8 @@ class FastOmicsPath:
                                "(the B200 path has no CPU fallback)")
         dev = hidden_states.device
         batch_size = hidden_states.shape[0]
+        if self._enc_modules:
+            self.refresh_encoders()
         nt_plan, pr_plan = planner.route(batch_size, omic_ids_list, omic_info_list)          # may raise ValueError
         # reference order: all DNA/RNA sequences, then all protein sequences (omics_one.py:120-134)
         work = [(name, plan) for name, plan in (("dna_rna", nt_plan), ("protein", pr_plan)) if len(plan)]  # :67-68
@@ -284,6 +292,28 @@ class FastOmicsPath:
         small B the ~200-450 launches, not the math, set the latency).  The returned callable copies the new ``input_ids``
         and ``omic_ids`` into its static buffers, replays, and returns its static ``inputs_embeds`` buffer."""
         return GraphedOmicsCall(self, embed_weight, batch_size, seq_len, omic_types, k_tokens, tuple(pad_token_ids))
+
+    @staticmethod
+    def _module_version(module) -> tuple:
+        """Changes whenever a parameter is updated in place (optimizer step, load_state_dict) or re-bound."""
+        v = p_sum = 0
+        for prm in module.parameters():
+            v += prm._version
+            p_sum ^= prm.data_ptr()
+        return (v, p_sum)
+
+    def refresh_encoders(self) -> List[str]:
+        """Re-pack (in place) the encoders whose live ``nn.Module`` weights changed since they were packed: encoders
+        trained with ``--train-bio`` (src/utils/tools.py:313-331) or checkpoints loaded after ``from_omics_one``.
+        Called at the top of every ``process_omic_sequences`` when live modules are attached."""
+        done = []
+        for name, module in self._enc_modules.items():
+            ver = self._module_version(module)
+            if self._enc_versions.get(name) != ver and name in self._ids:
+                ops.get_encoder(self._ids[name]).reload(module.state_dict())
+                self._enc_versions[name] = ver
+                done.append(name)
+        return done
 
     def _refresh_projector(self, name: str, enc: PackedEncoder, proj) -> None:
         ver = (proj.weight._version, proj.bias._version, proj.weight.data_ptr())

@@ -44,74 +44,90 @@ class PackedEncoder:
         if projector["weight"].shape[1] != h:
             raise ValueError(f"projector in_features {projector['weight'].shape[1]} != encoder hidden {h}")
 
-        def mat(t):   # bf16 matrix on device
-            o = t.detach().to(device=device, dtype=torch.float32).to(torch.bfloat16).contiguous()
+        self._recipes = []          # (kept tensor, builder(state_dict) -> source tensor): replayed by reload()
+
+        def mat(build):   # bf16 matrix on device
+            o = build(state_dict).detach().to(device=device, dtype=torch.float32).to(torch.bfloat16).contiguous()
             self._keep.append(o)
+            self._recipes.append((o, build))
             return o
 
-        def vec(t):   # fp32 vector on device
-            o = t.detach().to(device=device, dtype=torch.float32).contiguous()
+        def vec(build):   # fp32 vector on device
+            o = build(state_dict).detach().to(device=device, dtype=torch.float32).contiguous()
+            self._keep.append(o)
+            self._recipes.append((o, build))
+            return o
+
+        def key(name):
+            return lambda sd_: sd_[name]
+
+        def const(t):     # tables that do not depend on the checkpoint
+            o = t.to(device=device, dtype=torch.float32).contiguous()
             self._keep.append(o)
             return o
 
         sd = state_dict
         w = _lib.EncoderWeights()
-        w.word_emb_dev = _ptr(mat(sd["esm.embeddings.word_embeddings.weight"]))
+        w.word_emb_dev = _ptr(mat(key("esm.embeddings.word_embeddings.weight")))
         w.pos_emb_dev = None
         if cfg.position_embedding_type == "absolute":
-            w.pos_emb_dev = _ptr(mat(sd["esm.embeddings.position_embeddings.weight"]))
+            w.pos_emb_dev = _ptr(mat(key("esm.embeddings.position_embeddings.weight")))
         w.emb_ln_w_dev = w.emb_ln_b_dev = None
         if cfg.emb_layer_norm_before:
-            w.emb_ln_w_dev = _ptr(vec(sd["esm.embeddings.layer_norm.weight"]))
-            w.emb_ln_b_dev = _ptr(vec(sd["esm.embeddings.layer_norm.bias"]))
+            w.emb_ln_w_dev = _ptr(vec(key("esm.embeddings.layer_norm.weight")))
+            w.emb_ln_b_dev = _ptr(vec(key("esm.embeddings.layer_norm.bias")))
         # rotary tables exactly as HF:81-115 builds them, in fp32
         d = cfg.head_dim
         self.rope_len = max(int(rope_len), int(cfg.max_position_embeddings))
         inv_freq = 1.0 / (10000 ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))
         freqs = torch.outer(torch.arange(self.rope_len).float(), inv_freq)
-        w.rope_cos_dev = _ptr(vec(freqs.cos()))
-        w.rope_sin_dev = _ptr(vec(freqs.sin()))
+        w.rope_cos_dev = _ptr(const(freqs.cos()))
+        w.rope_sin_dev = _ptr(const(freqs.sin()))
         w.rope_len = self.rope_len
-        w.rope_cos_t_dev = _ptr(vec(freqs.cos().t()))      # frequency-major copies for the fused QKV epilogue
-        w.rope_sin_t_dev = _ptr(vec(freqs.sin().t()))
+        w.rope_cos_t_dev = _ptr(const(freqs.cos().t()))      # frequency-major copies for the fused QKV epilogue
+        w.rope_sin_t_dev = _ptr(const(freqs.sin().t()))
 
         names = ["ln1_w", "ln1_b", "w_qkv", "b_qkv", "w_attn_out", "b_attn_out", "ln2_w", "ln2_b", "w_ffn1", "b_ffn1",
                  "w_ffn2", "b_ffn2"]
         arrays: Dict[str, List[Optional[int]]] = {n: [] for n in names}
         for i in range(L):
             p = f"esm.encoder.layer.{i}."
-            arrays["ln1_w"].append(_ptr(vec(sd[p + "attention.LayerNorm.weight"])))
-            arrays["ln1_b"].append(_ptr(vec(sd[p + "attention.LayerNorm.bias"])))
-            wq, wk, wv = (sd[p + f"attention.self.{n}.weight"] for n in ("query", "key", "value"))
-            bq, bk, bv = (sd[p + f"attention.self.{n}.bias"] for n in ("query", "key", "value"))
-            arrays["w_qkv"].append(_ptr(mat(torch.cat([wq, wk, wv], dim=0))))
-            arrays["b_qkv"].append(_ptr(vec(torch.cat([bq, bk, bv], dim=0))))
-            arrays["w_attn_out"].append(_ptr(mat(sd[p + "attention.output.dense.weight"])))
-            arrays["b_attn_out"].append(_ptr(vec(sd[p + "attention.output.dense.bias"])))
-            arrays["ln2_w"].append(_ptr(vec(sd[p + "LayerNorm.weight"])))
-            arrays["ln2_b"].append(_ptr(vec(sd[p + "LayerNorm.bias"])))
-            w1 = sd[p + "intermediate.dense.weight"]
+            arrays["ln1_w"].append(_ptr(vec(key(p + "attention.LayerNorm.weight"))))
+            arrays["ln1_b"].append(_ptr(vec(key(p + "attention.LayerNorm.bias"))))
+            arrays["w_qkv"].append(_ptr(mat(lambda sd_, p=p: torch.cat(
+                [sd_[p + f"attention.self.{n}.weight"] for n in ("query", "key", "value")], dim=0))))
+            arrays["b_qkv"].append(_ptr(vec(lambda sd_, p=p: torch.cat(
+                [sd_[p + f"attention.self.{n}.bias"] for n in ("query", "key", "value")], dim=0))))
+            arrays["w_attn_out"].append(_ptr(mat(key(p + "attention.output.dense.weight"))))
+            arrays["b_attn_out"].append(_ptr(vec(key(p + "attention.output.dense.bias"))))
+            arrays["ln2_w"].append(_ptr(vec(key(p + "LayerNorm.weight"))))
+            arrays["ln2_b"].append(_ptr(vec(key(p + "LayerNorm.bias"))))
             if cfg.ffn_type == "glu":
-                if w1.shape[0] != 2 * Fi:
-                    raise ValueError(f"GLU intermediate.dense.weight must be [2F, h], got {tuple(w1.shape)}")
+                if sd[p + "intermediate.dense.weight"].shape[0] != 2 * Fi:
+                    raise ValueError(f"GLU intermediate.dense.weight must be [2F, h], got "
+                                     f"{tuple(sd[p + 'intermediate.dense.weight'].shape)}")
+
                 # silu(x1) * x2 with x1 = rows [0,F), x2 = rows [F,2F)  ->  interleave (x1_0, x2_0, x1_1, x2_1, ...)
-                w1 = torch.stack([w1[:Fi], w1[Fi:]], dim=1).reshape(2 * Fi, h)
-                arrays["w_ffn1"].append(_ptr(mat(w1)))
+                def glu(sd_, p=p):
+                    w1 = sd_[p + "intermediate.dense.weight"]
+                    return torch.stack([w1[:Fi], w1[Fi:]], dim=1).reshape(2 * Fi, h)
+
+                arrays["w_ffn1"].append(_ptr(mat(glu)))
                 arrays["b_ffn1"].append(None)
-                arrays["w_ffn2"].append(_ptr(mat(sd[p + "output.dense.weight"])))
+                arrays["w_ffn2"].append(_ptr(mat(key(p + "output.dense.weight"))))
                 arrays["b_ffn2"].append(None)
             else:
-                arrays["w_ffn1"].append(_ptr(mat(w1)))
-                arrays["b_ffn1"].append(_ptr(vec(sd[p + "intermediate.dense.bias"])))
-                arrays["w_ffn2"].append(_ptr(mat(sd[p + "output.dense.weight"])))
-                arrays["b_ffn2"].append(_ptr(vec(sd[p + "output.dense.bias"])))
+                arrays["w_ffn1"].append(_ptr(mat(key(p + "intermediate.dense.weight"))))
+                arrays["b_ffn1"].append(_ptr(vec(key(p + "intermediate.dense.bias"))))
+                arrays["w_ffn2"].append(_ptr(mat(key(p + "output.dense.weight"))))
+                arrays["b_ffn2"].append(_ptr(vec(key(p + "output.dense.bias"))))
         self._ptr_arrays = {}
         for n in names:
             arr = (C.c_void_p * L)(*arrays[n])
             self._ptr_arrays[n] = arr
             setattr(w, n + "_dev", C.cast(arr, _lib.c_void_pp))
-        w.final_ln_w_dev = _ptr(vec(sd["esm.encoder.emb_layer_norm_after.weight"]))
-        w.final_ln_b_dev = _ptr(vec(sd["esm.encoder.emb_layer_norm_after.bias"]))
+        w.final_ln_w_dev = _ptr(vec(key("esm.encoder.emb_layer_norm_after.weight")))
+        w.final_ln_b_dev = _ptr(vec(key("esm.encoder.emb_layer_norm_after.bias")))
         # projector buffers are refreshed in place when the nn.Linear trains (--train-mlp)
         self.proj_w = torch.empty(self.llm_hidden_size, h, dtype=torch.bfloat16, device=device)
         self.proj_b = torch.empty(self.llm_hidden_size, dtype=torch.float32, device=device)
@@ -135,6 +151,17 @@ class PackedEncoder:
                        "molly_encoder_create")
 
     # ------------------------------------------------------------------
+    @torch.no_grad()
+    def reload(self, state_dict: Mapping[str, torch.Tensor]) -> None:
+        """Refresh the packed ENCODER weights in place from a new state dict (same shapes): device addresses, the native
+        handle and its cached TMA descriptors stay valid.  SURVEY.md 8b: packed copies are caches that must follow the
+        ``nn.Module`` weights when the encoders train (``--train-bio``) or a checkpoint is loaded after construction."""
+        for dst, build in self._recipes:
+            src = build(state_dict)
+            if tuple(src.shape) != tuple(dst.shape):
+                raise ValueError(f"reload: shape {tuple(src.shape)} does not match the packed {tuple(dst.shape)}")
+            dst.copy_(src.detach().to(device=dst.device, dtype=torch.float32))
+
     def load_projector(self, weight: torch.Tensor, bias: torch.Tensor) -> None:
         """(Re)pack ``nn.Linear`` projector parameters into the buffers the kernels read."""
         self.proj_w.copy_(weight.detach())

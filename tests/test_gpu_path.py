@@ -307,3 +307,48 @@ def test_overlapping_ranges_keep_reference_order():
             assert_close("protein rows win", out[0, lo:lo + case.K].float().cpu(), ref[0, lo:lo + case.K], TOL)
     finally:
         path.close()
+
+
+def test_from_omics_one_follows_live_encoder_weights():
+    """SURVEY 8b ownership: the packed weights are caches of the three ``nn.Module``s.  Built from an ``OmicsOne``-shaped
+    object holding stock HF ``EsmForMaskedLM`` encoders, the path must (1) reproduce the oracle and (2) follow in-place weight
+    updates (``--train-bio`` optimizer steps, late ``load_state_dict``) without being rebuilt."""
+    import types
+    from molly_b200.omics_path import FastOmicsPath
+    from oracle.ref_import import build_hf_encoder
+    case = cases.golden_cases()["tiny_absolute_leftpad"]             # tiny_ntv1 (stock ESM classes) + tiny_esm2
+    om = types.SimpleNamespace()
+    om.dna_rna_model = build_hf_encoder(case.nt.spec, case.nt.weights)
+    om.protein_model = build_hf_encoder(case.pr.spec, case.pr.weights)
+    om.dna_rna_projector = torch.nn.Linear(case.nt.spec.hidden_size, case.D)
+    om.protein_projector = torch.nn.Linear(case.pr.spec.hidden_size, case.D)
+    om.dna_rna_projector.load_state_dict(case.nt.projector)
+    om.protein_projector.load_state_dict(case.pr.projector)
+    om.dna_rna_project_token_num = case.nt.project_token_num
+    om.protein_project_token_num = case.pr.project_token_num
+    path = FastOmicsPath.from_omics_one(om, DEV, strict=True)
+    try:
+        hs = case.batch.hidden_states.to(DEV)
+        with torch.no_grad():
+            out = path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
+        check_merged("from_omics_one", case, out, oracle_out(case), torch.float32)
+        assert path.refresh_encoders() == []
+        # an "optimizer step" on the protein encoder + a checkpoint load into the DNA/RNA encoder
+        import copy
+        new_pr = {k: (v * 1.05 if v.dtype.is_floating_point and v.dim() == 2 else v) for k, v in case.pr.weights.items()}
+        new_nt = {k: (v * 0.97 if v.dtype.is_floating_point and v.dim() == 2 else v) for k, v in case.nt.weights.items()}
+        with torch.no_grad():
+            for name, prm in om.protein_model.named_parameters():
+                if name in new_pr:
+                    prm.copy_(new_pr[name])
+        om.dna_rna_model.load_state_dict(new_nt, strict=False)
+        pr2, nt2 = copy.copy(case.pr), copy.copy(case.nt)
+        pr2.weights, nt2.weights = new_pr, new_nt
+        ref2 = case.batch.hidden_states.clone()
+        with torch.no_grad():
+            oracle_process(ref2, case.batch.omic_ids, case.batch.omic_info_list, nt2, pr2)
+            out2 = path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
+        assert not torch.equal(out2, out)
+        assert_close("after in-place weight updates", out2.float().cpu(), ref2, TOL)
+    finally:
+        path.close()
