@@ -447,7 +447,15 @@ def main() -> None:
             dist.destroy_process_group()
         return
     path = build_path(wl, dev, strict=False)
-    omic_ids, infos = make_inputs(wl, seed=1234 + rank)
+    if wl.get("layout") == "mixed_varlen" and world > 1:
+        # one global batch, samples dealt to ranks with equal counts and balanced attention cost
+        from molly_b200 import planner
+        g_ids, g_infos = make_inputs(dict(wl, B=wl["B"] * world), seed=1234)
+        costs = [float((g_ids[b] != 1).sum()) for b in range(g_ids.shape[0])]          # keys the attention really reads
+        mine = planner.balance_equal_count(costs, world)[rank]
+        omic_ids, infos = g_ids[mine].contiguous(), [g_infos[b] for b in mine]
+    else:
+        omic_ids, infos = make_inputs(wl, seed=1234 + rank)
     omic_ids_dev = omic_ids.to(dev)
     omic_ids_pinned = omic_ids.pin_memory()
     hs = (torch.randn(wl["B"], wl["T"], wl["D"], device=dev) * 0.02).to(torch.bfloat16)

@@ -123,3 +123,19 @@ def balance_by_cost(costs: Sequence[float], world_size: int) -> List[List[int]]:
     for lst in out:
         lst.sort()
     return out
+
+
+def balance_equal_count(costs: Sequence[float], world_size: int) -> List[List[int]]:
+    """Same number of samples on every rank (the per-sample cost is dominated by the K rows every sequence computes,
+    whatever its length), variable part balanced: samples sorted by cost and dealt in snake order (0..W-1, W-1..0, ...).
+    ``len(costs)`` must be a multiple of ``world_size``."""
+    if len(costs) % world_size:
+        raise ValueError(f"{len(costs)} samples do not split evenly over {world_size} ranks")
+    order = sorted(range(len(costs)), key=lambda i: -costs[i])
+    out: List[List[int]] = [[] for _ in range(world_size)]
+    for pos, i in enumerate(order):
+        rnd, off = divmod(pos, world_size)
+        out[off if rnd % 2 == 0 else world_size - 1 - off].append(i)
+    for lst in out:
+        lst.sort()
+    return out

@@ -179,3 +179,15 @@ def test_ranges_disjoint_decides_concurrency():
     assert not planner.ranges_disjoint(nt, 40, planner.ModalityPlan([0], [1], [49]), 40)   # [11,51) vs [50,90)
     assert planner.ranges_disjoint(nt, 40, planner.ModalityPlan([1], [1], [10]), 40) is False   # sample 1: [6,46) vs [11,51)
     assert planner.ranges_disjoint(nt, 40, planner.ModalityPlan([], [], []), 40)
+
+
+def test_balance_equal_count():
+    costs = [64, 2048, 100, 1500, 90, 700, 1024, 80]
+    parts = planner.balance_equal_count(costs, 2)
+    assert sorted(parts[0] + parts[1]) == list(range(8)) and len(parts[0]) == len(parts[1]) == 4
+    loads = [sum(costs[i] for i in p) for p in parts]
+    assert abs(loads[0] - loads[1]) <= 0.15 * max(loads), loads
+    naive = [sum(costs[:4]), sum(costs[4:])]
+    assert abs(loads[0] - loads[1]) < abs(naive[0] - naive[1])
+    with pytest.raises(ValueError):
+        planner.balance_equal_count(costs[:7], 2)
