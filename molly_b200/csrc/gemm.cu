@@ -24,7 +24,6 @@
 
 namespace molly {
 
-bool gemm_use_pair(int N, int epi);
 
 namespace {
 
@@ -32,6 +31,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                      // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int B_BOX_ROWS = 128;                  // rows of one TMA box of the weight map: every tile shape is built from these
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int STG_BUF_BYTES = 32 * 128;          // one staging buffer: 32 rows x 128 B (SWIZZLE_128B box)
@@ -200,7 +200,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     } else {
                         mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
                         tma_load_2d(sA + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], kb * BLOCK_K, a_row);
-                        tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tma_b, &full_bar[stage], kb * BLOCK_K, b_row);
+#pragma unroll
+                        for (int bx = 0; bx < BLOCK_N / B_BOX_ROWS; ++bx)      // the weight map has 128-row boxes
+                            tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES + bx * B_BOX_ROWS * BLOCK_K * 2, &tma_b,
+                                        &full_bar[stage], kb * BLOCK_K, b_row + bx * B_BOX_ROWS);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -527,35 +530,35 @@ bool g_pair_enabled() {
 }
 
 template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS = 1>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, bool pair,
                 cudaStream_t stream) {
     if constexpr (BLOCK_N == 256 && EPI != EPI_SCATTER) {
-        if (gemm_use_pair(p.N, EPI)) return launch_gemm_impl<256, EPI, OutT, STG_BUFS, true>(ta, tb, tc, p, stream);
+        if (pair) return launch_gemm_impl<256, EPI, OutT, STG_BUFS, true>(ta, tb, tc, p, stream);
     }
     return launch_gemm_impl<BLOCK_N, EPI, OutT, STG_BUFS, false>(ta, tb, tc, p, stream);
 }
 
 template <int BLOCK_N>
 int dispatch_epilogue(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int epi,
-                      int out_dtype, cudaStream_t stream) {
+                      int out_dtype, bool pair, cudaStream_t stream) {
     const bool f32 = out_dtype == DT_F32;
     switch (epi) {
         case EPI_BIAS:
-            return f32 ? launch_gemm<BLOCK_N, EPI_BIAS, float>(ta, tb, tc, p, stream)
-                       : launch_gemm<BLOCK_N, EPI_BIAS, __nv_bfloat16>(ta, tb, tc, p, stream);
+            return f32 ? launch_gemm<BLOCK_N, EPI_BIAS, float>(ta, tb, tc, p, pair, stream)
+                       : launch_gemm<BLOCK_N, EPI_BIAS, __nv_bfloat16>(ta, tb, tc, p, pair, stream);
         case EPI_BIAS_GELU:
-            return launch_gemm<BLOCK_N, EPI_BIAS_GELU, __nv_bfloat16>(ta, tb, tc, p, stream);
+            return launch_gemm<BLOCK_N, EPI_BIAS_GELU, __nv_bfloat16>(ta, tb, tc, p, pair, stream);
         case EPI_BIAS_RESID:       // short K: the epilogue is a large share -> prefetch residual chunks; long K: deeper ring
-            return p.K >= 2048 ? launch_gemm<BLOCK_N, EPI_BIAS_RESID, float, 1>(ta, tb, tc, p, stream)
-                               : launch_gemm<BLOCK_N, EPI_BIAS_RESID, float, 2>(ta, tb, tc, p, stream);
+            return p.K >= 2048 ? launch_gemm<BLOCK_N, EPI_BIAS_RESID, float, 1>(ta, tb, tc, p, pair, stream)
+                               : launch_gemm<BLOCK_N, EPI_BIAS_RESID, float, 2>(ta, tb, tc, p, pair, stream);
         case EPI_BIAS_ROPE:
-            return launch_gemm<BLOCK_N, EPI_BIAS_ROPE, __nv_bfloat16>(ta, tb, tc, p, stream);
+            return launch_gemm<BLOCK_N, EPI_BIAS_ROPE, __nv_bfloat16>(ta, tb, tc, p, pair, stream);
         case EPI_GLU:
-            if constexpr (BLOCK_N == 256) return launch_gemm<256, EPI_GLU, __nv_bfloat16>(ta, tb, tc, p, stream);
+            if constexpr (BLOCK_N == 256) return launch_gemm<256, EPI_GLU, __nv_bfloat16>(ta, tb, tc, p, pair, stream);
             MOLLY_CHECK(false, MOLLY_ERR_UNSUPPORTED, "gemm: GLU epilogue needs 256-wide tiles");
         case EPI_SCATTER:
-            return f32 ? launch_gemm<BLOCK_N, EPI_SCATTER, float>(ta, tb, tc, p, stream)
-                       : launch_gemm<BLOCK_N, EPI_SCATTER, __nv_bfloat16>(ta, tb, tc, p, stream);
+            return f32 ? launch_gemm<BLOCK_N, EPI_SCATTER, float>(ta, tb, tc, p, pair, stream)
+                       : launch_gemm<BLOCK_N, EPI_SCATTER, __nv_bfloat16>(ta, tb, tc, p, pair, stream);
         default:
             MOLLY_CHECK(false, MOLLY_ERR_INVALID, "gemm: unknown epilogue %d", epi);
     }
@@ -563,14 +566,18 @@ int dispatch_epilogue(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
 
 }  // namespace
 
-// CTA-pair (cta_group::2) tiles: 256 x 256 per pair; used whenever N is a whole number of 256-column tiles.
-bool gemm_use_pair(int N, int epi) { return g_pair_enabled() && epi != EPI_SCATTER && N % 256 == 0; }
-
-int gemm_block_n(int N, int epi) {
-    if (epi == EPI_GLU) return 256;
-    // 256-wide tiles unless the last tile would be mostly padding
-    const int t256 = (N + 255) / 256 * 256, t128 = (N + 127) / 128 * 128;
-    return (t256 * 10 > t128 * 11) ? 128 : 256;
+// Tile shape per problem: a CTA pair (cta_group::2) on 256 x 256, one CTA on 128 x 256 or one CTA on 128 x 128.  The pair
+// is the fastest per FLOP (half the B traffic per SM), but small problems (generate-sized batches) fill the GPU better with
+// smaller tiles.  Cost model: waves x per-SM work of one tile / measured relative efficiency of the shape.
+GemmTile gemm_pick_tile(int M, int N, int epi) {
+    const int sms = device_sm_count();
+    auto cdiv = [](int a, int b) { return (a + b - 1) / b; };
+    const bool pair_ok = g_pair_enabled() && epi != EPI_SCATTER && N % 256 == 0;
+    const double c_pair = pair_ok ? cdiv(cdiv(M, 256) * cdiv(N, 256), sms / 2) * 2.0 : 1e30;
+    const double c_256 = cdiv(cdiv(M, 128) * cdiv(N, 256), sms) * 2.0 / 0.90;
+    const double c_128 = epi == EPI_GLU ? 1e30 : cdiv(cdiv(M, 128) * cdiv(N, 128), sms) * 1.0 / 0.70;
+    if (c_pair <= c_256 && c_pair <= c_128) return GEMM_TILE_PAIR_256;
+    return c_256 <= c_128 ? GEMM_TILE_256 : GEMM_TILE_128;
 }
 
 int gemm_make_map_a(CUtensorMap* ta, const void* a, int lda, int M, int K) {
@@ -584,8 +591,9 @@ int gemm_make_map_b(CUtensorMap* tb, const void* w, int ldw, int N, int K, int e
     MOLLY_CHECK(K % 8 == 0 && ldw % 8 == 0, MOLLY_ERR_UNSUPPORTED,
                 "gemm: K and ldw must be multiples of 8 (16-B TMA strides); got K=%d ldw=%d", K, ldw);
     MOLLY_CHECK((reinterpret_cast<uintptr_t>(w) & 15) == 0, MOLLY_ERR_INVALID, "gemm: W must be 16-B aligned");
-    // a CTA pair splits the 256 B rows of a tile: each CTA loads a 128-row box
-    return make_tma_2d(tb, w, N, K, ldw, gemm_use_pair(N, epi) ? 128 : gemm_block_n(N, epi), BLOCK_K, 2);
+    // 128-row boxes: a CTA pair loads one per CTA, a single-CTA tile one or two (rows past N are zero-filled by the TMA unit)
+    (void)epi;
+    return make_tma_2d(tb, w, N, K, ldw, B_BOX_ROWS, BLOCK_K, 2);
 }
 
 // Output (and residual) map: 32-row x 128-byte boxes, 128-B swizzle.  `n_out` = columns of the OUTPUT matrix.
@@ -631,8 +639,9 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap*
     }
     GemmParams p{M, N, K, bias, out, ldo, seq_table, seq_k, B, T, k_cap, err_flag, scale_cols, scale,
                  rope_cos_t, rope_sin_t, rope_len, rope_cols, rope_head_dim};
-    if (gemm_block_n(N, epi) == 256) return dispatch_epilogue<256>(ta, tb, *tc, p, epi, out_dtype, stream);
-    return dispatch_epilogue<128>(ta, tb, *tc, p, epi, out_dtype, stream);
+    const GemmTile tile = gemm_pick_tile(M, N, epi);
+    if (tile == GEMM_TILE_128) return dispatch_epilogue<128>(ta, tb, *tc, p, epi, out_dtype, false, stream);
+    return dispatch_epilogue<256>(ta, tb, *tc, p, epi, out_dtype, tile == GEMM_TILE_PAIR_256, stream);
 }
 
 }  // namespace molly

@@ -27,8 +27,8 @@ void set_gemm_family(int f);  // tag for the next gemm_launch calls of this thre
 int gemm_family();
 
 // ---- gemm.cu ----
-int gemm_block_n(int N, int epi);
-bool gemm_use_pair(int N, int epi);
+enum GemmTile { GEMM_TILE_PAIR_256 = 0, GEMM_TILE_256 = 1, GEMM_TILE_128 = 2 };
+GemmTile gemm_pick_tile(int M, int N, int epi);
 int gemm_make_map_a(CUtensorMap* ta, const void* a, int lda, int M, int K);
 int gemm_make_map_b(CUtensorMap* tb, const void* w, int ldw, int N, int K, int epi);
 int gemm_make_map_c(CUtensorMap* tc, void* out, int out_dtype, int ldo, int M, int n_out);
