@@ -10,7 +10,7 @@ import torch
 
 from oracle import cases, synth
 from oracle.esm_oracle import process_omic_sequences as oracle_process
-from tests.test_gpu_path import build_path, check_merged
+from tests.test_gpu_path import TOL, build_path, check_merged
 from tests.util import assert_close
 
 pytestmark = pytest.mark.gpu
@@ -90,5 +90,64 @@ def test_cfg2_full_size_properties():
             h = base[sl].clone()
             parts.append(path.process_omic_sequences(h, omic_ids[sl], infos[sl], dev))
         assert torch.equal(torch.cat(parts), out)
+    finally:
+        path.close()
+
+
+def _trained_like(weights, seed):
+    """Make random-init weights look like a trained checkpoint where it matters for numerics: sharp attention (q/k x6),
+    a few dominant residual channels (LayerNorm gains x25, as in ESM-2's outlier features), non-zero biases."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, v in weights.items():
+        v = v.clone()
+        if k.endswith(("query.weight", "key.weight")):
+            v *= 6.0
+        elif k.endswith("LayerNorm.weight") or k.endswith("emb_layer_norm_after.weight"):
+            idx = torch.randperm(v.numel(), generator=g)[:3]
+            v[idx] *= 25.0
+        elif k.endswith(".bias") and v.dim() == 1:
+            v += torch.randn(v.shape, generator=g) * 0.05
+        out[k] = v.to(torch.bfloat16).float()                      # keep the case bf16-exact like the other cases
+    return out
+
+
+def _encoder_errors(path, case, name, mod):
+    """Normalised max error of the last hidden state against the fp32 oracle: (the reference's own stack -- HF modules in
+    bf16 on the GPU, eager attention --, this repo)."""
+    from oracle.esm_oracle import esm_encoder_forward
+    from oracle.ref_import import build_hf_encoder
+    rows = [case.batch.omic_ids[b, i] for b, row in enumerate(case.batch.omic_info_list) for i, info in enumerate(row)
+            if info["type"] != "pad" and (info["type"] == "protein") == (name == "protein")]
+    ids = torch.stack(rows)
+    with torch.no_grad():
+        ref = esm_encoder_forward(mod.spec, mod.weights, ids)
+        hf = build_hf_encoder(mod.spec, mod.weights).to(DEV).to(torch.bfloat16)
+        hf_out = hf(input_ids=ids.to(DEV), attention_mask=(ids != 1).to(DEV),
+                    output_hidden_states=True).hidden_states[-1].float().cpu()
+        ours = path.encode(name, ids.to(DEV)).float().cpu().view_as(ref)
+    scale = float(ref.abs().max())
+    return float((hf_out - ref).abs().max()) / scale, float((ours - ref).abs().max()) / scale
+
+
+@pytest.mark.parametrize("trained_like", [False, True])
+def test_closer_to_fp32_than_the_references_own_bf16_run(trained_like):
+    """The reference executes its encoders in bf16 (src/inference_lora.py:249, DeepSpeed bf16).  Against the fp32 oracle this
+    path must be at least as accurate as THAT execution (stock HF modules, bf16, same GPU) -- also for weights with trained-
+    checkpoint statistics (peaked softmax rows, outlier channels), where ANY bf16 evaluation is chaotic (near-ties in a hard
+    softmax flip) and the absolute 2e-2 bar of the random-init cases cannot be the criterion."""
+    case = cases.build_case("trained_like", "tiny_ntv2", "tiny_esm2", D=128, K=200, T=700, seed=5000,
+                            samples=[[("dna", 200), ("protein", 150)], [("rna", 77), ("protein", 200)]], mask_tokens=True)
+    if trained_like:
+        case.nt.weights = _trained_like(case.nt.weights, 1)
+        case.pr.weights = _trained_like(case.pr.weights, 2)
+    path = build_path(case)
+    try:
+        for name, mod in (("protein", case.pr), ("dna_rna", case.nt)):
+            hf_err, our_err = _encoder_errors(path, case, name, mod)
+            print(f"[{name} trained_like={trained_like}] vs fp32 oracle: HF bf16 {hf_err:.4f}  molly_b200 {our_err:.4f}")
+            assert our_err <= max(TOL, hf_err), (name, our_err, hf_err)
+            if not trained_like:
+                assert our_err <= TOL
     finally:
         path.close()
