@@ -33,7 +33,7 @@ namespace {
 #define ATT_ABLATE 0
 #endif
 
-// -DATT_TIMELINE: clock64 timeline of the first 2048 CTAs of the default kernel (tools/attn_timeline2.py), 72 slots each.
+// -DATT_TIMELINE: clock64 timeline of the first 2048 CTAs of the default kernel (tools/attn_timeline.py), 72 slots each.
 #ifdef ATT_TIMELINE
 __device__ long long* d_attn_tl = nullptr;
 #define TL(slot)                                                                                               \

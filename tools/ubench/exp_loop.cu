@@ -1,6 +1,7 @@
 // Microbenchmark: cycles per element of the attention exp2 loop (FFMA2 -> 2x MUFU.EX2 -> FADD2, 128 elements in
 // registers, as in softmax_block) as a function of the warps resident per SM sub-partition.
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o exp_loop exp_loop.cu
+// Measured on B200 (round 1), cycles per 128-element pass per warp: 1 warp/scheduler 1 145 (MUFU 89 % busy), 2 warps 2 111, 3 warps 3 127.
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
