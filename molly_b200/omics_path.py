@@ -135,6 +135,13 @@ class FastOmicsPath:
         batch_size = hidden_states.shape[0]
         if self._enc_modules:
             self.refresh_encoders()
+            if torch.is_grad_enabled():
+                for name, module in self._enc_modules.items():
+                    if any(prm.requires_grad for prm in module.parameters()):
+                        raise NotImplementedError(
+                            f"the {name} encoder has trainable parameters (--train-bio, src/utils/tools.py:313-331): the "
+                            "encoder backward is not built yet (SURVEY.md 8f N4); freeze the encoders or call under "
+                            "torch.no_grad() -- refusing to train them silently as frozen")
         nt_plan, pr_plan = planner.route(batch_size, omic_ids_list, omic_info_list)          # may raise ValueError
         # reference order: all DNA/RNA sequences, then all protein sequences (omics_one.py:120-134)
         work = [(name, plan) for name, plan in (("dna_rna", nt_plan), ("protein", pr_plan)) if len(plan)]  # :67-68

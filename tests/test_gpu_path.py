@@ -350,5 +350,14 @@ def test_from_omics_one_follows_live_encoder_weights():
             out2 = path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
         assert not torch.equal(out2, out)
         assert_close("after in-place weight updates", out2.float().cpu(), ref2, TOL)
+        # --train-bio is not built: trainable encoder parameters under autograd must fail loudly, never train as frozen
+        for prm in om.dna_rna_model.parameters():
+            prm.requires_grad_(False)
+        for prm in om.protein_model.parameters():
+            prm.requires_grad_(False)
+        path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)   # frozen: fine
+        next(om.protein_model.parameters()).requires_grad_(True)
+        with pytest.raises(NotImplementedError, match="train-bio"):
+            path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
     finally:
         path.close()
