@@ -204,12 +204,12 @@ def esm_self_attention(spec: EncoderSpec, W: Dict[str, Tensor], p: str, x_ln: Te
     v = lin("value").view(N, K, H, d).transpose(1, 2)
     q = q * d ** -0.5                                           # HF:341 scale BEFORE rotary
     if spec.position_embedding_type == "rotary":
-        cos, sin = rotary_tables(K, d, q.dtype)
+        cos, sin = (t.to(q.device) for t in rotary_tables(K, d, q.dtype))   # (tests also run this checker on a GPU)
         q = q * cos + rotate_half(q) * sin                      # HF:48-54
         k = k * cos + rotate_half(k) * sin
     scores = torch.matmul(q, k.transpose(2, 3))                 # scaling = 1.0 (HF:315)
     # HF:679-709 create_bidirectional_mask -> additive finfo.min at padded KEYS only (queries all computed)
-    add = torch.zeros(N, 1, 1, K, dtype=scores.dtype)
+    add = torch.zeros(N, 1, 1, K, dtype=scores.dtype, device=scores.device)
     add.masked_fill_(~key_mask.bool()[:, None, None, :], torch.finfo(scores.dtype).min)
     probs = torch.softmax(scores + add, dim=-1)
     out = torch.matmul(probs, v).transpose(1, 2).reshape(N, K, h)

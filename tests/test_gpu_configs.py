@@ -151,3 +151,51 @@ def test_closer_to_fp32_than_the_references_own_bf16_run(trained_like):
                 assert our_err <= TOL
     finally:
         path.close()
+
+
+@pytest.mark.parametrize("workload", ["molly_1p7b", "molly_4b", "molly_8b"])
+def test_full_size_vs_fp32_oracle_run_on_the_gpu(workload):
+    """BASELINE configs[1..3] at FULL size -- [1]: ESM-2 650M + NT-v2 500M, D=2048, 64 x (1 DNA + 1 protein) x 1024 tokens;
+    [2]: D=2560, 64 sequences of mixed kinds with log-uniform lengths in K=2048 slots; [3]: NT-v1 2.5B, D=4096, 256 x 1000-bp
+    DNA windows -- against the fp32 oracle itself.  The oracle is plain torch code, so as the CHECKER it can run on the GPU in
+    fp32 (TF32 off), eight samples at a time; the candidate is the bf16 product path.  Same (bf16-exact) weights on both sides."""
+    import bench
+    from oracle.esm_oracle import SPECS, OracleModality
+    from molly_b200.config import EncoderConfig
+    from molly_b200.omics_path import FastOmicsPath
+    from molly_b200.packing import PackedEncoder
+    torch.backends.cuda.matmul.allow_tf32 = False
+    wl = dict(bench.WORKLOADS[workload])
+    if torch.cuda.mem_get_info()[0] < 80 * 2 ** 30:
+        wl["B"] = 16
+    dev = torch.device(DEV, 0)
+    mods, packed = [], []
+    for i, key in enumerate(("nt", "pr")):
+        e = bench.ENC[wl[key]]
+        sd = {k: v.to(torch.bfloat16).float() for k, v in bench.gpu_state_dict(e, dev, 70 + i).items()}
+        g = torch.Generator(device=DEV).manual_seed(80 + i)
+        proj = {"weight": (torch.randn(wl["D"], e["hidden_size"], device=DEV, generator=g) / e["hidden_size"] ** 0.5
+                           ).to(torch.bfloat16).float(),
+                "bias": (torch.randn(wl["D"], device=DEV, generator=g) * 0.02).to(torch.bfloat16).float()}
+        mods.append(OracleModality(SPECS[wl[key]], sd, proj, wl["K"]))
+        packed.append(PackedEncoder(EncoderConfig.from_mapping(dict(e, name=wl[key])), sd, proj, wl["K"], dev))
+    path = FastOmicsPath(packed[0], packed[1], strict=True)
+    try:
+        omic_ids, infos = bench.make_inputs(wl, seed=321)
+        g = torch.Generator(device=DEV).manual_seed(9)
+        base = (torch.randn(wl["B"], wl["T"], wl["D"], device=DEV, generator=g) * 0.02).to(torch.bfloat16)
+        got = path.process_omic_sequences(base.clone(), omic_ids, infos, dev).float()
+        ref = base.float()
+        ids_dev = omic_ids.to(DEV)
+        with torch.no_grad():
+            for s0 in range(0, wl["B"], 8):
+                oracle_process(ref[s0:s0 + 8], ids_dev[s0:s0 + 8], infos[s0:s0 + 8], mods[0], mods[1])
+        scale = float(ref.abs().max())
+        err = float((got - ref).abs().max()) / scale
+        print(f"[{workload} full size, B={wl['B']}] normalised max err vs fp32 oracle (run on the GPU): {err:.4f}")
+        assert err <= TOL, err
+        written = (ref != base.float()).any(-1)
+        assert torch.equal((got != base.float()).any(-1), written)            # same written-row index set
+        assert int(written.sum()) == wl["K"] * sum(len(r) for r in infos)
+    finally:
+        path.close()
