@@ -199,3 +199,46 @@ def test_full_size_vs_fp32_oracle_run_on_the_gpu(workload):
         assert int(written.sum()) == wl["K"] * sum(len(r) for r in infos)
     finally:
         path.close()
+
+
+def test_cfg5_projector_grads_full_size_vs_fp32_oracle_run_on_the_gpu():
+    """BASELINE configs[4] (train step, --train-mlp): projector weight / bias gradients of both modalities at full model size
+    (ESM-2 650M + NT-v2 500M, D=2048, B=8 x (1 DNA + 1 protein) x 1024) against autograd of the fp32 oracle run on the GPU."""
+    import bench
+    from oracle.esm_oracle import SPECS, OracleModality
+    from molly_b200.config import EncoderConfig
+    from molly_b200.omics_path import FastOmicsPath
+    from molly_b200.packing import PackedEncoder
+    torch.backends.cuda.matmul.allow_tf32 = False
+    wl = dict(bench.WORKLOADS["train_1p7b"])
+    dev = torch.device(DEV, 0)
+    mods, packed, lins = [], [], {}
+    for i, (key, name) in enumerate((("nt", "dna_rna"), ("pr", "protein"))):
+        e = bench.ENC[wl[key]]
+        sd = {k: v.to(torch.bfloat16).float() for k, v in bench.gpu_state_dict(e, dev, 90 + i).items()}
+        g = torch.Generator(device=DEV).manual_seed(95 + i)
+        proj = {"weight": (torch.randn(wl["D"], e["hidden_size"], device=DEV, generator=g) / e["hidden_size"] ** 0.5
+                           ).to(torch.bfloat16).float(),
+                "bias": (torch.randn(wl["D"], device=DEV, generator=g) * 0.02).to(torch.bfloat16).float()}
+        mods.append(OracleModality(SPECS[wl[key]], sd, {k: v.clone().requires_grad_(True) for k, v in proj.items()},
+                                   wl["K"]))
+        packed.append(PackedEncoder(EncoderConfig.from_mapping(dict(e, name=wl[key])), sd, proj, wl["K"], dev))
+        lin = torch.nn.Linear(e["hidden_size"], wl["D"], device=dev, dtype=torch.bfloat16)
+        lin.load_state_dict(proj)
+        lins[name] = lin
+    path = FastOmicsPath(packed[0], packed[1], strict=True)
+    path._proj_modules = lins
+    try:
+        omic_ids, infos = bench.make_inputs(wl, seed=654)
+        g = torch.Generator(device=DEV).manual_seed(19)
+        base = (torch.randn(wl["B"], wl["T"], wl["D"], device=DEV, generator=g) * 0.02).to(torch.bfloat16)
+        d_out = (torch.randn(wl["B"], wl["T"], wl["D"], device=DEV, generator=g) * 1e-2).to(torch.bfloat16)
+        out = path.process_omic_sequences(base.clone(), omic_ids, infos, dev)
+        out.backward(d_out)
+        ref = oracle_process(base.float(), omic_ids.to(DEV), infos, mods[0], mods[1])
+        ref.backward(d_out.float())
+        for name, mod in (("dna_rna", mods[0]), ("protein", mods[1])):
+            assert_close(f"cfg5 d {name}_projector.weight", lins[name].weight.grad.float(), mod.projector["weight"].grad, TOL)
+            assert_close(f"cfg5 d {name}_projector.bias", lins[name].bias.grad.float(), mod.projector["bias"].grad, TOL)
+    finally:
+        path.close()
