@@ -190,6 +190,17 @@ int molly_rotary(void* qkv_dev /*bf16 [rows, 3h] in place on q and k*/, int32_t 
 int molly_attention(const void* qkv_dev /*bf16 [n_seq*k, 3h]*/, int32_t n_seq, int32_t k_tokens, int32_t h,
                     int32_t heads, const int32_t* kv_info_dev /*[n_seq,2] from molly_embed*/,
                     const uint8_t* key_mask_dev, void* out_dev /*bf16 [n_seq*k, h]*/, void* stream);
+/* same, additionally writing the row log-sum-exp of the scores in the log2 domain (P = exp2(S*log2e - lse2)),
+ * fp32 [n_seq, heads, k_tokens]: the statistic the attention backward starts from */
+int molly_attention_lse(const void* qkv_dev, int32_t n_seq, int32_t k_tokens, int32_t h, int32_t heads,
+                        const int32_t* kv_info_dev, const uint8_t* key_mask_dev, void* out_dev, float* lse2_dev,
+                        void* stream);
+/* Attention backward (first piece of the encoder backward; autograd of HF:257-282 given the packed, scaled and
+ * rotated q', k', v of the forward): d_qkv [n_seq*k, 3h] bf16 receives d(q'), d(k'), d(v) from d_out [n_seq*k, h] bf16, the
+ * forward output `out` and its lse2.  delta_ws: fp32 scratch of n_seq*heads*k elements. */
+int molly_attention_bwd(const void* qkv_dev, const void* out_dev, const void* d_out_dev, const float* lse2_dev, int32_t n_seq,
+                        int32_t k_tokens, int32_t h, int32_t heads, const int32_t* kv_info_dev, const uint8_t* key_mask_dev,
+                        void* d_qkv_dev, float* delta_ws_dev, void* stream);
 /* bring-up aid: when non-NULL, CTA 0 of the attention kernel records clock64() stamps into timeline_dev
  * (int64 [2 roles][64 iterations][8 slots]); NULL (default) disables it */
 int molly_attention_debug(long long* timeline_dev);

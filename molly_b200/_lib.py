@@ -86,6 +86,8 @@ SIGNATURES = {
     "molly_build_seq_table": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "molly_embed_tokens_skip": (C.c_int, [_vp, _vp, C.POINTER(C.c_int64), _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i32,
                                           _i32, _vp, _vp]),
+    "molly_attention_lse": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "molly_attention_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "molly_attention_debug": (C.c_int, [_vp]),
     "molly_merge_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "molly_profile_start": (C.c_int, []),

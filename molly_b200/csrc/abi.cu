@@ -403,6 +403,27 @@ int molly_build_seq_table(const int32_t* b_idx_dev, const int32_t* slot_idx_dev,
                                   static_cast<cudaStream_t>(stream));
 }
 
+int molly_attention_lse(const void* qkv_dev, int32_t n_seq, int32_t k_tokens, int32_t h, int32_t heads,
+                        const int32_t* kv_info_dev, const uint8_t* key_mask_dev, void* out_dev, float* lse2_dev,
+                        void* stream) {
+    MOLLY_CHECK(qkv_dev && kv_info_dev && key_mask_dev && out_dev && lse2_dev, MOLLY_ERR_INVALID,
+                "molly_attention_lse: NULL pointer");
+    AttnMaps tm;
+    int rc = attention_make_map(&tm, qkv_dev, n_seq * k_tokens, h, heads);
+    if (rc) return rc;
+    return attention_launch(tm, n_seq, k_tokens, h, heads, kv_info_dev, key_mask_dev, out_dev,
+                            static_cast<cudaStream_t>(stream), lse2_dev);
+}
+
+int molly_attention_bwd(const void* qkv_dev, const void* out_dev, const void* d_out_dev, const float* lse2_dev, int32_t n_seq,
+                        int32_t k_tokens, int32_t h, int32_t heads, const int32_t* kv_info_dev, const uint8_t* key_mask_dev,
+                        void* d_qkv_dev, float* delta_ws_dev, void* stream) {
+    MOLLY_CHECK(qkv_dev && out_dev && d_out_dev && lse2_dev && kv_info_dev && key_mask_dev && d_qkv_dev && delta_ws_dev,
+                MOLLY_ERR_INVALID, "molly_attention_bwd: NULL pointer");
+    return attention_bwd_launch(qkv_dev, out_dev, d_out_dev, lse2_dev, n_seq, k_tokens, h, heads, kv_info_dev, key_mask_dev,
+                                d_qkv_dev, delta_ws_dev, static_cast<cudaStream_t>(stream));
+}
+
 int molly_attention_debug(long long* timeline_dev) {
     attention_set_debug(timeline_dev);
     return MOLLY_OK;

@@ -256,7 +256,7 @@ template <int D, int KVB, int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D, KVB>::MIN_CTAS)
 attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_kv, int n_seq,
                  int heads, int k_tokens, int h, const int32_t* __restrict__ kv_info,
-                 const uint8_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out) {
+                 const uint8_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2) {
     using Cfg = AttnCfg<D, KVB>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -447,6 +447,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
             if (q0 + r < k_tokens) {
                 uint4* o = reinterpret_cast<uint4*>(out + (row_base + q0 + r) * h + head * D);
                 for (int i = 0; i < D / 8; ++i) o[i] = make_uint4(0, 0, 0, 0);
+                if (lse2 != nullptr) lse2[(static_cast<size_t>(w.n) * heads + head) * k_tokens + q0 + r] = -CUDART_INF_F;
             }
             continue;
         }
@@ -465,6 +466,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
         const float inv_l = 1.0f / l_run;
         const bool row_ok = q0 + r < k_tokens;
         __nv_bfloat16* orow = out + (row_base + q0 + r) * h + head * D;
+        // row log-sum-exp in the log2 domain (P = exp2(S log2e - lse2)): what the attention backward needs
+        if (lse2 != nullptr && row_ok)
+            lse2[(static_cast<size_t>(w.n) * heads + head) * k_tokens + q0 + r] = m_run + log2f(l_run);
 #pragma unroll
         for (int c = 0; c < D / 16; ++c) {
             uint32_t o[16];
@@ -913,7 +917,7 @@ int attention_grid(int total_items, int ctas_per_sm) {
 
 template <int D, int KVB>
 int launch_attention_kvb(const AttnMaps& maps, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
-                         const uint8_t* key_mask, void* out, cudaStream_t stream) {
+                         const uint8_t* key_mask, void* out, float* lse, cudaStream_t stream) {
     using Cfg = AttnCfg<D, KVB>;
     auto kernel = attention_kernel<D, KVB, 0>;
     static bool configured = false;
@@ -925,7 +929,7 @@ int launch_attention_kvb(const AttnMaps& maps, int n_seq, int k_tokens, int h, i
     {
         ProfScope prof(PF_ATTENTION, 4.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
         kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(maps.q, maps.kv64, n_seq, heads, k_tokens, h, kv_info,
-                                                               key_mask, static_cast<__nv_bfloat16*>(out));
+                                                               key_mask, static_cast<__nv_bfloat16*>(out), lse);
     }
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
@@ -984,13 +988,13 @@ bool attention_pipe_enabled() {         // MOLLY_ATTN_PIPE = 0 | 1 overrides the
 
 template <int D>
 int launch_attention(const AttnMaps& maps, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
-                     const uint8_t* key_mask, void* out, cudaStream_t stream) {
+                     const uint8_t* key_mask, void* out, float* lse, cudaStream_t stream) {
     const CUtensorMap& tm = maps.q;
     if constexpr (D <= 64) {
-        if (attention_pipe_enabled())
+        if (attention_pipe_enabled() && lse == nullptr)
             return launch_attention_pipe<D>(maps, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
         if (attention_kvb(D) == 64)
-            return launch_attention_kvb<D, 64>(maps, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
+            return launch_attention_kvb<D, 64>(maps, n_seq, k_tokens, h, heads, kv_info, key_mask, out, lse, stream);
     }
     using Cfg = AttnCfg<D>;
     static int poly = -1;             // pairs out of 4 whose exp2 runs on the FMA pipe (MOLLY_ATTN_POLY = 0 | 1 | 2)
@@ -1011,7 +1015,7 @@ int launch_attention(const AttnMaps& maps, int n_seq, int k_tokens, int h, int h
     {   // dense-equivalent work 4*n*K*K*h (exact when every sequence is full length)
         ProfScope prof(PF_ATTENTION, 4.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
         kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, tm, n_seq, heads, k_tokens, h, kv_info, key_mask,
-                                                               static_cast<__nv_bfloat16*>(out));
+                                                               static_cast<__nv_bfloat16*>(out), lse);
     }
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
@@ -1038,17 +1042,17 @@ int attention_make_map(AttnMaps* maps, const void* qkv, int rows, int h, int hea
 }
 
 int attention_launch(const AttnMaps& tqkv, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
-                     const uint8_t* key_mask, void* out, cudaStream_t stream) {
+                     const uint8_t* key_mask, void* out, cudaStream_t stream, float* lse) {
     MOLLY_CHECK(n_seq > 0 && k_tokens > 0 && heads > 0 && h % heads == 0, MOLLY_ERR_INVALID,
                 "attention: bad shape n_seq=%d k=%d h=%d heads=%d", n_seq, k_tokens, h, heads);
     MOLLY_CHECK(static_cast<long long>(n_seq) * k_tokens < (1ll << 31), MOLLY_ERR_UNSUPPORTED,
                 "attention: n_seq*k_tokens exceeds int32 TMA coordinates");
     MOLLY_CHECK(n_seq <= 65535 && heads <= 65535, MOLLY_ERR_UNSUPPORTED, "attention: grid too large");
     switch (h / heads) {
-        case 16: return launch_attention<16>(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
-        case 32: return launch_attention<32>(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
-        case 64: return launch_attention<64>(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
-        case 128: return launch_attention<128>(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
+        case 16: return launch_attention<16>(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, lse, stream);
+        case 32: return launch_attention<32>(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, lse, stream);
+        case 64: return launch_attention<64>(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, lse, stream);
+        case 128: return launch_attention<128>(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, lse, stream);
         default: MOLLY_CHECK(false, MOLLY_ERR_UNSUPPORTED, "attention: head_dim %d unsupported", h / heads);
     }
 }

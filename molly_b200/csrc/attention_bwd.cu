@@ -1,0 +1,562 @@
+// Attention backward (first piece of the encoder backward): d(q', k', v) from d(out) for the fused
+// bidirectional MHA of attention.cu.  q' is the scaled + rotated query as stored in the packed QKV activation, so no score
+// scaling appears here; the inverse rotation / scale belongs to the rotary backward.
+//
+// With P = softmax(S), S = q' k'^T (keys masked like the forward), dP = dO V^T, delta = rowsum(dO * O):
+//     dS = P * (dP - delta)        dQ' = dS K'        dK' = dS^T Q'        dV = P^T dO
+// Two kernels shaped like the forward one (TMA -> swizzled smem -> tcgen05.mma -> TMEM -> registers, thread = one row):
+//   * attn_bwd_dq_kernel : CTA = 128 query rows; streams key blocks.  S and dP land in TMEM, the threads rebuild
+//     P = exp2(S log2e - lse2) from the forward's row log-sum-exp (no running max, no rescaling), write dS as the bf16 K-major
+//     A operand and dQ' += dS K' uses the K tile as the MN-major B operand (exactly how the forward feeds V).
+//   * attn_bwd_dkv_kernel: CTA = 128 keys; streams query blocks with the roles swapped -- S^T = K' Q'^T, dP^T = V dO^T, so a
+//     thread owns a KEY row, P^T and dS^T are K-major A operands, and dV += P^T dO, dK' += dS^T Q' take dO / Q' as MN-major B.
+// One CTA per SM (512 TMEM columns: two 128-column score tiles + the accumulators).  First, correct version: loads are
+// double-buffered, the score tiles are not.
+#include <math_constants.h>
+
+#include "common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace molly {
+
+namespace {
+
+constexpr int BW_BLOCK = 128;
+constexpr int BW_THREADS = 160;                // 4 compute warps + 1 control warp
+constexpr float BW_LOG2E = 1.4426950408889634f;
+
+template <int D>
+struct BwdCfg {
+    static constexpr int BOX_D = D < 64 ? D : 64;
+    static constexpr int NBOX = D / BOX_D;
+    static constexpr int ROW_BYTES = BOX_D * 2;
+    static constexpr uint32_t LAYOUT = ROW_BYTES == 128 ? kLayoutSW128 : (ROW_BYTES == 64 ? kLayoutSW64 : kLayoutSW32);
+    static constexpr int BOX_BYTES = BW_BLOCK * ROW_BYTES;
+    static constexpr int TILE = NBOX * BOX_BYTES;                      // one 128 x D bf16 tile
+    static constexpr int PT_BYTES = BW_BLOCK * BW_BLOCK * 2;           // one 128 x 128 bf16 operand tile (two swizzle atoms)
+    static constexpr int STAGES = D == 128 ? 1 : 2;                    // streamed-tile ring depth
+    // dQ kernel: Q | dO | K ring | V ring | dS
+    static constexpr int DQ_OFF_Q = 0, DQ_OFF_DO = TILE, DQ_OFF_K = 2 * TILE, DQ_OFF_V = DQ_OFF_K + STAGES * TILE;
+    static constexpr int DQ_OFF_DS = DQ_OFF_V + STAGES * TILE, DQ_OFF_BAR = DQ_OFF_DS + PT_BYTES;
+    static constexpr int DQ_SMEM = DQ_OFF_BAR + 256;
+    // dK/dV kernel: K | V | Q ring | dO ring | P^T | dS^T | row statistics of the streamed query block (2 x {lse2, delta})
+    static constexpr int KV_OFF_K = 0, KV_OFF_V = TILE, KV_OFF_Q = 2 * TILE, KV_OFF_DO = KV_OFF_Q + STAGES * TILE;
+    static constexpr int KV_OFF_PT = KV_OFF_DO + STAGES * TILE, KV_OFF_DST = KV_OFF_PT + PT_BYTES;
+    static constexpr int KV_OFF_STAT = KV_OFF_DST + PT_BYTES, KV_OFF_BAR = KV_OFF_STAT + 2 * 2 * BW_BLOCK * 4;
+    static constexpr int KV_SMEM = KV_OFF_BAR + 256;
+};
+
+__device__ __forceinline__ float bw_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// delta[n, head, t] = sum_d dO[row, head*D + d] * O[row, head*D + d]      (one thread per (row, head))
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ d_out, const __nv_bfloat16* __restrict__ out, int n_seq,
+                                  int k_tokens, int heads, int d, float* __restrict__ delta) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(n_seq) * k_tokens * heads;
+    if (idx >= total) return;
+    const int head = static_cast<int>(idx % heads);
+    const long long row = idx / heads;
+    const int h = heads * d;
+    const uint4* a = reinterpret_cast<const uint4*>(d_out + row * h + head * d);
+    const uint4* b = reinterpret_cast<const uint4*>(out + row * h + head * d);
+    float acc = 0.f;
+    for (int v = 0; v < d / 8; ++v) {
+        const uint4 x = __ldg(a + v), y = __ldg(b + v);
+        const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&x);
+        const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 xf = __bfloat1622float2(xp[i]), yf = __bfloat1622float2(yp[i]);
+            acc += xf.x * yf.x + xf.y * yf.y;
+        }
+    }
+    const long long n = row / k_tokens, t = row % k_tokens;
+    delta[(n * heads + head) * k_tokens + t] = acc;
+}
+
+// store 32 bf16 values of operand-tile row r (K-major, 128-B swizzle, atom = 64 columns): columns [qt*32, qt*32 + 32)
+__device__ __forceinline__ void store_quarter_row(uint8_t* tile, int r, int qt, const float* v) {
+    uint8_t* row = tile + (qt >> 1) * (BW_BLOCK * 128) + (r >> 3) * 1024 + (r & 7) * 128;
+    const int sw = r & 7, c0 = (qt & 1) * 4;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint4 u;
+        u.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]);
+        u.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
+        u.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]);
+        u.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
+        *reinterpret_cast<uint4*>(row + (((c0 + c) ^ sw) << 4)) = u;
+    }
+}
+
+// 128 x D fp32 accumulator rows from TMEM -> bf16 -> global (row-major, ld = ldo elements)
+template <int D>
+__device__ __forceinline__ void store_acc_rows(uint32_t tmem_acc, uint32_t lane_addr, __nv_bfloat16* dst, bool row_ok) {
+#pragma unroll
+    for (int c = 0; c < D / 16; ++c) {
+        uint32_t o[16];
+        tmem_ld16(tmem_acc + lane_addr + c * 16, o);
+        tmem_ld_wait();
+        if (row_ok) {
+            uint4 u0, u1;
+            u0.x = pack_bf16x2(__uint_as_float(o[0]), __uint_as_float(o[1]));
+            u0.y = pack_bf16x2(__uint_as_float(o[2]), __uint_as_float(o[3]));
+            u0.z = pack_bf16x2(__uint_as_float(o[4]), __uint_as_float(o[5]));
+            u0.w = pack_bf16x2(__uint_as_float(o[6]), __uint_as_float(o[7]));
+            u1.x = pack_bf16x2(__uint_as_float(o[8]), __uint_as_float(o[9]));
+            u1.y = pack_bf16x2(__uint_as_float(o[10]), __uint_as_float(o[11]));
+            u1.z = pack_bf16x2(__uint_as_float(o[12]), __uint_as_float(o[13]));
+            u1.w = pack_bf16x2(__uint_as_float(o[14]), __uint_as_float(o[15]));
+            reinterpret_cast<uint4*>(dst + c * 16)[0] = u0;
+            reinterpret_cast<uint4*>(dst + c * 16)[1] = u1;
+        }
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void zero_row(__nv_bfloat16* dst) {
+    for (int i = 0; i < D / 8; ++i) reinterpret_cast<uint4*>(dst)[i] = make_uint4(0, 0, 0, 0);
+}
+
+// ------------------------------------------------------------------------------------------------- dQ'
+template <int D>
+__global__ void __launch_bounds__(BW_THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do, int k_tokens,
+                   int h, const int32_t* __restrict__ kv_info, const uint8_t* __restrict__ key_mask,
+                   const float* __restrict__ lse2, const float* __restrict__ delta, __nv_bfloat16* __restrict__ d_qkv) {
+    using Cfg = BwdCfg<D>;
+    constexpr int NST = Cfg::STAGES;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::DQ_OFF_BAR);
+    uint64_t* bar_qdo = bars + 0;
+    uint64_t* bar_kv_full = bars + 1;        // [NST]
+    uint64_t* bar_kv_empty = bars + 3;       // [NST]  dQ MMA of the block done: the K/V stage and the dS tile are free
+    uint64_t* bar_sdp_full = bars + 5;       // S and dP of the block are in TMEM
+    uint64_t* bar_s_free = bars + 6;         // 128 arrivals: both are in registers
+    uint64_t* bar_ds_full = bars + 7;        // 128 arrivals: dS is in smem
+    uint64_t* bar_dq_full = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BW_BLOCK, head = blockIdx.y, n = blockIdx.z, heads = gridDim.y;
+    const int kvl = kv_info[2 * n], n_nonpad = kv_info[2 * n + 1];
+    const bool interior = n_nonpad != kvl;
+    const int nkv = (kvl + BW_BLOCK - 1) / BW_BLOCK;
+    const long long row_base = static_cast<long long>(n) * k_tokens;
+    if (nkv == 0) {                                          // no valid key: the forward wrote zeros, nothing flows back
+        if (warp < 4 && q0 + threadIdx.x < k_tokens) zero_row<D>(d_qkv + (row_base + q0 + threadIdx.x) * 3 * h + head * D);
+        return;
+    }
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tma_qkv);
+            tma_prefetch_desc(&tma_do);
+            mbar_init(bar_qdo, 1);
+            for (int s = 0; s < NST; ++s) { mbar_init(&bar_kv_full[s], 1); mbar_init(&bar_kv_empty[s], 1); }
+            mbar_init(bar_sdp_full, 1);
+            mbar_init(bar_s_free, 128);
+            mbar_init(bar_ds_full, 128);
+            mbar_init(bar_dq_full, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(BW_BLOCK, BW_BLOCK, false, false);
+            constexpr uint32_t idesc_acc = make_idesc_bf16(BW_BLOCK, D, false, true);       // B MN-major
+            const uint32_t s_q = smem_u32(smem + Cfg::DQ_OFF_Q), s_do = smem_u32(smem + Cfg::DQ_OFF_DO);
+            const uint32_t s_k = smem_u32(smem + Cfg::DQ_OFF_K), s_v = smem_u32(smem + Cfg::DQ_OFF_V);
+            const uint32_t s_ds = smem_u32(smem + Cfg::DQ_OFF_DS);
+            auto load_tile = [&](int off, const CUtensorMap* map, uint64_t* bar, int col, int row) {
+#pragma unroll
+                for (int b = 0; b < Cfg::NBOX; ++b)
+                    tma_load_2d(smem + off + b * Cfg::BOX_BYTES, map, bar, col + b * Cfg::BOX_D, row);
+            };
+            auto load_kv = [&](int blk) {
+                const int st = blk % NST;
+                mbar_arrive_expect_tx(&bar_kv_full[st], 2 * Cfg::TILE);
+                load_tile(Cfg::DQ_OFF_K + st * Cfg::TILE, &tma_qkv, &bar_kv_full[st], h + head * D,
+                          static_cast<int>(row_base) + blk * BW_BLOCK);
+                load_tile(Cfg::DQ_OFF_V + st * Cfg::TILE, &tma_qkv, &bar_kv_full[st], 2 * h + head * D,
+                          static_cast<int>(row_base) + blk * BW_BLOCK);
+            };
+            auto issue_scores = [&](int blk) {               // S = Q K^T and dP = dO V^T (all four operands K-major)
+                const int st = blk % NST;
+                mbar_wait(&bar_kv_full[st], (blk / NST) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < D / 16; ++s) {
+                    const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
+                    umma_bf16_ss(tmem_s, make_smem_desc(s_q + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT),
+                                 make_smem_desc(s_k + st * Cfg::TILE + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT), idesc_s,
+                                 s != 0);
+                }
+#pragma unroll
+                for (int s = 0; s < D / 16; ++s) {
+                    const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
+                    umma_bf16_ss(tmem_dp, make_smem_desc(s_do + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT),
+                                 make_smem_desc(s_v + st * Cfg::TILE + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT), idesc_s,
+                                 s != 0);
+                }
+                umma_commit(bar_sdp_full);
+            };
+            mbar_arrive_expect_tx(bar_qdo, 2 * Cfg::TILE);
+            load_tile(Cfg::DQ_OFF_Q, &tma_qkv, bar_qdo, head * D, static_cast<int>(row_base) + q0);
+            load_tile(Cfg::DQ_OFF_DO, &tma_do, bar_qdo, head * D, static_cast<int>(row_base) + q0);
+            for (int b = 0; b < NST && b < nkv; ++b) load_kv(b);
+            mbar_wait(bar_qdo, 0);
+            issue_scores(0);
+            for (int j = 0; j < nkv; ++j) {
+                const int st = j % NST;
+                if (NST == 2 && j + 1 < nkv) {               // scores of block j+1 run under the element-wise work of block j
+                    mbar_wait(bar_s_free, j & 1);
+                    tc_fence_after();
+                    issue_scores(j + 1);
+                }
+                mbar_wait(bar_ds_full, j & 1);               // dS(j) is in smem
+                tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < BW_BLOCK / 16; ++s) {    // dQ += dS K : A K-major (two 64-key atoms), B = K tile MN-major
+                    const uint64_t ad = make_smem_desc(s_ds + (s >> 2) * (BW_BLOCK * 128) + (s & 3) * 32, 16, 1024, kLayoutSW128);
+                    const uint64_t bd = make_smem_desc(s_k + st * Cfg::TILE + s * 16 * Cfg::ROW_BYTES, Cfg::BOX_BYTES,
+                                                       8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
+                    umma_bf16_ss(tmem_dq, ad, bd, idesc_acc, (j | s) != 0);
+                }
+                umma_commit(&bar_kv_empty[st]);
+                if (j == nkv - 1) umma_commit(bar_dq_full);
+                if (NST == 1 && j + 1 < nkv) {               // single stage: the next K/V overwrite this one after its dQ MMA
+                    mbar_wait(&bar_kv_empty[0], j & 1);
+                    load_kv(j + 1);
+                    mbar_wait(bar_s_free, j & 1);
+                    tc_fence_after();
+                    issue_scores(j + 1);
+                }
+                if (NST == 2 && j + 2 < nkv) {
+                    mbar_wait(&bar_kv_empty[st], (j >> 1) & 1);
+                    load_kv(j + 2);
+                }
+            }
+        }
+    } else {
+        const int r = threadIdx.x;
+        const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+        const bool row_ok = q0 + r < k_tokens;
+        const size_t stat = (static_cast<size_t>(n) * heads + head) * k_tokens + (row_ok ? q0 + r : 0);
+        const float my_lse = row_ok ? lse2[stat] : CUDART_INF_F;             // +inf: P = 0 for rows outside the sequence
+        const float my_delta = row_ok ? delta[stat] : 0.f;
+        uint8_t* ds_tile = smem + Cfg::DQ_OFF_DS;
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(bar_sdp_full, j & 1);
+            tc_fence_after();
+            if (j > 0) {                                     // dQ MMA (j-1) has drained the dS tile
+                mbar_wait(&bar_kv_empty[(j - 1) % NST], ((j - 1) / NST) & 1);
+                tc_fence_after();
+            }
+#pragma unroll
+            for (int qt = 0; qt < 4; ++qt) {                 // 32 keys at a time
+                uint32_t sr[32], pr[32];
+                tmem_ld32(tmem_s + lane_addr + qt * 32, sr);
+                tmem_ld32(tmem_dp + lane_addr + qt * 32, pr);
+                tmem_ld_wait();
+                if (qt == 3) {
+                    tc_fence_before();
+                    mbar_arrive(bar_s_free);                 // S / dP are in registers: the next block's scores may be issued
+                }
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int key = j * BW_BLOCK + qt * 32 + i;
+                    bool ok = key < kvl;
+                    if (interior && ok) ok = key_mask[row_base + key] != 0;
+                    const float p = ok ? bw_ex2(__uint_as_float(sr[i]) * BW_LOG2E - my_lse) : 0.f;
+                    v[i] = p * (__uint_as_float(pr[i]) - my_delta);
+                }
+                store_quarter_row(ds_tile, r, qt, v);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_ds_full);
+        }
+        mbar_wait(bar_dq_full, 0);
+        tc_fence_after();
+        store_acc_rows<D>(tmem_dq, lane_addr, d_qkv + (row_base + q0 + r) * 3 * h + head * D, row_ok);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- dK', dV
+template <int D>
+__global__ void __launch_bounds__(BW_THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do, int k_tokens,
+                    int h, const int32_t* __restrict__ kv_info, const uint8_t* __restrict__ key_mask,
+                    const float* __restrict__ lse2, const float* __restrict__ delta, __nv_bfloat16* __restrict__ d_qkv) {
+    using Cfg = BwdCfg<D>;
+    constexpr int NST = Cfg::STAGES;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::KV_OFF_BAR);
+    uint64_t* bar_kv = bars + 0;
+    uint64_t* bar_q_full = bars + 1;         // [NST]  Q_i and dO_i landed
+    uint64_t* bar_q_empty = bars + 3;        // [NST]  dV / dK MMAs of the block done: stage, P^T and dS^T tiles are free
+    uint64_t* bar_sdp_full = bars + 5;
+    uint64_t* bar_s_free = bars + 6;         // 128 arrivals
+    uint64_t* bar_pt_full = bars + 7;        // 128 arrivals
+    uint64_t* bar_out_full = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * BW_BLOCK, head = blockIdx.y, n = blockIdx.z, heads = gridDim.y;
+    const int kvl = kv_info[2 * n], n_nonpad = kv_info[2 * n + 1];
+    const bool interior = n_nonpad != kvl;
+    const long long row_base = static_cast<long long>(n) * k_tokens;
+    const int nq = (k_tokens + BW_BLOCK - 1) / BW_BLOCK;     // every query row of the sequence attends (pad queries too)
+    if (k0 >= kvl) {                                         // keys past the last valid one never receive probability mass
+        if (warp < 4 && k0 + threadIdx.x < k_tokens) {
+            __nv_bfloat16* row = d_qkv + (row_base + k0 + threadIdx.x) * 3 * h + head * D;
+            zero_row<D>(row + h);
+            zero_row<D>(row + 2 * h);
+        }
+        return;
+    }
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tma_qkv);
+            tma_prefetch_desc(&tma_do);
+            mbar_init(bar_kv, 1);
+            for (int s = 0; s < NST; ++s) { mbar_init(&bar_q_full[s], 1); mbar_init(&bar_q_empty[s], 1); }
+            mbar_init(bar_sdp_full, 1);
+            mbar_init(bar_s_free, 128);
+            mbar_init(bar_pt_full, 128);
+            mbar_init(bar_out_full, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_st = tmem_base, tmem_dpt = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 384;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(BW_BLOCK, BW_BLOCK, false, false);
+            constexpr uint32_t idesc_acc = make_idesc_bf16(BW_BLOCK, D, false, true);       // B MN-major
+            const uint32_t s_k = smem_u32(smem + Cfg::KV_OFF_K), s_v = smem_u32(smem + Cfg::KV_OFF_V);
+            const uint32_t s_q = smem_u32(smem + Cfg::KV_OFF_Q), s_do = smem_u32(smem + Cfg::KV_OFF_DO);
+            const uint32_t s_pt = smem_u32(smem + Cfg::KV_OFF_PT), s_dst = smem_u32(smem + Cfg::KV_OFF_DST);
+            auto load_tile = [&](int off, const CUtensorMap* map, uint64_t* bar, int col, int row) {
+#pragma unroll
+                for (int b = 0; b < Cfg::NBOX; ++b)
+                    tma_load_2d(smem + off + b * Cfg::BOX_BYTES, map, bar, col + b * Cfg::BOX_D, row);
+            };
+            auto load_q = [&](int blk) {
+                const int st = blk % NST;
+                mbar_arrive_expect_tx(&bar_q_full[st], 2 * Cfg::TILE);
+                load_tile(Cfg::KV_OFF_Q + st * Cfg::TILE, &tma_qkv, &bar_q_full[st], head * D,
+                          static_cast<int>(row_base) + blk * BW_BLOCK);
+                load_tile(Cfg::KV_OFF_DO + st * Cfg::TILE, &tma_do, &bar_q_full[st], head * D,
+                          static_cast<int>(row_base) + blk * BW_BLOCK);
+            };
+            auto issue_scores = [&](int blk) {               // S^T = K Q^T and dP^T = V dO^T
+                const int st = blk % NST;
+                mbar_wait(&bar_q_full[st], (blk / NST) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < D / 16; ++s) {
+                    const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
+                    umma_bf16_ss(tmem_st, make_smem_desc(s_k + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT),
+                                 make_smem_desc(s_q + st * Cfg::TILE + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT), idesc_s,
+                                 s != 0);
+                }
+#pragma unroll
+                for (int s = 0; s < D / 16; ++s) {
+                    const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
+                    umma_bf16_ss(tmem_dpt, make_smem_desc(s_v + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT),
+                                 make_smem_desc(s_do + st * Cfg::TILE + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT), idesc_s,
+                                 s != 0);
+                }
+                umma_commit(bar_sdp_full);
+            };
+            mbar_arrive_expect_tx(bar_kv, 2 * Cfg::TILE);
+            load_tile(Cfg::KV_OFF_K, &tma_qkv, bar_kv, h + head * D, static_cast<int>(row_base) + k0);
+            load_tile(Cfg::KV_OFF_V, &tma_qkv, bar_kv, 2 * h + head * D, static_cast<int>(row_base) + k0);
+            for (int b = 0; b < NST && b < nq; ++b) load_q(b);
+            mbar_wait(bar_kv, 0);
+            issue_scores(0);
+            for (int i = 0; i < nq; ++i) {
+                const int st = i % NST;
+                if (NST == 2 && i + 1 < nq) {
+                    mbar_wait(bar_s_free, i & 1);
+                    tc_fence_after();
+                    issue_scores(i + 1);
+                }
+                mbar_wait(bar_pt_full, i & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < BW_BLOCK / 16; ++s) {    // contraction over the 128 queries of the block
+                    const uint32_t a_off = (s >> 2) * (BW_BLOCK * 128) + (s & 3) * 32;
+                    const uint64_t pd = make_smem_desc(s_pt + a_off, 16, 1024, kLayoutSW128);
+                    const uint64_t dd = make_smem_desc(s_dst + a_off, 16, 1024, kLayoutSW128);
+                    const uint64_t bo = make_smem_desc(s_do + st * Cfg::TILE + s * 16 * Cfg::ROW_BYTES, Cfg::BOX_BYTES,
+                                                       8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
+                    const uint64_t bq = make_smem_desc(s_q + st * Cfg::TILE + s * 16 * Cfg::ROW_BYTES, Cfg::BOX_BYTES,
+                                                       8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
+                    umma_bf16_ss(tmem_dv, pd, bo, idesc_acc, (i | s) != 0);      // dV  += P^T  dO
+                    umma_bf16_ss(tmem_dk, dd, bq, idesc_acc, (i | s) != 0);      // dK' += dS^T Q'
+                }
+                umma_commit(&bar_q_empty[st]);
+                if (i == nq - 1) umma_commit(bar_out_full);
+                if (NST == 1 && i + 1 < nq) {
+                    mbar_wait(&bar_q_empty[0], i & 1);
+                    load_q(i + 1);
+                    mbar_wait(bar_s_free, i & 1);
+                    tc_fence_after();
+                    issue_scores(i + 1);
+                }
+                if (NST == 2 && i + 2 < nq) {
+                    mbar_wait(&bar_q_empty[st], (i >> 1) & 1);
+                    load_q(i + 2);
+                }
+            }
+        }
+    } else {
+        const int r = threadIdx.x;                           // key row k0 + r
+        const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+        const int key = k0 + r;
+        bool key_ok = key < kvl;
+        if (interior && key_ok) key_ok = key_mask[row_base + key] != 0;
+        float* stats = reinterpret_cast<float*>(smem + Cfg::KV_OFF_STAT);
+        uint8_t* pt_tile = smem + Cfg::KV_OFF_PT;
+        uint8_t* dst_tile = smem + Cfg::KV_OFF_DST;
+        const size_t stat_base = (static_cast<size_t>(n) * heads + head) * k_tokens;
+        for (int i = 0; i < nq; ++i) {
+            // row statistics of the 128 queries of this block -> smem (thread r brings query i*128 + r)
+            float* st_lse = stats + (i & 1) * 2 * BW_BLOCK;
+            float* st_delta = st_lse + BW_BLOCK;
+            const int q = i * BW_BLOCK + r;
+            st_lse[r] = q < k_tokens ? lse2[stat_base + q] : CUDART_INF_F;       // +inf: P = 0 beyond the sequence
+            st_delta[r] = q < k_tokens ? delta[stat_base + q] : 0.f;
+            named_bar_sync(1, 128);
+            mbar_wait(bar_sdp_full, i & 1);
+            tc_fence_after();
+            if (i > 0) {                                     // dV / dK MMAs (i-1) have drained the P^T / dS^T tiles
+                mbar_wait(&bar_q_empty[(i - 1) % NST], ((i - 1) / NST) & 1);
+                tc_fence_after();
+            }
+#pragma unroll
+            for (int qt = 0; qt < 4; ++qt) {                 // 32 queries at a time
+                uint32_t sr[32], pr[32];
+                tmem_ld32(tmem_st + lane_addr + qt * 32, sr);
+                tmem_ld32(tmem_dpt + lane_addr + qt * 32, pr);
+                tmem_ld_wait();
+                if (qt == 3) {
+                    tc_fence_before();
+                    mbar_arrive(bar_s_free);
+                }
+                float pv[32], dv[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float l = st_lse[qt * 32 + c], dl = st_delta[qt * 32 + c];
+                    const float p = key_ok ? bw_ex2(__uint_as_float(sr[c]) * BW_LOG2E - l) : 0.f;
+                    pv[c] = p;
+                    dv[c] = p * (__uint_as_float(pr[c]) - dl);
+                }
+                store_quarter_row(pt_tile, r, qt, pv);
+                store_quarter_row(dst_tile, r, qt, dv);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_pt_full);
+        }
+        mbar_wait(bar_out_full, 0);
+        tc_fence_after();
+        __nv_bfloat16* row = d_qkv + (row_base + key) * 3 * h + head * D;
+        store_acc_rows<D>(tmem_dk, lane_addr, row + h, key < k_tokens);
+        store_acc_rows<D>(tmem_dv, lane_addr, row + 2 * h, key < k_tokens);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int D>
+int launch_attention_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, int n_seq, int k_tokens, int h, int heads,
+                         const int32_t* kv_info, const uint8_t* key_mask, const float* lse2, const float* delta,
+                         __nv_bfloat16* d_qkv, cudaStream_t stream) {
+    using Cfg = BwdCfg<D>;
+    static bool configured = false;
+    if (!configured) {
+        MOLLY_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::DQ_SMEM));
+        MOLLY_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::KV_SMEM));
+        configured = true;
+    }
+    dim3 grid((k_tokens + BW_BLOCK - 1) / BW_BLOCK, heads, n_seq);
+    {   // 4 MMAs of 2*K*K*d each per (sequence, head) in each kernel... dense-equivalent 2.5x the forward in total
+        ProfScope prof(PF_OTHER, 10.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
+        attn_bwd_dq_kernel<D><<<grid, BW_THREADS, Cfg::DQ_SMEM, stream>>>(tq, tdo, k_tokens, h, kv_info, key_mask, lse2, delta,
+                                                                          d_qkv);
+        attn_bwd_dkv_kernel<D><<<grid, BW_THREADS, Cfg::KV_SMEM, stream>>>(tq, tdo, k_tokens, h, kv_info, key_mask, lse2, delta,
+                                                                           d_qkv);
+    }
+    count_launch();
+    count_launch();
+    MOLLY_CUDA(cudaGetLastError());
+    return MOLLY_OK;
+}
+
+}  // namespace
+
+int attention_bwd_launch(const void* qkv, const void* out, const void* d_out, const float* lse2, int n_seq, int k_tokens, int h,
+                         int heads, const int32_t* kv_info, const uint8_t* key_mask, void* d_qkv, float* delta_ws,
+                         cudaStream_t stream) {
+    MOLLY_CHECK(n_seq > 0 && k_tokens > 0 && heads > 0 && h % heads == 0, MOLLY_ERR_INVALID,
+                "attention_bwd: bad shape n_seq=%d k=%d h=%d heads=%d", n_seq, k_tokens, h, heads);
+    const int d = h / heads;
+    MOLLY_CHECK(d == 16 || d == 32 || d == 64 || d == 128, MOLLY_ERR_UNSUPPORTED, "attention_bwd: head_dim %d unsupported", d);
+    MOLLY_CHECK(static_cast<long long>(n_seq) * k_tokens < (1ll << 31) && n_seq <= 65535 && heads <= 65535,
+                MOLLY_ERR_UNSUPPORTED, "attention_bwd: problem too large for the grid / TMA coordinates");
+    const long long items = static_cast<long long>(n_seq) * k_tokens * heads;
+    attn_delta_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(d_out), static_cast<const __nv_bfloat16*>(out), n_seq, k_tokens, heads, d, delta_ws);
+    count_launch();
+    MOLLY_CUDA(cudaGetLastError());
+    const int box_d = d < 64 ? d : 64;
+    CUtensorMap tq, tdo;
+    int rc = make_tma_2d(&tq, qkv, n_seq * k_tokens, 3 * h, 3 * h, BW_BLOCK, box_d, 2);
+    if (rc) return rc;
+    rc = make_tma_2d(&tdo, d_out, n_seq * k_tokens, h, h, BW_BLOCK, box_d, 2);
+    if (rc) return rc;
+    __nv_bfloat16* dq = static_cast<__nv_bfloat16*>(d_qkv);
+    switch (d) {
+        case 16: return launch_attention_bwd<16>(tq, tdo, n_seq, k_tokens, h, heads, kv_info, key_mask, lse2, delta_ws, dq, stream);
+        case 32: return launch_attention_bwd<32>(tq, tdo, n_seq, k_tokens, h, heads, kv_info, key_mask, lse2, delta_ws, dq, stream);
+        case 64: return launch_attention_bwd<64>(tq, tdo, n_seq, k_tokens, h, heads, kv_info, key_mask, lse2, delta_ws, dq, stream);
+        default: return launch_attention_bwd<128>(tq, tdo, n_seq, k_tokens, h, heads, kv_info, key_mask, lse2, delta_ws, dq, stream);
+    }
+}
+
+}  // namespace molly

@@ -46,8 +46,9 @@ struct AttnMaps {          // views of the packed [rows, 3h] QKV activation
     CUtensorMap kv64;      // 64-row boxes (K/V tiles of the 64-key kernel)
 };
 int attention_make_map(AttnMaps* maps, const void* qkv, int rows, int h, int heads);
+// lse2 (optional, fp32 [n_seq, heads, k_tokens]): row log-sum-exp of the scores in the log2 domain, for the backward
 int attention_launch(const AttnMaps& tqkv, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_len,
-                     const uint8_t* key_mask, void* out, cudaStream_t stream);
+                     const uint8_t* key_mask, void* out, cudaStream_t stream, float* lse2 = nullptr);
 
 // ---- rowwise.cu ----
 struct EmbedArgs {
@@ -82,6 +83,11 @@ int embed_tokens_skip_launch(const int64_t* input_ids, const int32_t* pos_j, int
 int build_seq_table_launch(const int32_t* b_idx, const int32_t* slot_idx, int n, const int32_t* run_start,
                            const int32_t* run_kind, const int32_t* run_len, const int32_t* n_runs, int max_runs,
                            int expect_protein, int k_need, int32_t* seq_table, int32_t* err_flag, cudaStream_t stream);
+
+// ---- attention_bwd.cu ----  d(q', k', v) [rows, 3h] bf16 from d(out); delta_ws: fp32 [n_seq * heads * k_tokens] scratch
+int attention_bwd_launch(const void* qkv, const void* out, const void* d_out, const float* lse2, int n_seq, int k_tokens, int h,
+                         int heads, const int32_t* kv_info, const uint8_t* key_mask, void* d_qkv, float* delta_ws,
+                         cudaStream_t stream);
 
 // ---- bwd.cu ----
 int project_bwd_launch(const void* dy_bf16, const void* x_bf16, int M, int D, int h, float* d_weight, float* d_bias,

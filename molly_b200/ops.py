@@ -402,6 +402,36 @@ def attention(qkv: Tensor, n_seq: int, k_tokens: int, heads: int, kv_info: Tenso
     return out
 
 
+def attention_lse(qkv: Tensor, n_seq: int, k_tokens: int, heads: int, kv_info: Tensor, key_mask: Tensor):
+    """``attention`` that also returns the row log-sum-exp in the log2 domain, fp32 [n_seq, heads, k_tokens]."""
+    dev = _require_cuda(qkv, kv_info, key_mask)
+    h = qkv.shape[1] // 3
+    out = torch.empty(qkv.shape[0], h, dtype=torch.bfloat16, device=dev)
+    lse2 = torch.empty(n_seq, heads, k_tokens, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_attention_lse(qkv.data_ptr(), n_seq, k_tokens, h, heads, kv_info.data_ptr(),
+                                                   key_mask.data_ptr(), out.data_ptr(), lse2.data_ptr(), _stream(dev)),
+                   "molly_attention_lse")
+    return out, lse2
+
+
+def attention_bwd(qkv: Tensor, out: Tensor, d_out: Tensor, lse2: Tensor, n_seq: int, k_tokens: int, heads: int,
+                  kv_info: Tensor, key_mask: Tensor) -> Tensor:
+    """d(q', k', v) packed like ``qkv`` (bf16 [n_seq*k, 3h]) from ``d_out`` (bf16 [n_seq*k, h])."""
+    dev = _require_cuda(qkv, out, d_out, lse2, kv_info, key_mask)
+    h = qkv.shape[1] // 3
+    for t, shape in ((out, (qkv.shape[0], h)), (d_out, (qkv.shape[0], h))):
+        if t.dtype != torch.bfloat16 or tuple(t.shape) != shape or not t.is_contiguous():
+            raise ValueError("out / d_out must be contiguous bf16 [n_seq*k, h]")
+    d_qkv = torch.empty_like(qkv)
+    delta = torch.empty(n_seq * heads * k_tokens, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_attention_bwd(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse2.data_ptr(), n_seq,
+                                                   k_tokens, h, heads, kv_info.data_ptr(), key_mask.data_ptr(),
+                                                   d_qkv.data_ptr(), delta.data_ptr(), _stream(dev)), "molly_attention_bwd")
+    return d_qkv
+
+
 def merge_rows_(hidden_states: Tensor, src: Tensor, seq_table: Tensor, k_tokens: int, k_cap: int) -> Tensor:
     dev = _require_cuda(hidden_states, src, seq_table)
     B, T, D = hidden_states.shape

@@ -209,6 +209,74 @@ def test_attention(heads, d, k, lens):
     assert_close(f"attention H={heads} d={d} k={k}", got, ref, 1e-2)
 
 
+@pytest.mark.parametrize("heads,d,k,lens", [(4, 64, 256, [256, 200, 129, 1]), (3, 64, 171, [171, 50, 100]),
+                                            (16, 32, 300, [300, 256, 17]), (2, 128, 256, [256, 171])])
+def test_attention_log_sum_exp(heads, d, k, lens):
+    """The statistic the attention backward starts from: lse2 = log2(sum_j exp(s_j)) per (sequence, head, query row)."""
+    import math
+    ops, _ = _ops()
+    n_seq, h = len(lens), heads * d
+    qkv = bf16r(n_seq * k, 3 * h, seed=27)
+    qkv.view(n_seq * k, 3, h)[:, 0] *= d ** -0.5
+    key_mask = torch.zeros(n_seq, k, dtype=torch.uint8)
+    for i, ln in enumerate(lens):
+        key_mask[i, :ln] = 1
+    kv_info = torch.tensor([[ln, ln] for ln in lens], dtype=torch.int32)
+    x = qkv.float().view(n_seq, k, 3, heads, d)
+    q, kk = x[:, :, 0].permute(0, 2, 1, 3), x[:, :, 1].permute(0, 2, 1, 3)
+    s_ = (q @ kk.transpose(2, 3)).masked_fill(~key_mask.bool().view(n_seq, 1, 1, k), float("-inf"))
+    want = torch.logsumexp(s_, -1) / math.log(2.0)                    # [n, H, k]
+    out, lse2 = ops.attention_lse(qkv.to(DEV), n_seq, k, heads, kv_info.to(DEV), key_mask.reshape(-1).to(DEV))
+    assert_close("attention (lse variant) output", out, _attention_ref(qkv, n_seq, k, heads, key_mask), 1e-2)
+    assert float((lse2.cpu() - want).abs().max()) < 2e-3, float((lse2.cpu() - want).abs().max())
+
+
+@pytest.mark.parametrize("heads,d,k,lens", [(4, 64, 128, [128, 128]), (4, 64, 256, [256, 200, 129, 1]),
+                                            (3, 64, 171, [171, 50, 100]), (16, 32, 300, [300, 256, 17]),
+                                            (2, 128, 256, [256, 171]), (20, 16, 512, [512, 33]), (20, 64, 1024, [1024, 700])])
+def test_attention_backward(heads, d, k, lens):
+    """d(q', k', v) of the fused MHA against fp32 autograd of its plain statement (q' = scaled + rotated query as stored)."""
+    ops, _ = _ops()
+    n_seq, h = len(lens), heads * d
+    qkv = bf16r(n_seq * k, 3 * h, seed=41)
+    qkv.view(n_seq * k, 3, h)[:, 0] *= d ** -0.5
+    key_mask = torch.zeros(n_seq, k, dtype=torch.uint8)
+    for i, ln in enumerate(lens):
+        key_mask[i, :ln] = 1
+    kv_info = torch.tensor([[ln, ln] for ln in lens], dtype=torch.int32)
+    d_out = bf16r(n_seq * k, h, seed=42)
+    x = qkv.float().requires_grad_(True)
+    _attention_ref(x, n_seq, k, heads, key_mask).backward(d_out.float())
+    ref = x.grad.view(n_seq * k, 3, h)
+    qd, km = qkv.to(DEV), key_mask.reshape(-1).to(DEV)
+    out, lse2 = ops.attention_lse(qd, n_seq, k, heads, kv_info.to(DEV), km)
+    got = ops.attention_bwd(qd, out, d_out.to(DEV), lse2, n_seq, k, heads, kv_info.to(DEV), km).view(n_seq * k, 3, h)
+    for i, name in enumerate(("dq", "dk", "dv")):
+        assert_close(f"attention backward {name} H={heads} d={d} k={k}", got[:, i], ref[:, i], 1.5e-2)
+
+
+def test_attention_backward_interior_pads():
+    ops, _ = _ops()
+    heads, d, k, n_seq = 4, 64, 300, 3
+    h = heads * d
+    qkv = bf16r(n_seq * k, 3 * h, seed=43)
+    g = torch.Generator().manual_seed(44)
+    key_mask = (torch.rand(n_seq, k, generator=g) > 0.3).to(torch.uint8)
+    key_mask[0, :] = 1
+    key_mask[1, 250:] = 0
+    key_mask[2, :130] = 0
+    kv_info = torch.tensor([[int(m.nonzero().max()) + 1, int(m.sum())] for m in key_mask], dtype=torch.int32)
+    d_out = bf16r(n_seq * k, h, seed=45)
+    x = qkv.float().requires_grad_(True)
+    _attention_ref(x, n_seq, k, heads, key_mask).backward(d_out.float())
+    ref = x.grad.view(n_seq * k, 3, h)
+    qd, km = qkv.to(DEV), key_mask.reshape(-1).to(DEV)
+    out, lse2 = ops.attention_lse(qd, n_seq, k, heads, kv_info.to(DEV), km)
+    got = ops.attention_bwd(qd, out, d_out.to(DEV), lse2, n_seq, k, heads, kv_info.to(DEV), km).view(n_seq * k, 3, h)
+    for i, name in enumerate(("dq", "dk", "dv")):
+        assert_close(f"attention backward interior pads {name}", got[:, i], ref[:, i], 1.5e-2)
+
+
 def test_attention_interior_pads():
     """`mask = ids != 1` is not required to be a prefix: interior pad ids must be masked as keys (omics_one.py:70)."""
     ops, _ = _ops()
