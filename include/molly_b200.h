@@ -201,6 +201,31 @@ int molly_attention_lse(const void* qkv_dev, int32_t n_seq, int32_t k_tokens, in
 int molly_attention_bwd(const void* qkv_dev, const void* out_dev, const void* d_out_dev, const float* lse2_dev, int32_t n_seq,
                         int32_t k_tokens, int32_t h, int32_t heads, const int32_t* kv_info_dev, const uint8_t* key_mask_dev,
                         void* d_qkv_dev, float* delta_ws_dev, void* stream);
+/* ---- encoder backward building blocks (--train-bio, src/utils/tools.py:313-331): autograd of the HF modules
+ * the forward kernels replace.  All activations bf16 row-major unless noted; gradients of parameters fp32. */
+/* d_weight[N,K] = dy[M,N]^T x[M,K], d_bias[N] = colsum(dy): autograd of nn.Linear (workspace >= (N + K) * roundup8(M) * 2 B) */
+int molly_linear_wgrad(const void* dy_dev, const void* x_dev, int32_t M, int32_t N, int32_t K, float* d_weight_dev,
+                       float* d_bias_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* dy[n*k + j, :] = d_hidden[b, start+1+j, :] for j < k_cap (0 beyond): autograd of the slice-assign, omics_one.py:93-97;
+ * zero_rows != 0 additionally zeroes those rows of d_hidden (the gradient that flows on to embed_tokens) */
+int molly_gather_rows(void* d_hidden_dev, int32_t hs_dtype, const int32_t* seq_table_dev, int32_t n_seq, int32_t k_tokens,
+                      int32_t k_cap, int32_t B, int32_t T, int32_t D, void* dy_dev, int32_t zero_rows, void* stream);
+int molly_transpose_bf16(const void* in_dev /*[rows, cols]*/, int32_t rows, int32_t cols, void* out_dev /*[cols, rows]*/,
+                         void* stream);
+/* LayerNorm backward (HF:394, 479, 511): d_x (fp32) = or += dx; stats_dev fp32 [rows, 2] scratch; d_gamma / d_beta (fp32,
+ * pre-zeroed, accumulated with atomics) may be NULL */
+int molly_layernorm_bwd(const float* x_dev, const void* dy_dev, const float* gamma_dev, int32_t rows, int32_t h, float eps,
+                        float* d_x_dev, int32_t accumulate, float* stats_dev, float* d_gamma_dev, float* d_beta_dev,
+                        void* stream);
+/* FFN activation forward + backward in one pass: glu == 0: act = gelu_erf(pre) [rows, f_out], d_pre likewise (HF:57-61);
+ * glu != 0: pre = (a,b) interleaved [rows, 2 f_out], act = silu(a) * b, d_pre interleaved (NT-v2 gated FFN) */
+int molly_act_fwd_bwd(int32_t glu, const void* pre_dev, const void* d_act_dev, int64_t rows, int32_t f_out, void* act_dev,
+                      void* d_pre_dev, void* stream);
+int molly_cast_f32_bf16(const float* in_dev, int64_t n, void* out_dev, void* stream);
+int molly_scale_cols(void* x_dev /*bf16 [rows, ld]*/, int32_t rows, int32_t ld, int32_t cols, float scale, void* stream);
+/* table[index[r], :] += scale[r] * src[r, :] (fp32 atomics): autograd of the embedding gathers (HF:189-236) */
+int molly_scatter_add_rows(const float* src_dev, const int32_t* index_dev, const float* scale_dev, int32_t rows, int32_t h,
+                           float* table_dev, void* stream);
 /* bring-up aid: when non-NULL, CTA 0 of the attention kernel records clock64() stamps into timeline_dev
  * (int64 [2 roles][64 iterations][8 slots]); NULL (default) disables it */
 int molly_attention_debug(long long* timeline_dev);

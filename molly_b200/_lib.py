@@ -88,6 +88,14 @@ SIGNATURES = {
                                           _i32, _vp, _vp]),
     "molly_attention_lse": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "molly_attention_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "molly_linear_wgrad": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "molly_gather_rows": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "molly_transpose_bf16": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
+    "molly_layernorm_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, C.c_float, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "molly_act_fwd_bwd": (C.c_int, [_i32, _vp, _vp, C.c_int64, _i32, _vp, _vp, _vp]),
+    "molly_cast_f32_bf16": (C.c_int, [_vp, C.c_int64, _vp, _vp]),
+    "molly_scale_cols": (C.c_int, [_vp, _i32, _i32, _i32, C.c_float, _vp]),
+    "molly_scatter_add_rows": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "molly_attention_debug": (C.c_int, [_vp]),
     "molly_merge_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "molly_profile_start": (C.c_int, []),

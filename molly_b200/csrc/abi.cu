@@ -312,6 +312,57 @@ int molly_project_bwd(molly_encoder_t* enc, void* d_hidden_dev, int32_t hs_dtype
                               static_cast<uint8_t*>(workspace_dev) + dy_bytes, workspace_bytes - dy_bytes, s);
 }
 
+// ------------------------------------ encoder backward building blocks ------------------------------------
+int molly_linear_wgrad(const void* dy_dev, const void* x_dev, int32_t M, int32_t N, int32_t K, float* d_weight_dev,
+                       float* d_bias_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    MOLLY_CHECK(dy_dev && x_dev && d_weight_dev && d_bias_dev && workspace_dev, MOLLY_ERR_INVALID,
+                "molly_linear_wgrad: NULL pointer");
+    return project_bwd_launch(dy_dev, x_dev, M, N, K, d_weight_dev, d_bias_dev, workspace_dev, workspace_bytes,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int molly_gather_rows(void* d_hidden_dev, int32_t hs_dtype, const int32_t* seq_table_dev, int32_t n_seq, int32_t k_tokens,
+                      int32_t k_cap, int32_t B, int32_t T, int32_t D, void* dy_dev, int32_t zero_rows, void* stream) {
+    MOLLY_CHECK(d_hidden_dev && seq_table_dev && dy_dev, MOLLY_ERR_INVALID, "molly_gather_rows: NULL pointer");
+    return gather_grad_rows_launch(d_hidden_dev, hs_dtype, seq_table_dev, n_seq, k_tokens, k_cap, B, T, D, dy_dev, zero_rows,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int molly_transpose_bf16(const void* in_dev, int32_t rows, int32_t cols, void* out_dev, void* stream) {
+    MOLLY_CHECK(in_dev && out_dev, MOLLY_ERR_INVALID, "molly_transpose_bf16: NULL pointer");
+    return transpose_bf16_launch(in_dev, rows, cols, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int molly_layernorm_bwd(const float* x_dev, const void* dy_dev, const float* gamma_dev, int32_t rows, int32_t h, float eps,
+                        float* d_x_dev, int32_t accumulate, float* stats_dev, float* d_gamma_dev, float* d_beta_dev,
+                        void* stream) {
+    MOLLY_CHECK(x_dev && dy_dev && gamma_dev && d_x_dev && stats_dev, MOLLY_ERR_INVALID, "molly_layernorm_bwd: NULL pointer");
+    return ln_bwd_launch(x_dev, dy_dev, gamma_dev, rows, h, eps, d_x_dev, accumulate, stats_dev, d_gamma_dev, d_beta_dev,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int molly_act_fwd_bwd(int32_t glu, const void* pre_dev, const void* d_act_dev, int64_t rows, int32_t f_out, void* act_dev,
+                      void* d_pre_dev, void* stream) {
+    MOLLY_CHECK(pre_dev && d_act_dev && act_dev && d_pre_dev, MOLLY_ERR_INVALID, "molly_act_fwd_bwd: NULL pointer");
+    return act_fwd_bwd_launch(glu, pre_dev, d_act_dev, rows, f_out, act_dev, d_pre_dev, static_cast<cudaStream_t>(stream));
+}
+
+int molly_cast_f32_bf16(const float* in_dev, int64_t n, void* out_dev, void* stream) {
+    MOLLY_CHECK(in_dev && out_dev, MOLLY_ERR_INVALID, "molly_cast_f32_bf16: NULL pointer");
+    return cast_f32_bf16_launch(in_dev, n, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int molly_scale_cols(void* x_dev, int32_t rows, int32_t ld, int32_t cols, float scale, void* stream) {
+    MOLLY_CHECK(x_dev, MOLLY_ERR_INVALID, "molly_scale_cols: NULL pointer");
+    return scale_cols_launch(x_dev, rows, ld, cols, scale, static_cast<cudaStream_t>(stream));
+}
+
+int molly_scatter_add_rows(const float* src_dev, const int32_t* index_dev, const float* scale_dev, int32_t rows, int32_t h,
+                           float* table_dev, void* stream) {
+    MOLLY_CHECK(src_dev && index_dev && scale_dev && table_dev, MOLLY_ERR_INVALID, "molly_scatter_add_rows: NULL pointer");
+    return scatter_add_rows_launch(src_dev, index_dev, scale_dev, rows, h, table_dev, static_cast<cudaStream_t>(stream));
+}
+
 // ------------------------------------ single kernels ------------------------------------
 int molly_gemm_bf16(const void* a_dev, int32_t lda, const void* w_dev, int32_t ldw, int32_t M, int32_t N, int32_t K,
                     int32_t epilogue, const float* bias_dev, const float* residual_dev, void* out_dev,

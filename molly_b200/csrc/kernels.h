@@ -89,7 +89,18 @@ int attention_bwd_launch(const void* qkv, const void* out, const void* d_out, co
                          int heads, const int32_t* kv_info, const uint8_t* key_mask, void* d_qkv, float* delta_ws,
                          cudaStream_t stream);
 
+// ---- rowwise_bwd.cu ----
+int ln_bwd_launch(const float* x, const void* dy_bf16, const float* gamma, int rows, int h, float eps, float* d_x,
+                  int accumulate, float* stats, float* d_gamma, float* d_beta, cudaStream_t stream);
+int act_fwd_bwd_launch(int glu, const void* pre, const void* d_act, long long rows, int f_out, void* act, void* d_pre,
+                       cudaStream_t stream);
+int cast_f32_bf16_launch(const float* in, long long n, void* out, cudaStream_t stream);
+int scale_cols_launch(void* x_bf16, int rows, int ld, int cols, float scale, cudaStream_t stream);
+int scatter_add_rows_launch(const float* src, const int32_t* index, const float* scale, int rows, int h, float* table,
+                            cudaStream_t stream);
+
 // ---- bwd.cu ----
+int transpose_bf16_launch(const void* in, int rows, int cols, void* out, cudaStream_t stream);
 int project_bwd_launch(const void* dy_bf16, const void* x_bf16, int M, int D, int h, float* d_weight, float* d_bias,
                        void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
