@@ -432,6 +432,100 @@ def attention_bwd(qkv: Tensor, out: Tensor, d_out: Tensor, lse2: Tensor, n_seq: 
     return d_qkv
 
 
+# ---- encoder-backward building blocks ------------------------------------------------------------
+def linear_wgrad(dy: Tensor, x: Tensor):
+    """Autograd of ``nn.Linear`` w.r.t. its parameters: (dW [N, K] = dy^T x, db [N] = colsum(dy)), fp32."""
+    dev = _require_cuda(dy, x)
+    M, N = dy.shape
+    K = x.shape[1]
+    if dy.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or x.shape[0] != M or not (dy.is_contiguous() and x.is_contiguous()):
+        raise ValueError("linear_wgrad: dy [M, N] and x [M, K] must be contiguous bf16")
+    dW = torch.empty(N, K, dtype=torch.float32, device=dev)
+    db = torch.empty(N, dtype=torch.float32, device=dev)
+    ws = workspace(dev, (N + K) * ((M + 7) // 8 * 8) * 2 + 4096)
+    ws_ptr, ws_bytes = _aligned(ws)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_linear_wgrad(dy.data_ptr(), x.data_ptr(), M, N, K, dW.data_ptr(), db.data_ptr(), ws_ptr,
+                                                  ws_bytes, _stream(dev)), "molly_linear_wgrad")
+    return dW, db
+
+
+def gather_rows(d_hidden: Tensor, seq_table: Tensor, k_tokens: int, k_cap: int, zero_rows: bool) -> Tensor:
+    """bf16 [n_seq*k, D]: the rows of ``d_hidden`` [B, T, D] the forward's slice-assign wrote (0 beyond k_cap)."""
+    dev = _require_cuda(d_hidden, seq_table)
+    B, T, D = d_hidden.shape
+    n_seq = seq_table.shape[0]
+    dy = torch.empty(n_seq * k_tokens, D, dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_gather_rows(d_hidden.data_ptr(), _dtype_code(d_hidden), seq_table.data_ptr(), n_seq,
+                                                 k_tokens, k_cap, B, T, D, dy.data_ptr(), int(zero_rows), _stream(dev)),
+                   "molly_gather_rows")
+    return dy
+
+
+def transpose_bf16(x: Tensor) -> Tensor:
+    dev = _require_cuda(x)
+    rows, cols = x.shape
+    out = torch.empty(cols, rows, dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_transpose_bf16(x.data_ptr(), rows, cols, out.data_ptr(), _stream(dev)),
+                   "molly_transpose_bf16")
+    return out
+
+
+def layernorm_bwd(x: Tensor, dy: Tensor, gamma: Tensor, eps: float, d_x: Tensor, accumulate: bool,
+                  d_gamma: Optional[Tensor] = None, d_beta: Optional[Tensor] = None) -> Tensor:
+    """``d_x`` (fp32 [rows, h]) = or += LayerNorm-backward(dy); ``d_gamma`` / ``d_beta`` (fp32, pre-zeroed) accumulate."""
+    dev = _require_cuda(x, dy, gamma, d_x, d_gamma, d_beta)
+    rows, h = x.shape
+    stats = torch.empty(rows, 2, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_layernorm_bwd(x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), rows, h, eps, d_x.data_ptr(),
+                                                   int(accumulate), stats.data_ptr(),
+                                                   None if d_gamma is None else d_gamma.data_ptr(),
+                                                   None if d_beta is None else d_beta.data_ptr(), _stream(dev)),
+                   "molly_layernorm_bwd")
+    return d_x
+
+
+def act_fwd_bwd(glu: bool, pre: Tensor, d_act: Tensor):
+    """(act, d_pre) of the FFN activation: erf-GELU on ``pre`` [rows, F] or gated SiLU on interleaved ``pre`` [rows, 2F]."""
+    dev = _require_cuda(pre, d_act)
+    rows, f_out = d_act.shape
+    act = torch.empty(rows, f_out, dtype=torch.bfloat16, device=dev)
+    d_pre = torch.empty_like(pre)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_act_fwd_bwd(int(glu), pre.data_ptr(), d_act.data_ptr(), rows, f_out, act.data_ptr(),
+                                                 d_pre.data_ptr(), _stream(dev)), "molly_act_fwd_bwd")
+    return act, d_pre
+
+
+def cast_bf16(x: Tensor) -> Tensor:
+    dev = _require_cuda(x)
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_cast_f32_bf16(x.data_ptr(), x.numel(), out.data_ptr(), _stream(dev)),
+                   "molly_cast_f32_bf16")
+    return out
+
+
+def scale_cols_(x: Tensor, cols: int, scale: float) -> Tensor:
+    dev = _require_cuda(x)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_scale_cols(x.data_ptr(), x.shape[0], x.stride(0), cols, scale, _stream(dev)),
+                   "molly_scale_cols")
+    return x
+
+
+def scatter_add_rows_(table: Tensor, src: Tensor, index: Tensor, scale: Tensor) -> Tensor:
+    dev = _require_cuda(table, src, index, scale)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_scatter_add_rows(src.data_ptr(), index.data_ptr(), scale.data_ptr(), src.shape[0],
+                                                      src.shape[1], table.data_ptr(), _stream(dev)),
+                   "molly_scatter_add_rows")
+    return table
+
+
 def merge_rows_(hidden_states: Tensor, src: Tensor, seq_table: Tensor, k_tokens: int, k_cap: int) -> Tensor:
     dev = _require_cuda(hidden_states, src, seq_table)
     B, T, D = hidden_states.shape

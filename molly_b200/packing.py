@@ -68,10 +68,13 @@ class PackedEncoder:
 
         sd = state_dict
         w = _lib.EncoderWeights()
-        w.word_emb_dev = _ptr(mat(key("esm.embeddings.word_embeddings.weight")))
+        self.word_emb = mat(key("esm.embeddings.word_embeddings.weight"))
+        w.word_emb_dev = _ptr(self.word_emb)
         w.pos_emb_dev = None
+        self.pos_emb = None
         if cfg.position_embedding_type == "absolute":
-            w.pos_emb_dev = _ptr(mat(key("esm.embeddings.position_embeddings.weight")))
+            self.pos_emb = mat(key("esm.embeddings.position_embeddings.weight"))
+            w.pos_emb_dev = _ptr(self.pos_emb)
         w.emb_ln_w_dev = w.emb_ln_b_dev = None
         if cfg.emb_layer_norm_before:
             w.emb_ln_w_dev = _ptr(vec(key("esm.embeddings.layer_norm.weight")))
@@ -81,15 +84,18 @@ class PackedEncoder:
         self.rope_len = max(int(rope_len), int(cfg.max_position_embeddings))
         inv_freq = 1.0 / (10000 ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))
         freqs = torch.outer(torch.arange(self.rope_len).float(), inv_freq)
-        w.rope_cos_dev = _ptr(const(freqs.cos()))
-        w.rope_sin_dev = _ptr(const(freqs.sin()))
+        self.rope_cos, self.rope_sin = const(freqs.cos()), const(freqs.sin())
+        self.rope_neg_sin = const(-freqs.sin())              # inverse rotation = rotary backward
+        self.rope_cos_t, self.rope_sin_t = const(freqs.cos().t()), const(freqs.sin().t())
+        w.rope_cos_dev, w.rope_sin_dev = _ptr(self.rope_cos), _ptr(self.rope_sin)
         w.rope_len = self.rope_len
-        w.rope_cos_t_dev = _ptr(const(freqs.cos().t()))      # frequency-major copies for the fused QKV epilogue
-        w.rope_sin_t_dev = _ptr(const(freqs.sin().t()))
+        w.rope_cos_t_dev = _ptr(self.rope_cos_t)             # frequency-major copies for the fused QKV epilogue
+        w.rope_sin_t_dev = _ptr(self.rope_sin_t)
 
         names = ["ln1_w", "ln1_b", "w_qkv", "b_qkv", "w_attn_out", "b_attn_out", "ln2_w", "ln2_b", "w_ffn1", "b_ffn1",
                  "w_ffn2", "b_ffn2"]
         arrays: Dict[str, List[Optional[int]]] = {n: [] for n in names}
+        self.layer_tensors: List[Dict[str, Optional[torch.Tensor]]] = []     # named views of the packed weights (train.py)
         for i in range(L):
             p = f"esm.encoder.layer.{i}."
             arrays["ln1_w"].append(_ptr(vec(key(p + "attention.LayerNorm.weight"))))
@@ -121,13 +127,17 @@ class PackedEncoder:
                 arrays["b_ffn1"].append(_ptr(vec(key(p + "intermediate.dense.bias"))))
                 arrays["w_ffn2"].append(_ptr(mat(key(p + "output.dense.weight"))))
                 arrays["b_ffn2"].append(_ptr(vec(key(p + "output.dense.bias"))))
+        by_ptr = {t.data_ptr(): t for t in self._keep}
+        for i in range(L):
+            self.layer_tensors.append({n: (by_ptr[arrays[n][i]] if arrays[n][i] is not None else None) for n in names})
         self._ptr_arrays = {}
         for n in names:
             arr = (C.c_void_p * L)(*arrays[n])
             self._ptr_arrays[n] = arr
             setattr(w, n + "_dev", C.cast(arr, _lib.c_void_pp))
-        w.final_ln_w_dev = _ptr(vec(key("esm.encoder.emb_layer_norm_after.weight")))
-        w.final_ln_b_dev = _ptr(vec(key("esm.encoder.emb_layer_norm_after.bias")))
+        self.final_ln_w = vec(key("esm.encoder.emb_layer_norm_after.weight"))
+        self.final_ln_b = vec(key("esm.encoder.emb_layer_norm_after.bias"))
+        w.final_ln_w_dev, w.final_ln_b_dev = _ptr(self.final_ln_w), _ptr(self.final_ln_b)
         # projector buffers are refreshed in place when the nn.Linear trains (--train-mlp)
         self.proj_w = torch.empty(self.llm_hidden_size, h, dtype=torch.bfloat16, device=device)
         self.proj_b = torch.empty(self.llm_hidden_size, dtype=torch.float32, device=device)

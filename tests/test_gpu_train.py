@@ -1,0 +1,92 @@
+"""GPU parity of the encoder training path (--train-bio): forward with the tape == inference forward, and
+the gradient of EVERY encoder parameter against fp32 autograd of the oracle (the reference's HF modules restated)."""
+import pytest
+import torch
+
+from oracle import synth
+from oracle.esm_oracle import SPECS, esm_encoder_forward, init_encoder_weights, init_projector
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 2e-2
+
+
+def _ids(spec, K, valids, seed):
+    g = torch.Generator().manual_seed(seed)
+    rows = [synth.protein_ids(g, K, v) if spec.vocab_size == 33 else synth.nucleotide_ids(g, K, v, spec.vocab_size)
+            for v in valids]
+    ids = torch.stack(rows)
+    if spec.token_dropout:
+        ids[0, 4] = spec.mask_token_id                      # token-dropout rescale path
+    return ids
+
+
+@pytest.mark.parametrize("spec_name,K,valids", [
+    ("tiny_esm2", 150, [150, 77, 130]),                    # rotary, erf-GELU, token dropout, K not a multiple of 128
+    ("tiny_ntv2", 140, [140, 9]),                          # gated SiLU, no biases in the FFN
+    ("tiny_ntv1", 96, [96, 40, 96]),                       # learned absolute positions
+    ("esm2_t6_8m", 256, [256, 100]),                       # head_dim 16
+    ("nt_v2_50m", 130, [130, 64]),                         # head_dim 32
+])
+def test_encoder_backward_vs_oracle_autograd(spec_name, K, valids):
+    from molly_b200.config import EncoderConfig
+    from molly_b200.packing import PackedEncoder
+    from molly_b200 import train
+    spec = SPECS[spec_name]
+    W = init_encoder_weights(spec, 7)
+    proj = init_projector(spec.hidden_size, 64, 8)
+    ids = _ids(spec, K, valids, 9)
+    g = torch.Generator().manual_seed(10)
+    d_out = (torch.randn(len(valids) * K, spec.hidden_size, generator=g) * 0.1).to(torch.bfloat16)
+    # oracle: fp32 autograd on the CPU
+    Wg = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in W.items()}
+    ref_out = esm_encoder_forward(spec, Wg, ids)
+    (ref_out.reshape(-1, spec.hidden_size) * d_out.float()).sum().backward()
+    # the reference's own execution: stock HF modules in bf16 on the GPU (what --train-bio trains with), same d_out
+    from oracle.ref_import import build_hf_encoder
+    hf = build_hf_encoder(spec, W).to(DEV).to(torch.bfloat16).train(False)
+    for prm in hf.parameters():
+        prm.requires_grad_(True)
+    hf_out = hf(input_ids=ids.to(DEV), attention_mask=(ids != 1).to(DEV), output_hidden_states=True).hidden_states[-1]
+    (hf_out.reshape(-1, spec.hidden_size).float() * d_out.to(DEV).float()).sum().backward()
+    hf_grads = {k: v.grad.float().cpu() for k, v in hf.named_parameters() if v.grad is not None}
+    # candidate
+    enc = PackedEncoder(EncoderConfig.from_mapping(spec.as_dict()), W, proj, K, torch.device(DEV))
+    try:
+        out, tape = train.encoder_forward_train(enc, ids.to(DEV))
+        assert_close(f"{spec_name} train-mode forward", out.float().cpu(), ref_out.detach().reshape(-1, spec.hidden_size), TOL)
+        grads = train.encoder_backward(enc, tape, d_out.to(DEV))
+        checked, worst_fro, worst_ratio = 0, 0.0, 0.0
+        for name, ref in Wg.items():
+            if ref.grad is None or name.startswith("lm_head") or "contact_head" in name or "inv_freq" in name:
+                continue
+            assert name in grads, f"no gradient produced for {name}"
+            got = grads[name].cpu()
+            if float(ref.grad.abs().max()) == 0.0:
+                assert float(got.abs().max()) == 0.0, name
+            else:
+                # gradients are sums of many bf16-rounded products (dS, P, activations): the aggregate error is the bar
+                # (relative Frobenius <= 2e-2); single elements of small-magnitude tensors (q / k weights) may sit at 3-5e-2
+                scale_n, scale_m = ref.grad.norm(), ref.grad.abs().max()
+                if name.endswith("key.bias"):
+                    # softmax is invariant to a constant added to every key, so d(key bias) is a near-total cancellation
+                    # (exactly 0 without rotary): judge it on the scale of the query-bias gradient of the same layer
+                    q = Wg[name.replace("key.bias", "query.bias")].grad
+                    scale_n, scale_m = max(scale_n, q.norm()), max(scale_m, q.abs().max())
+                fro = float((got - ref.grad).norm() / scale_n)
+                worst = float((got - ref.grad).abs().max() / scale_m)
+                # the bar: 2e-2, or -- where bf16 itself cannot do better (d(q), d(k) pass through dS = P * (dP - delta), a
+                # cancellation of bf16-rounded terms) -- the error of the reference's own bf16 backward on the same weights
+                hf_fro = float((hf_grads[name] - ref.grad).norm() / scale_n) if name in hf_grads else 0.0
+                tol = max(TOL, 2.0 * hf_fro)
+                assert fro <= tol, (f"{spec_name} d {name}: rel Frobenius {fro:.4f} (reference's bf16 backward: {hf_fro:.4f}), "
+                                    f"normalised max {worst:.4f}")
+                worst_ratio = max(worst_ratio, fro / max(hf_fro, 1e-9))
+                worst_fro = max(worst_fro, fro)
+            checked += 1
+        assert checked >= 12 * spec.num_hidden_layers
+        print(f"[{spec_name}] {checked} parameter gradients checked, worst relative Frobenius error {worst_fro:.4f}, "
+              f"at most {worst_ratio:.2f}x the error of the reference's bf16 backward")
+    finally:
+        enc.close()
