@@ -20,7 +20,7 @@ from typing import Any, List, Mapping, Optional
 
 import torch
 
-from . import ops, planner
+from . import _lib, ops, planner
 from .config import EncoderConfig
 from .packing import PackedEncoder
 
@@ -38,7 +38,7 @@ class _InjectFn(torch.autograd.Function):
         ctx.enc_id = enc_id
         ctx.k_tokens = ids.shape[1]
         ctx.save_for_backward(seq_table, enc_out)
-        ctx.w_dtype, ctx.b_dtype = proj_weight.dtype, proj_bias.dtype
+        ctx.w_meta, ctx.b_meta = (proj_weight.dtype, proj_weight.device), (proj_bias.dtype, proj_bias.device)
         return hidden_states
 
     @staticmethod
@@ -51,8 +51,50 @@ class _InjectFn(torch.autograd.Function):
         dW = db = None
         if enc_out.numel() > 0:
             dW, db = ops.project_bwd(g, seq_table, enc_out, ctx.enc_id, ctx.k_tokens, bool(need_h))
-            dW, db = dW.to(ctx.w_dtype), db.to(ctx.b_dtype)
+            dW = dW.to(device=ctx.w_meta[1], dtype=ctx.w_meta[0])
+            db = db.to(device=ctx.b_meta[1], dtype=ctx.b_meta[0])
         return (g if need_h else None), dW, db, None, None, None
+
+
+class _InjectTrainFn(torch.autograd.Function):
+    """Autograd of one modality with a TRAINABLE encoder (``--train-bio``, src/utils/tools.py:313-331): forward through
+    ``train.encoder_forward_train`` (same kernels, layer inputs kept), backward through ``train.encoder_backward``; grads
+    reach every encoder parameter (by HF name), the projector, and -- zeroed on the overwritten rows -- ``hidden_states``."""
+
+    @staticmethod
+    def forward(ctx, hidden_states, proj_weight, proj_bias, ids, seq_table, enc_id: int, names, *enc_params):
+        from . import train
+        enc = ops.get_encoder(enc_id)
+        k_tokens = ids.shape[1]
+        enc_out, tape = train.encoder_forward_train(enc, ids)
+        ops.gemm_bf16(enc_out, enc.proj_w, _lib.EPI_SCATTER, bias=enc.proj_b, out=hidden_states, seq_table=seq_table,
+                      seq_k=k_tokens, k_cap=min(enc.project_token_num, k_tokens))
+        ctx.mark_dirty(hidden_states)
+        ctx.enc_id, ctx.k_tokens, ctx.names, ctx.tape = enc_id, k_tokens, names, tape
+        ctx.save_for_backward(seq_table, enc_out)
+        ctx.metas = ((proj_weight.dtype, proj_weight.device), (proj_bias.dtype, proj_bias.device),
+                     [(p.dtype, p.device) for p in enc_params])          # grads go back in each parameter's dtype / device
+        return hidden_states
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from . import train
+        seq_table, enc_out = ctx.saved_tensors
+        enc = ops.get_encoder(ctx.enc_id)
+        need_h = ctx.needs_input_grad[0]
+        g = grad_out.contiguous()
+        if need_h:
+            g = g.clone() if g.data_ptr() == grad_out.data_ptr() else g
+        dy = ops.gather_rows(g, seq_table, ctx.k_tokens, min(enc.project_token_num, ctx.k_tokens), bool(need_h))
+        dW, db = ops.linear_wgrad(dy, enc_out)
+        d_enc = ops.gemm_bf16(dy, ops.transpose_bf16(enc.proj_w), _lib.EPI_BIAS)
+        grads = train.encoder_backward(enc, ctx.tape, d_enc)
+        ctx.tape = None
+        w_m, b_m, p_ms = ctx.metas
+        enc_grads = [grads[n].to(device=dv, dtype=dt) if (n in grads and need) else None
+                     for n, (dt, dv), need in zip(ctx.names, p_ms, ctx.needs_input_grad[7:])]
+        return ((g if need_h else None), dW.to(device=w_m[1], dtype=w_m[0]), db.to(device=b_m[1], dtype=b_m[0]), None, None,
+                None, None, *enc_grads)
 
 
 class FastOmicsPath:
@@ -135,13 +177,6 @@ class FastOmicsPath:
         batch_size = hidden_states.shape[0]
         if self._enc_modules:
             self.refresh_encoders()
-            if torch.is_grad_enabled():
-                for name, module in self._enc_modules.items():
-                    if any(prm.requires_grad for prm in module.parameters()):
-                        raise NotImplementedError(
-                            f"the {name} encoder has trainable parameters (--train-bio, src/utils/tools.py:313-331): the "
-                            "encoder backward is not built yet (SURVEY.md 8f N4); freeze the encoders or call under "
-                            "torch.no_grad() -- refusing to train them silently as frozen")
         nt_plan, pr_plan = planner.route(batch_size, omic_ids_list, omic_info_list)          # may raise ValueError
         # reference order: all DNA/RNA sequences, then all protein sequences (omics_one.py:120-134)
         work = [(name, plan) for name, plan in (("dna_rna", nt_plan), ("protein", pr_plan)) if len(plan)]  # :67-68
@@ -195,8 +230,15 @@ class FastOmicsPath:
         proj = self._proj_modules.get(name)
         if proj is not None:
             self._refresh_projector(name, enc, proj)
-        if proj is not None and torch.is_grad_enabled() and (proj.weight.requires_grad or proj.bias.requires_grad
-                                                              or hidden_states.requires_grad):
+        enc_module = self._enc_modules.get(name)
+        train_enc = (proj is not None and enc_module is not None and torch.is_grad_enabled()
+                     and any(prm.requires_grad for prm in enc_module.parameters()))
+        if train_enc:                                        # --train-bio: the encoder's own parameters get gradients
+            named = list(enc_module.named_parameters())
+            _InjectTrainFn.apply(target, proj.weight, proj.bias, ids, seq_table, enc_id, tuple(n for n, _ in named),
+                                 *[prm for _, prm in named])
+        elif proj is not None and torch.is_grad_enabled() and (proj.weight.requires_grad or proj.bias.requires_grad
+                                                                or hidden_states.requires_grad):
             _InjectFn.apply(target, proj.weight, proj.bias, ids, seq_table, enc_id)
         else:
             ops.encode_project_merge(target, ids, seq_table, enc_id, False)

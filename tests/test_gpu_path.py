@@ -350,14 +350,26 @@ def test_from_omics_one_follows_live_encoder_weights():
             out2 = path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
         assert not torch.equal(out2, out)
         assert_close("after in-place weight updates", out2.float().cpu(), ref2, TOL)
-        # --train-bio is not built: trainable encoder parameters under autograd must fail loudly, never train as frozen
+        # --train-bio: trainable encoder parameters receive gradients through the path (tests/test_gpu_train.py checks every one)
         for prm in om.dna_rna_model.parameters():
             prm.requires_grad_(False)
-        for prm in om.protein_model.parameters():
-            prm.requires_grad_(False)
-        path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)   # frozen: fine
-        next(om.protein_model.parameters()).requires_grad_(True)
-        with pytest.raises(NotImplementedError, match="train-bio"):
-            path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
+        hs2 = hs.clone().requires_grad_(True)
+        out3 = path.process_omic_sequences(hs2 * 1.0, case.batch.omic_ids, case.batch.omic_info_list, hs.device)
+        gw = torch.randn(out3.shape, generator=torch.Generator().manual_seed(77)).to(DEV)
+        (out3 * gw).sum().backward()
+        pr3 = copy.copy(pr2)
+        pr3.weights = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in new_pr.items()}
+        pr3.projector = {k: v.clone().requires_grad_(True) for k, v in case.pr.projector.items()}
+        emb_ref = case.batch.hidden_states.clone().requires_grad_(True)
+        o3 = oracle_process(emb_ref * 1.0, case.batch.omic_ids, case.batch.omic_info_list, nt2, pr3)
+        (o3 * gw.cpu()).sum().backward()
+        assert all(prm.grad is None for prm in om.dna_rna_model.parameters())          # frozen encoder: untouched
+        got_g = dict(om.protein_model.named_parameters())
+        for key in ("esm.encoder.layer.0.attention.self.value.weight", "esm.encoder.layer.1.output.dense.weight",
+                    "esm.encoder.emb_layer_norm_after.weight", "esm.embeddings.word_embeddings.weight"):
+            assert_close(f"train-bio d {key}", got_g[key].grad.float().cpu(), pr3.weights[key].grad, 3e-2)
+        assert_close("train-bio d protein_projector.weight", om.protein_projector.weight.grad.float().cpu(),
+                     pr3.projector["weight"].grad, TOL)
+        assert torch.equal(hs2.grad.cpu(), emb_ref.grad)                                 # zero on overwritten rows
     finally:
         path.close()
