@@ -75,6 +75,10 @@ WORKLOADS = {
                      nt="nt_v1_2p5b", pr="esm2_t6_8m", D=4096, B=256, K=256, T=512, valid=171, layout="dna_only"),
     "train_1p7b": dict(desc="Molly-1.7B train step, path only: fwd + projector bwd + grad all-reduce (B=8/GPU)",
                        nt="nt_v2_500m", pr="esm2_t33_650m", D=2048, B=8, K=1024, T=3072, valid=1024, train=True),
+    # the same step with the encoders unfrozen (--train-bio): training forward with a tape + the full encoder backward
+    "train_bio_1p7b": dict(desc="Molly-1.7B train step with trainable encoders (--train-bio), path only (B=8/GPU)",
+                           nt="nt_v2_500m", pr="esm2_t33_650m", D=2048, B=8, K=1024, T=3072, valid=1024, train=True,
+                           train_encoders=True),
 }
 
 
@@ -359,6 +363,23 @@ def run_reference_arm(args, wl: dict, rank: int, world: int) -> None:
 
 
 # ------------------------------------------------------------------------------------------------------------------
+class ParamBag:
+    """Duck-typed stand-in for an ``EsmForMaskedLM``: live bf16 parameters under their HF ``state_dict`` names."""
+
+    def __init__(self, state_dict):
+        import torch
+        self._p = {k: torch.nn.Parameter(v.to(torch.bfloat16)) for k, v in state_dict.items()}
+
+    def named_parameters(self):
+        return list(self._p.items())
+
+    def parameters(self):
+        return list(self._p.values())
+
+    def state_dict(self):
+        return {k: v.detach() for k, v in self._p.items()}
+
+
 def run_train_step(args, wl: dict, dev, rank: int, world: int, warmup: int) -> None:
     """cfg-5: what the path contributes to one training step.  The LLM's own forward/backward is out of
     scope; its product, d(loss)/d(inputs_embeds), is a fixed synthetic bf16 tensor."""
@@ -376,6 +397,12 @@ def run_train_step(args, wl: dict, dev, rank: int, world: int, warmup: int) -> N
         projs[name] = lin
     path._proj_modules = projs
     params = [p for lin in projs.values() for p in lin.parameters()]
+    if wl.get("train_encoders"):
+        for i, (name, key) in enumerate((("dna_rna", "nt"), ("protein", "pr"))):
+            bag = ParamBag(gpu_state_dict(ENC[wl[key]], dev, 10 + i))       # same seeds as build_path: same weights
+            path._enc_modules[name] = bag
+            path._enc_versions[name] = path._module_version(bag)
+            params += bag.parameters()
     bucket = FlatGradBucket(params) if world > 1 else None
     omic_ids, infos = make_inputs(wl, seed=1234 + rank)
     omic_ids_dev = omic_ids.to(dev)
@@ -430,7 +457,8 @@ def run_train_step(args, wl: dict, dev, rank: int, world: int, warmup: int) -> N
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl["desc"], "B_per_gpu": wl["B"], "K": wl["K"], "T": wl["T"], "D": wl["D"],
                        "parallelism": f"sample-sharded x{world}, flat grad bucket all-reduce ({grad_elems} elements)",
-                       "trainable": "both projectors (weight + bias); encoders frozen"},
+                       "trainable": ("both projectors and every encoder parameter (--train-bio)" if wl.get("train_encoders")
+                                     else "both projectors (weight + bias); encoders frozen")},
             "clocks": clocks, "gpu_launches": launches, "kernels": kernels}
     if rank == 0:
         print(json.dumps(line), flush=True)
