@@ -236,7 +236,7 @@ int molly_merge_rows(const void* src_dev /*[n_seq*k, D]*/, const int32_t* seq_ta
 /* ---- per-kernel-family timing with CUDA events on the launching stream (bench.py's roofline numbers) ------------
  * molly_profile_start() arms it; every kernel launched by this library afterwards is bracketed by two events;
  * molly_profile_stop() synchronises them and fills MOLLY_PROFILE_FAMILIES entries.  Off by default (zero overhead). */
-#define MOLLY_PROFILE_FAMILIES 12
+#define MOLLY_PROFILE_FAMILIES 14
 typedef struct molly_profile_entry {
     const char* name;      /* embed, layernorm, gemm_qkv, rotary, attention, gemm_attn_out, gemm_ffn1, gemm_ffn2, ... */
     int32_t launches;

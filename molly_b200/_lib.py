@@ -61,7 +61,7 @@ class ProfileEntry(C.Structure):
                 ("total_ms", C.c_double), ("work", C.c_double)]
 
 
-PROFILE_FAMILIES = 12
+PROFILE_FAMILIES = 14
 _i32, _i64p, _vp, _sz = C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t
 
 # name -> (restype, argtypes); must list every function declared in include/molly_b200.h (tests/test_abi.py checks)

@@ -175,8 +175,9 @@ int molly_kernel_launch_count(void) { return launch_count(); }
 int molly_profile_start(void) { prof_start(); return MOLLY_OK; }
 int molly_profile_stop(molly_profile_entry* out, int32_t max_entries) {
     static const char* names[PF_COUNT] = {"embed", "layernorm", "gemm_qkv", "rotary", "attention", "gemm_attn_out",
-                                          "gemm_ffn1", "gemm_ffn2", "gemm_proj", "gemm_other", "merge", "other"};
-    static const int is_flops[PF_COUNT] = {0, 0, 1, 0, 1, 1, 1, 1, 1, 1, 0, 0};
+                                          "gemm_ffn1", "gemm_ffn2", "gemm_proj", "gemm_other", "merge", "other",
+                                          "attention_bwd", "rowwise_bwd"};
+    static const int is_flops[PF_COUNT] = {0, 0, 1, 0, 1, 1, 1, 1, 1, 1, 0, 0, 1, 0};
     int launches[PF_COUNT]; double ms[PF_COUNT], work[PF_COUNT];
     int rc = prof_stop(launches, ms, work);
     MOLLY_CHECK(out != nullptr && max_entries >= PF_COUNT, MOLLY_ERR_INVALID, "molly_profile_stop: need %d entries", PF_COUNT);
@@ -185,7 +186,7 @@ int molly_profile_stop(molly_profile_entry* out, int32_t max_entries) {
         out[f].work_is_flops = is_flops[f];
     }
     MOLLY_CHECK(rc == 0, MOLLY_ERR_CUDA, "molly_profile_stop: event timing failed");
-    return PF_COUNT == 12 ? MOLLY_OK : MOLLY_ERR_INVALID;
+    return PF_COUNT == MOLLY_PROFILE_FAMILIES ? MOLLY_OK : MOLLY_ERR_INVALID;
 }
 
 int molly_encoder_create(const molly_encoder_config* cfg, const molly_encoder_weights* w, molly_encoder_t** out) {

@@ -70,6 +70,7 @@ int project_bwd_launch(const void* dy_bf16, const void* x_bf16, int M, int D, in
 // out[c, r] = in[r, c] (bf16): weight transposes for the dgrad GEMMs of the encoder backward
 int transpose_bf16_launch(const void* in, int rows, int cols, void* out, cudaStream_t stream) {
     MOLLY_CHECK(rows > 0 && cols > 0, MOLLY_ERR_INVALID, "transpose: rows=%d cols=%d", rows, cols);
+    ProfScope prof(PF_ROWWISE_BWD, static_cast<double>(rows) * cols * 4.0, stream);
     transpose_bf16_kernel<<<dim3((rows + 63) / 64, (cols + 63) / 64), 256, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(in), rows, cols, static_cast<__nv_bfloat16*>(out), rows);
     count_launch();

@@ -15,7 +15,7 @@ int launch_count();
 // ---- optional per-launch profiling (CUDA events on the launching stream; off by default) ----
 enum ProfFamily {
     PF_EMBED = 0, PF_LAYERNORM, PF_GEMM_QKV, PF_ROTARY, PF_ATTENTION, PF_GEMM_ATTN_OUT, PF_GEMM_FFN1, PF_GEMM_FFN2,
-    PF_GEMM_PROJ, PF_GEMM_OTHER, PF_MERGE, PF_OTHER, PF_COUNT
+    PF_GEMM_PROJ, PF_GEMM_OTHER, PF_MERGE, PF_OTHER, PF_ATTENTION_BWD, PF_ROWWISE_BWD, PF_COUNT
 };
 struct ProfScope {            // brackets ONE kernel launch with two events when profiling is on
     cudaStream_t stream;

@@ -157,6 +157,7 @@ int ln_bwd_launch(const float* x, const void* dy_bf16, const float* gamma, int r
                   int accumulate, float* stats, float* d_gamma, float* d_beta, cudaStream_t stream) {
     MOLLY_CHECK(rows > 0 && h > 0, MOLLY_ERR_INVALID, "ln_bwd: rows=%d h=%d", rows, h);
     const auto* dy = static_cast<const __nv_bfloat16*>(dy_bf16);
+    ProfScope prof(PF_ROWWISE_BWD, static_cast<double>(rows) * h * (d_gamma ? 20.0 : 14.0), stream);
     ln_bwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, dy, gamma, rows, h, eps, d_x, accumulate, stats);
     count_launch();
     if (d_gamma != nullptr && d_beta != nullptr) {
@@ -173,6 +174,7 @@ int act_fwd_bwd_launch(int glu, const void* pre, const void* d_act, long long ro
                        cudaStream_t stream) {
     const long long n = rows * f_out;
     MOLLY_CHECK(n > 0 && f_out % 2 == 0, MOLLY_ERR_INVALID, "act_fwd_bwd: rows=%lld F=%d", rows, f_out);
+    ProfScope prof(PF_ROWWISE_BWD, static_cast<double>(n) * (glu ? 12.0 : 8.0), stream);
     if (glu)
         glu_fwd_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
             static_cast<const __nv_bfloat16*>(pre), static_cast<const __nv_bfloat16*>(d_act), n,
@@ -188,6 +190,7 @@ int act_fwd_bwd_launch(int glu, const void* pre, const void* d_act, long long ro
 
 int cast_f32_bf16_launch(const float* in, long long n, void* out, cudaStream_t stream) {
     MOLLY_CHECK(n > 0 && n % 4 == 0, MOLLY_ERR_INVALID, "cast: n=%lld must be a positive multiple of 4", n);
+    ProfScope prof(PF_ROWWISE_BWD, static_cast<double>(n) * 6.0, stream);
     cast_f32_bf16_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, stream>>>(in, n,
                                                                                       static_cast<__nv_bfloat16*>(out));
     count_launch();
