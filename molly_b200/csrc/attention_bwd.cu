@@ -10,8 +10,9 @@
 //     A operand and dQ' += dS K' uses the K tile as the MN-major B operand (exactly how the forward feeds V).
 //   * attn_bwd_dkv_kernel: CTA = 128 keys; streams query blocks with the roles swapped -- S^T = K' Q'^T, dP^T = V dO^T, so a
 //     thread owns a KEY row, P^T and dS^T are K-major A operands, and dV += P^T dO, dK' += dS^T Q' take dO / Q' as MN-major B.
-// One CTA per SM (512 TMEM columns: two 128-column score tiles + the accumulators).  First, correct version: loads are
-// double-buffered, the score tiles are not.
+// One CTA per SM (512 TMEM columns: two 128-column score tiles + the accumulators).  The element-wise work has no row
+// reduction (P comes from the stored log-sum-exp), so TWO threads share a row, 64 columns each: warps w and w+4 address the
+// same TMEM lanes.  First version: loads are double-buffered, the score tiles are not.
 #include <math_constants.h>
 
 #include "common.h"
@@ -23,7 +24,8 @@ namespace molly {
 namespace {
 
 constexpr int BW_BLOCK = 128;
-constexpr int BW_THREADS = 160;                // 4 compute warps + 1 control warp
+constexpr int BW_THREADS = 288;                // 8 compute warps (two per query / key row: 64 columns each) + 1 control warp
+constexpr int BW_COMPUTE = 256;
 constexpr float BW_LOG2E = 1.4426950408889634f;
 
 template <int D>
@@ -137,8 +139,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
     uint64_t* bar_kv_full = bars + 1;        // [NST]
     uint64_t* bar_kv_empty = bars + 3;       // [NST]  dQ MMA of the block done: the K/V stage and the dS tile are free
     uint64_t* bar_sdp_full = bars + 5;       // S and dP of the block are in TMEM
-    uint64_t* bar_s_free = bars + 6;         // 128 arrivals: both are in registers
-    uint64_t* bar_ds_full = bars + 7;        // 128 arrivals: dS is in smem
+    uint64_t* bar_s_free = bars + 6;         // 256 arrivals: both are in registers
+    uint64_t* bar_ds_full = bars + 7;        // 256 arrivals: dS is in smem
     uint64_t* bar_dq_full = bars + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
@@ -149,18 +151,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
     const int nkv = (kvl + BW_BLOCK - 1) / BW_BLOCK;
     const long long row_base = static_cast<long long>(n) * k_tokens;
     if (nkv == 0) {                                          // no valid key: the forward wrote zeros, nothing flows back
-        if (warp < 4 && q0 + threadIdx.x < k_tokens) zero_row<D>(d_qkv + (row_base + q0 + threadIdx.x) * 3 * h + head * D);
+        if (threadIdx.x < BW_BLOCK && q0 + threadIdx.x < k_tokens)
+            zero_row<D>(d_qkv + (row_base + q0 + threadIdx.x) * 3 * h + head * D);
         return;
     }
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             tma_prefetch_desc(&tma_qkv);
             tma_prefetch_desc(&tma_do);
             mbar_init(bar_qdo, 1);
             for (int s = 0; s < NST; ++s) { mbar_init(&bar_kv_full[s], 1); mbar_init(&bar_kv_empty[s], 1); }
             mbar_init(bar_sdp_full, 1);
-            mbar_init(bar_s_free, 128);
-            mbar_init(bar_ds_full, 128);
+            mbar_init(bar_s_free, BW_COMPUTE);
+            mbar_init(bar_ds_full, BW_COMPUTE);
             mbar_init(bar_dq_full, 1);
             fence_mbar_init();
         }
@@ -174,7 +177,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16(BW_BLOCK, BW_BLOCK, false, false);
             constexpr uint32_t idesc_acc = make_idesc_bf16(BW_BLOCK, D, false, true);       // B MN-major
@@ -252,8 +255,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
             }
         }
     } else {
-        const int r = threadIdx.x;
-        const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+        const int r = threadIdx.x & (BW_BLOCK - 1), half = threadIdx.x >> 7;     // row, and which 64 key columns of it
+        const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const bool row_ok = q0 + r < k_tokens;
         const size_t stat = (static_cast<size_t>(n) * heads + head) * k_tokens + (row_ok ? q0 + r : 0);
         const float my_lse = row_ok ? lse2[stat] : CUDART_INF_F;             // +inf: P = 0 for rows outside the sequence
@@ -267,12 +270,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                 tc_fence_after();
             }
 #pragma unroll
-            for (int qt = 0; qt < 4; ++qt) {                 // 32 keys at a time
+            for (int qq = 0; qq < 2; ++qq) {                 // 32 keys at a time
+                const int qt = 2 * half + qq;
                 uint32_t sr[32], pr[32];
                 tmem_ld32(tmem_s + lane_addr + qt * 32, sr);
                 tmem_ld32(tmem_dp + lane_addr + qt * 32, pr);
                 tmem_ld_wait();
-                if (qt == 3) {
+                if (qq == 1) {
                     tc_fence_before();
                     mbar_arrive(bar_s_free);                 // S / dP are in registers: the next block's scores may be issued
                 }
@@ -291,13 +295,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
             tc_fence_before();
             mbar_arrive(bar_ds_full);
         }
-        mbar_wait(bar_dq_full, 0);
-        tc_fence_after();
-        store_acc_rows<D>(tmem_dq, lane_addr, d_qkv + (row_base + q0 + r) * 3 * h + head * D, row_ok);
+        if (half == 0) {
+            mbar_wait(bar_dq_full, 0);
+            tc_fence_after();
+            store_acc_rows<D>(tmem_dq, lane_addr, d_qkv + (row_base + q0 + r) * 3 * h + head * D, row_ok);
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -317,8 +323,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     uint64_t* bar_q_full = bars + 1;         // [NST]  Q_i and dO_i landed
     uint64_t* bar_q_empty = bars + 3;        // [NST]  dV / dK MMAs of the block done: stage, P^T and dS^T tiles are free
     uint64_t* bar_sdp_full = bars + 5;
-    uint64_t* bar_s_free = bars + 6;         // 128 arrivals
-    uint64_t* bar_pt_full = bars + 7;        // 128 arrivals
+    uint64_t* bar_s_free = bars + 6;         // 256 arrivals
+    uint64_t* bar_pt_full = bars + 7;        // 256 arrivals
     uint64_t* bar_out_full = bars + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
@@ -329,22 +335,22 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     const long long row_base = static_cast<long long>(n) * k_tokens;
     const int nq = (k_tokens + BW_BLOCK - 1) / BW_BLOCK;     // every query row of the sequence attends (pad queries too)
     if (k0 >= kvl) {                                         // keys past the last valid one never receive probability mass
-        if (warp < 4 && k0 + threadIdx.x < k_tokens) {
+        if (threadIdx.x < BW_BLOCK && k0 + threadIdx.x < k_tokens) {
             __nv_bfloat16* row = d_qkv + (row_base + k0 + threadIdx.x) * 3 * h + head * D;
             zero_row<D>(row + h);
             zero_row<D>(row + 2 * h);
         }
         return;
     }
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             tma_prefetch_desc(&tma_qkv);
             tma_prefetch_desc(&tma_do);
             mbar_init(bar_kv, 1);
             for (int s = 0; s < NST; ++s) { mbar_init(&bar_q_full[s], 1); mbar_init(&bar_q_empty[s], 1); }
             mbar_init(bar_sdp_full, 1);
-            mbar_init(bar_s_free, 128);
-            mbar_init(bar_pt_full, 128);
+            mbar_init(bar_s_free, BW_COMPUTE);
+            mbar_init(bar_pt_full, BW_COMPUTE);
             mbar_init(bar_out_full, 1);
             fence_mbar_init();
         }
@@ -358,7 +364,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_st = tmem_base, tmem_dpt = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 384;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16(BW_BLOCK, BW_BLOCK, false, false);
             constexpr uint32_t idesc_acc = make_idesc_bf16(BW_BLOCK, D, false, true);       // B MN-major
@@ -441,8 +447,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
             }
         }
     } else {
-        const int r = threadIdx.x;                           // key row k0 + r
-        const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+        const int r = threadIdx.x & (BW_BLOCK - 1), half = threadIdx.x >> 7;     // key row k0 + r, 64 of the 128 queries
+        const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const int key = k0 + r;
         bool key_ok = key < kvl;
         if (interior && key_ok) key_ok = key_mask[row_base + key] != 0;
@@ -455,9 +461,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
             float* st_lse = stats + (i & 1) * 2 * BW_BLOCK;
             float* st_delta = st_lse + BW_BLOCK;
             const int q = i * BW_BLOCK + r;
-            st_lse[r] = q < k_tokens ? lse2[stat_base + q] : CUDART_INF_F;       // +inf: P = 0 beyond the sequence
-            st_delta[r] = q < k_tokens ? delta[stat_base + q] : 0.f;
-            named_bar_sync(1, 128);
+            if (half == 0) st_lse[r] = q < k_tokens ? lse2[stat_base + q] : CUDART_INF_F;    // +inf: P = 0 beyond the sequence
+            else st_delta[r] = q < k_tokens ? delta[stat_base + q] : 0.f;
+            named_bar_sync(1, BW_COMPUTE);
             mbar_wait(bar_sdp_full, i & 1);
             tc_fence_after();
             if (i > 0) {                                     // dV / dK MMAs (i-1) have drained the P^T / dS^T tiles
@@ -465,12 +471,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
                 tc_fence_after();
             }
 #pragma unroll
-            for (int qt = 0; qt < 4; ++qt) {                 // 32 queries at a time
+            for (int qq = 0; qq < 2; ++qq) {                 // 32 queries at a time
+                const int qt = 2 * half + qq;
                 uint32_t sr[32], pr[32];
                 tmem_ld32(tmem_st + lane_addr + qt * 32, sr);
                 tmem_ld32(tmem_dpt + lane_addr + qt * 32, pr);
                 tmem_ld_wait();
-                if (qt == 3) {
+                if (qq == 1) {
                     tc_fence_before();
                     mbar_arrive(bar_s_free);
                 }
@@ -492,12 +499,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
         mbar_wait(bar_out_full, 0);
         tc_fence_after();
         __nv_bfloat16* row = d_qkv + (row_base + key) * 3 * h + head * D;
-        store_acc_rows<D>(tmem_dk, lane_addr, row + h, key < k_tokens);
-        store_acc_rows<D>(tmem_dv, lane_addr, row + 2 * h, key < k_tokens);
+        if (half == 0) store_acc_rows<D>(tmem_dk, lane_addr, row + h, key < k_tokens);
+        else store_acc_rows<D>(tmem_dv, lane_addr, row + 2 * h, key < k_tokens);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
