@@ -218,7 +218,8 @@ int molly_layernorm_bwd(const float* x_dev, const void* dy_dev, const float* gam
                         float* d_x_dev, int32_t accumulate, float* stats_dev, float* d_gamma_dev, float* d_beta_dev,
                         void* stream);
 /* FFN activation forward + backward in one pass: glu == 0: act = gelu_erf(pre) [rows, f_out], d_pre likewise (HF:57-61);
- * glu != 0: pre = (a,b) interleaved [rows, 2 f_out], act = silu(a) * b, d_pre interleaved (NT-v2 gated FFN) */
+ * glu != 0: pre = (a,b) interleaved [rows, 2 f_out], act = silu(a) * b, d_pre interleaved (NT-v2 gated FFN).
+ * d_act_dev == NULL: forward only (act is written, d_pre is not touched) */
 int molly_act_fwd_bwd(int32_t glu, const void* pre_dev, const void* d_act_dev, int64_t rows, int32_t f_out, void* act_dev,
                       void* d_pre_dev, void* stream);
 int molly_cast_f32_bf16(const float* in_dev, int64_t n, void* out_dev, void* stream);

@@ -344,7 +344,8 @@ int molly_layernorm_bwd(const float* x_dev, const void* dy_dev, const float* gam
 
 int molly_act_fwd_bwd(int32_t glu, const void* pre_dev, const void* d_act_dev, int64_t rows, int32_t f_out, void* act_dev,
                       void* d_pre_dev, void* stream) {
-    MOLLY_CHECK(pre_dev && d_act_dev && act_dev && d_pre_dev, MOLLY_ERR_INVALID, "molly_act_fwd_bwd: NULL pointer");
+    MOLLY_CHECK(pre_dev && act_dev && (d_act_dev == nullptr || d_pre_dev != nullptr), MOLLY_ERR_INVALID,
+                "molly_act_fwd_bwd: NULL pointer");
     return act_fwd_bwd_launch(glu, pre_dev, d_act_dev, rows, f_out, act_dev, d_pre_dev, static_cast<cudaStream_t>(stream));
 }
 

@@ -84,7 +84,8 @@ gelu_fwd_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* 
     const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
     if (i >= n) return;
     const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pre + i));
-    const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d_act + i));
+    const float2 d = d_act != nullptr ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d_act + i))
+                                      : make_float2(0.f, 0.f);
     auto f = [](float x, float dd, float& a, float& g) {
         const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
         const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
@@ -95,7 +96,7 @@ gelu_fwd_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* 
     f(p.x, d.x, a0, g0);
     f(p.y, d.y, a1, g1);
     *reinterpret_cast<__nv_bfloat162*>(act + i) = __floats2bfloat162_rn(a0, a1);
-    *reinterpret_cast<__nv_bfloat162*>(d_pre + i) = __floats2bfloat162_rn(g0, g1);
+    if (d_act != nullptr) *reinterpret_cast<__nv_bfloat162*>(d_pre + i) = __floats2bfloat162_rn(g0, g1);
 }
 
 // u = (a_0, b_0, a_1, b_1, ...) interleaved [rows, 2F]; act = silu(a) * b [rows, F]; d_u = (d_a, d_b) interleaved
@@ -105,13 +106,13 @@ glu_fwd_bwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __r
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n_out) return;
     const float2 ab = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(u + 2 * i));
-    const float d = __bfloat162float(d_act[i]);
+    const float d = d_act != nullptr ? __bfloat162float(d_act[i]) : 0.f;
     const float sig = 1.0f / (1.0f + __expf(-ab.x));
     const float sl = ab.x * sig;
     act[i] = __float2bfloat16(sl * ab.y);
     const float da = d * ab.y * sig * (1.0f + ab.x * (1.0f - sig));
     const float db = d * sl;
-    *reinterpret_cast<__nv_bfloat162*>(d_u + 2 * i) = __floats2bfloat162_rn(da, db);
+    if (d_act != nullptr) *reinterpret_cast<__nv_bfloat162*>(d_u + 2 * i) = __floats2bfloat162_rn(da, db);
 }
 
 __global__ void __launch_bounds__(256)

@@ -488,15 +488,18 @@ def layernorm_bwd(x: Tensor, dy: Tensor, gamma: Tensor, eps: float, d_x: Tensor,
     return d_x
 
 
-def act_fwd_bwd(glu: bool, pre: Tensor, d_act: Tensor):
-    """(act, d_pre) of the FFN activation: erf-GELU on ``pre`` [rows, F] or gated SiLU on interleaved ``pre`` [rows, 2F]."""
+def act_fwd_bwd(glu: bool, pre: Tensor, d_act: Optional[Tensor]):
+    """(act, d_pre) of the FFN activation: erf-GELU on ``pre`` [rows, F] or gated SiLU on interleaved ``pre`` [rows, 2F];
+    ``d_act`` None: forward only, returns (act, None)."""
     dev = _require_cuda(pre, d_act)
-    rows, f_out = d_act.shape
+    rows = pre.shape[0]
+    f_out = pre.shape[1] // 2 if glu else pre.shape[1]
     act = torch.empty(rows, f_out, dtype=torch.bfloat16, device=dev)
-    d_pre = torch.empty_like(pre)
+    d_pre = torch.empty_like(pre) if d_act is not None else None
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().molly_act_fwd_bwd(int(glu), pre.data_ptr(), d_act.data_ptr(), rows, f_out, act.data_ptr(),
-                                                 d_pre.data_ptr(), _stream(dev)), "molly_act_fwd_bwd")
+        _lib.check(_lib.load().molly_act_fwd_bwd(int(glu), pre.data_ptr(), None if d_act is None else d_act.data_ptr(), rows,
+                                                 f_out, act.data_ptr(), None if d_pre is None else d_pre.data_ptr(),
+                                                 _stream(dev)), "molly_act_fwd_bwd")
     return act, d_pre
 
 

@@ -40,12 +40,28 @@ def _emb_meta(enc: PackedEncoder, ids: torch.Tensor):
 
 
 class EncoderTape:
-    """What the training forward keeps for the backward: fp32 layer inputs, the final pre-LN stream, masks."""
+    """What the training forward keeps for the backward.  ``saved[i]`` holds layer i's activations (ln1, qkv, attn, lse2,
+    x_mid, ln2, FFN pre-activation) when they fit the memory budget; otherwise only the fp32 layer input is kept and the
+    backward recomputes the layer (activation checkpointing per layer)."""
 
     def __init__(self):
         self.layer_inputs: List[torch.Tensor] = []
+        self.saved: List[tuple] = []
         self.x_final = None
         self.kv_info = self.key_mask = self.ids = None
+
+
+def _save_activations(enc: PackedEncoder, n_tokens: int) -> bool:
+    """Keep every layer's activations (no recompute) when they take less than 35 % of the free device memory;
+    MOLLY_TRAIN_RECOMPUTE=1 / 0 forces per-layer recompute / saving."""
+    import os
+    env = os.environ.get("MOLLY_TRAIN_RECOMPUTE")
+    if env is not None:
+        return env == "0"
+    cfg = enc.cfg
+    f_pre = cfg.intermediate_size * (2 if cfg.ffn_type == "glu" else 1)
+    per_layer = n_tokens * (cfg.hidden_size * (4 + 2 + 6 + 2 + 4 + 2) + f_pre * 2)
+    return per_layer * cfg.num_hidden_layers < 0.35 * torch.cuda.mem_get_info(enc.device)[0]
 
 
 def encoder_forward_train(enc: PackedEncoder, ids: torch.Tensor) -> Tuple[torch.Tensor, EncoderTape]:
@@ -59,9 +75,16 @@ def encoder_forward_train(enc: PackedEncoder, ids: torch.Tensor) -> Tuple[torch.
     tape = EncoderTape()
     tape.ids = ids
     x, tape.kv_info, tape.key_mask = ops.embed(ids, enc.c_config, enc.word_emb, enc.pos_emb)
+    save = _save_activations(enc, n_seq * K)
     for lt in enc.layer_tensors:
         tape.layer_inputs.append(x.clone())
-        x = _layer_forward(enc, lt, x, n_seq, K, tape.kv_info, tape.key_mask)[0]
+        if save:
+            kept = _layer_forward(enc, lt, x, n_seq, K, tape.kv_info, tape.key_mask, keep=True)
+            tape.saved.append(kept[1:])
+            mid, _ = ops.act_fwd_bwd(cfg.ffn_type == "glu", kept[7], None)       # finish the layer: FFN activation + FFN2
+            ops.gemm_bf16(mid, lt["w_ffn2"], L.EPI_BIAS_RESIDUAL, bias=lt["b_ffn2"], residual=x, out=x)
+        else:
+            x = _layer_forward(enc, lt, x, n_seq, K, tape.kv_info, tape.key_mask)[0]
     tape.x_final = x
     out = ops.layernorm(x, enc.final_ln_w, enc.final_ln_b, cfg.layer_norm_eps, torch.bfloat16)
     return out, tape
@@ -117,8 +140,12 @@ def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor)
         lt = enc.layer_tensors[i]
         p = f"esm.encoder.layer.{i}."
         x_in = tape.layer_inputs[i]
-        _, ln1, qkv, attn, lse2, x_mid, ln2, pre = _layer_forward(enc, lt, x_in.clone(), n_seq, K, tape.kv_info, tape.key_mask,
-                                                                   keep=True)
+        if tape.saved:
+            ln1, qkv, attn, lse2, x_mid, ln2, pre = tape.saved[i]
+            tape.saved[i] = None                                              # release as we go
+        else:
+            _, ln1, qkv, attn, lse2, x_mid, ln2, pre = _layer_forward(enc, lt, x_in.clone(), n_seq, K, tape.kv_info,
+                                                                       tape.key_mask, keep=True)
         # ---- feed-forward block: x_out = x_mid + W2 act(W1 LN2(x_mid) + b1) + b2
         dy = ops.cast_bf16(d_x)
         d_act = ops.gemm_bf16(dy, ops.transpose_bf16(lt["w_ffn2"]), L.EPI_BIAS)

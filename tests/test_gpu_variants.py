@@ -52,3 +52,9 @@ def test_concurrent_modalities():
     graph in the captured form); results must not change."""
     _run({"MOLLY_CONCURRENT_MODALITIES": "1"}, "golden or graph or embed_and_process or ids_on_device",
          files=("tests/test_gpu_path.py", "tests/test_gpu_graph.py", "tests/test_gpu_inputs.py"))
+
+
+def test_encoder_backward_with_per_layer_recompute():
+    """MOLLY_TRAIN_RECOMPUTE=1: the training tape keeps only each layer's fp32 input and the backward recomputes the layer
+    (the default keeps the activations when they fit the memory budget)."""
+    _run({"MOLLY_TRAIN_RECOMPUTE": "1"}, "backward", files=("tests/test_gpu_train.py",))
