@@ -425,7 +425,7 @@ def run_train_step(args, wl: dict, dev, rank: int, world: int, warmup: int) -> N
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(warmup):
+    for _ in range(max(warmup, 6)):            # the caching allocator needs a few steps to settle on the tape's block sizes
         step()
     assert all(p.grad is not None and torch.isfinite(p.grad.float()).all() for p in params)
     props = torch.cuda.get_device_properties(dev)

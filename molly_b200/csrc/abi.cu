@@ -7,6 +7,8 @@
 #include <vector>
 
 #include "../../include/molly_b200.h"
+#include <stdlib.h>
+
 #include "common.h"
 #include "kernels.h"
 
@@ -166,6 +168,17 @@ int encode(molly_encoder* e, const int64_t* ids, int n_seq, int k, void* final_o
 
 }  // namespace
 
+namespace {
+bool wgrad_through_transposes() {     // MOLLY_WGRAD_TRANSPOSE=1: the first version (explicit bf16 transposes + K-major GEMM)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOLLY_WGRAD_TRANSPOSE");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+}  // namespace
+
 extern "C" {
 
 const char* molly_last_error(void) { return get_last_error(); }
@@ -309,8 +322,10 @@ int molly_project_bwd(molly_encoder_t* enc, void* d_hidden_dev, int32_t hs_dtype
     int rc = gather_grad_rows_launch(d_hidden_dev, hs_dtype, seq_table_dev, n_seq, k_tokens, k_cap, B, T, D, workspace_dev,
                                      zero_rows, s);
     if (rc) return rc;
-    return project_bwd_launch(workspace_dev, enc_out_save_dev, M, D, h, d_weight_dev, d_bias_dev,
-                              static_cast<uint8_t*>(workspace_dev) + dy_bytes, workspace_bytes - dy_bytes, s);
+    if (wgrad_through_transposes())
+        return project_bwd_launch(workspace_dev, enc_out_save_dev, M, D, h, d_weight_dev, d_bias_dev,
+                                  static_cast<uint8_t*>(workspace_dev) + dy_bytes, workspace_bytes - dy_bytes, s);
+    return linear_wgrad_launch(workspace_dev, enc_out_save_dev, M, D, h, d_weight_dev, d_bias_dev, s);
 }
 
 // ------------------------------------ encoder backward building blocks ------------------------------------
@@ -318,8 +333,10 @@ int molly_linear_wgrad(const void* dy_dev, const void* x_dev, int32_t M, int32_t
                        float* d_bias_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
     MOLLY_CHECK(dy_dev && x_dev && d_weight_dev && d_bias_dev && workspace_dev, MOLLY_ERR_INVALID,
                 "molly_linear_wgrad: NULL pointer");
-    return project_bwd_launch(dy_dev, x_dev, M, N, K, d_weight_dev, d_bias_dev, workspace_dev, workspace_bytes,
-                              static_cast<cudaStream_t>(stream));
+    if (wgrad_through_transposes())
+        return project_bwd_launch(dy_dev, x_dev, M, N, K, d_weight_dev, d_bias_dev, workspace_dev, workspace_bytes,
+                                  static_cast<cudaStream_t>(stream));
+    return linear_wgrad_launch(dy_dev, x_dev, M, N, K, d_weight_dev, d_bias_dev, static_cast<cudaStream_t>(stream));
 }
 
 int molly_gather_rows(void* d_hidden_dev, int32_t hs_dtype, const int32_t* seq_table_dev, int32_t n_seq, int32_t k_tokens,

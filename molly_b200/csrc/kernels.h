@@ -101,6 +101,8 @@ int scatter_add_rows_launch(const float* src, const int32_t* index, const float*
 
 // ---- bwd.cu ----
 int transpose_bf16_launch(const void* in, int rows, int cols, void* out, cudaStream_t stream);
+int linear_wgrad_launch(const void* dy_bf16, const void* x_bf16, int M, int N, int K, float* d_weight, float* d_bias,
+                        cudaStream_t stream);
 int project_bwd_launch(const void* dy_bf16, const void* x_bf16, int M, int D, int h, float* d_weight, float* d_bias,
                        void* workspace, size_t workspace_bytes, cudaStream_t stream);
 

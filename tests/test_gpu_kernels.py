@@ -140,6 +140,16 @@ def test_gemm_scatter(dtype):
     assert_close(f"gemm_scatter {dtype}", hs, ref, BF16_EPS if dtype == torch.bfloat16 else 2e-5)
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (300, 320, 96), (1000, 1280, 5120), (8192, 3840, 1280), (77, 96, 64)])
+def test_linear_wgrad(M, N, K):
+    """Autograd of nn.Linear w.r.t. weight and bias: dW = dy^T x (both operands MN-major for the MMA, no transposes)."""
+    ops, _ = _ops()
+    dy, x = bf16r(M, N, seed=80), bf16r(M, K, seed=81)
+    dW, db = ops.linear_wgrad(dy.to(DEV), x.to(DEV))
+    assert_close(f"linear_wgrad dW {M}x{N}x{K}", dW, dy.float().t() @ x.float(), 2e-5 * max(1.0, M / 128) ** 0.5)
+    assert_close(f"linear_wgrad db {M}x{N}", db, dy.float().sum(0), 1e-5 * max(1.0, M / 128) ** 0.5)
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm
 @pytest.mark.parametrize("rows,h,eps", [(1000, 1280, 1e-5), (77, 320, 1e-5), (513, 512, 1e-12), (64, 2560, 1e-12),
                                         (33, 64, 1e-5)])

@@ -58,3 +58,8 @@ def test_encoder_backward_with_per_layer_recompute():
     """MOLLY_TRAIN_RECOMPUTE=1: the training tape keeps only each layer's fp32 input and the backward recomputes the layer
     (the default keeps the activations when they fit the memory budget)."""
     _run({"MOLLY_TRAIN_RECOMPUTE": "1"}, "backward", files=("tests/test_gpu_train.py",))
+
+
+def test_wgrad_through_transposes():
+    """MOLLY_WGRAD_TRANSPOSE=1: the first wgrad version (explicit bf16 transposes + the K-major GEMM)."""
+    _run({"MOLLY_WGRAD_TRANSPOSE": "1"}, "linear_wgrad")

@@ -36,3 +36,12 @@ for mode in ("1", "0"):
         del grads, tape, out
     print(f"recompute={mode}: forward {statistics.median(fw):.1f} ms, backward {statistics.median(bw):.1f} ms, "
           f"host time to enqueue the step {statistics.median(wall):.1f} ms, peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
+
+if os.environ.get("TOP_KERNELS"):
+    from torch.profiler import profile, ProfilerActivity
+    os.environ["MOLLY_TRAIN_RECOMPUTE"] = "0"
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        out, tape = train.encoder_forward_train(enc, ids)
+        grads = train.encoder_backward(enc, tape, d_out)
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=18, max_name_column_width=70))
