@@ -411,8 +411,9 @@ def run_train_step(args, wl: dict, dev, rank: int, world: int, warmup: int) -> N
     tokens_per_step = wl["B"] * 2 * wl["K"]
 
     def step():
-        for p in params:
-            p.grad = None
+        for p in params:                       # zero in place (optimizer.zero_grad(set_to_none=False)): stable allocations
+            if p.grad is not None:
+                p.grad.zero_()
         hs = base.clone()
         out = path.process_omic_sequences(hs, omic_ids_dev, infos, dev)
         out.backward(d_out)
