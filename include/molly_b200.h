@@ -203,7 +203,8 @@ int molly_attention_bwd(const void* qkv_dev, const void* out_dev, const void* d_
                         void* d_qkv_dev, float* delta_ws_dev, void* stream);
 /* ---- encoder backward building blocks (--train-bio, src/utils/tools.py:313-331): autograd of the HF modules
  * the forward kernels replace.  All activations bf16 row-major unless noted; gradients of parameters fp32. */
-/* d_weight[N,K] = dy[M,N]^T x[M,K], d_bias[N] = colsum(dy): autograd of nn.Linear (workspace >= (N + K) * roundup8(M) * 2 B) */
+/* d_weight[N,K] = dy[M,N]^T x[M,K], d_bias[N] = colsum(dy) (d_bias_dev may be NULL): autograd of nn.Linear.  The workspace
+ * ((N + K) * roundup8(M) * 2 B) is only used by the MOLLY_WGRAD_TRANSPOSE=1 variant */
 int molly_linear_wgrad(const void* dy_dev, const void* x_dev, int32_t M, int32_t N, int32_t K, float* d_weight_dev,
                        float* d_bias_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 /* dy[n*k + j, :] = d_hidden[b, start+1+j, :] for j < k_cap (0 beyond): autograd of the slice-assign, omics_one.py:93-97;

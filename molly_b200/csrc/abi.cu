@@ -331,9 +331,8 @@ int molly_project_bwd(molly_encoder_t* enc, void* d_hidden_dev, int32_t hs_dtype
 // ------------------------------------ encoder backward building blocks ------------------------------------
 int molly_linear_wgrad(const void* dy_dev, const void* x_dev, int32_t M, int32_t N, int32_t K, float* d_weight_dev,
                        float* d_bias_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
-    MOLLY_CHECK(dy_dev && x_dev && d_weight_dev && d_bias_dev && workspace_dev, MOLLY_ERR_INVALID,
-                "molly_linear_wgrad: NULL pointer");
-    if (wgrad_through_transposes())
+    MOLLY_CHECK(dy_dev && x_dev && d_weight_dev && workspace_dev, MOLLY_ERR_INVALID, "molly_linear_wgrad: NULL pointer");
+    if (wgrad_through_transposes() && d_bias_dev != nullptr)
         return project_bwd_launch(dy_dev, x_dev, M, N, K, d_weight_dev, d_bias_dev, workspace_dev, workspace_bytes,
                                   static_cast<cudaStream_t>(stream));
     return linear_wgrad_launch(dy_dev, x_dev, M, N, K, d_weight_dev, d_bias_dev, static_cast<cudaStream_t>(stream));

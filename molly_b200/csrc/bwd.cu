@@ -165,22 +165,28 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_constan
     }
 }
 
-// out[c] = sum_r in[r, c]  (bf16 [rows, cols] -> fp32): block = 32 columns x 32 row lanes per row chunk, atomics across chunks
+// out[c] += sum_r in[r, c]  (bf16 [rows, cols], cols even -> fp32): block = 64 columns (one bf16x2 per thread) x 32 row lanes
+// per row chunk, one atomicAdd per (chunk, column)
 __global__ void __launch_bounds__(1024)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, int rows, int cols, int rows_per_chunk, float* __restrict__ out) {
-    __shared__ float sm[32][33];
+    __shared__ float2 sm[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + tx;
+    const int c = blockIdx.x * 64 + tx * 2;
     const int r0 = blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
-    float a = 0.f;
+    float2 a = make_float2(0.f, 0.f);
     if (c < cols)
-        for (int r = r0 + ty; r < r1; r += 32) a += __bfloat162float(in[static_cast<size_t>(r) * cols + c]);
+        for (int r = r0 + ty; r < r1; r += 32) {
+            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(in + static_cast<size_t>(r) * cols + c));
+            a.x += v.x;
+            a.y += v.y;
+        }
     sm[ty][tx] = a;
     __syncthreads();
     if (ty == 0 && c < cols) {
-        float t = 0.f;
-        for (int i = 0; i < 32; ++i) t += sm[i][tx];
-        atomicAdd(out + c, t);
+        float2 t = make_float2(0.f, 0.f);
+        for (int i = 0; i < 32; ++i) { t.x += sm[i][tx].x; t.y += sm[i][tx].y; }
+        atomicAdd(out + c, t.x);
+        atomicAdd(out + c + 1, t.y);
     }
 }
 
@@ -237,7 +243,7 @@ int linear_wgrad_launch(const void* dy_bf16, const void* x_bf16, int M, int N, i
         const int chunks = max(1, min(64, M / 64));
         const int rpc = (M + chunks - 1) / chunks;
         ProfScope prof(PF_ROWWISE_BWD, static_cast<double>(M) * N * 2.0, stream);
-        colsum_bf16_kernel<<<dim3((N + 31) / 32, chunks), 1024, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy_bf16), M, N,
+        colsum_bf16_kernel<<<dim3((N + 63) / 64, chunks), 1024, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy_bf16), M, N,
                                                                            rpc, d_bias);
         count_launch();
     }

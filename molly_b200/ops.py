@@ -433,20 +433,21 @@ def attention_bwd(qkv: Tensor, out: Tensor, d_out: Tensor, lse2: Tensor, n_seq: 
 
 
 # ---- encoder-backward building blocks ------------------------------------------------------------
-def linear_wgrad(dy: Tensor, x: Tensor):
-    """Autograd of ``nn.Linear`` w.r.t. its parameters: (dW [N, K] = dy^T x, db [N] = colsum(dy)), fp32."""
+def linear_wgrad(dy: Tensor, x: Tensor, with_bias: bool = True):
+    """Autograd of ``nn.Linear`` w.r.t. its parameters: (dW [N, K] = dy^T x, db [N] = colsum(dy) or None), fp32."""
     dev = _require_cuda(dy, x)
     M, N = dy.shape
     K = x.shape[1]
     if dy.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or x.shape[0] != M or not (dy.is_contiguous() and x.is_contiguous()):
         raise ValueError("linear_wgrad: dy [M, N] and x [M, K] must be contiguous bf16")
     dW = torch.empty(N, K, dtype=torch.float32, device=dev)
-    db = torch.empty(N, dtype=torch.float32, device=dev)
+    db = torch.empty(N, dtype=torch.float32, device=dev) if with_bias else None
     ws = workspace(dev, (N + K) * ((M + 7) // 8 * 8) * 2 + 4096)
     ws_ptr, ws_bytes = _aligned(ws)
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().molly_linear_wgrad(dy.data_ptr(), x.data_ptr(), M, N, K, dW.data_ptr(), db.data_ptr(), ws_ptr,
-                                                  ws_bytes, _stream(dev)), "molly_linear_wgrad")
+        _lib.check(_lib.load().molly_linear_wgrad(dy.data_ptr(), x.data_ptr(), M, N, K, dW.data_ptr(),
+                                                  None if db is None else db.data_ptr(), ws_ptr, ws_bytes, _stream(dev)),
+                   "molly_linear_wgrad")
     return dW, db
 
 

@@ -150,8 +150,8 @@ def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor)
         dy = ops.cast_bf16(d_x)
         d_act = ops.gemm_bf16(dy, ops.transpose_bf16(lt["w_ffn2"]), L.EPI_BIAS)
         act, d_pre = ops.act_fwd_bwd(glu, pre, d_act)
-        dW2, db2 = ops.linear_wgrad(dy, act)
-        dW1, db1 = ops.linear_wgrad(d_pre, ln2)
+        dW2, db2 = ops.linear_wgrad(dy, act, with_bias=not glu)                 # NT-v2's gated FFN has no biases
+        dW1, db1 = ops.linear_wgrad(d_pre, ln2, with_bias=not glu)
         d_ln2 = ops.gemm_bf16(d_pre, ops.transpose_bf16(lt["w_ffn1"]), L.EPI_BIAS)
         g_w, g_b = z(h), z(h)
         ops.layernorm_bwd(x_mid, d_ln2, lt["ln2_w"], cfg.layer_norm_eps, d_x, True, g_w, g_b)      # d_x is now d(x_mid)
