@@ -16,35 +16,69 @@ __device__ __forceinline__ float wsum(float v) {
     return v;
 }
 
-// LayerNorm backward w.r.t. its input, one warp per row:
+// LayerNorm backward w.r.t. its input, one warp per row, the row held in registers (VPL float4 vectors per lane, like the
+// forward kernel): one read of x and dy, one read-modify-write of d_x.
 //   g = dy * gamma,  xhat = (x - mean) * rstd,  dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
 // d_x (fp32) receives dx (accumulate == 0) or has it added (accumulate != 0: the residual branch).  stats[row] = (mean, rstd).
+template <int VPL>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const float* __restrict__ gamma, int rows,
               int h, float eps, float* __restrict__ d_x, int accumulate, float* __restrict__ stats) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
-    const int lane = threadIdx.x & 31;
-    const float* xr = x + static_cast<size_t>(row) * h;
-    const __nv_bfloat16* dr = dy + static_cast<size_t>(row) * h;
+    const int lane = threadIdx.x & 31, nvec = h >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * h);
+    const uint2* dr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(row) * h);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    float4 xv[VPL], gv[VPL];                                   // x, then xhat;  g = dy * gamma
     float s = 0.f;
-    for (int c = lane; c < h; c += 32) s += xr[c];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int idx = lane + 32 * i;
+        xv[i] = idx < nvec ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+    }
     const float mean = wsum(s) / h;
     float ss = 0.f;
-    for (int c = lane; c < h; c += 32) { const float d = xr[c] - mean; ss += d * d; }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+        if (lane + 32 * i < nvec) {
+            const float a = xv[i].x - mean, b = xv[i].y - mean, c = xv[i].z - mean, d = xv[i].w - mean;
+            ss += (a * a + b * b) + (c * c + d * d);
+        }
     const float rstd = rsqrtf(wsum(ss) / h + eps);
     float sg = 0.f, sgx = 0.f;
-    for (int c = lane; c < h; c += 32) {
-        const float g = __bfloat162float(dr[c]) * gamma[c];
-        sg += g;
-        sgx += g * (xr[c] - mean) * rstd;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nvec) {
+            const uint2 u = dr[idx];
+            const float2 d0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+            const float2 d1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+            const float4 gm = __ldg(g4 + idx);
+            gv[i] = make_float4(d0.x * gm.x, d0.y * gm.y, d1.x * gm.z, d1.y * gm.w);
+            xv[i] = make_float4((xv[i].x - mean) * rstd, (xv[i].y - mean) * rstd, (xv[i].z - mean) * rstd,
+                                (xv[i].w - mean) * rstd);
+            sg += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+            sgx += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
+        } else {
+            gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     const float mg = wsum(sg) / h, mgx = wsum(sgx) / h;
-    float* out = d_x + static_cast<size_t>(row) * h;
-    for (int c = lane; c < h; c += 32) {
-        const float g = __bfloat162float(dr[c]) * gamma[c];
-        const float dx = rstd * (g - mg - (xr[c] - mean) * rstd * mgx);
-        out[c] = accumulate ? out[c] + dx : dx;
+    float4* out = reinterpret_cast<float4*>(d_x + static_cast<size_t>(row) * h);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nvec) {
+            float4 r = make_float4(rstd * (gv[i].x - mg - xv[i].x * mgx), rstd * (gv[i].y - mg - xv[i].y * mgx),
+                                   rstd * (gv[i].z - mg - xv[i].z * mgx), rstd * (gv[i].w - mg - xv[i].w * mgx));
+            if (accumulate) {
+                const float4 o = out[idx];
+                r = make_float4(r.x + o.x, r.y + o.y, r.z + o.z, r.w + o.w);
+            }
+            out[idx] = r;
+        }
     }
     if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
 }
@@ -177,10 +211,17 @@ scatter_add_rows_kernel(const float* __restrict__ src, const int32_t* __restrict
 
 int ln_bwd_launch(const float* x, const void* dy_bf16, const float* gamma, int rows, int h, float eps, float* d_x,
                   int accumulate, float* stats, float* d_gamma, float* d_beta, cudaStream_t stream) {
-    MOLLY_CHECK(rows > 0 && h > 0, MOLLY_ERR_INVALID, "ln_bwd: rows=%d h=%d", rows, h);
+    MOLLY_CHECK(rows > 0 && h > 0 && h % 4 == 0 && h <= 20 * 128, MOLLY_ERR_UNSUPPORTED,
+                "ln_bwd: rows=%d h=%d (h %% 4 == 0, h <= 2560)", rows, h);
     const auto* dy = static_cast<const __nv_bfloat16*>(dy_bf16);
     ProfScope prof(PF_ROWWISE_BWD, static_cast<double>(rows) * h * (d_gamma ? 20.0 : 14.0), stream);
-    ln_bwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, dy, gamma, rows, h, eps, d_x, accumulate, stats);
+    {
+        const int vpl = (h / 4 + 31) / 32;
+#define MOLLY_LNB_CASE(V) \
+        if (vpl <= V) ln_bwd_kernel<V><<<(rows + 7) / 8, 256, 0, stream>>>(x, dy, gamma, rows, h, eps, d_x, accumulate, stats); else
+        MOLLY_LNB_CASE(1) MOLLY_LNB_CASE(2) MOLLY_LNB_CASE(4) MOLLY_LNB_CASE(8) MOLLY_LNB_CASE(10) MOLLY_LNB_CASE(20) {}
+#undef MOLLY_LNB_CASE
+    }
     count_launch();
     if (d_gamma != nullptr && d_beta != nullptr) {
         const int chunks = max(1, min(64, rows / 64));

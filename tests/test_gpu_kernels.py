@@ -163,6 +163,29 @@ def test_layernorm(rows, h, eps):
     assert_close(f"layernorm_bf16 h={h}", ops.layernorm(x, w, b, eps, torch.bfloat16), ref, BF16_EPS)
 
 
+@pytest.mark.parametrize("rows,h,eps", [(1000, 1280, 1e-5), (77, 320, 1e-5), (513, 1024, 1e-12), (64, 2560, 1e-12),
+                                        (33, 64, 1e-5)])
+def test_layernorm_backward(rows, h, eps):
+    """Autograd of LayerNorm w.r.t. input, weight and bias; the input gradient accumulates into the residual gradient."""
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(90)
+    x = (torch.randn(rows, h, generator=g) * 3 + 0.5).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(h, generator=g)).requires_grad_(True)
+    b = (0.1 * torch.randn(h, generator=g)).requires_grad_(True)
+    dy = bf16r(rows, h, seed=91)
+    resid = torch.randn(rows, h, generator=g)
+    torch.nn.functional.layer_norm(x, (h,), w, b, eps).backward(dy.float())
+    d_x = resid.clone().to(DEV)
+    d_w, d_b = torch.zeros(h, device=DEV), torch.zeros(h, device=DEV)
+    ops.layernorm_bwd(x.detach().to(DEV), dy.to(DEV), w.detach().to(DEV), eps, d_x, True, d_w, d_b)
+    assert_close(f"layernorm_bwd dx (+residual) h={h}", d_x, x.grad + resid, 2e-5)
+    assert_close(f"layernorm_bwd dgamma h={h}", d_w, w.grad, 1e-4)
+    assert_close(f"layernorm_bwd dbeta h={h}", d_b, b.grad, 1e-4)
+    d_x2 = torch.empty(rows, h, device=DEV)
+    ops.layernorm_bwd(x.detach().to(DEV), dy.to(DEV), w.detach().to(DEV), eps, d_x2, False)
+    assert_close(f"layernorm_bwd dx h={h}", d_x2, x.grad, 2e-5)
+
+
 # ------------------------------------------------------------------------------------------------ rotary
 @pytest.mark.parametrize("heads,d,k", [(20, 64, 100), (20, 16, 37), (16, 32, 64), (4, 128, 50)])
 def test_rotary(heads, d, k):
