@@ -252,7 +252,9 @@ __device__ __forceinline__ void softmax_block(uint64_t* bar_s_full, uint32_t s_p
     if (tl_on) TL(tl_base + 4);
 }
 
-template <int D, int KVB, int POLY>
+// LSE: also write the row log-sum-exp (training forward).  A template flag, not a runtime test: the inference instantiation must
+// stay exactly at the 168-register cap of two CTAs per SM (one more live pointer makes it spill: -9 % measured).
+template <int D, int KVB, int POLY, bool LSE = false>
 __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D, KVB>::MIN_CTAS)
 attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_kv, int n_seq,
                  int heads, int k_tokens, int h, const int32_t* __restrict__ kv_info,
@@ -447,7 +449,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
             if (q0 + r < k_tokens) {
                 uint4* o = reinterpret_cast<uint4*>(out + (row_base + q0 + r) * h + head * D);
                 for (int i = 0; i < D / 8; ++i) o[i] = make_uint4(0, 0, 0, 0);
-                if (lse2 != nullptr) lse2[(static_cast<size_t>(w.n) * heads + head) * k_tokens + q0 + r] = -CUDART_INF_F;
+                if constexpr (LSE) lse2[(static_cast<size_t>(w.n) * heads + head) * k_tokens + q0 + r] = -CUDART_INF_F;
             }
             continue;
         }
@@ -467,8 +469,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
         const bool row_ok = q0 + r < k_tokens;
         __nv_bfloat16* orow = out + (row_base + q0 + r) * h + head * D;
         // row log-sum-exp in the log2 domain (P = exp2(S log2e - lse2)): what the attention backward needs
-        if (lse2 != nullptr && row_ok)
-            lse2[(static_cast<size_t>(w.n) * heads + head) * k_tokens + q0 + r] = m_run + log2f(l_run);
+        if constexpr (LSE) {
+            if (row_ok) lse2[(static_cast<size_t>(w.n) * heads + head) * k_tokens + q0 + r] = m_run + log2f(l_run);
+        }
 #pragma unroll
         for (int c = 0; c < D / 16; ++c) {
             uint32_t o[16];
@@ -993,7 +996,7 @@ int launch_attention(const AttnMaps& maps, int n_seq, int k_tokens, int h, int h
     if constexpr (D <= 64) {
         if (attention_pipe_enabled() && lse == nullptr)
             return launch_attention_pipe<D>(maps, n_seq, k_tokens, h, heads, kv_info, key_mask, out, stream);
-        if (attention_kvb(D) == 64)
+        if (attention_kvb(D) == 64 && lse == nullptr)
             return launch_attention_kvb<D, 64>(maps, n_seq, k_tokens, h, heads, kv_info, key_mask, out, lse, stream);
     }
     using Cfg = AttnCfg<D>;
@@ -1002,13 +1005,16 @@ int launch_attention(const AttnMaps& maps, int n_seq, int k_tokens, int h, int h
         const char* e = getenv("MOLLY_ATTN_POLY");
         poly = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : ATTN_POLY_DEFAULT;
     }
-    auto kernel = poly == 0 ? attention_kernel<D, 128, 0>
-                            : (poly == 1 ? attention_kernel<D, 128, 1> : attention_kernel<D, 128, 2>);
+    auto kernel = lse != nullptr ? attention_kernel<D, 128, 0, true>
+                                 : (poly == 0 ? attention_kernel<D, 128, 0>
+                                              : (poly == 1 ? attention_kernel<D, 128, 1> : attention_kernel<D, 128, 2>));
     static bool configured = false;
     if (!configured) {
         MOLLY_CUDA(cudaFuncSetAttribute(attention_kernel<D, 128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         MOLLY_CUDA(cudaFuncSetAttribute(attention_kernel<D, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         MOLLY_CUDA(cudaFuncSetAttribute(attention_kernel<D, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MOLLY_CUDA(cudaFuncSetAttribute(attention_kernel<D, 128, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
         configured = true;
     }
     const int grid = attention_grid(n_seq * heads * ((k_tokens + ATT_BLOCK - 1) / ATT_BLOCK), Cfg::MIN_CTAS);
