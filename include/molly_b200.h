@@ -240,7 +240,8 @@ int molly_merge_rows(const void* src_dev /*[n_seq*k, D]*/, const int32_t* seq_ta
  * molly_profile_stop() synchronises them and fills MOLLY_PROFILE_FAMILIES entries.  Off by default (zero overhead). */
 #define MOLLY_PROFILE_FAMILIES 14
 typedef struct molly_profile_entry {
-    const char* name;      /* embed, layernorm, gemm_qkv, rotary, attention, gemm_attn_out, gemm_ffn1, gemm_ffn2, ... */
+    const char* name;      /* embed, layernorm, gemm_qkv, rotary, attention, gemm_attn_out, gemm_ffn1, gemm_ffn2, gemm_proj,
+                              gemm_other, merge, other, attention_bwd, rowwise_bwd */
     int32_t launches;
     int32_t work_is_flops; /* 1: `work` is algorithmic FLOP; 0: algorithmic HBM bytes */
     double total_ms;
