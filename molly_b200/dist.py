@@ -6,7 +6,7 @@ all-reduced (mean) with NCCL on a side stream so it overlaps whatever backward w
 Works with the gloo backend too (CPU tests)."""
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist

@@ -5,7 +5,7 @@ modality instead of one ``.to(device)`` per sequence.  Pure host logic (numpy / 
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 

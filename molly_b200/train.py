@@ -70,8 +70,6 @@ def encoder_forward_train(enc: PackedEncoder, ids: torch.Tensor) -> Tuple[torch.
     if cfg.emb_layer_norm_before:
         raise NotImplementedError("emb_layer_norm_before encoders are not covered by the training path")
     n_seq, K = ids.shape
-    h, H = cfg.hidden_size, cfg.num_attention_heads
-    d = h // H
     tape = EncoderTape()
     tape.ids = ids
     x, tape.kv_info, tape.key_mask = ops.embed(ids, enc.c_config, enc.word_emb, enc.pos_emb)

@@ -191,3 +191,33 @@ def test_balance_equal_count():
     assert abs(loads[0] - loads[1]) < abs(naive[0] - naive[1])
     with pytest.raises(ValueError):
         planner.balance_equal_count(costs[:7], 2)
+
+
+def test_embedding_backward_metadata_matches_autograd():
+    """train._emb_meta (scatter indices / scales of the embedding backward) against autograd of the oracle's embedding block:
+    pad rows and <mask> rows receive nothing, token-dropout rescales per sequence, learned positions follow cumsum(mask)."""
+    import types
+    from molly_b200 import train
+    from oracle.esm_oracle import SPECS, esm_embeddings, init_encoder_weights
+    for spec_name in ("tiny_esm2", "tiny_ntv1"):
+        spec = SPECS[spec_name]
+        W = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in init_encoder_weights(spec, 3).items()}
+        g = torch.Generator().manual_seed(4)
+        K = 24
+        ids = torch.stack([synth.protein_ids(g, K, v) if spec.vocab_size == 33 else synth.nucleotide_ids(g, K, v, spec.vocab_size)
+                           for v in (24, 9, 17)])
+        if spec.token_dropout:
+            ids[0, 3] = spec.mask_token_id
+            ids[2, 5] = spec.mask_token_id
+        d_x = torch.randn(ids.numel(), spec.hidden_size, generator=g)
+        x = esm_embeddings(spec, W, ids, (ids != 1).long())
+        (x.reshape(-1, spec.hidden_size) * d_x).sum().backward()
+        enc = types.SimpleNamespace(cfg=EncoderConfig.from_mapping(spec.as_dict()))
+        word_index, word_scale, pos_index, pos_scale = train._emb_meta(enc, ids)
+        d_word = torch.zeros_like(W["esm.embeddings.word_embeddings.weight"])
+        d_word.index_add_(0, word_index.long(), d_x * word_scale[:, None])
+        assert torch.allclose(d_word, W["esm.embeddings.word_embeddings.weight"].grad, atol=1e-5)
+        if pos_index is not None:
+            d_pos = torch.zeros_like(W["esm.embeddings.position_embeddings.weight"])
+            d_pos.index_add_(0, pos_index.long(), d_x * pos_scale[:, None])
+            assert torch.allclose(d_pos, W["esm.embeddings.position_embeddings.weight"].grad, atol=1e-5)

@@ -10,7 +10,7 @@ import sys
 import torch
 sys.path.insert(0, ".")
 import bench
-from molly_b200 import ops
+
 
 
 def time_fn(fn, n=10, warm=3):

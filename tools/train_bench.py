@@ -4,7 +4,7 @@ import os, sys, time, statistics
 import torch
 sys.path.insert(0, ".")
 import bench
-from molly_b200 import train, ops
+from molly_b200 import train
 from molly_b200.config import EncoderConfig
 from molly_b200.packing import PackedEncoder
 
