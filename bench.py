@@ -403,7 +403,13 @@ def run_train_step(args, wl: dict, dev, rank: int, world: int, warmup: int) -> N
             path._enc_modules[name] = bag
             path._enc_versions[name] = path._module_version(bag)
             params += bag.parameters()
-    bucket = FlatGradBucket(params) if world > 1 else None
+    overlap = bool(wl.get("train_encoders")) and world > 1 and os.environ.get("MOLLY_BENCH_FLAT_BUCKET", "0") != "1"
+    bucket = None
+    if overlap:                                # gradients are averaged layer by layer under the backward: no flat bucket
+        from molly_b200.dist import LayerwiseGradReducer
+        path.grad_reducer = LayerwiseGradReducer()
+    elif world > 1:
+        bucket = FlatGradBucket(params)
     omic_ids, infos = make_inputs(wl, seed=1234 + rank)
     omic_ids_dev = omic_ids.to(dev)
     base = (torch.randn(wl["B"], wl["T"], wl["D"], device=dev) * 0.02).to(torch.bfloat16)
@@ -457,7 +463,9 @@ def run_train_step(args, wl: dict, dev, rank: int, world: int, warmup: int) -> N
             "steps": args.steps, "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl["desc"], "B_per_gpu": wl["B"], "K": wl["K"], "T": wl["T"], "D": wl["D"],
-                       "parallelism": f"sample-sharded x{world}, flat grad bucket all-reduce ({grad_elems} elements)",
+                       "parallelism": (f"sample-sharded x{world}, " + ("layer-wise grad all-reduce overlapped with the backward"
+                                                                        if overlap else "flat grad bucket all-reduce")
+                                       + f" ({grad_elems} elements)"),
                        "trainable": ("both projectors and every encoder parameter (--train-bio)" if wl.get("train_encoders")
                                      else "both projectors (weight + bias); encoders frozen")},
             "clocks": clocks, "gpu_launches": launches, "kernels": kernels}

@@ -77,6 +77,53 @@ class FlatGradBucket:
         self._work = None
 
 
+class LayerwiseGradReducer:
+    """Mean all-reduce of the encoder gradients WHILE the backward is still running (``--train-bio`` at N > 1).
+
+    ``train.encoder_backward`` hands over each layer's gradients as soon as they exist: they are flattened into one
+    buffer in the parameters' dtype (the dict entries become views of it), and its all-reduce is launched on a side stream
+    so that NCCL traffic over NVLink overlaps the backward kernels of the layers below.  ``finish()`` makes the current
+    stream wait for every collective; the gradients returned to autograd are already averaged, so the caller must not
+    reduce them again.  Works with gloo on CPU tensors too (no streams)."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, dtype: torch.dtype = torch.bfloat16):
+        self.group, self.dtype = group, dtype
+        self._stream = None
+        self._works = []
+        self.bytes_reduced = 0
+
+    def reduce_(self, grads: dict, names: Sequence[str]) -> None:
+        names = [n for n in names if n in grads and grads[n] is not None]
+        if not names or dist.get_world_size(self.group) == 1:
+            return
+        world = dist.get_world_size(self.group)
+        flat = torch.cat([grads[n].reshape(-1).to(self.dtype) for n in names])
+        flat.div_(world)
+        off = 0
+        for n in names:
+            k = grads[n].numel()
+            grads[n] = flat[off:off + k].view(grads[n].shape)
+            off += k
+        self.bytes_reduced += flat.numel() * flat.element_size()
+        if flat.is_cuda:
+            cur = torch.cuda.current_stream(flat.device)
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(flat.device)
+            self._stream.wait_stream(cur)
+            flat.record_stream(self._stream)
+            with torch.cuda.stream(self._stream):
+                self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        else:
+            self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self) -> None:
+        for w in self._works:
+            w.wait()
+        self._works = []
+        if self._stream is not None:
+            torch.cuda.current_stream(self._stream.device).wait_stream(self._stream)
+
+
 class _Null:
     def __enter__(self):
         return self

@@ -62,9 +62,10 @@ class _InjectTrainFn(torch.autograd.Function):
     reach every encoder parameter (by HF name), the projector, and -- zeroed on the overwritten rows -- ``hidden_states``."""
 
     @staticmethod
-    def forward(ctx, hidden_states, proj_weight, proj_bias, ids, seq_table, enc_id: int, names, *enc_params):
+    def forward(ctx, hidden_states, proj_weight, proj_bias, ids, seq_table, enc_id: int, names, reducer, *enc_params):
         from . import train
         enc = ops.get_encoder(enc_id)
+        ctx.reducer = reducer
         k_tokens = ids.shape[1]
         enc_out, tape = train.encoder_forward_train(enc, ids)
         ops.gemm_bf16(enc_out, enc.proj_w, _lib.EPI_SCATTER, bias=enc.proj_b, out=hidden_states, seq_table=seq_table,
@@ -88,13 +89,20 @@ class _InjectTrainFn(torch.autograd.Function):
         dy = ops.gather_rows(g, seq_table, ctx.k_tokens, min(enc.project_token_num, ctx.k_tokens), bool(need_h))
         dW, db = ops.linear_wgrad(dy, enc_out)
         d_enc = ops.gemm_bf16(dy, ops.transpose_bf16(enc.proj_w), _lib.EPI_BIAS)
-        grads = train.encoder_backward(enc, ctx.tape, d_enc)
+        reducer = ctx.reducer
+        if reducer is not None:
+            pg = {"projector.weight": dW, "projector.bias": db}
+            reducer.reduce_(pg, list(pg))
+            dW, db = pg["projector.weight"], pg["projector.bias"]
+        grads = train.encoder_backward(enc, ctx.tape, d_enc, reducer)
+        if reducer is not None:
+            reducer.finish()
         ctx.tape = None
         w_m, b_m, p_ms = ctx.metas
         enc_grads = [grads[n].to(device=dv, dtype=dt) if (n in grads and need) else None
-                     for n, (dt, dv), need in zip(ctx.names, p_ms, ctx.needs_input_grad[7:])]
+                     for n, (dt, dv), need in zip(ctx.names, p_ms, ctx.needs_input_grad[8:])]
         return ((g if need_h else None), dW.to(device=w_m[1], dtype=w_m[0]), db.to(device=b_m[1], dtype=b_m[0]), None, None,
-                None, None, *enc_grads)
+                None, None, None, *enc_grads)
 
 
 class FastOmicsPath:
@@ -119,6 +127,8 @@ class FastOmicsPath:
         self._proj_versions = {}
         self._enc_modules = {}              # name -> EsmForMaskedLM (live parameters: --train-bio, late checkpoint loads)
         self._enc_versions = {}
+        # optional dist.LayerwiseGradReducer: the path then returns ALREADY AVERAGED encoder / projector gradients
+        self.grad_reducer = None
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -236,7 +246,7 @@ class FastOmicsPath:
         if train_enc:                                        # --train-bio: the encoder's own parameters get gradients
             named = list(enc_module.named_parameters())
             _InjectTrainFn.apply(target, proj.weight, proj.bias, ids, seq_table, enc_id, tuple(n for n, _ in named),
-                                 *[prm for _, prm in named])
+                                 self.grad_reducer, *[prm for _, prm in named])
         elif proj is not None and torch.is_grad_enabled() and (proj.weight.requires_grad or proj.bias.requires_grad
                                                                 or hidden_states.requires_grad):
             _InjectFn.apply(target, proj.weight, proj.bias, ids, seq_table, enc_id)

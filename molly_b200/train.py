@@ -115,9 +115,10 @@ def _layer_forward(enc, lt, x, n_seq, K, kv_info, key_mask, keep: bool = False):
     return (x,)
 
 
-def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor) -> Dict[str, torch.Tensor]:
+def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor, reducer=None) -> Dict[str, torch.Tensor]:
     """Gradients of every encoder parameter (HF ``state_dict`` names, fp32) from ``d_out`` = d(loss)/d(hidden_states[-1]),
-    bf16 [n*K, h]."""
+    bf16 [n*K, h].  ``reducer`` (``dist.LayerwiseGradReducer``): each layer's gradients are handed to it as soon as they
+    exist, so their all-reduce overlaps the layers below; they come back averaged, in the reducer's dtype."""
     cfg, L = enc.cfg, _lib
     n_seq, K = tape.ids.shape
     h, H, F = cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size
@@ -178,6 +179,8 @@ def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor)
         for j, nm in enumerate(("query", "key", "value")):
             grads[p + f"attention.self.{nm}.weight"] = dWqkv[j * h:(j + 1) * h]
             grads[p + f"attention.self.{nm}.bias"] = dbqkv[j * h:(j + 1) * h]
+        if reducer is not None:
+            reducer.reduce_(grads, [n for n in grads if n.startswith(p)])
 
     # ---- embeddings
     word_index, word_scale, pos_index, pos_scale = _emb_meta(enc, tape.ids)
@@ -188,4 +191,6 @@ def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor)
         d_pos = torch.zeros(enc.pos_emb.shape, dtype=torch.float32, device=dev)
         ops.scatter_add_rows_(d_pos, d_x, pos_index, pos_scale)
         grads["esm.embeddings.position_embeddings.weight"] = d_pos
+    if reducer is not None:
+        reducer.reduce_(grads, [n for n in grads if not n.startswith("esm.encoder.layer.")])
     return grads

@@ -44,6 +44,16 @@ def _worker(rank, world, port, out_q):
         bucket.finish()
         plan["w_grad"] = float(lin.weight.grad.mean())
         plan["b_grad"] = float(lin.bias.grad.mean())
+        # layer-wise reducer of the encoder backward: entries become views of one averaged buffer per call
+        from molly_b200.dist import LayerwiseGradReducer
+        red = LayerwiseGradReducer(dtype=torch.float32)
+        grads = {"layer.0.w": torch.full((3, 4), float(rank + 1)), "layer.0.b": torch.full((4,), float(2 * rank)),
+                 "layer.1.w": torch.full((2, 2), 7.0 * (rank + 1))}
+        red.reduce_(grads, ["layer.0.w", "layer.0.b"])
+        red.reduce_(grads, ["layer.1.w", "missing"])
+        red.finish()
+        plan["lw"] = [float(grads["layer.0.w"].mean()), float(grads["layer.0.b"].mean()), float(grads["layer.1.w"].mean())]
+        plan["lw_shapes"] = [tuple(grads[k].shape) for k in ("layer.0.w", "layer.0.b", "layer.1.w")]
         # bench.py's timing reduction: max over ranks
         t = torch.tensor([float(rank + 1)])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -74,3 +84,5 @@ def test_two_rank_gloo_sharding_and_grad_bucket():
     for p in plans:
         assert p["w_grad"] == pytest.approx(1.5) and p["b_grad"] == pytest.approx(15.0)
         assert p["t_max"] == 2.0
+        assert p["lw"] == pytest.approx([1.5, 1.0, 10.5])            # means over ranks of (1,2), (0,2), (7,14)
+        assert p["lw_shapes"] == [(3, 4), (4,), (2, 2)]
