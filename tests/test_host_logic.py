@@ -2,6 +2,7 @@
 import ctypes
 import os
 import subprocess
+import sys
 
 import pytest
 import torch
@@ -221,3 +222,26 @@ def test_embedding_backward_metadata_matches_autograd():
             d_pos = torch.zeros_like(W["esm.embeddings.position_embeddings.weight"])
             d_pos.index_add_(0, pos_index.long(), d_x * pos_scale[:, None])
             assert torch.allclose(d_pos, W["esm.embeddings.position_embeddings.weight"].grad, atol=1e-5)
+
+
+@pytest.mark.timeout(300)
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (runs on the CPU): one JSON line with the contract's keys, same metric / unit / config keys
+    as the product arm, `impl: reference`, a cpu_baseline describing the run and a zero-copy e2e object."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--workload", "molly_mini", "--steps", "1",
+                        "--warmup", "0"], cwd=root, capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["metric"] == "omics tokens/sec (encode+project+merge)" and line["unit"] == "omics tokens/s"
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    for key in ("workload", "B_per_gpu", "K", "T", "D", "parallelism", "l2"):
+        assert key in line["config"], key
