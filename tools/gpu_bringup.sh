@@ -25,6 +25,11 @@ run attn_other    400 $PT tests/test_gpu_kernels.py -k "test_attention and not 6
 run path_encoder  600 $PT tests/test_gpu_path.py -k "encoder_forward"
 run path_golden   600 $PT tests/test_gpu_path.py -k "golden"
 run path_rest     900 $PT tests/test_gpu_path.py -k "not golden and not encoder_forward"
+run backward      600 $PT tests/test_gpu_kernels.py -k "backward or linear_wgrad or log_sum_exp"
+run inputs_graph  600 $PT tests/test_gpu_inputs.py tests/test_gpu_graph.py
+run train         900 $PT tests/test_gpu_train.py
+run configs       1200 $PT tests/test_gpu_configs.py
+run variants      1200 $PT tests/test_gpu_variants.py
 run smoke         300 python __graft_entry__.py smoke
 echo "---- summary ----"; cat $OUT/summary.txt
 # compact failure digest (full logs stay in gpurun_out/bringup/)
