@@ -571,6 +571,20 @@ def main() -> None:
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
     e2e_value = world * tokens_per_step * args.steps / (e2e_ms / 1e3)
+    # the same call with the WHOLE merged tensor copied back to pinned host memory every step (the reference keeps it on the
+    # device for the LLM, omics_one.py:164 -> :175; reported for completeness)
+    host_out = torch.empty(hs.shape, dtype=hs.dtype, pin_memory=True)
+
+    def step_e2e_full():
+        path.process_omic_sequences(hs, omic_ids_pinned, infos, dev)
+        host_out.copy_(hs, non_blocking=True)
+
+    step_e2e_full()
+    full_ms = timed(step_e2e_full, args.steps)
+    e2e_full = {"value": world * tokens_per_step * args.steps / (full_ms / 1e3), "unit": UNIT,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": hs.numel() * hs.element_size(),
+                "ms_per_step": full_ms / args.steps}
+    del host_out
     path.strict = False
 
     # ---- embed_tokens(input_ids) fused with the path (run scan on the device is the index source)
@@ -647,6 +661,7 @@ def main() -> None:
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps},
+        "e2e_full_readback": e2e_full,
         "gpu_launches": launches,
         "roofline": roofline,
         "model_tflops_per_gpu": round(model_flops / (step_ms * 1e-3) / 1e12, 1),
