@@ -554,8 +554,11 @@ int dispatch_epilogue(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
         case EPI_BIAS_ROPE:
             return launch_gemm<BLOCK_N, EPI_BIAS_ROPE, __nv_bfloat16>(ta, tb, tc, p, pair, stream);
         case EPI_GLU:
-            if constexpr (BLOCK_N == 256) return launch_gemm<256, EPI_GLU, __nv_bfloat16>(ta, tb, tc, p, pair, stream);
-            MOLLY_CHECK(false, MOLLY_ERR_UNSUPPORTED, "gemm: GLU epilogue needs 256-wide tiles");
+            if constexpr (BLOCK_N == 256) {
+                return launch_gemm<256, EPI_GLU, __nv_bfloat16>(ta, tb, tc, p, pair, stream);
+            } else {
+                MOLLY_CHECK(false, MOLLY_ERR_UNSUPPORTED, "gemm: GLU epilogue needs 256-wide tiles");
+            }
         case EPI_SCATTER:
             return f32 ? launch_gemm<BLOCK_N, EPI_SCATTER, float>(ta, tb, tc, p, pair, stream)
                        : launch_gemm<BLOCK_N, EPI_SCATTER, __nv_bfloat16>(ta, tb, tc, p, pair, stream);
