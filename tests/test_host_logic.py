@@ -245,3 +245,32 @@ def test_bench_reference_arm_contract():
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     for key in ("workload", "B_per_gpu", "K", "T", "D", "parallelism", "l2"):
         assert key in line["config"], key
+
+
+def test_planner_properties_randomised():
+    """Property tests (hypothesis): ranges_disjoint == brute force over written rows; balance_equal_count is a partition with
+    equal counts whose load spread never exceeds the largest single cost."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.tuples(st.integers(0, 3), st.integers(-1, 60)), max_size=6),
+           st.lists(st.tuples(st.integers(0, 3), st.integers(-1, 60)), max_size=6), st.integers(1, 12), st.integers(1, 12))
+    def disjoint(nt_items, pr_items, k_nt, k_pr):
+        nt = planner.ModalityPlan([b for b, _ in nt_items], list(range(len(nt_items))), [s for _, s in nt_items])
+        pr = planner.ModalityPlan([b for b, _ in pr_items], list(range(len(pr_items))), [s for _, s in pr_items])
+        rows_nt = {(b, s + 1 + j) for b, s in nt_items if s != -1 for j in range(k_nt)}
+        rows_pr = {(b, s + 1 + j) for b, s in pr_items if s != -1 for j in range(k_pr)}
+        assert planner.ranges_disjoint(nt, k_nt, pr, k_pr) == (not (rows_nt & rows_pr))
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 4), st.integers(1, 6), st.data())
+    def balanced(world, per_rank, data):
+        costs = data.draw(st.lists(st.floats(1.0, 4096.0), min_size=world * per_rank, max_size=world * per_rank))
+        parts = planner.balance_equal_count(costs, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(costs)))
+        assert all(len(p) == per_rank for p in parts)
+        loads = [sum(costs[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(costs) + 1e-6
+
+    disjoint()
+    balanced()
