@@ -930,6 +930,7 @@ int launch_attention_kvb(const AttnMaps& maps, int n_seq, int k_tokens, int h, i
     }
     const int grid = attention_grid(n_seq * heads * ((k_tokens + ATT_BLOCK - 1) / ATT_BLOCK), Cfg::MIN_CTAS);
     {
+        prof_attention_work(kv_info, n_seq, k_tokens, h, 4.0, stream);      // work = 4 h K sum(kv_len), known on the device only
         ProfScope prof(PF_ATTENTION, 4.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
         kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(maps.q, maps.kv64, n_seq, heads, k_tokens, h, kv_info,
                                                                key_mask, static_cast<__nv_bfloat16*>(out), lse);
@@ -971,6 +972,7 @@ int launch_attention_pipe(const AttnMaps& maps, int n_seq, int k_tokens, int h, 
     }
     const int grid = attention_grid(n_seq * heads * ((k_tokens + ATT_BLOCK - 1) / ATT_BLOCK), 2);
     {
+        prof_attention_work(kv_info, n_seq, k_tokens, h, 4.0, stream);      // work = 4 h K sum(kv_len), known on the device only
         ProfScope prof(PF_ATTENTION, 4.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
         kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(maps.q, maps.kv64, n_seq, heads, k_tokens, h, kv_info,
                                                                key_mask, static_cast<__nv_bfloat16*>(out));
@@ -1019,6 +1021,7 @@ int launch_attention(const AttnMaps& maps, int n_seq, int k_tokens, int h, int h
     }
     const int grid = attention_grid(n_seq * heads * ((k_tokens + ATT_BLOCK - 1) / ATT_BLOCK), Cfg::MIN_CTAS);
     {   // dense-equivalent work 4*n*K*K*h (exact when every sequence is full length)
+        prof_attention_work(kv_info, n_seq, k_tokens, h, 4.0, stream);      // work = 4 h K sum(kv_len), known on the device only
         ProfScope prof(PF_ATTENTION, 4.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
         kernel<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, tm, n_seq, heads, k_tokens, h, kv_info, key_mask,
                                                                static_cast<__nv_bfloat16*>(out), lse);
@@ -1054,6 +1057,8 @@ int attention_launch(const AttnMaps& tqkv, int n_seq, int k_tokens, int h, int h
     MOLLY_CHECK(static_cast<long long>(n_seq) * k_tokens < (1ll << 31), MOLLY_ERR_UNSUPPORTED,
                 "attention: n_seq*k_tokens exceeds int32 TMA coordinates");
     MOLLY_CHECK(n_seq <= 65535 && heads <= 65535, MOLLY_ERR_UNSUPPORTED, "attention: grid too large");
+    if (attention2_enabled(h / heads))
+        return attention2_launch(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, lse, stream);
     switch (h / heads) {
         case 16: return launch_attention<16>(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, lse, stream);
         case 32: return launch_attention<32>(tqkv, n_seq, k_tokens, h, heads, kv_info, key_mask, out, lse, stream);

@@ -523,6 +523,7 @@ int launch_attention_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, int n_se
     }
     dim3 grid((k_tokens + BW_BLOCK - 1) / BW_BLOCK, heads, n_seq);
     {   // 4 MMAs of 2*K*K*d each per (sequence, head) in each kernel... dense-equivalent 2.5x the forward in total
+        prof_attention_work(kv_info, n_seq, k_tokens, h, 10.0, stream);     // work = 10 h K sum(kv_len), known on the device only
         ProfScope prof(PF_ATTENTION_BWD, 10.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
         attn_bwd_dq_kernel<D><<<grid, BW_THREADS, Cfg::DQ_SMEM, stream>>>(tq, tdo, k_tokens, h, kv_info, key_mask, lse2, delta,
                                                                           d_qkv);

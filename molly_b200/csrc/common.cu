@@ -35,9 +35,26 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 const char* get_last_error() { return g_last_error.c_str(); }
 
 namespace {
-struct ProfRecord { int family; double work; cudaEvent_t a, b; };
+struct ProfRecord { int family; double work; cudaEvent_t a, b; int dev_slot; };
 bool g_prof_on = false;
 std::vector<ProfRecord> g_prof;
+constexpr int PROF_DEV_SLOTS = 1 << 16;
+double* g_prof_dev = nullptr;          // device-side work values (launches whose work depends on device data)
+int g_prof_dev_used = 0;
+int g_prof_dev_pending = -1;           // slot handed out by prof_next_device_work for the next record
+
+__global__ void attention_work_kernel(const int32_t* __restrict__ kv_info, int n_seq, double per_key, double* out) {
+    __shared__ double part[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_seq; i += blockDim.x) acc += kv_info[2 * i] > 0 ? kv_info[2 * i] : 0;
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = part[0] * per_key;
+}
 thread_local int g_gemm_family = PF_GEMM_OTHER;
 }  // namespace
 
@@ -46,7 +63,8 @@ int gemm_family() { return g_gemm_family; }
 
 ProfScope::ProfScope(int family, double work, cudaStream_t s) : stream(s), slot(-1) {
     if (!g_prof_on) return;
-    ProfRecord r{family, work, nullptr, nullptr};
+    ProfRecord r{family, work, nullptr, nullptr, g_prof_dev_pending};
+    g_prof_dev_pending = -1;
     if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
     cudaEventRecord(r.a, s);
     g_prof.push_back(r);
@@ -56,9 +74,23 @@ ProfScope::~ProfScope() {
     if (slot >= 0) cudaEventRecord(g_prof[slot].b, stream);
 }
 
+double* prof_next_device_work() {
+    if (!g_prof_on || g_prof_dev == nullptr || g_prof_dev_used >= PROF_DEV_SLOTS) return nullptr;
+    g_prof_dev_pending = g_prof_dev_used++;
+    return g_prof_dev + g_prof_dev_pending;
+}
+
+void prof_attention_work(const int32_t* kv_info, int n_seq, int k_tokens, int h, double coef, cudaStream_t stream) {
+    if (double* slot = prof_next_device_work())
+        attention_work_kernel<<<1, 256, 0, stream>>>(kv_info, n_seq, coef * k_tokens * static_cast<double>(h), slot);
+}
+
 void prof_start() {
     for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     g_prof.clear();
+    if (g_prof_dev == nullptr && cudaMalloc(&g_prof_dev, PROF_DEV_SLOTS * sizeof(double)) != cudaSuccess) g_prof_dev = nullptr;
+    g_prof_dev_used = 0;
+    g_prof_dev_pending = -1;
     g_prof_on = true;
 }
 // aggregates per family: launches[f], ms[f], work[f]; returns 0 on success
@@ -66,10 +98,16 @@ int prof_stop(int* launches, double* ms, double* work) {
     g_prof_on = false;
     for (int f = 0; f < PF_COUNT; ++f) { launches[f] = 0; ms[f] = 0.0; work[f] = 0.0; }
     int rc = 0;
+    std::vector<double> dev_work(g_prof_dev_used > 0 ? g_prof_dev_used : 1, 0.0);
+    if (g_prof_dev_used > 0 &&
+        (cudaDeviceSynchronize() != cudaSuccess ||
+         cudaMemcpy(dev_work.data(), g_prof_dev, g_prof_dev_used * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess))
+        rc = 1;
     for (auto& r : g_prof) {
         float t = 0.f;
         if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) rc = 1;
-        launches[r.family] += 1; ms[r.family] += t; work[r.family] += r.work;
+        launches[r.family] += 1; ms[r.family] += t;
+        work[r.family] += (r.dev_slot >= 0 && r.dev_slot < g_prof_dev_used && rc == 0) ? dev_work[r.dev_slot] : r.work;
         cudaEventDestroy(r.a); cudaEventDestroy(r.b);
     }
     g_prof.clear();

@@ -23,6 +23,11 @@ struct ProfScope {            // brackets ONE kernel launch with two events when
     ProfScope(int family, double work, cudaStream_t s);
     ~ProfScope();
 };
+// Work of a launch that only the device knows (attention over kv_len keys): when profiling is on, returns the device slot
+// the NEXT ProfScope's record will read its work from at prof_stop (fill it on `stream` before constructing the scope).
+double* prof_next_device_work();
+// attention work = coef * k_tokens * h * sum_seq kv_len FLOP (forward: coef 4 = QK^T + PV over kv_len keys for all K query rows)
+void prof_attention_work(const int32_t* kv_info, int n_seq, int k_tokens, int h, double coef, cudaStream_t stream);
 void set_gemm_family(int f);  // tag for the next gemm_launch calls of this thread
 int gemm_family();
 
@@ -49,6 +54,13 @@ int attention_make_map(AttnMaps* maps, const void* qkv, int rows, int h, int hea
 // lse2 (optional, fp32 [n_seq, heads, k_tokens]): row log-sum-exp of the scores in the log2 domain, for the backward
 int attention_launch(const AttnMaps& tqkv, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_len,
                      const uint8_t* key_mask, void* out, cudaStream_t stream, float* lse2 = nullptr);
+
+// ---- attention2.cu ----  one CTA per SM, two 128-row tiles, P in tensor memory (head_dim <= 64)
+constexpr int ATTENTION2_DEFAULT = 1;          // MOLLY_ATTN_V2 = 0 | 1 overrides
+constexpr int ATTENTION2_POLY_DEFAULT = 0;     // MOLLY_ATTN_POLY = 0 | 1 | 2 overrides
+bool attention2_enabled(int head_dim);
+int attention2_launch(const AttnMaps& maps, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
+                      const uint8_t* key_mask, void* out, float* lse2, cudaStream_t stream);
 
 // ---- rowwise.cu ----
 struct EmbedArgs {
