@@ -64,9 +64,11 @@ class FlatGradBucket:
         """Wait for the collective and scatter the averaged grads back into ``p.grad``."""
         if self._work is None:
             return
-        self._work.wait()
         ctx = torch.cuda.stream(self.stream) if self.stream is not None else _Null()
         with ctx:
+            # Work.wait() orders the CURRENT stream after NCCL's internal stream: it has to run inside the side-stream
+            # context, or the copy-back below could read `flat` while it is still being reduced.
+            self._work.wait()
             for v, p in zip(self._views(), self.params):
                 if p.grad is None:
                     p.grad = v.clone()
@@ -115,6 +117,13 @@ class LayerwiseGradReducer:
                 self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         else:
             self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def reduce_zeros_(self, numel: int, device) -> None:
+        """The collective a rank issues in place of ``reduce_`` for gradients it does not have (a modality absent from its
+        micro-batch): same size, same dtype, same position in the schedule, all zeros."""
+        if numel <= 0 or dist.get_world_size(self.group) == 1:
+            return
+        self.reduce_({"_zeros": torch.zeros(int(numel), dtype=self.dtype, device=device)}, ["_zeros"])
 
     def finish(self) -> None:
         for w in self._works:

@@ -53,6 +53,11 @@ class _InjectFn(torch.autograd.Function):
             dW, db = ops.project_bwd(g, seq_table, enc_out, ctx.enc_id, ctx.k_tokens, bool(need_h))
             dW = dW.to(device=ctx.w_meta[1], dtype=ctx.w_meta[0])
             db = db.to(device=ctx.b_meta[1], dtype=ctx.b_meta[0])
+        elif need_h:
+            # frozen projector (--train-llm without --train-mlp): nothing was saved for dW, but the rows the slice-assign
+            # overwrote must still get ZERO gradient (omics_one.py:97), or the *_pad embedding rows pick up the upstream one
+            k_cap = min(ops.get_encoder(ctx.enc_id).project_token_num, ctx.k_tokens)
+            ops.gather_rows(g, seq_table, ctx.k_tokens, k_cap, True)
         return (g if need_h else None), dW, db, None, None, None
 
 
@@ -103,6 +108,29 @@ class _InjectTrainFn(torch.autograd.Function):
                      for n, (dt, dv), need in zip(ctx.names, p_ms, ctx.needs_input_grad[8:])]
         return ((g if need_h else None), dW.to(device=w_m[1], dtype=w_m[0]), db.to(device=b_m[1], dtype=b_m[0]), None, None,
                 None, None, None, *enc_grads)
+
+
+class _AbsentModalityFn(torch.autograd.Function):
+    """A modality with a TRAINABLE encoder that has no sequence in this rank's micro-batch while a gradient reducer is
+    attached: the other ranks all-reduce that encoder's gradients layer by layer inside their backward, so this rank must
+    issue the SAME sequence of collectives (with zeros) at the same point of its backward, or NCCL pairs the wrong
+    buffers / hangs.  Forward is the identity on ``hidden_states``; every parameter gets a zero gradient."""
+
+    @staticmethod
+    def forward(ctx, hidden_states, reducer, numels, *params):
+        ctx.reducer, ctx.numels = reducer, numels
+        ctx.metas = [(p.shape, p.dtype, p.device) for p in params]
+        ctx.mark_dirty(hidden_states)
+        return hidden_states
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        for n in ctx.numels:
+            ctx.reducer.reduce_zeros_(n, grad_out.device)
+        ctx.reducer.finish()
+        zeros = [torch.zeros(sh, dtype=dt, device=dv) if need else None
+                 for (sh, dt, dv), need in zip(ctx.metas, ctx.needs_input_grad[3:])]
+        return (grad_out if ctx.needs_input_grad[0] else None), None, None, *zeros
 
 
 class FastOmicsPath:
@@ -203,8 +231,11 @@ class FastOmicsPath:
             self._inject(work[0][0], work[0][1], hidden_states, omic_ids_list, dev)
             cur.wait_stream(side)
         else:
-            for name, plan in work:
-                self._inject(name, plan, hidden_states, omic_ids_list, dev)
+            for name, plan in (("dna_rna", nt_plan), ("protein", pr_plan)):
+                if len(plan):
+                    self._inject(name, plan, hidden_states, omic_ids_list, dev)
+                elif self.grad_reducer is not None and torch.is_grad_enabled():
+                    self._absent_modality(name, hidden_states)       # same position in every rank's autograd graph
         if self.strict:
             ops.check_device_errors(dev)
         return hidden_states
@@ -220,6 +251,19 @@ class FastOmicsPath:
         enc_id = self._ids.get(name)
         cap = ops.get_encoder(enc_id).project_token_num if enc_id is not None else int(k_ids)
         return min(cap, int(k_ids))
+
+    def _absent_modality(self, name: str, hidden_states: torch.Tensor) -> None:
+        """Keep the reducer's collective schedule independent of the batch (see ``_AbsentModalityFn``)."""
+        proj, enc_module, enc_id = self._proj_modules.get(name), self._enc_modules.get(name), self._ids.get(name)
+        if proj is None or enc_module is None or enc_id is None:
+            return
+        params = [prm for prm in enc_module.parameters() if prm.requires_grad]
+        if not params:                                   # frozen encoder: its backward launches no collective
+            return
+        from . import train
+        params += [prm for prm in (proj.weight, proj.bias) if prm.requires_grad]
+        _AbsentModalityFn.apply(hidden_states, self.grad_reducer, tuple(train.reduce_schedule(ops.get_encoder(enc_id))),
+                                *params)
 
     def _inject(self, name: str, plan: planner.ModalityPlan, hidden_states: torch.Tensor, omic_ids_list, dev) -> None:
         enc_id = self._ids.get(name)
@@ -354,29 +398,46 @@ class FastOmicsPath:
 
     @staticmethod
     def _module_version(module) -> tuple:
-        """Changes whenever a parameter is updated in place (optimizer step, load_state_dict) or re-bound."""
+        """Changes when a parameter is updated through autograd-visible in-place ops (``load_state_dict``, ``p.add_``) or
+        re-bound.  It does NOT see ``p.data.copy_`` or writes through a flat buffer the parameters are views of -- which is
+        how DeepSpeed's ZeRO optimizers update bf16 parameters -- so it is trusted for FROZEN modules only."""
         v = p_sum = 0
         for prm in module.parameters():
             v += prm._version
             p_sum ^= prm.data_ptr()
         return (v, p_sum)
 
+    @staticmethod
+    def _trainable(module) -> bool:
+        return any(prm.requires_grad for prm in module.parameters())
+
+    def mark_weights_dirty(self) -> None:
+        """Force a re-pack of every live module on the next call (e.g. after writing frozen weights through ``.data``)."""
+        self._enc_versions = {}
+        self._proj_versions = {}
+
     def refresh_encoders(self) -> List[str]:
-        """Re-pack (in place) the encoders whose live ``nn.Module`` weights changed since they were packed: encoders
-        trained with ``--train-bio`` (src/utils/tools.py:313-331) or checkpoints loaded after ``from_omics_one``.
-        Called at the top of every ``process_omic_sequences`` when live modules are attached."""
+        """Re-pack (in place) the encoders whose live ``nn.Module`` weights may have changed since they were packed.
+        A module with TRAINABLE parameters (``--train-bio``, src/utils/tools.py:313-331) is re-packed on every call: the
+        reference trains under DeepSpeed ZeRO-2 in bf16 (scripts/train/*.sh, src/configs/ds_z2_config.json), whose
+        optimizer step writes the parameters through ``.data`` / flat-buffer views and leaves no trace in the version
+        counters.  A frozen module is re-packed when its version counters or storage moved (checkpoint loaded late), or
+        after ``mark_weights_dirty()``.  Called at the top of every ``process_omic_sequences`` with live modules."""
         done = []
         for name, module in self._enc_modules.items():
+            if name not in self._ids:
+                continue
             ver = self._module_version(module)
-            if self._enc_versions.get(name) != ver and name in self._ids:
+            if self._trainable(module) or self._enc_versions.get(name) != ver:
                 ops.get_encoder(self._ids[name]).reload(module.state_dict())
                 self._enc_versions[name] = ver
                 done.append(name)
         return done
 
     def _refresh_projector(self, name: str, enc: PackedEncoder, proj) -> None:
+        """Same rule for the projector (``--train-mlp``): trainable -> re-packed every call (4.7 M elements at Molly-1.7B)."""
         ver = (proj.weight._version, proj.bias._version, proj.weight.data_ptr())
-        if self._proj_versions.get(name) != ver:
+        if proj.weight.requires_grad or proj.bias.requires_grad or self._proj_versions.get(name) != ver:
             enc.load_projector(proj.weight, proj.bias)
             self._proj_versions[name] = ver
 

@@ -25,7 +25,7 @@ from .packing import PackedEncoder
 def _emb_meta(enc: PackedEncoder, ids: torch.Tensor):
     """Per-row scatter indices / scales of the embedding backward, from the ids alone (tiny integer work, HF:189-236)."""
     cfg = enc.cfg
-    mask = ids != cfg.pad_token_id                                            # omics_one.py:70 hard-codes pad id 1
+    mask = ids != 1                       # the attention / padding mask is the reference's literal 1 (omics_one.py:70), as in
     word_scale = mask.float()
     if cfg.token_dropout:
         is_mask_tok = ids == cfg.mask_token_id
@@ -34,9 +34,23 @@ def _emb_meta(enc: PackedEncoder, ids: torch.Tensor):
     pos_index = None
     if cfg.position_embedding_type == "absolute":
         m = mask.int()
+        # the forward kernels (rowwise.cu); cfg.pad_token_id is only HF's padding_idx offset of the position ids (HF:971-984)
         pos_index = ((torch.cumsum(m, dim=1) * m).long() + cfg.pad_token_id).to(torch.int32).reshape(-1).contiguous()
     return (ids.to(torch.int32).reshape(-1).contiguous(), word_scale.reshape(-1).contiguous(), pos_index,
             mask.float().reshape(-1).contiguous())
+
+
+def reduce_schedule(enc: PackedEncoder) -> List[int]:
+    """Element counts of the gradient groups ``_InjectTrainFn.backward`` hands to a ``LayerwiseGradReducer``, in order:
+    projector, encoder layers L-1 .. 0, then final LayerNorm + embeddings.  A rank whose micro-batch lacks the modality
+    issues all-reduces of exactly these sizes (``omics_path._AbsentModalityFn``)."""
+    cfg = enc.cfg
+    h = cfg.hidden_size
+    out = [enc.proj_w.numel() + enc.proj_b.numel()]
+    for lt in reversed(enc.layer_tensors):
+        out.append(sum(t.numel() for t in lt.values() if t is not None))
+    out.append(2 * h + enc.word_emb.numel() + (enc.pos_emb.numel() if enc.pos_emb is not None else 0))
+    return out
 
 
 class EncoderTape:

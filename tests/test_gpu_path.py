@@ -332,7 +332,11 @@ def test_from_omics_one_follows_live_encoder_weights():
         with torch.no_grad():
             out = path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
         check_merged("from_omics_one", case, out, oracle_out(case), torch.float32)
-        assert path.refresh_encoders() == []
+        assert sorted(path.refresh_encoders()) == ["dna_rna", "protein"]    # trainable modules are re-packed on every call
+        for m in (om.dna_rna_model, om.protein_model):
+            for prm in m.parameters():
+                prm.requires_grad_(False)
+        assert path.refresh_encoders() == []                                # frozen: only when the version counters moved
         # an "optimizer step" on the protein encoder + a checkpoint load into the DNA/RNA encoder
         import copy
         new_pr = {k: (v * 1.05 if v.dtype.is_floating_point and v.dim() == 2 else v) for k, v in case.pr.weights.items()}
@@ -351,8 +355,8 @@ def test_from_omics_one_follows_live_encoder_weights():
         assert not torch.equal(out2, out)
         assert_close("after in-place weight updates", out2.float().cpu(), ref2, TOL)
         # --train-bio: trainable encoder parameters receive gradients through the path (tests/test_gpu_train.py checks every one)
-        for prm in om.dna_rna_model.parameters():
-            prm.requires_grad_(False)
+        for prm in om.protein_model.parameters():
+            prm.requires_grad_(True)
         hs2 = hs.clone().requires_grad_(True)
         out3 = path.process_omic_sequences(hs2 * 1.0, case.batch.omic_ids, case.batch.omic_info_list, hs.device)
         gw = torch.randn(out3.shape, generator=torch.Generator().manual_seed(77)).to(DEV)
@@ -371,5 +375,112 @@ def test_from_omics_one_follows_live_encoder_weights():
         assert_close("train-bio d protein_projector.weight", om.protein_projector.weight.grad.float().cpu(),
                      pr3.projector["weight"].grad, TOL)
         assert torch.equal(hs2.grad.cpu(), emb_ref.grad)                                 # zero on overwritten rows
+    finally:
+        path.close()
+
+
+def _omics_one_like(case):
+    import types
+    from oracle.ref_import import build_hf_encoder
+    om = types.SimpleNamespace()
+    om.dna_rna_model = build_hf_encoder(case.nt.spec, case.nt.weights)
+    om.protein_model = build_hf_encoder(case.pr.spec, case.pr.weights)
+    om.dna_rna_projector = torch.nn.Linear(case.nt.spec.hidden_size, case.D)
+    om.protein_projector = torch.nn.Linear(case.pr.spec.hidden_size, case.D)
+    om.dna_rna_projector.load_state_dict(case.nt.projector)
+    om.protein_projector.load_state_dict(case.pr.projector)
+    om.dna_rna_project_token_num = case.nt.project_token_num
+    om.protein_project_token_num = case.pr.project_token_num
+    return om
+
+
+def test_trainable_weights_follow_data_copy_and_flat_buffer_views():
+    """DeepSpeed's ZeRO optimizers (the reference trains with ds_z2_config.json, bf16) update parameters with
+    ``p.data.copy_`` or by writing a flat buffer the parameters are views of.  Neither bumps ``p._version`` nor moves
+    ``data_ptr``; the packed copies of TRAINABLE modules must follow anyway."""
+    import copy
+    from molly_b200.omics_path import FastOmicsPath
+    case = cases.golden_cases()["tiny_absolute_leftpad"]
+    om = _omics_one_like(case)
+    for prm in om.dna_rna_model.parameters():
+        prm.requires_grad_(False)                                    # --train-bio protein only + --train-mlp
+    path = FastOmicsPath.from_omics_one(om, DEV, strict=True)
+    try:
+        hs = case.batch.hidden_states.to(DEV)
+        with torch.no_grad():
+            path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
+        # (1) p.data.copy_ on encoder matrices and on the projector
+        new_pr = {k: (v * 1.04 if v.dtype.is_floating_point and v.dim() == 2 else v) for k, v in case.pr.weights.items()}
+        versions = {n: p._version for n, p in om.protein_model.named_parameters()}
+        for name, prm in om.protein_model.named_parameters():
+            if name in new_pr:
+                prm.data.copy_(new_pr[name])
+        new_proj = {"weight": case.pr.projector["weight"] * 0.9, "bias": case.pr.projector["bias"] + 0.01}
+        om.protein_projector.weight.data.copy_(new_proj["weight"])
+        om.protein_projector.bias.data.copy_(new_proj["bias"])
+        assert all(p._version == versions[n] for n, p in om.protein_model.named_parameters())   # invisible to the counters
+        pr2 = copy.copy(case.pr)
+        pr2.weights, pr2.projector = new_pr, new_proj
+        ref = case.batch.hidden_states.clone()
+        with torch.no_grad():
+            oracle_process(ref, case.batch.omic_ids, case.batch.omic_info_list, case.nt, pr2)
+            out = path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
+        assert_close("after p.data.copy_", out.float().cpu(), ref, TOL)
+        # (2) parameters re-bound as views of one flat buffer, then the buffer is written
+        prms = list(om.protein_projector.parameters())
+        flat = torch.cat([p.data.reshape(-1) for p in prms]).clone()
+        off = 0
+        for p in prms:
+            p.data = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        with torch.no_grad():
+            path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
+        flat.mul_(1.1)                                               # the "optimizer step"
+        pr3 = copy.copy(pr2)
+        pr3.projector = {"weight": new_proj["weight"] * 1.1, "bias": new_proj["bias"] * 1.1}
+        ref3 = case.batch.hidden_states.clone()
+        with torch.no_grad():
+            oracle_process(ref3, case.batch.omic_ids, case.batch.omic_info_list, case.nt, pr3)
+            out3 = path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
+        assert_close("after a flat-buffer write", out3.float().cpu(), ref3, TOL)
+        # (3) frozen weights written through .data need the explicit hook
+        om.dna_rna_projector.weight.requires_grad_(False)
+        om.dna_rna_projector.bias.requires_grad_(False)
+        with torch.no_grad():
+            path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
+        om.dna_rna_projector.weight.data.mul_(0.5)
+        path.mark_weights_dirty()
+        nt4 = copy.copy(case.nt)
+        nt4.projector = {"weight": case.nt.projector["weight"] * 0.5, "bias": case.nt.projector["bias"]}
+        ref4 = case.batch.hidden_states.clone()
+        with torch.no_grad():
+            oracle_process(ref4, case.batch.omic_ids, case.batch.omic_info_list, nt4, pr3)
+            out4 = path.process_omic_sequences(hs.clone(), case.batch.omic_ids, case.batch.omic_info_list, hs.device)
+        assert_close("after mark_weights_dirty", out4.float().cpu(), ref4, TOL)
+    finally:
+        path.close()
+
+
+def test_frozen_projector_still_zeroes_the_overwritten_rows_of_the_embedding_gradient():
+    """--train-llm without --train-mlp (src/utils/tools.py:332-335): the projector is frozen, ``hidden_states`` requires
+    grad.  The reference's slice-assign gives the overwritten rows zero gradient (omics_one.py:97)."""
+    from molly_b200.omics_path import FastOmicsPath
+    case = cases.golden_cases()["tiny_rotary_glu"]
+    om = _omics_one_like(case)
+    for m in (om.dna_rna_model, om.protein_model, om.dna_rna_projector, om.protein_projector):
+        for prm in m.parameters():
+            prm.requires_grad_(False)
+    path = FastOmicsPath.from_omics_one(om, DEV, strict=True)
+    try:
+        emb = case.batch.hidden_states.to(DEV).requires_grad_(True)
+        out = path.process_omic_sequences(emb * 1.0, case.batch.omic_ids, case.batch.omic_info_list, emb.device)
+        gw = torch.randn(out.shape, generator=torch.Generator().manual_seed(61)).to(DEV)
+        (out * gw).sum().backward()
+        emb_ref = case.batch.hidden_states.clone().requires_grad_(True)
+        o = oracle_process(emb_ref * 1.0, case.batch.omic_ids, case.batch.omic_info_list, case.nt, case.pr)
+        (o * gw.cpu()).sum().backward()
+        assert torch.equal(emb.grad.cpu(), emb_ref.grad)
+        written = (emb_ref.grad == 0).all(dim=-1)
+        assert int(written.sum()) > 0
     finally:
         path.close()

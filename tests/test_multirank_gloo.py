@@ -54,6 +54,19 @@ def _worker(rank, world, port, out_q):
         red.finish()
         plan["lw"] = [float(grads["layer.0.w"].mean()), float(grads["layer.0.b"].mean()), float(grads["layer.1.w"].mean())]
         plan["lw_shapes"] = [tuple(grads[k].shape) for k in ("layer.0.w", "layer.0.b", "layer.1.w")]
+        # asymmetric micro-batches: rank 1 has no sequence of the modality and issues zero all-reduces of the same sizes
+        red2 = LayerwiseGradReducer(dtype=torch.float32)
+        if rank == 0:
+            g2 = {"a": torch.full((5,), 4.0), "b": torch.full((2, 3), 8.0)}
+            red2.reduce_(g2, ["a"])
+            red2.reduce_(g2, ["b"])
+            red2.finish()
+            plan["asym"] = [float(g2["a"].mean()), float(g2["b"].mean())]
+        else:
+            red2.reduce_zeros_(5, torch.device("cpu"))
+            red2.reduce_zeros_(6, torch.device("cpu"))
+            red2.finish()
+            plan["asym"] = [2.0, 4.0]
         # bench.py's timing reduction: max over ranks
         t = torch.tensor([float(rank + 1)])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -86,3 +99,4 @@ def test_two_rank_gloo_sharding_and_grad_bucket():
         assert p["t_max"] == 2.0
         assert p["lw"] == pytest.approx([1.5, 1.0, 10.5])            # means over ranks of (1,2), (0,2), (7,14)
         assert p["lw_shapes"] == [(3, 4), (4,), (2, 2)]
+        assert p["asym"] == pytest.approx([2.0, 4.0])                # (4 + 0) / 2, (8 + 0) / 2: no hang, no mis-pairing
