@@ -2,7 +2,7 @@
 # Round-2 bring-up of attention2 (one CTA per SM, two tiles, P in TMEM): parity, isolated A/B timing, ncu, then the whole suite.
 set -u
 cd "$(dirname "$0")/.."
-OUT=gpurun_out/r02a
+OUT=gpurun_out/${TAG:-r02b}
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
 echo "== attention parity (v2 default)"
@@ -20,7 +20,7 @@ echo "== bench"
 timeout -k 10 600 python bench.py --steps 10 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "rc=$?"
 python - <<'PY'
 import json
-d = json.loads(open("gpurun_out/r02a/bench.json").read().strip().splitlines()[-1])
+d = json.loads(open("gpurun_out/r02b/bench.json").read().strip().splitlines()[-1])
 print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"])
 print({k: (v.get("ms"), v.get("tflops", v.get("gbs"))) for k, v in d["kernels"].items()})
 print(d["clocks"])
