@@ -439,6 +439,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
         uint8_t* p_row = smem + Cfg::OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
         const int sw = r & 7;
         int it = 0, g = 0;
+#ifdef ATT_SKEW
+        // experiment: the second resident CTA of every SM starts ATT_SKEW cycles late (exp2 phases out of lock-step)
+        if (2 * blockIdx.x >= gridDim.x) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < ATT_SKEW) { }
+        }
+#endif
         for (int item = blockIdx.x; item < total; item += gridDim.x) {
         const Item w = decode(item);
         const int kvl = w.kvl, nkv = w.nkv, q0 = w.q0, head = w.head;
@@ -1033,8 +1040,10 @@ int launch_attention(const AttnMaps& maps, int n_seq, int k_tokens, int h, int h
 
 }  // namespace
 
+void attention2_set_debug(long long* buf);
 void attention_set_debug(long long* buf) {
     g_attn_debug = buf;
+    attention2_set_debug(buf);
 #ifdef ATT_TIMELINE
     cudaMemcpyToSymbol(d_attn_tl, &buf, sizeof(buf));
 #endif

@@ -28,6 +28,18 @@
 
 namespace molly {
 
+// -DA2_TIMELINE: clock64 stamps of the softmax thread r == 0 of both tiles of the first 8 CTAs, 8 slots per stream block
+// (tools/attn2_timeline.py): 0 step start, 1 keys 0..63 exponentiated, 2 PV(g-1) seen, 3 S(g+1) seen, 4 keys 64..95 done,
+// 5 keys 96..127 done, 6 p_full arrived, 7 step end (next block's max, item epilogue).
+#ifdef A2_TIMELINE
+__device__ long long* d_a2_tl = nullptr;
+void attention2_set_debug(long long* buf) { cudaMemcpyToSymbol(d_a2_tl, &buf, sizeof(buf)); }
+#define TL2(slot) do { if (tl_on) d_a2_tl[tl_base + (slot)] = clock64(); } while (0)
+#else
+void attention2_set_debug(long long*) {}
+#define TL2(slot) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int A2_BLOCK = 128;                  // query rows per tile == keys per KV block
@@ -102,30 +114,20 @@ __device__ __forceinline__ void a2_seek(A2Cur& c, const A2Shape& sh, const int32
         c.item += stride;
     }
 }
-template <typename F>
-__device__ __forceinline__ A2Cur a2_first(int slot, const A2Shape& sh, const int32_t* __restrict__ kv_info, int stride,
-                                          F&& on_empty) {
-    A2Cur c;
-    c.item = slot; c.it = 0; c.j = 0; c.g = 0;
-    c.n = c.head = c.q0 = c.kvl = c.nkv = c.n_nonpad = 0;
-    a2_seek(c, sh, kv_info, stride, on_empty);
-    return c;
+// the control thread's decode, out of line (five cursors advance through it; register-only interface):
+// returns (item, n, head, q0) of the first work item >= `item` of this tile's stride that has keys (item >= total: none)
+__device__ __forceinline__ int4 a2_seek_ctrl(int item, int total, int nqb, int heads, int stride,
+                                          const int32_t* __restrict__ kv_info) {
+    int4 r = make_int4(item, 0, 0, 0);
+    while (r.x < total) {
+        r.w = (r.x % nqb) * A2_BLOCK;
+        r.z = (r.x / nqb) % heads;
+        r.y = r.x / (nqb * heads);
+        if (kv_info[2 * r.y] > 0) break;
+        r.x += stride;
+    }
+    return r;
 }
-template <typename F>
-__device__ __forceinline__ void a2_next_item(A2Cur& c, const A2Shape& sh, const int32_t* __restrict__ kv_info, int stride,
-                                             F&& on_empty) {
-    ++c.it;
-    c.j = 0;
-    c.item += stride;
-    a2_seek(c, sh, kv_info, stride, on_empty);
-}
-template <typename F>
-__device__ __forceinline__ void a2_advance(A2Cur& c, const A2Shape& sh, const int32_t* __restrict__ kv_info, int stride,
-                                           F&& on_empty) {
-    ++c.g;
-    if (++c.j == c.nkv) a2_next_item(c, sh, kv_info, stride, on_empty);
-}
-
 // The softmax threads keep two of these live next to ~170 data registers: only what every block needs; (n, head, q0) are
 // re-derived from `item` once per item (epilogue) or in the rare interior-pad path.
 struct A2Lite {
@@ -204,9 +206,25 @@ __device__ __forceinline__ void a2_control(uint8_t* slice, const A2Bars& bar, ui
     const uint32_t s_q = smem_u32(slice + Cfg::OFF_Q), s_k = smem_u32(slice + Cfg::OFF_K), s_v = smem_u32(slice + Cfg::OFF_V);
     const uint32_t tmem_s = tmem_tile + Cfg::TM_S, tmem_p = tmem_tile + Cfg::TM_P, tmem_o = tmem_tile + Cfg::TM_O;
     const int h = sh.h, k_tokens = sh.k_tokens;
-    auto nop = [](const A2Cur&) {};
     auto valid = [&](const A2Cur& c) { return a2_valid(c, sh); };
-    auto advance = [&](A2Cur& c) { a2_advance(c, sh, kv_info, stride, nop); };
+    auto seek = [&](A2Cur& c, int item) {
+        const int4 r = a2_seek_ctrl(item, sh.total, sh.nqb, sh.heads, stride, kv_info);
+        c.item = r.x; c.n = r.y; c.head = r.z; c.q0 = r.w;
+        if (c.item < sh.total) {
+            c.kvl = kv_info[2 * c.n];
+            c.n_nonpad = kv_info[2 * c.n + 1];
+            c.nkv = (c.kvl + A2_BLOCK - 1) / A2_BLOCK;
+        }
+    };
+    auto next_item = [&](A2Cur& c) {
+        ++c.it;
+        c.j = 0;
+        seek(c, c.item + stride);
+    };
+    auto advance = [&](A2Cur& c) {
+        ++c.g;
+        if (++c.j == c.nkv) next_item(c);
+    };
 
     auto load_q = [&](const A2Cur& c) {                      // Q of item c.it -> buffer c.it & 1
         const int b = c.it & 1;
@@ -238,12 +256,15 @@ __device__ __forceinline__ void a2_control(uint8_t* slice, const A2Bars& bar, ui
         umma_commit(bar.s_full);
     };
 
-    A2Cur cp = a2_first(slot, sh, kv_info, stride, nop);     // PV cursor = the block the loop is at
+    A2Cur cp;                                                // PV cursor = the block the loop is at
+    cp.item = slot; cp.it = 0; cp.j = 0; cp.g = 0;
+    cp.n = cp.head = cp.q0 = cp.kvl = cp.nkv = cp.n_nonpad = 0;
+    seek(cp, slot);
     if (!valid(cp)) return;
     A2Cur cq = cp, ck = cp, cv = cp, cs = cp, cf = cp;       // Q-load (item-granular) / K-load / V-load / S-issue / s_free cursors
     load_q(cq);
-    a2_next_item(cq, sh, kv_info, stride, nop);
-    if (valid(cq)) { load_q(cq); a2_next_item(cq, sh, kv_info, stride, nop); }
+    next_item(cq);
+    if (valid(cq)) { load_q(cq); next_item(cq); }
     load_k(ck); advance(ck);
     if (valid(ck)) { load_k(ck); advance(ck); }
     load_v(cv); advance(cv);
@@ -257,7 +278,7 @@ __device__ __forceinline__ void a2_control(uint8_t* slice, const A2Bars& bar, ui
         if (valid(ck)) { load_k(ck); advance(ck); }          // K(g+2) -> the stage S(g) has been read from
         if (cf.j == cf.nkv - 1 && valid(cq)) {               // the item's last S: its Q buffer takes the item after next
             load_q(cq);
-            a2_next_item(cq, sh, kv_info, stride, nop);
+            next_item(cq);
         }
         advance(cf);
     };
@@ -286,43 +307,38 @@ __device__ __forceinline__ void a2_control(uint8_t* slice, const A2Bars& bar, ui
 // ------------------------------------------------------------------------------------------------------------------
 // softmax warps of one tile: thread r owns query row r
 // ------------------------------------------------------------------------------------------------------------------
+// bit i = key j0 + i of the sequence is not a pad id (interior-pad sequences only: kept out of line, the hot loop must stay
+// small enough for the instruction cache -- the first pipelined build inlined it eight times and stalled on instruction fetch)
+__device__ __noinline__ uint32_t a2_key_bits(const uint8_t* __restrict__ key_mask, long long row_base, int j0, int k_tokens) {
+    uint32_t bits = 0;
+    if (((row_base + j0) & 15) == 0 && j0 + 32 <= k_tokens) {
+        const uint4* p = reinterpret_cast<const uint4*>(key_mask + row_base + j0);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint4 u = __ldg(p + q);
+            const uint32_t wd[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if ((wd[i >> 2] >> (8 * (i & 3))) & 0xffu) bits |= 1u << (q * 16 + i);
+        }
+    } else {
+        for (int i = 0; i < 32; ++i)
+            if (j0 + i < k_tokens && key_mask[row_base + j0 + i] != 0) bits |= 1u << i;
+    }
+    return bits;
+}
 // keys of chunk `c` (32 keys) of block `b` that are padding -> -inf
 __device__ __forceinline__ void a2_mask_chunk(float* s, int c, const A2Lite& b, const uint8_t* __restrict__ key_mask,
                                               const A2Shape& sh) {
     const int j0 = b.j * A2_BLOCK + c * 32;
-    const int k_tokens = sh.k_tokens;
-    if (b.interior) {                                                         // pad ids before the last real token
-        const long long row_base = static_cast<long long>(b.item / (sh.nqb * sh.heads)) * k_tokens;
-        const bool vec_ok = ((row_base + j0) & 15) == 0 && j0 + 32 <= k_tokens;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            uint32_t wd[4];
-            if (vec_ok) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(key_mask + row_base + j0) + q);
-                wd[0] = u.x; wd[1] = u.y; wd[2] = u.z; wd[3] = u.w;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    wd[i] = 0;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int col = j0 + q * 16 + i * 4 + t;
-                        const uint32_t v = (col < k_tokens) ? key_mask[row_base + col] : 0;
-                        wd[i] |= (v & 0xffu) << (8 * t);
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const bool ok = ((wd[i >> 2] >> (8 * (i & 3))) & 0xffu) != 0 && (j0 + q * 16 + i < b.kvl);
-                if (!ok) s[q * 16 + i] = -CUDART_INF_F;
-            }
-        }
-    } else if (j0 + 32 > b.kvl) {
-        const int lim = b.kvl - j0;
+    const int lim = b.kvl - j0;                                               // keys of this chunk inside kv_len
+    uint32_t valid = lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
+    if (b.interior)                                                           // pad ids before the last real token
+        valid &= a2_key_bits(key_mask, static_cast<long long>(b.item / (sh.nqb * sh.heads)) * sh.k_tokens, j0, sh.k_tokens);
+    if (valid != 0xffffffffu) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-            if (i >= lim) s[i] = -CUDART_INF_F;
+            if (!((valid >> i) & 1u)) s[i] = -CUDART_INF_F;
     }
 }
 // running row max over one 32-key chunk: four independent FMNMX3 chains
@@ -379,6 +395,14 @@ __device__ __forceinline__ void a2_softmax(const A2Bars& bar, uint32_t tmem_tile
             if (lrow != nullptr) *lrow = -CUDART_INF_F;
         }
     };
+#ifdef A2_SKEW
+    // experiment: start tile 1 A2_SKEW cycles late so that the two softmax warps of a scheduler do not run their exp2 phases
+    // in lock-step (both tiles start together and identical work keeps them in phase)
+    if (tmem_tile & 256u) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < A2_SKEW) { }
+    }
+#endif
     A2Lite c;                                                                 // the block being exponentiated
     c.item = slot; c.j = 0; c.nkv = 0; c.kvl = 0; c.interior = false;
     a2_seek_lite(c, sh, kv_info, stride, zero_fill);
@@ -416,6 +440,11 @@ __device__ __forceinline__ void a2_softmax(const A2Bars& bar, uint32_t tmem_tile
         A2Lite b1 = c;
         a2_advance_lite(b1, sh, kv_info, stride, zero_fill);
         const bool has_next = b1.item < sh.total;
+#ifdef A2_TIMELINE
+        const bool tl_on = d_a2_tl != nullptr && r == 0 && blockIdx.x < 8 && g < 64;
+        const int tl_base = ((blockIdx.x * 2 + ((tmem_tile >> 8) & 1)) * 64 + g) * 8;
+#endif
+        TL2(0);
         uint32_t* nraw = reinterpret_cast<uint32_t*>(nxt);
         if (b0.j == 0) { m_run = -CUDART_INF_F; l_run = 0.f; }
         // Lazy rescaling (see attention.cu): the reference max moves only when the row max grew by more than 2^8, so
@@ -434,16 +463,19 @@ __device__ __forceinline__ void a2_softmax(const A2Bars& bar, uint32_t tmem_tile
         // keys 0..63: exponentials first, so that O += P(g-1) V(g-1) and S(g+1) have time to complete
         a2_exp_chunk<POLY>(cur, sc2, nm2, sum2, pk0);
         a2_exp_chunk<POLY>(cur + 32, sc2, nm2, sum2, pk1);
+        TL2(1);
         if (b0.j > 0) {                                                       // PV(g-1) consumed P and finished O
             mbar_wait(&bar.pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);         // (j == 0: the previous item's o_full)
             tc_fence_after();
         }
+        TL2(2);
         tmem_st16(tmem_p, pk0);
         tmem_st16(tmem_p + 16, pk1);
         if (has_next) {
             mbar_wait(bar.s_full, (g + 1) & 1);
             tc_fence_after();
         }
+        TL2(3);
         tmem_ld32(tmem_s, nraw);                                              // next keys 0..63 -> the registers just vacated
         tmem_ld32(tmem_s + 32, nraw + 32);                                    // (end of stream: reads stale S, never used)
         // keys 64..95
@@ -452,6 +484,7 @@ __device__ __forceinline__ void a2_softmax(const A2Bars& bar, uint32_t tmem_tile
         tmem_ld_wait_regs32(nraw);
         tmem_ld_wait_regs32(nraw + 32);
         tmem_ld32(tmem_s + 64, nraw + 64);
+        TL2(4);
         if (has_next) {
             a2_mask_chunk(nxt, 0, b1, key_mask, sh);
             a2_mask_chunk(nxt + 32, 1, b1, key_mask, sh);
@@ -463,6 +496,7 @@ __device__ __forceinline__ void a2_softmax(const A2Bars& bar, uint32_t tmem_tile
         tmem_st16(tmem_p + 48, pk1);
         tmem_ld_wait_regs32(nraw + 64);
         tmem_ld32(tmem_s + 96, nraw + 96);
+        TL2(5);
         if (has_next) a2_mask_chunk(nxt + 64, 2, b1, key_mask, sh);
         a2_max_chunk(nxt + 64, nm4);
         float sa, sb, sc, sd;
@@ -483,6 +517,7 @@ __device__ __forceinline__ void a2_softmax(const A2Bars& bar, uint32_t tmem_tile
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar.p_full);                                              // the control thread may issue O += P(g) V(g)
+        TL2(6);
         tmem_ld_wait_regs32(nraw + 96);
         if (has_next) {
             tc_fence_before();
@@ -523,6 +558,7 @@ __device__ __forceinline__ void a2_softmax(const A2Bars& bar, uint32_t tmem_tile
             }
             tc_fence_before();                                                // O is read: the next item's PV may overwrite it
         }
+        TL2(7);
         c = b1;
         ++g;
     };
