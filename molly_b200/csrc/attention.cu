@@ -44,6 +44,19 @@ __device__ long long* d_attn_tl = nullptr;
 #define TL(slot) do { } while (0)
 #endif
 
+// A/B build switches (tools/build_variant.sh): -DATT_DIRECT_EPI=1 stores O rows straight from registers (round-1 epilogue),
+// -DATT_MAX2=1 two-input row max, -DATT_THREAD_ARRIVE=1 every softmax thread arrives on s_free / p_full (128 arrivals)
+#ifndef ATT_DIRECT_EPI
+#define ATT_DIRECT_EPI 0
+#endif
+#ifndef ATT_MAX2
+#define ATT_MAX2 0
+#endif
+#ifndef ATT_THREAD_ARRIVE
+#define ATT_THREAD_ARRIVE 1       // measured (profiles/r02_attention.md): one elected arrival per warp is SLOWER with the staged epilogue
+#endif
+constexpr int ATT_ARRIVALS = ATT_THREAD_ARRIVE ? 128 : 4;       // arrivals per phase of s_free / p_full
+
 constexpr int ATT_BLOCK = 128;                 // query rows per CTA == keys per KV block
 constexpr int ATT_THREADS = 160;               // 4 softmax warps + 1 control warp
 constexpr float LOG2E = 1.4426950408889634f;
@@ -75,10 +88,27 @@ struct AttnCfg {
     static constexpr int MIN_CTAS = MIN_CTAS_RAW > 3 ? 3 : (MIN_CTAS_RAW < 1 ? 1 : MIN_CTAS_RAW);
 };
 
+// Hand-off of a softmax warp: every lane has fenced its tcgen05 / shared-memory work; ONE lane arrives for the warp
+// (128 single-thread arrivals are 128 serialized updates of the same mbarrier word before the control thread wakes up).
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+#if ATT_THREAD_ARRIVE
+    mbar_arrive(bar);
+#else
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+#endif
+}
+
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+__device__ __forceinline__ float max3(float a, float b, float c) {             // FMNMX3
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
 }
 
 // exp2 on the FMA pipe (FlashAttention-4 style) for POLY out of every 4 element pairs: the softmax is bound by the
@@ -99,6 +129,50 @@ __device__ __forceinline__ void exp2_poly_pair(float& x0, float& x1) {
     unpack_f32x2(t2, t0, t1);
     x0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
     x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+// O / l -> bf16 -> HBM for one warp's 32 query rows.  A thread owns a whole row in TMEM, and storing it directly costs 32
+// scattered 16-B pieces per STG (one per row, row pitch h * 2 bytes): the round-2 timeline showed ~4 000 cycles per work item
+// in this epilogue.  Instead the rows are staged in shared memory -- the warp's OWN 4 KB slice of the P buffer(s), free
+// between the item's last O += P V and the next item's first P store, touched by no other warp -- and written out with
+// D/8 lanes per row, so every STG covers whole 128-B lines.  16-B chunks are XOR-swizzled by the row: conflict-free.
+template <int D, int KVB>
+__device__ __forceinline__ void store_o_rows(uint8_t* p_buf, uint32_t tmem_o_lane, float inv_l, int warp, int lane,
+                                             __nv_bfloat16* __restrict__ out_tile, int rows_valid, int h) {
+    constexpr int CPR = D / 8;                                 // 16-B chunks per row
+    static_assert(D <= 64 || KVB == 128, "head_dim 128 stages through both 16 KB atoms of the P buffer");
+    uint8_t* base = p_buf + warp * 4096;
+    auto chunk_addr = [&](int lr, int c) -> uint8_t* {
+        if constexpr (D >= 64) return base + (c >> 3) * (ATT_BLOCK * 128) + lr * 128 + (((c & 7) ^ (lr & 7)) << 4);
+        else return base + lr * (CPR * 16) + (c << 4);
+    };
+#pragma unroll
+    for (int c = 0; c < D / 16; ++c) {
+        uint32_t o[16];
+        tmem_ld16(tmem_o_lane + c * 16, o);
+        tmem_ld_wait();
+        uint4 u0, u1;
+        u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l);
+        u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l);
+        u0.z = pack_bf16x2(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l);
+        u0.w = pack_bf16x2(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l);
+        u1.x = pack_bf16x2(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l);
+        u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l);
+        u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l);
+        u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l);
+        *reinterpret_cast<uint4*>(chunk_addr(lane, 2 * c)) = u0;
+        *reinterpret_cast<uint4*>(chunk_addr(lane, 2 * c + 1)) = u1;
+    }
+    __syncwarp();
+    constexpr int RPI = 32 / CPR;                              // rows per store instruction
+#pragma unroll
+    for (int k = 0; k < CPR; ++k) {
+        const int lr = k * RPI + lane / CPR, c = lane % CPR;
+        const uint4 v = *reinterpret_cast<const uint4*>(chunk_addr(lr, c));
+        if (warp * 32 + lr < rows_valid)
+            *reinterpret_cast<uint4*>(out_tile + static_cast<size_t>(warp * 32 + lr) * h + c * 8) = v;
+    }
+    __syncwarp();                                              // the slice goes back to P
 }
 
 // One KV block of the online softmax for the 128 threads of a softmax group (thread = query row): S(g) from TMEM ->
@@ -124,7 +198,7 @@ __device__ __forceinline__ void softmax_block(uint64_t* bar_s_full, uint32_t s_p
         for (int i = 0; i < KVB; ++i) s[i] = __uint_as_float(raw[i]);
     }
     tc_fence_before();
-    mbar_arrive(bar_s_free);                         // S(j) is in registers: the MMA warp may start S(j+1)
+    warp_arrive(bar_s_free);                         // S(j) is in registers: the MMA warp may start S(j+1)
     if (tl_on) TL(tl_base + 1);
     if (interior) {
         const uint4* mk = reinterpret_cast<const uint4*>(key_mask + row_base + j0);
@@ -159,12 +233,22 @@ __device__ __forceinline__ void softmax_block(uint64_t* bar_s_full, uint32_t s_p
         for (int i = 0; i < KVB; ++i)
             if (i >= lim) s[i] = -CUDART_INF_F;
     }
-    float mx4[4] = {s[0], s[1], s[2], s[3]};          // 4 independent chains instead of one 127-deep one
+    float mx4[4] = {s[0], s[1], s[2], s[3]};          // 4 independent chains of 3-input max (FMNMX3)
+#if ATT_MAX2
 #pragma unroll
     for (int i = 4; i < KVB; i += 4) {
         mx4[0] = fmaxf(mx4[0], s[i]); mx4[1] = fmaxf(mx4[1], s[i + 1]);
         mx4[2] = fmaxf(mx4[2], s[i + 2]); mx4[3] = fmaxf(mx4[3], s[i + 3]);
     }
+#else
+#pragma unroll
+    for (int i = 4; i + 8 <= KVB; i += 8) {
+        mx4[0] = max3(mx4[0], s[i], s[i + 1]); mx4[1] = max3(mx4[1], s[i + 2], s[i + 3]);
+        mx4[2] = max3(mx4[2], s[i + 4], s[i + 5]); mx4[3] = max3(mx4[3], s[i + 6], s[i + 7]);
+    }
+    mx4[0] = max3(mx4[0], s[KVB - 4], s[KVB - 3]);
+    mx4[1] = max3(mx4[1], s[KVB - 2], s[KVB - 1]);
+#endif
 #if ATT_ABLATE & 8
     const float mx = fmaxf(s[0], s[KVB - 1]);
 #else
@@ -248,7 +332,7 @@ __device__ __forceinline__ void softmax_block(uint64_t* bar_s_full, uint32_t s_p
     }
     fence_proxy_async_smem();
     tc_fence_before();
-    mbar_arrive(bar_p_full);
+    warp_arrive(bar_p_full);
     if (tl_on) TL(tl_base + 4);
 }
 
@@ -302,9 +386,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
             mbar_init(&bar_kv_full[0], 1); mbar_init(&bar_kv_full[1], 1);
             mbar_init(&bar_kv_empty[0], 1); mbar_init(&bar_kv_empty[1], 1);
             mbar_init(bar_s_full, 1);
-            mbar_init(bar_p_full, 128);
+            mbar_init(bar_p_full, ATT_ARRIVALS);
             mbar_init(bar_o_full, 1);
-            mbar_init(bar_s_free, 128);
+            mbar_init(bar_s_free, ATT_ARRIVALS);
             fence_mbar_init();
         }
         __syncwarp();
@@ -473,31 +557,38 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
         if (r == 0) TL(34);
         tc_fence_after();
         const float inv_l = 1.0f / l_run;
-        const bool row_ok = q0 + r < k_tokens;
-        __nv_bfloat16* orow = out + (row_base + q0 + r) * h + head * D;
         // row log-sum-exp in the log2 domain (P = exp2(S log2e - lse2)): what the attention backward needs
         if constexpr (LSE) {
-            if (row_ok) lse2[(static_cast<size_t>(w.n) * heads + head) * k_tokens + q0 + r] = m_run + log2f(l_run);
+            if (q0 + r < k_tokens) lse2[(static_cast<size_t>(w.n) * heads + head) * k_tokens + q0 + r] = m_run + log2f(l_run);
         }
+#if ATT_DIRECT_EPI
+        {
+            const bool row_ok = q0 + r < k_tokens;
+            __nv_bfloat16* orow = out + (row_base + q0 + r) * h + head * D;
 #pragma unroll
-        for (int c = 0; c < D / 16; ++c) {
-            uint32_t o[16];
-            tmem_ld16(tmem_o + lane_addr + c * 16, o);
-            tmem_ld_wait();
-            if (row_ok) {
-                uint4 u0, u1;
-                u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l);
-                u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l);
-                u0.z = pack_bf16x2(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l);
-                u0.w = pack_bf16x2(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l);
-                u1.x = pack_bf16x2(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l);
-                u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l);
-                u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l);
-                u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l);
-                reinterpret_cast<uint4*>(orow + c * 16)[0] = u0;
-                reinterpret_cast<uint4*>(orow + c * 16)[1] = u1;
+            for (int c = 0; c < D / 16; ++c) {
+                uint32_t o[16];
+                tmem_ld16(tmem_o + lane_addr + c * 16, o);
+                tmem_ld_wait();
+                if (row_ok) {
+                    uint4 u0, u1;
+                    u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l);
+                    u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l);
+                    u0.z = pack_bf16x2(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l);
+                    u0.w = pack_bf16x2(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l);
+                    u1.x = pack_bf16x2(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l);
+                    u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l);
+                    u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l);
+                    u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l);
+                    reinterpret_cast<uint4*>(orow + c * 16)[0] = u0;
+                    reinterpret_cast<uint4*>(orow + c * 16)[1] = u1;
+                }
             }
         }
+#else
+        store_o_rows<D, KVB>(smem + Cfg::OFF_P, tmem_o + lane_addr, inv_l, warp, lane,
+                             out + (row_base + q0) * h + head * D, k_tokens - q0, h);
+#endif
         tc_fence_before();                                    // O is read: the next item's PV may overwrite it
         }   // item loop
     }

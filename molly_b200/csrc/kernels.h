@@ -56,7 +56,7 @@ int attention_launch(const AttnMaps& tqkv, int n_seq, int k_tokens, int h, int h
                      const uint8_t* key_mask, void* out, cudaStream_t stream, float* lse2 = nullptr);
 
 // ---- attention2.cu ----  one CTA per SM, two 128-row tiles, P in tensor memory (head_dim <= 64)
-constexpr int ATTENTION2_DEFAULT = 1;          // MOLLY_ATTN_V2 = 0 | 1 overrides
+constexpr int ATTENTION2_DEFAULT = 0;          // MOLLY_ATTN_V2 = 0 | 1 overrides
 constexpr int ATTENTION2_POLY_DEFAULT = 0;     // MOLLY_ATTN_POLY = 0 | 1 | 2 overrides
 bool attention2_enabled(int head_dim);
 int attention2_launch(const AttnMaps& maps, int n_seq, int k_tokens, int h, int heads, const int32_t* kv_info,
