@@ -377,10 +377,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                             uint32_t raw[32];
                             tmem_ld32(tacc + c * 128 + hh * 32, raw);
                             tmem_ld_wait();
+                            float v[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                            if (p.bias != nullptr) add_bias32(v, p.bias, col0 + hh * 32);   // add_bias_fnn variants: interleaved like W
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const float g0 = silu(__uint_as_float(raw[4 * i])) * __uint_as_float(raw[4 * i + 1]);
-                                const float g1 = silu(__uint_as_float(raw[4 * i + 2])) * __uint_as_float(raw[4 * i + 3]);
+                                const float g0 = silu(v[4 * i]) * v[4 * i + 1];
+                                const float g1 = silu(v[4 * i + 2]) * v[4 * i + 3];
                                 pw[hh * 8 + i] = pack_bf16x2(g0, g1);
                             }
                         }

@@ -26,6 +26,23 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def glu_interleave(t: torch.Tensor, gate_first: bool = True) -> torch.Tensor:
+    """``intermediate.dense`` weight [2F, h] (or bias [2F]) of the gated FFN -> rows (gate_0, up_0, gate_1, up_1, ...): one
+    accumulator tile of the FFN1 GEMM then holds both halves of every pair and its epilogue computes silu(even) * odd.
+    ``gate_first``: the SiLU half is rows [0, F) (x1 of ``x1, x2 = split``), else rows [F, 2F)."""
+    f = t.shape[0] // 2
+    gate, up = (t[:f], t[f:]) if gate_first else (t[f:], t[:f])
+    return torch.stack([gate, up], dim=1).reshape(t.shape)
+
+
+def glu_deinterleave(t: torch.Tensor, gate_first: bool = True) -> torch.Tensor:
+    """Inverse of ``glu_interleave`` (gradients go back in the HF layout)."""
+    f = t.shape[0] // 2
+    pair = t.reshape(f, 2, *t.shape[1:])
+    gate, up = pair[:, 0], pair[:, 1]
+    return torch.cat([gate, up] if gate_first else [up, gate], dim=0).contiguous()
+
+
 class PackedEncoder:
     """Owns the packed weights of one modality (encoder + projector) and the native handle built on them."""
 
@@ -108,25 +125,25 @@ class PackedEncoder:
             arrays["b_attn_out"].append(_ptr(vec(key(p + "attention.output.dense.bias"))))
             arrays["ln2_w"].append(_ptr(vec(key(p + "LayerNorm.weight"))))
             arrays["ln2_b"].append(_ptr(vec(key(p + "LayerNorm.bias"))))
+            has_bias = (p + "intermediate.dense.bias") in sd
+            if cfg.ffn_bias is not None and bool(cfg.ffn_bias) != has_bias:
+                raise ValueError(f"EncoderConfig.ffn_bias={cfg.ffn_bias} but the state dict "
+                                 f"{'has' if has_bias else 'lacks'} {p}intermediate.dense.bias")
+            if cfg.ffn_type != "glu" and not has_bias:
+                raise ValueError(f"the GELU FFN needs {p}intermediate.dense.bias (HF:406-427)")
             if cfg.ffn_type == "glu":
                 if sd[p + "intermediate.dense.weight"].shape[0] != 2 * Fi:
                     raise ValueError(f"GLU intermediate.dense.weight must be [2F, h], got "
                                      f"{tuple(sd[p + 'intermediate.dense.weight'].shape)}")
-
-                # silu(x1) * x2 with x1 = rows [0,F), x2 = rows [F,2F)  ->  interleave (x1_0, x2_0, x1_1, x2_1, ...)
-                def glu(sd_, p=p):
-                    w1 = sd_[p + "intermediate.dense.weight"]
-                    return torch.stack([w1[:Fi], w1[Fi:]], dim=1).reshape(2 * Fi, h)
-
-                arrays["w_ffn1"].append(_ptr(mat(glu)))
-                arrays["b_ffn1"].append(None)
-                arrays["w_ffn2"].append(_ptr(mat(key(p + "output.dense.weight"))))
-                arrays["b_ffn2"].append(None)
+                gf = cfg.glu_gate_first
+                arrays["w_ffn1"].append(_ptr(mat(lambda sd_, p=p: glu_interleave(sd_[p + "intermediate.dense.weight"], gf))))
+                arrays["b_ffn1"].append(_ptr(vec(lambda sd_, p=p: glu_interleave(sd_[p + "intermediate.dense.bias"], gf)))
+                                        if has_bias else None)
             else:
                 arrays["w_ffn1"].append(_ptr(mat(key(p + "intermediate.dense.weight"))))
                 arrays["b_ffn1"].append(_ptr(vec(key(p + "intermediate.dense.bias"))))
-                arrays["w_ffn2"].append(_ptr(mat(key(p + "output.dense.weight"))))
-                arrays["b_ffn2"].append(_ptr(vec(key(p + "output.dense.bias"))))
+            arrays["w_ffn2"].append(_ptr(mat(key(p + "output.dense.weight"))))
+            arrays["b_ffn2"].append(_ptr(vec(key(p + "output.dense.bias"))) if has_bias else None)
         by_ptr = {t.data_ptr(): t for t in self._keep}
         for i in range(L):
             self.layer_tensors.append({n: (by_ptr[arrays[n][i]] if arrays[n][i] is not None else None) for n in names})

@@ -19,7 +19,7 @@ from typing import Dict, List, Tuple
 import torch
 
 from . import _lib, ops
-from .packing import PackedEncoder
+from .packing import PackedEncoder, glu_deinterleave
 
 
 def _emb_meta(enc: PackedEncoder, ids: torch.Tensor):
@@ -163,18 +163,22 @@ def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor,
         dy = ops.cast_bf16(d_x)
         d_act = ops.gemm_bf16(dy, ops.transpose_bf16(lt["w_ffn2"]), L.EPI_BIAS)
         act, d_pre = ops.act_fwd_bwd(glu, pre, d_act)
-        dW2, db2 = ops.linear_wgrad(dy, act, with_bias=not glu)                 # NT-v2's gated FFN has no biases
-        dW1, db1 = ops.linear_wgrad(d_pre, ln2, with_bias=not glu)
+        ffn_bias = lt["b_ffn1"] is not None                                     # NT-v2's gated FFN has none (add_bias_fnn = False)
+        dW2, db2 = ops.linear_wgrad(dy, act, with_bias=ffn_bias)
+        dW1, db1 = ops.linear_wgrad(d_pre, ln2, with_bias=ffn_bias)
         d_ln2 = ops.gemm_bf16(d_pre, ops.transpose_bf16(lt["w_ffn1"]), L.EPI_BIAS)
         g_w, g_b = z(h), z(h)
         ops.layernorm_bwd(x_mid, d_ln2, lt["ln2_w"], cfg.layer_norm_eps, d_x, True, g_w, g_b)      # d_x is now d(x_mid)
         grads[p + "LayerNorm.weight"], grads[p + "LayerNorm.bias"] = g_w, g_b
         grads[p + "output.dense.weight"] = dW2
-        if glu:                                # packed rows are (gate_0, up_0, gate_1, up_1, ...): back to [gate; up]
-            grads[p + "intermediate.dense.weight"] = dW1.view(F, 2, h).transpose(0, 1).reshape(2 * F, h).contiguous()
+        if glu:                                # packed rows are (gate_0, up_0, gate_1, up_1, ...): back to the HF halves
+            grads[p + "intermediate.dense.weight"] = glu_deinterleave(dW1, cfg.glu_gate_first)
+            if ffn_bias:
+                grads[p + "intermediate.dense.bias"] = glu_deinterleave(db1, cfg.glu_gate_first)
         else:
             grads[p + "intermediate.dense.weight"] = dW1
             grads[p + "intermediate.dense.bias"] = db1
+        if ffn_bias:
             grads[p + "output.dense.bias"] = db2
         # ---- attention block: x_mid = x_in + Wo Attn(LN1(x_in)) + bo
         dy = ops.cast_bf16(d_x)

@@ -37,7 +37,8 @@ class EncoderSpec:
     mask_token_id: int = 32
     position_embedding_type: str = "rotary"     # "rotary" | "absolute"
     max_position_embeddings: int = 1026
-    ffn_type: str = "gelu"                      # "gelu" (bias, erf-GELU) | "glu" (gated SiLU, no bias)
+    ffn_type: str = "gelu"                      # "gelu" (bias, erf-GELU) | "glu" (gated SiLU; biases iff the weights have them)
+    glu_gate_first: bool = True                 # NT-v2 variant switch: silu(x1) * x2 (True) or silu(x2) * x1
     token_dropout: bool = True
     emb_layer_norm_before: bool = False
     layer_norm_eps: float = 1e-5
@@ -227,10 +228,10 @@ def esm_layer(spec: EncoderSpec, W: Dict[str, Tensor], i: int, x: Tensor, key_ma
     a_ln = F.layer_norm(a, (h,), W[p + "LayerNorm.weight"], W[p + "LayerNorm.bias"], spec.layer_norm_eps)
     if spec.ffn_type == "glu":
         # NT-v2 remote code (PARITY UNPINNED): dense(h -> 2F, no bias); x1, x2 = split halves; silu(x1) * x2
-        u = F.linear(a_ln, W[p + "intermediate.dense.weight"])
+        u = F.linear(a_ln, W[p + "intermediate.dense.weight"], W.get(p + "intermediate.dense.bias"))
         x1, x2 = u.split(u.size(-1) // 2, dim=-1)
-        mid = F.silu(x1) * x2
-        y = F.linear(mid, W[p + "output.dense.weight"]) + a
+        mid = F.silu(x1) * x2 if spec.glu_gate_first else F.silu(x2) * x1
+        y = F.linear(mid, W[p + "output.dense.weight"], W.get(p + "output.dense.bias")) + a
     else:
         mid = gelu_erf(F.linear(a_ln, W[p + "intermediate.dense.weight"], W[p + "intermediate.dense.bias"]))
         y = F.linear(mid, W[p + "output.dense.weight"], W[p + "output.dense.bias"]) + a

@@ -23,11 +23,33 @@ import torch
 from .esm_oracle import EncoderSpec
 
 REFERENCE_ROOT = "/root/reference"
+# A copy of the ONE reference file this path executes, made by ``__graft_entry__.build()`` where /root/reference exists.
+# oracle/_ref/ is git-ignored (reference sources never enter the history) but travels to the GPU box with gpurun, so the
+# reference arm of bench.py and the real-class install test can run the reference's own code there.
+LOCAL_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "omics_one.py")
 _REF_MOD = None
 
 
+def reference_file():
+    for p in (os.path.join(REFERENCE_ROOT, "src/model/omics_one.py"), LOCAL_COPY):
+        if os.path.isfile(p):
+            return p
+    return None
+
+
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "src/model/omics_one.py"))
+    return reference_file() is not None
+
+
+def stage_reference_copy() -> bool:
+    """build(): copy /root/reference/src/model/omics_one.py -> oracle/_ref/omics_one.py (unmodified)."""
+    src = os.path.join(REFERENCE_ROOT, "src/model/omics_one.py")
+    if not os.path.isfile(src):
+        return os.path.isfile(LOCAL_COPY)
+    import shutil
+    os.makedirs(os.path.dirname(LOCAL_COPY), exist_ok=True)
+    shutil.copyfile(src, LOCAL_COPY)
+    return True
 
 
 def load_reference_module():
@@ -42,8 +64,7 @@ def load_reference_module():
     saved = {k: sys.modules.get(k) for k in ("utils", "utils.tools", "trainer")}
     sys.modules.update({"utils": u, "utils.tools": t, "trainer": tr})
     try:
-        spec = importlib.util.spec_from_file_location(
-            "ref_omics_one", os.path.join(REFERENCE_ROOT, "src/model/omics_one.py"))
+        spec = importlib.util.spec_from_file_location("ref_omics_one", reference_file())
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
     finally:
@@ -92,12 +113,28 @@ def build_hf_encoder(spec: EncoderSpec, weights: Dict[str, torch.Tensor]):
         for layer in model.esm.encoder.layer:
             layer.intermediate = _GluIntermediate(spec.hidden_size, spec.intermediate_size)
             layer.output = _GluOutput(spec.hidden_size, spec.intermediate_size)
-    missing, unexpected = model.load_state_dict(weights, strict=False)
-    assert not unexpected, unexpected
-    bad = [k for k in missing if not (k.startswith("lm_head") or "inv_freq" in k or "contact_head" in k
-                                      or "position_ids" in k)]
-    assert not bad, f"weights missing for {bad}"
+    if weights:
+        missing, unexpected = model.load_state_dict(weights, strict=False)
+        assert not unexpected, unexpected
+        bad = [k for k in missing if not (k.startswith("lm_head") or "inv_freq" in k or "contact_head" in k
+                                          or "position_ids" in k)]
+        assert not bad, f"weights missing for {bad}"
     return model.float().eval()
+
+
+def build_reference_omics_random(nt_spec: EncoderSpec, pr_spec: EncoderSpec, d_llm: int, k_tokens: int, seed: int = 0):
+    """The reference's ``OmicsOne`` with stock HF encoders in their own random init (timing only: bench.py --impl reference)."""
+    ref = load_reference_module()
+    cfg = types.SimpleNamespace(
+        text_config=types.SimpleNamespace(hidden_size=d_llm, use_return_dict=True),
+        dna_rna_config=types.SimpleNamespace(hidden_size=nt_spec.hidden_size),
+        protein_config=types.SimpleNamespace(hidden_size=pr_spec.hidden_size),
+        dna_rna_project_token_num=k_tokens, protein_project_token_num=k_tokens)
+    torch.manual_seed(seed)
+    om = ref.OmicsOne(cfg)
+    om.dna_rna_model = build_hf_encoder(nt_spec, {})
+    om.protein_model = build_hf_encoder(pr_spec, {})
+    return om.eval()
 
 
 def build_reference_omics(nt, pr, d_llm: int):

@@ -241,7 +241,9 @@ def test_bench_reference_arm_contract():
         assert key in line, key
     assert line["impl"] == "reference" and line["higher_is_better"] is True and line["vs_baseline"] is None
     assert line["metric"] == "omics tokens/sec (encode+project+merge)" and line["unit"] == "omics tokens/s"
-    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    from oracle import ref_import                      # "reference": oracle/_ref/omics_one.py staged by build(); else the port
+    want_kind = "reference" if ref_import.reference_available() else "port"
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == want_kind and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     for key in ("workload", "B_per_gpu", "K", "T", "D", "parallelism", "l2"):
         assert key in line["config"], key
@@ -274,3 +276,47 @@ def test_planner_properties_randomised():
 
     disjoint()
     balanced()
+
+
+def test_nt_v2_loader_variants_pack_what_the_module_computes():
+    """The gated-FFN packing for both half orders and with / without biases, checked on the CPU against the formula of the
+    module it replaces: ``x1, x2 = dense(x).split(F); silu(x1) * x2`` (NT-v2 remote code, `add_bias_fnn`), or the swapped
+    order.  The FFN1 epilogue computes silu(even column) * odd column of ``x @ W_packed^T + b_packed``."""
+    import types
+    import torch
+    from molly_b200.config import EncoderConfig
+    from molly_b200.packing import glu_deinterleave, glu_interleave
+    g = torch.Generator().manual_seed(0)
+    h, F = 8, 6
+    W, b, x = torch.randn(2 * F, h, generator=g), torch.randn(2 * F, generator=g), torch.randn(5, h, generator=g)
+    u = x @ W.t() + b
+    x1, x2 = u.split(F, dim=-1)
+    for gate_first, want in ((True, torch.nn.functional.silu(x1) * x2), (False, torch.nn.functional.silu(x2) * x1)):
+        acc = x @ glu_interleave(W, gate_first).t() + glu_interleave(b, gate_first)
+        got = torch.nn.functional.silu(acc[:, 0::2]) * acc[:, 1::2]
+        assert torch.allclose(got, want, atol=1e-6)
+        assert torch.equal(glu_deinterleave(glu_interleave(W, gate_first), gate_first), W)       # gradients go back unchanged
+        assert torch.equal(glu_deinterleave(glu_interleave(b, gate_first), gate_first), b)
+
+    # key names + config flags of the remote code as documented on the model card: same module paths as stock ESM,
+    # intermediate.dense is [2F, h], biases present iff add_bias_fnn
+    def hf_cfg(**kw):
+        base = dict(hidden_size=h, num_hidden_layers=1, num_attention_heads=2, intermediate_size=F, vocab_size=4107,
+                    pad_token_id=1, mask_token_id=2, position_embedding_type="rotary", max_position_embeddings=2050,
+                    token_dropout=False, emb_layer_norm_before=False, layer_norm_eps=1e-12)
+        base.update(kw)
+        return types.SimpleNamespace(**base)
+    sd_nobias = {"esm.encoder.layer.0.intermediate.dense.weight": W}
+    sd_bias = dict(sd_nobias, **{"esm.encoder.layer.0.intermediate.dense.bias": b})
+    c = EncoderConfig.from_hf_config(hf_cfg(add_bias_fnn=False), sd_nobias)
+    assert (c.ffn_type, c.ffn_bias, c.glu_gate_first) == ("glu", False, True)
+    c = EncoderConfig.from_hf_config(hf_cfg(add_bias_fnn=True), sd_bias)                          # biased gated FFN
+    assert (c.ffn_type, c.ffn_bias) == ("glu", True)
+    c = EncoderConfig.from_hf_config(hf_cfg(glu_gate_first=False), sd_nobias)                      # explicit half order
+    assert (c.ffn_type, c.glu_gate_first) == ("glu", False)
+    import pytest
+    with pytest.raises(ValueError):                                                                # config and checkpoint disagree
+        EncoderConfig.from_hf_config(hf_cfg(add_bias_fnn=False), sd_bias)
+    stock = EncoderConfig.from_hf_config(hf_cfg(), {"esm.encoder.layer.0.intermediate.dense.weight": W[:F],
+                                                    "esm.encoder.layer.0.intermediate.dense.bias": b[:F]})
+    assert (stock.ffn_type, stock.ffn_bias) == ("gelu", True)
