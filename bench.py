@@ -209,6 +209,17 @@ def batch_stats(wl: dict, omic_ids, infos):
     return rows, valid, flops
 
 
+def sample_cost(wl: dict, ids_b, infos_b) -> float:
+    """Model FLOP of one sample (balance by work, not by count) -- the weight of planner.balance_equal_count."""
+    c = 0.0
+    for i, info in enumerate(infos_b):
+        if info["type"] == "pad":
+            continue
+        e = ENC[wl["pr"] if info["type"] == "protein" else wl["nt"]]
+        c += wl["K"] * flops_per_token(e, int((ids_b[i] != 1).sum()), wl["D"])
+    return c
+
+
 LLM_VOCAB = 151936                                         # Qwen3 embedding rows (config.json vocab_size)
 PLACEHOLDER_BASE = 151669                                  # first id after Qwen3's own specials: the 9 added omics tags
 PAD_TOKEN_IDS = (PLACEHOLDER_BASE + 1, PLACEHOLDER_BASE + 4, PLACEHOLDER_BASE + 7)
@@ -560,7 +571,9 @@ def varlen_section(args, dev, rank: int, world: int, steps: int, warmup: int) ->
     wl = WORKLOADS["molly_4b"]
     path = build_path(wl, dev, strict=False)
     g_ids, g_infos = make_inputs(dict(wl, B=wl["B"] * world), seed=1234)
-    costs = [float((g_ids[b] != 1).sum()) for b in range(g_ids.shape[0])]              # keys the attention really reads
+    # cost of a sample = model FLOP of its sequences: K rows through the GEMMs of ITS encoder (ESM-2 650M is 1.34x NT-v2 500M
+    # per row; pad rows are computed like the reference) + attention over its valid keys
+    costs = [sample_cost(wl, g_ids[b], g_infos[b]) for b in range(g_ids.shape[0])]
     mine = planner.balance_equal_count(costs, world)[rank]
     omic_ids, infos = g_ids[mine].contiguous(), [g_infos[b] for b in mine]
     omic_ids_dev = omic_ids.to(dev)
@@ -591,13 +604,13 @@ def varlen_section(args, dev, rank: int, world: int, steps: int, warmup: int) ->
     del path
     torch.cuda.empty_cache()
     return {"workload": wl["desc"], "B_per_gpu": wl["B"], "K": wl["K"], "T": wl["T"], "D": wl["D"],
-            "split": "planner.balance_equal_count over the global batch (equal counts, balanced key counts)",
+            "split": "planner.balance_equal_count over the global batch (equal sample counts, balanced model FLOP)",
             "ms_per_step_max": round(max(ms), 3), "ms_per_step_min": round(min(ms), 3),
             "rank_imbalance": round(max(ms) / min(ms) - 1.0, 4),
             "tokens_per_s": round(sum(float(t[1]) for t in allst) / (max(ms) * 1e-3), 1),
             "valid_tokens_per_s": round(sum(float(t[2]) for t in allst) / (max(ms) * 1e-3), 1),
             "model_tflops_per_gpu": round(sum(float(t[3]) for t in allst) / world / (max(ms) * 1e-3) / 1e12, 1),
-            "valid_keys_per_rank": [int(t[4]) for t in allst]}
+            "model_tflop_per_rank": [round(float(t[4]) / 1e12, 2) for t in allst]}
 
 
 def gpu_library_baseline(dev, path_cfg2, steps: int = 5, warmup: int = 2) -> dict:
@@ -720,7 +733,7 @@ def main() -> None:
         # one global batch, samples dealt to ranks with equal counts and balanced attention cost
         from molly_b200 import planner
         g_ids, g_infos = make_inputs(dict(wl, B=wl["B"] * world), seed=1234)
-        costs = [float((g_ids[b] != 1).sum()) for b in range(g_ids.shape[0])]          # keys the attention really reads
+        costs = [sample_cost(wl, g_ids[b], g_infos[b]) for b in range(g_ids.shape[0])]
         mine = planner.balance_equal_count(costs, world)[rank]
         omic_ids, infos = g_ids[mine].contiguous(), [g_infos[b] for b in mine]
     else:

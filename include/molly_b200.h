@@ -139,6 +139,9 @@ int molly_placeholder_scan(const int64_t* input_ids_dev, int32_t B, int32_t T, c
  *   n_slots, which the reference's zip never reaches)                                       (omics_dataset.py:270-288)
  * molly_build_seq_table: seq_table[n] = (b, run_start[b][slot]-1): exactly info["start"] of the reference, paired with the
  *   omic_ids slots BY INDEX like the reference's zip (omics_one.py:105); mismatches OR MOLLY_ERRBIT_LAYOUT
+ * molly_placeholder_reject: runs that molly_build_seq_table will reject (shorter than the K cap of their kind, kind not
+ *   the modality of the omic_ids slot they pair with -- slot_expect[b][r] 0 dna/rna, 1 protein, -1 none) get pos_j = -1
+ *   again, so the lookup below embeds them normally: no row of inputs_embeds is ever left unwritten
  * molly_embed_tokens_skip: inputs_embeds = embed_tokens(input_ids) (omics_one.py:164, :209) for every row the omics path
  *   will not overwrite (j >= K cap or not a placeholder) -- the overwritten rows are never read or written            */
 int molly_placeholder_runs(const int64_t* input_ids_dev, int32_t B, int32_t T, const int64_t pad_token_ids[3],
@@ -148,6 +151,9 @@ int molly_build_seq_table(const int32_t* b_idx_dev, const int32_t* slot_idx_dev,
                           const int32_t* run_kind_dev, const int32_t* run_len_dev, const int32_t* n_runs_dev,
                           int32_t max_runs, int32_t expect_protein, int32_t k_need, int32_t* seq_table_dev /*[n,2]*/,
                           int32_t* err_flag_dev, void* stream);
+int molly_placeholder_reject(int32_t* pos_j_dev /*[B,T]*/, const int32_t* run_start_dev, const int32_t* run_kind_dev,
+                             const int32_t* run_len_dev, const int32_t* n_runs_dev, const int32_t* slot_expect_dev /*[B,max_runs]*/,
+                             int32_t B, int32_t T, int32_t max_runs, int32_t cap_dna_rna, int32_t cap_protein, void* stream);
 int molly_embed_tokens_skip(const int64_t* input_ids_dev, const int32_t* pos_j_dev, const int64_t pad_token_ids[3],
                             int32_t cap_dna_rna, int32_t cap_protein, const void* table_dev /*[vocab,D]*/, int32_t dtype,
                             int32_t vocab, int32_t D, void* out_dev /*[B,T,D]*/, int32_t B, int32_t T,

@@ -83,6 +83,7 @@ SIGNATURES = {
     "molly_rotary": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "molly_attention": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "molly_placeholder_runs": (C.c_int, [_vp, _i32, _i32, C.POINTER(C.c_int64), _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "molly_placeholder_reject": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "molly_build_seq_table": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "molly_embed_tokens_skip": (C.c_int, [_vp, _vp, C.POINTER(C.c_int64), _i32, _i32, _vp, _i32, _i32, _i32, _vp, _i32,
                                           _i32, _vp, _vp]),

@@ -450,6 +450,15 @@ int molly_placeholder_runs(const int64_t* input_ids_dev, int32_t B, int32_t T, c
                                    static_cast<cudaStream_t>(stream));
 }
 
+int molly_placeholder_reject(int32_t* pos_j_dev, const int32_t* run_start_dev, const int32_t* run_kind_dev,
+                             const int32_t* run_len_dev, const int32_t* n_runs_dev, const int32_t* slot_expect_dev, int32_t B,
+                             int32_t T, int32_t max_runs, int32_t cap_dna_rna, int32_t cap_protein, void* stream) {
+    MOLLY_CHECK(pos_j_dev && run_start_dev && run_kind_dev && run_len_dev && n_runs_dev && slot_expect_dev, MOLLY_ERR_INVALID,
+                "molly_placeholder_reject: NULL pointer");
+    return placeholder_reject_launch(pos_j_dev, run_start_dev, run_kind_dev, run_len_dev, n_runs_dev, slot_expect_dev, B, T,
+                                     max_runs, cap_dna_rna, cap_protein, static_cast<cudaStream_t>(stream));
+}
+
 int molly_embed_tokens_skip(const int64_t* input_ids_dev, const int32_t* pos_j_dev, const int64_t pad_token_ids[3],
                             int32_t cap_dna_rna, int32_t cap_protein, const void* table_dev, int32_t dtype,
                             int32_t vocab, int32_t D, void* out_dev, int32_t B, int32_t T, int32_t* err_flag_dev,

@@ -171,7 +171,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
     }
     tc_fence_before();
-    if constexpr (CTA2) cluster_sync_all(); else __syncthreads();      // barriers of BOTH CTAs are initialised
+    __syncthreads();                          // the TMEM base written by tcgen05.alloc is published inside the CTA by bar.sync
+    if constexpr (CTA2) cluster_sync_all();   // (what compute-sanitizer racecheck models) ... and the barriers of BOTH CTAs are initialised
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 

@@ -89,6 +89,9 @@ int gather_grad_rows_launch(void* d_hidden, int dtype, const int32_t* seq_table,
 int placeholder_runs_launch(const int64_t* input_ids, int B, int T, int64_t pad0, int64_t pad1, int64_t pad2,
                             const int32_t* n_slots, int max_runs, int32_t* run_start, int32_t* run_kind, int32_t* run_len, int32_t* n_runs,
                             int32_t* pos_j, cudaStream_t stream);
+int placeholder_reject_launch(int32_t* pos_j, const int32_t* run_start, const int32_t* run_kind, const int32_t* run_len,
+                              const int32_t* n_runs, const int32_t* slot_expect, int B, int T, int max_runs, int cap_nt,
+                              int cap_pr, cudaStream_t stream);
 int embed_tokens_skip_launch(const int64_t* input_ids, const int32_t* pos_j, int64_t pad0, int64_t pad1, int cap_nt,
                              int cap_pr, const void* table, int dtype, int vocab, int D, void* out, int B, int T,
                              int32_t* err_flag, cudaStream_t stream);

@@ -242,6 +242,28 @@ embed_tokens_skip_kernel(const int64_t* __restrict__ input_ids, const int32_t* _
     for (int v = lane; v < static_cast<int>(row_bytes / 16); v += 32) d[v] = __ldg(s + v);
 }
 
+// Runs that build_seq_table will REJECT (shorter than the K cap of their kind, kind != the modality of the omic_ids slot they
+// pair with, or no slot at all) are never overwritten by a projector: their positions go back to pos_j = -1, so that the
+// skipping lookup embeds them like any other token instead of leaving rows of the torch.empty output uninitialised.
+// One CTA per sample; the runs of a sample are few.
+__global__ void __launch_bounds__(256)
+placeholder_reject_kernel(int32_t* __restrict__ pos_j, const int32_t* __restrict__ run_start,
+                          const int32_t* __restrict__ run_kind, const int32_t* __restrict__ run_len,
+                          const int32_t* __restrict__ n_runs, const int32_t* __restrict__ slot_expect, int T, int max_runs,
+                          int cap_nt, int cap_pr) {
+    const int b = blockIdx.x;
+    const int nr = n_runs[b] < max_runs ? n_runs[b] : max_runs;
+    for (int r = 0; r < nr; ++r) {
+        const size_t o = static_cast<size_t>(b) * max_runs + r;
+        const int kind = run_kind[o], len = run_len[o], expect = slot_expect[o];      // expect: 0 dna/rna, 1 protein, -1 no slot
+        const bool is_pr = kind == 2;
+        const bool ok = expect >= 0 && (expect == 1) == is_pr && len >= (is_pr ? cap_pr : cap_nt);
+        if (ok) continue;
+        const int s0 = run_start[o];
+        for (int t = s0 + threadIdx.x; t < s0 + len && t < T; t += blockDim.x) pos_j[static_cast<size_t>(b) * T + t] = -1;
+    }
+}
+
 // seq_table[n] = (b, start) with start = (first pad position of run `slot`) - 1, i.e. the x_start token: exactly
 // info["start"] of the reference (omics_dataset.py:277).  Runs pair with omic_ids slots BY INDEX (the reference's zip).
 __global__ void build_seq_table_kernel(const int32_t* __restrict__ b_idx, const int32_t* __restrict__ slot_idx, int n,
@@ -271,6 +293,17 @@ int placeholder_runs_launch(const int64_t* input_ids, int B, int T, int64_t pad0
     MOLLY_CHECK(B > 0 && T > 0 && max_runs > 0, MOLLY_ERR_INVALID, "placeholder_runs: B=%d T=%d max_runs=%d", B, T, max_runs);
     placeholder_runs_kernel<<<B, SCAN_THREADS, 0, stream>>>(input_ids, T, pad0, pad1, pad2, n_slots, max_runs, run_start,
                                                            run_kind, run_len, n_runs, pos_j);
+    count_launch();
+    MOLLY_CUDA(cudaGetLastError());
+    return MOLLY_OK;
+}
+
+int placeholder_reject_launch(int32_t* pos_j, const int32_t* run_start, const int32_t* run_kind, const int32_t* run_len,
+                              const int32_t* n_runs, const int32_t* slot_expect, int B, int T, int max_runs, int cap_nt,
+                              int cap_pr, cudaStream_t stream) {
+    MOLLY_CHECK(B > 0 && T > 0 && max_runs > 0, MOLLY_ERR_INVALID, "placeholder_reject: B=%d T=%d max_runs=%d", B, T, max_runs);
+    placeholder_reject_kernel<<<B, 256, 0, stream>>>(pos_j, run_start, run_kind, run_len, n_runs, slot_expect, T, max_runs,
+                                                     cap_nt, cap_pr);
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
     return MOLLY_OK;

@@ -347,11 +347,19 @@ class FastOmicsPath:
             idx[name] = torch.tensor([plan.b_idx, plan.run_idx, plan.slot_idx], dtype=torch.int32).pin_memory().to(
                 dev, non_blocking=True)
         slots_dev = torch.tensor(n_slots, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
-        return {"plans": plans, "caps": caps, "idx": idx, "slots": slots_dev, "max_runs": max(1, max(n_slots))}
+        max_runs = max(1, max(n_slots))
+        expect = torch.full((batch_size, max_runs), -1, dtype=torch.int32)       # modality each run pairs with (0 / 1), -1: none
+        for name, plan in plans.items():
+            for b, r in zip(plan.b_idx, plan.run_idx):
+                expect[b, r] = 1 if name == "protein" else 0
+        return {"plans": plans, "caps": caps, "idx": idx, "slots": slots_dev, "max_runs": max_runs,
+                "slot_expect": expect.pin_memory().to(dev, non_blocking=True)}
 
     def _fused_run(self, input_ids, embed_weight, ids: dict, meta: dict, pad_token_ids) -> torch.Tensor:
         """Device-only part (capturable): run scan -> skipping embedding lookup -> per modality seq_table + encode/merge."""
         runs = ops.placeholder_runs(input_ids, pad_token_ids, meta["slots"], meta["max_runs"])
+        # runs the seq_table will reject are embedded like text: no row of the (uninitialised) output stays unwritten
+        ops.placeholder_reject(runs, meta["slot_expect"], max(1, meta["caps"]["dna_rna"]), max(1, meta["caps"]["protein"]))
         hidden = ops.embed_tokens_skip(input_ids, runs[4], pad_token_ids, meta["caps"]["dna_rna"], meta["caps"]["protein"],
                                        embed_weight)
 

@@ -294,6 +294,20 @@ def placeholder_runs(input_ids: Tensor, pad_ids: Tuple[int, int, int], n_slots: 
     return run_start, run_kind, run_len, n_runs, pos_j
 
 
+def placeholder_reject(runs, slot_expect: Tensor, cap_dna_rna: int, cap_protein: int) -> None:
+    """In place on ``runs[4]`` (pos_j): runs that ``build_seq_table`` will reject go back to -1 (embedded like text)."""
+    run_start, run_kind, run_len, n_runs, pos_j = runs
+    dev = _require_cuda(pos_j, slot_expect)
+    B, T = pos_j.shape
+    if slot_expect.dtype != torch.int32 or tuple(slot_expect.shape) != tuple(run_start.shape) or not slot_expect.is_contiguous():
+        raise ValueError("slot_expect must be contiguous int32 [B, max_runs]")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_placeholder_reject(
+            pos_j.data_ptr(), run_start.data_ptr(), run_kind.data_ptr(), run_len.data_ptr(), n_runs.data_ptr(),
+            slot_expect.data_ptr(), B, T, run_start.shape[1], int(cap_dna_rna), int(cap_protein), _stream(dev)),
+            "molly_placeholder_reject")
+
+
 def build_seq_table(b_idx: Tensor, run_idx: Tensor, runs, expect_protein: bool, k_need: int = 1) -> Tensor:
     """seq_table [n, 2] = (b, x_start position) from the device-side runs: the reference's info["start"]."""
     dev = _require_cuda(b_idx, run_idx)

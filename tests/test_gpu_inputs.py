@@ -146,3 +146,40 @@ def test_layout_mismatch_and_bad_token_raise():
                                    [row[:-1] for row in case.batch.omic_info_list], synth.PAD_TOKEN_IDS)
     finally:
         path.close()
+
+
+def test_rejected_runs_are_embedded_like_text_in_lazy_mode():
+    """strict=False (the default): a layout whose runs do not pair with the ids (wrong kind, or a run shorter than K after
+    text truncation, omics_dataset.py:370-373) only sets MOLLY_ERRBIT_LAYOUT.  The rows of those runs must then hold the
+    plain embedding lookup -- the output buffer is torch.empty, nothing may be left unwritten."""
+    from molly_b200 import ops
+    case = _case("tiny_rotary_glu")
+    g = torch.Generator().manual_seed(12)
+    table = (torch.randn(VOCAB, case.D, generator=g) * 0.02)
+    ids = case.batch.input_ids.clone()
+    b0 = 0
+    dna_run = (ids[b0] == synth.PAD_TOKEN_IDS[0]).nonzero().flatten()
+    ids[b0, dna_run[-3:]] = 17                              # sample 0: the DNA run is 3 tokens short of K
+    pr_rows = (ids == synth.PAD_TOKEN_IDS[2]).any(1).nonzero().flatten()
+    b1 = int(pr_rows[-1])
+    ids[b1][ids[b1] == synth.PAD_TOKEN_IDS[2]] = synth.PAD_TOKEN_IDS[1]    # last sample: "rna" text where the ids hold a protein
+    path = build_path(case, strict=False)
+    try:
+        # poison the caching allocator's next block so that an unwritten row cannot look right by accident
+        junk = torch.full((ids.shape[0], ids.shape[1], case.D), float("nan"), device=DEV)
+        del junk
+        got = path.embed_and_process(ids.to(DEV), table.to(DEV), case.batch.omic_ids, case.batch.omic_info_list,
+                                     synth.PAD_TOKEN_IDS)
+        assert int(ops.error_flag(torch.device(DEV, 0)).item()) & 8          # MOLLY_ERRBIT_LAYOUT, not raised in lazy mode
+        ops.error_flag(torch.device(DEV, 0)).zero_()
+        got = got.float().cpu()
+        assert not torch.isnan(got).any()
+        plain = table[ids]
+        rejected = torch.zeros(ids.shape, dtype=torch.bool)
+        rejected[b0, dna_run[:-3]] = True
+        rejected[b1][ids[b1] == synth.PAD_TOKEN_IDS[1]] = True
+        assert torch.equal(got[rejected], plain[rejected]), "rows of rejected runs must be the plain lookup"
+        text = ~torch.isin(ids, torch.tensor(synth.PAD_TOKEN_IDS))
+        assert torch.equal(got[text], plain[text])
+    finally:
+        path.close()
