@@ -140,7 +140,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint64_t* res_bar = tmem_empty + 2;                      // [NUM_EPI_WARPS][2] residual-load barriers
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * NUM_EPI_WARPS);
+    // the TMEM base lives in its own 16-B granule at the end of the barrier area: tcgen05.alloc's write is tracked by
+    // compute-sanitizer racecheck as a 16-B access, which overlapped the neighbouring mbarrier words being initialised
+    static_assert((2 * STAGES + 4 + 2 * NUM_EPI_WARPS) * 8 <= 496, "barrier area overflows into the TMEM slot");
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::BAR_OFFSET + 496);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;

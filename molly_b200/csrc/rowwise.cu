@@ -287,7 +287,7 @@ int embed_launch(const int64_t* ids, int n_seq, int k_tokens, const EmbedArgs& a
                  cudaStream_t stream) {
     MOLLY_CHECK(a.hidden % 8 == 0, MOLLY_ERR_UNSUPPORTED, "embed: hidden_size %% 8 != 0 (%d)", a.hidden);
     MOLLY_CHECK(a.position_type == 0 || pos_emb != nullptr, MOLLY_ERR_INVALID, "embed: absolute positions need pos_emb");
-    int splits = (2 * device_sm_count() + n_seq - 1) / n_seq;
+    int splits = (4 * device_sm_count() + n_seq - 1) / n_seq;      // ~4 CTAs per SM: a write-bound kernel needs the stores in flight
     splits = max(1, min(splits, (k_tokens + 63) / 64));
     const size_t smem = a.position_type == 1 ? sizeof(int32_t) * k_tokens : 0;
     MOLLY_CHECK(smem <= 48 * 1024, MOLLY_ERR_UNSUPPORTED, "embed: k_tokens %d too long for absolute positions", k_tokens);

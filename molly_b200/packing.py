@@ -183,11 +183,21 @@ class PackedEncoder:
         """Refresh the packed ENCODER weights in place from a new state dict (same shapes): device addresses, the native
         handle and its cached TMA descriptors stay valid.  SURVEY.md 8b: packed copies are caches that must follow the
         ``nn.Module`` weights when the encoders train (``--train-bio``) or a checkpoint is loaded after construction."""
+        same_d, same_s, conv_d, conv_s = [], [], [], []
         for dst, build in self._recipes:
-            src = build(state_dict)
+            src = build(state_dict).detach()
             if tuple(src.shape) != tuple(dst.shape):
                 raise ValueError(f"reload: shape {tuple(src.shape)} does not match the packed {tuple(dst.shape)}")
-            dst.copy_(src.detach().to(device=dst.device, dtype=torch.float32))
+            if src.device != dst.device:
+                src = src.to(dst.device, non_blocking=True)
+            (same_d if src.dtype == dst.dtype else conv_d).append(dst)
+            (same_s if src.dtype == dst.dtype else conv_s).append(src)
+        # trainable encoders are re-packed on EVERY call (omics_path.refresh_encoders): a few multi-tensor launches instead
+        # of ~800 single copies (bf16 parameters under DeepSpeed bf16 go straight into the bf16 matrices)
+        if same_d:
+            torch._foreach_copy_(same_d, same_s)
+        if conv_d:
+            torch._foreach_copy_(conv_d, conv_s)
 
     def load_projector(self, weight: torch.Tensor, bias: torch.Tensor) -> None:
         """(Re)pack ``nn.Linear`` projector parameters into the buffers the kernels read."""

@@ -162,7 +162,8 @@ def test_rejected_runs_are_embedded_like_text_in_lazy_mode():
     ids[b0, dna_run[-3:]] = 17                              # sample 0: the DNA run is 3 tokens short of K
     pr_rows = (ids == synth.PAD_TOKEN_IDS[2]).any(1).nonzero().flatten()
     b1 = int(pr_rows[-1])
-    ids[b1][ids[b1] == synth.PAD_TOKEN_IDS[2]] = synth.PAD_TOKEN_IDS[1]    # last sample: "rna" text where the ids hold a protein
+    pr_pos = ids[b1] == synth.PAD_TOKEN_IDS[2]
+    ids[b1, pr_pos] = synth.PAD_TOKEN_IDS[1]                # last sample: "rna" text where the ids hold a protein
     path = build_path(case, strict=False)
     try:
         # poison the caching allocator's next block so that an unwritten row cannot look right by accident
@@ -177,7 +178,7 @@ def test_rejected_runs_are_embedded_like_text_in_lazy_mode():
         plain = table[ids]
         rejected = torch.zeros(ids.shape, dtype=torch.bool)
         rejected[b0, dna_run[:-3]] = True
-        rejected[b1][ids[b1] == synth.PAD_TOKEN_IDS[1]] = True
+        rejected[b1, pr_pos] = True
         assert torch.equal(got[rejected], plain[rejected]), "rows of rejected runs must be the plain lookup"
         text = ~torch.isin(ids, torch.tensor(synth.PAD_TOKEN_IDS))
         assert torch.equal(got[text], plain[text])
