@@ -34,9 +34,11 @@ class FlatGradBucket:
         dev = self.params[0].device
         self.dtype = dtype or self.params[0].dtype
         self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(self.numel, dtype=self.dtype, device=dev)
+        # (a one-tensor bucket reduces its gradient in place and only needs `flat` if that gradient is missing / strided)
+        self.flat = torch.zeros(self.numel if len(self.params) > 1 else 1, dtype=self.dtype, device=dev)
         self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self._work = None
+        self._inplace = False
 
     def _views(self) -> List[torch.Tensor]:
         out, off = [], 0
@@ -45,20 +47,36 @@ class FlatGradBucket:
             off += p.numel()
         return out
 
+    def _mean_all_reduce(self, t: torch.Tensor):
+        """Mean over ranks: NCCL averages inside the collective (ReduceOp.AVG); gloo has no AVG -> pre-divide + SUM."""
+        if dist.get_backend(self.group) == "nccl":
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        t.div_(dist.get_world_size(self.group))
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
     def launch(self) -> None:
-        """Pack grads and start the (async) mean all-reduce.  Call right after the path's backward produced them."""
-        world = dist.get_world_size(self.group)
+        """Start the (async) mean all-reduce.  Call right after the backward produced the gradients.  A bucket of ONE
+        contiguous gradient (the LoRA-sized tensor of cfg-5) is reduced in place: no pack / unpack passes over it."""
         if self.stream is not None:
             self.stream.wait_stream(torch.cuda.current_stream(self.flat.device))
         ctx = torch.cuda.stream(self.stream) if self.stream is not None else _Null()
         with ctx:
+            g = self.params[0].grad if len(self.params) == 1 else None
+            if g is not None and g.is_contiguous() and g.dtype == self.dtype:
+                self._inplace = True
+                if self.stream is not None:
+                    g.record_stream(self.stream)
+                self._work = self._mean_all_reduce(g.view(-1))
+                return
+            self._inplace = False
+            if self.flat.numel() != self.numel:
+                self.flat = torch.zeros(self.numel, dtype=self.dtype, device=self.flat.device)
             for v, p in zip(self._views(), self.params):
                 if p.grad is None:
                     v.zero_()
                 else:
                     v.copy_(p.grad)
-            self.flat.div_(world)
-            self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._work = self._mean_all_reduce(self.flat)
 
     def finish(self) -> None:
         """Wait for the collective and scatter the averaged grads back into ``p.grad``."""
@@ -69,11 +87,12 @@ class FlatGradBucket:
             # Work.wait() orders the CURRENT stream after NCCL's internal stream: it has to run inside the side-stream
             # context, or the copy-back below could read `flat` while it is still being reduced.
             self._work.wait()
-            for v, p in zip(self._views(), self.params):
-                if p.grad is None:
-                    p.grad = v.clone()
-                else:
-                    p.grad.copy_(v)
+            if not self._inplace:
+                for v, p in zip(self._views(), self.params):
+                    if p.grad is None:
+                        p.grad = v.clone()
+                    else:
+                        p.grad.copy_(v)
         if self.stream is not None:
             torch.cuda.current_stream(self.flat.device).wait_stream(self.stream)
         self._work = None

@@ -42,6 +42,14 @@ def _worker(rank, world, port, out_q):
         bucket = FlatGradBucket(list(lin.parameters()))
         bucket.launch()
         bucket.finish()
+        # a one-tensor bucket (the LoRA-sized gradient of cfg-5) is averaged in place: same storage before and after
+        lora = torch.nn.Parameter(torch.zeros(1000))
+        lora.grad = torch.full((1000,), float(3 * (rank + 1)))
+        ptr = lora.grad.data_ptr()
+        lb = FlatGradBucket([lora])
+        lb.launch()
+        lb.finish()
+        plan["lora"] = (float(lora.grad.mean()), lora.grad.data_ptr() == ptr)
         plan["w_grad"] = float(lin.weight.grad.mean())
         plan["b_grad"] = float(lin.bias.grad.mean())
         # layer-wise reducer of the encoder backward: entries become views of one averaged buffer per call
@@ -97,6 +105,7 @@ def test_two_rank_gloo_sharding_and_grad_bucket():
     for p in plans:
         assert p["w_grad"] == pytest.approx(1.5) and p["b_grad"] == pytest.approx(15.0)
         assert p["t_max"] == 2.0
+        assert p["lora"][0] == pytest.approx(4.5) and p["lora"][1]
         assert p["lw"] == pytest.approx([1.5, 1.0, 10.5])            # means over ranks of (1,2), (0,2), (7,14)
         assert p["lw_shapes"] == [(3, 4), (4,), (2, 2)]
         assert p["asym"] == pytest.approx([2.0, 4.0])                # (4 + 0) / 2, (8 + 0) / 2: no hang, no mis-pairing
