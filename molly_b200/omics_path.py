@@ -113,24 +113,28 @@ class _InjectTrainFn(torch.autograd.Function):
 class _AbsentModalityFn(torch.autograd.Function):
     """A modality with a TRAINABLE encoder that has no sequence in this rank's micro-batch while a gradient reducer is
     attached: the other ranks all-reduce that encoder's gradients layer by layer inside their backward, so this rank must
-    issue the SAME sequence of collectives (with zeros) at the same point of its backward, or NCCL pairs the wrong
-    buffers / hangs.  Forward is the identity on ``hidden_states``; every parameter gets a zero gradient."""
+    issue the SAME sequence of collectives at the same point of its backward, or NCCL pairs the wrong buffers / hangs.  It
+    contributes zeros laid out like ``train.reduce_schedule`` and gets back what every rank gets: the averaged gradients.
+    Forward is the identity on ``hidden_states``."""
 
     @staticmethod
-    def forward(ctx, hidden_states, reducer, numels, *params):
-        ctx.reducer, ctx.numels = reducer, numels
-        ctx.metas = [(p.shape, p.dtype, p.device) for p in params]
+    def forward(ctx, hidden_states, reducer, schedule, names, *params):
+        ctx.reducer, ctx.schedule, ctx.names = reducer, schedule, names
+        ctx.metas = [(p.dtype, p.device) for p in params]
         ctx.mark_dirty(hidden_states)
         return hidden_states
 
     @staticmethod
     def backward(ctx, grad_out):
-        for n in ctx.numels:
-            ctx.reducer.reduce_zeros_(n, grad_out.device)
+        got = {}
+        for group in ctx.schedule:
+            d = {n: torch.zeros(shape, dtype=ctx.reducer.dtype, device=grad_out.device) for n, shape in group}
+            ctx.reducer.reduce_(d, [n for n, _ in group])
+            got.update(d)
         ctx.reducer.finish()
-        zeros = [torch.zeros(sh, dtype=dt, device=dv) if need else None
-                 for (sh, dt, dv), need in zip(ctx.metas, ctx.needs_input_grad[3:])]
-        return (grad_out if ctx.needs_input_grad[0] else None), None, None, *zeros
+        grads = [got[n].to(device=dv, dtype=dt) if (n in got and need) else None
+                 for n, (dt, dv), need in zip(ctx.names, ctx.metas, ctx.needs_input_grad[4:])]
+        return (grad_out if ctx.needs_input_grad[0] else None), None, None, None, *grads
 
 
 class FastOmicsPath:
@@ -257,13 +261,13 @@ class FastOmicsPath:
         proj, enc_module, enc_id = self._proj_modules.get(name), self._enc_modules.get(name), self._ids.get(name)
         if proj is None or enc_module is None or enc_id is None:
             return
-        params = [prm for prm in enc_module.parameters() if prm.requires_grad]
-        if not params:                                   # frozen encoder: its backward launches no collective
+        named = [(n, prm) for n, prm in enc_module.named_parameters()]
+        if not any(prm.requires_grad for _, prm in named):        # frozen encoder: its backward launches no collective
             return
         from . import train
-        params += [prm for prm in (proj.weight, proj.bias) if prm.requires_grad]
-        _AbsentModalityFn.apply(hidden_states, self.grad_reducer, tuple(train.reduce_schedule(ops.get_encoder(enc_id))),
-                                *params)
+        named += [("projector.weight", proj.weight), ("projector.bias", proj.bias)]
+        _AbsentModalityFn.apply(hidden_states, self.grad_reducer, train.reduce_schedule(ops.get_encoder(enc_id)),
+                                tuple(n for n, _ in named), *[prm for _, prm in named])
 
     def _inject(self, name: str, plan: planner.ModalityPlan, hidden_states: torch.Tensor, omic_ids_list, dev) -> None:
         enc_id = self._ids.get(name)

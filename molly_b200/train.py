@@ -40,17 +40,33 @@ def _emb_meta(enc: PackedEncoder, ids: torch.Tensor):
             mask.float().reshape(-1).contiguous())
 
 
-def reduce_schedule(enc: PackedEncoder) -> List[int]:
-    """Element counts of the gradient groups ``_InjectTrainFn.backward`` hands to a ``LayerwiseGradReducer``, in order:
-    projector, encoder layers L-1 .. 0, then final LayerNorm + embeddings.  A rank whose micro-batch lacks the modality
-    issues all-reduces of exactly these sizes (``omics_path._AbsentModalityFn``)."""
+def reduce_schedule(enc: PackedEncoder) -> List[List[Tuple[str, Tuple[int, ...]]]]:
+    """The gradient groups ``_InjectTrainFn.backward`` hands to a ``LayerwiseGradReducer``, in order, as (HF name, shape)
+    lists: the projector, the encoder layers L-1 .. 0, then final LayerNorm + embeddings.  ``encoder_backward`` reduces
+    exactly these lists; a rank whose micro-batch lacks the modality all-reduces zeros laid out the same way
+    (``omics_path._AbsentModalityFn``) and so receives the other ranks' averaged gradients."""
     cfg = enc.cfg
-    h = cfg.hidden_size
-    out = [enc.proj_w.numel() + enc.proj_b.numel()]
-    for lt in reversed(enc.layer_tensors):
-        out.append(sum(t.numel() for t in lt.values() if t is not None))
-    out.append(2 * h + enc.word_emb.numel() + (enc.pos_emb.numel() if enc.pos_emb is not None else 0))
-    return out
+    h, F = cfg.hidden_size, cfg.intermediate_size
+    glu = cfg.ffn_type == "glu"
+    groups = [[("projector.weight", tuple(enc.proj_w.shape)), ("projector.bias", tuple(enc.proj_b.shape))]]
+    for i in range(cfg.num_hidden_layers - 1, -1, -1):
+        p = f"esm.encoder.layer.{i}."
+        ffn_bias = enc.layer_tensors[i]["b_ffn1"] is not None
+        g = [(p + "LayerNorm.weight", (h,)), (p + "LayerNorm.bias", (h,)), (p + "output.dense.weight", (h, F)),
+             (p + "intermediate.dense.weight", ((2 * F if glu else F), h))]
+        if ffn_bias:
+            g += [(p + "intermediate.dense.bias", ((2 * F if glu else F),)), (p + "output.dense.bias", (h,))]
+        g += [(p + "attention.LayerNorm.weight", (h,)), (p + "attention.LayerNorm.bias", (h,)),
+              (p + "attention.output.dense.weight", (h, h)), (p + "attention.output.dense.bias", (h,))]
+        for nm in ("query", "key", "value"):
+            g += [(p + f"attention.self.{nm}.weight", (h, h)), (p + f"attention.self.{nm}.bias", (h,))]
+        groups.append(g)
+    last = [("esm.encoder.emb_layer_norm_after.weight", (h,)), ("esm.encoder.emb_layer_norm_after.bias", (h,)),
+            ("esm.embeddings.word_embeddings.weight", tuple(enc.word_emb.shape))]
+    if enc.pos_emb is not None:
+        last.append(("esm.embeddings.position_embeddings.weight", tuple(enc.pos_emb.shape)))
+    groups.append(last)
+    return groups
 
 
 class EncoderTape:
@@ -142,6 +158,7 @@ def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor,
     rope = cfg.position_embedding_type == "rotary"
     grads: Dict[str, torch.Tensor] = {}
     z = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
+    schedule = reduce_schedule(enc) if reducer is not None else None     # [0] projector, [1 + (L-1-i)] layer i, [-1] the rest
 
     # emb_layer_norm_after
     d_x = torch.empty_like(tape.x_final)
@@ -198,7 +215,9 @@ def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor,
             grads[p + f"attention.self.{nm}.weight"] = dWqkv[j * h:(j + 1) * h]
             grads[p + f"attention.self.{nm}.bias"] = dbqkv[j * h:(j + 1) * h]
         if reducer is not None:
-            reducer.reduce_(grads, [n for n in grads if n.startswith(p)])
+            names = [n for n, _ in schedule[cfg.num_hidden_layers - i]]
+            assert sorted(names) == sorted(n for n in grads if n.startswith(p)), "reduce_schedule is out of date"
+            reducer.reduce_(grads, names)
 
     # ---- embeddings
     word_index, word_scale, pos_index, pos_scale = _emb_meta(enc, tape.ids)
@@ -210,5 +229,7 @@ def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor,
         ops.scatter_add_rows_(d_pos, d_x, pos_index, pos_scale)
         grads["esm.embeddings.position_embeddings.weight"] = d_pos
     if reducer is not None:
-        reducer.reduce_(grads, [n for n in grads if not n.startswith("esm.encoder.layer.")])
+        names = [n for n, _ in schedule[-1]]
+        assert sorted(names) == sorted(n for n in grads if not n.startswith("esm.encoder.layer.")), "reduce_schedule is out of date"
+        reducer.reduce_(grads, names)
     return grads

@@ -53,4 +53,49 @@ mb = path.grad_reducer.bytes_reduced / 2 ** 20
 print(f"rank {rank}/{world}: {len(params)} parameter gradients, averaged vs single-rank: relative error of the whole "
       f"gradient {num / den:.2e}, {mb:.0f} MiB all-reduced in layer-wise buckets", flush=True)
 assert num / den < 2e-3, num / den
+
+# ---- asymmetric micro-batches: rank 1's batch has NO protein sequence.  Its backward must issue zero
+#      all-reduces of the same sizes at the same point (omics_path._AbsentModalityFn) -- without them NCCL hangs or pairs
+#      the wrong buffers.  Expected averaged gradients: dna_rna = the single-rank ones (every rank has the same DNA batch),
+#      protein = single-rank x (ranks that had the protein) / world.
+infos_asym = [[i if (i["type"] != "protein" or rank != 1) else {"type": "pad", "start": -1} for i in row] for row in infos]
+def asym_step():
+    for p in params:
+        p.grad = None
+    out = path.process_omic_sequences(base.clone(), omic_ids.to(dev), infos_asym, dev)
+    out.backward(d_out)
+    torch.cuda.synchronize()
+    return [None if p.grad is None else p.grad.float().clone() for p in params]
+asym = asym_step()
+n_pr_params = len(list(projs["protein"].parameters())) + len(path._enc_modules["protein"].parameters())
+names = ([("dna_rna", p) for p in projs["dna_rna"].parameters()] + [("protein", p) for p in projs["protein"].parameters()]
+         + [("dna_rna", p) for p in path._enc_modules["dna_rna"].parameters()]
+         + [("protein", p) for p in path._enc_modules["protein"].parameters()])
+scale = {"dna_rna": 1.0, "protein": (world - 1) / world if world > 1 else 1.0}
+num = den = 0.0
+for (mod, _), a, b in zip(names, asym, ref):
+    a = torch.zeros_like(b) if a is None else a
+    num += float((a - b * scale[mod]).pow(2).sum()); den += float((b * scale[mod]).pow(2).sum())
+print(f"rank {rank}/{world}: asymmetric modalities (rank 1 without protein): relative error of the averaged gradient "
+      f"{(num / den) ** 0.5:.2e}", flush=True)
+assert (num / den) ** 0.5 < 2e-3
+
+# ---- FlatGradBucket over NCCL (its stream path was only covered by the gloo CPU test): multi-tensor bucket with
+#      pack / unpack on the side stream, and the one-tensor bucket reduced in place
+from molly_b200.dist import FlatGradBucket
+lin = torch.nn.Linear(256, 128, device=dev, dtype=torch.bfloat16)
+big = torch.nn.Parameter(torch.zeros(8 << 20, device=dev, dtype=torch.bfloat16))
+for trial in range(3):
+    lin.weight.grad = torch.full_like(lin.weight, float(rank + 1 + trial))
+    lin.bias.grad = torch.full_like(lin.bias, float(10 * (rank + 1)))
+    big.grad = torch.full_like(big, float(2 * rank + trial))
+    b1, b2 = FlatGradBucket(list(lin.parameters())), FlatGradBucket([big])
+    b2.launch(); b1.launch(); b1.finish(); b2.finish()
+    torch.cuda.synchronize()
+    want_w = sum(r + 1 + trial for r in range(world)) / world
+    want_b = sum(10 * (r + 1) for r in range(world)) / world
+    want_big = sum(2 * r + trial for r in range(world)) / world
+    assert float((lin.weight.grad.float() - want_w).abs().max()) < 1e-2 and float((lin.bias.grad.float() - want_b).abs().max()) < 1e-1
+    assert float((big.grad.float() - want_big).abs().max()) < 1e-2, (float(big.grad.float().mean()), want_big)
+print(f"rank {rank}/{world}: FlatGradBucket (packed + in-place) over NCCL ok", flush=True)
 dist.destroy_process_group()
