@@ -1,19 +1,17 @@
 // Fused bidirectional multi-head attention, second generation (head_dim <= 64): ONE CTA per SM that runs TWO independent
-// 128-query-row pipelines ("tiles"), each the stream-of-work-items pipeline of attention.cu, restructured around what the
-// round-2 timelines showed (tools/attn2_timeline.py, profiles/r02_attention.md): a softmax warp that owns whole 128-key rows
-// runs its exp2 stream at 12.5 cycles per MUFU.EX2 alone (8 is the pipe's rate) and spends as long again outside it (wait
-// for S, tcgen05.ld, row max, hand-offs, item epilogue), and with two such warps per scheduler running in lock-step the MUFU
-// idles ~45 % of the time.  A single warp's instruction stream, not a pipe, was the bound -- so this kernel puts FOUR softmax
-// warps on every scheduler:
-//   * 20 warps: softmax warps 0-7 (tile 0) and 8-15 (tile 1); TWO threads per query row -- warps w and w+4 of a tile share
-//     TMEM lane quarter w % 4, the first takes keys 0..63 of every KV block, the second keys 64..127.  The row max goes
-//     through shared memory (one float + a 64-thread named barrier per block); the row sums stay per thread and are added
-//     in the item epilogue; each thread rescales / writes out half of the O columns.
-//     Warps 16 / 17 lane 0 = the tiles' control threads (TMA producer + tcgen05.mma issuer); warp 18 allocates TMEM.
-//     `setmaxnreg`: control group 96 -> 64, softmax warps 96 -> 104 registers.
+// 128-query-row pipelines ("tiles") over streams of work items (sequence, head, 128-query block), FlashAttention-4 style:
+//   * 16 warps.  Softmax warps 0-3 (tile 0) and 4-7 (tile 1): thread r owns query row r of its tile and does nothing but
+//     S -> row max -> exp2 -> P.  Epilogue warps 8-11: O / l -> bf16 -> HBM of BOTH tiles (and the zero rows of all-pad
+//     sequences), so the softmax warps never wait for the item's last O += P V, never read O, never store (the round-2
+//     timeline of the first version of this kernel: ~4 000 cycles per work item went there).  Warps 12 / 13 lane 0: the
+//     tiles' control threads (TMA producer + tcgen05.mma issuer); warp 14 allocates the 512 TMEM columns.
+//     `setmaxnreg`: softmax 128 -> 200 registers, epilogue and control groups 128 -> 56.
+//   * the exp2 phases of the two softmax warps that share a scheduler are SEQUENCED (a token per warp pair, passed through
+//     an mbarrier): the timelines showed both tiles entering their exp2 phase together -- each warp then gets half of the
+//     MUFU -- and leaving it together, after which the MUFU idles while both do their serial work (wait for S, tcgen05.ld,
+//     row max, hand-offs).  Taking turns, one warp's exp2 phase runs at the full MUFU rate under the other's serial work.
 //   * P never touches shared memory: packed bf16 pairs go straight into TMEM (tcgen05.st) and O += P V takes its A operand
-//     from tensor memory -- no STS.128 + fence.proxy.async on the softmax chain, no P traffic on the shared-memory pipe.
-//   * row max with the 3-input FMNMX3; P stored in 32-key chunks as the exponentials retire.
+//     from tensor memory; row max with the 3-input FMNMX3; P stored in 32-key chunks as the exponentials retire.
 // TMEM columns of tile t (base 256 t): S [0,128) fp32 | P [128,192) bf16x2 | O [192, 192 + D) fp32.
 // Semantics are those of attention.cu (HF:257-282 eager attention with the key-padding mask of HF:679-709).
 #include <math_constants.h>
@@ -25,15 +23,27 @@
 
 namespace molly {
 
+// -DA2_TIMELINE: clock64 stamps of the softmax thread r == 0 of both tiles of the first 8 CTAs, 8 slots per stream block
+// (tools/attn2_timeline.py): 0 block start, 1 S seen, 2 S in registers, 3 row max done, 4 exp2 turn acquired,
+// 5 exp2 done / turn passed on, 6 P stored + p_full arrived.
+#ifdef A2_TIMELINE
+__device__ long long* d_a2_tl = nullptr;
+void attention2_set_debug(long long* buf) { cudaMemcpyToSymbol(d_a2_tl, &buf, sizeof(buf)); }
+#define TL2(slot) do { if (tl_on) tl_buf[tl_base + (slot)] = clock64(); } while (0)
+#else
 void attention2_set_debug(long long*) {}
+#define TL2(slot) do { } while (0)
+#endif
 
 namespace {
 
 constexpr int A2_BLOCK = 128;                  // query rows per tile == keys per KV block
-constexpr int A2_THREADS = 640;                // 16 softmax warps + the control warp-group
-constexpr int A2_REGS_SOFTMAX = 104;
-constexpr int A2_REGS_CONTROL = 64;
-constexpr int A2_HALF = A2_BLOCK / 2;          // keys per thread per KV block
+constexpr int A2_THREADS = 512;                // 8 softmax warps + the epilogue warp-group + the control warp-group
+constexpr int A2_REGS_SOFTMAX = 200;
+constexpr int A2_REGS_OTHER = 56;
+#ifndef A2_SEQUENCE
+#define A2_SEQUENCE 1                          // 0: the tiles' exp2 phases are not sequenced (A/B build)
+#endif
 constexpr float A2_LOG2E = 1.4426950408889634f;
 
 template <int D, int NST>
@@ -47,10 +57,12 @@ struct A2Cfg {
     static constexpr int OFF_V = OFF_K + NST * TILE_BYTES;
     static constexpr int SLICE_BYTES = (1 + 2 * NST) * TILE_BYTES;
     static constexpr int OFF_BAR = 2 * SLICE_BYTES;
-    static constexpr int NBAR = 5 + 2 * NST;                                  // per tile
-    static constexpr int OFF_X = OFF_BAR + 2 * NBAR * 8 + 16;                 // row-max / row-sum exchange of the half-row threads
-    static constexpr int X_FLOATS = 2 * 2 * A2_BLOCK + 2 * A2_BLOCK;          // per tile: max [g parity][half][row], sum [half][row]
-    static constexpr int SMEM_BYTES = OFF_X + 2 * X_FLOATS * 4;
+    static constexpr int NBAR = 7 + 2 * NST;                                  // per tile
+    static constexpr int OFF_SEQ = OFF_BAR + 2 * NBAR * 8;                    // [2 tiles][4 lane quarters] exp2-turn barriers
+    static constexpr int OFF_DONE = OFF_SEQ + 8 * 8;                          // [2][4] int: that softmax warp has left its stream
+    static constexpr int OFF_SLOT = OFF_DONE + 8 * 4;                         // TMEM base
+    static constexpr int OFF_STATS = (OFF_SLOT + 16 + 15) / 16 * 16;          // [2 tiles][2 item parities][128 rows] (l, m)
+    static constexpr int SMEM_BYTES = OFF_STATS + 2 * 2 * A2_BLOCK * 8;
     static constexpr int TM_S = 0, TM_P = 128, TM_O = 192, TM_TILE = 256;
 };
 
@@ -59,9 +71,11 @@ struct A2Bars {                                // one tile's barriers
     uint64_t* kv_full;                         // [NST]
     uint64_t* kv_empty;                        // [NST]  PV(g) complete: stage g % NST, P and O are free
     uint64_t* s_full;
-    uint64_t* p_full;                          // 256 arrivals
-    uint64_t* o_full;
-    uint64_t* s_free;                          // 256 arrivals: S(g) is in registers
+    uint64_t* p_full;                          // 128 arrivals
+    uint64_t* o_full;                          // the item's last O += P V completed
+    uint64_t* s_free;                          // 128 arrivals: S(g) is in registers
+    uint64_t* stats_full;                      // 128 arrivals: the item's row sums / maxima are in shared memory
+    uint64_t* o_free;                          // 128 arrivals: the epilogue warps have read the item's O
 };
 template <int NST>
 __device__ __forceinline__ A2Bars a2_bars(uint64_t* base) {
@@ -73,6 +87,8 @@ __device__ __forceinline__ A2Bars a2_bars(uint64_t* base) {
     b.p_full = base + 2 + 2 * NST;
     b.o_full = base + 3 + 2 * NST;
     b.s_free = base + 4 + 2 * NST;
+    b.stats_full = base + 5 + 2 * NST;
+    b.o_free = base + 6 + 2 * NST;
     return b;
 }
 
@@ -190,6 +206,7 @@ __device__ __forceinline__ void a2_control(uint8_t* slice, const A2Bars& bar, ui
             else if (nxt < total) load_q(a2_decode(nxt, sh, kv_info));
             // (2) O += P(g) V(g) : P from tensor memory (lane = query row, 8 packed columns per 16 keys), V MN-major from smem
             mbar_wait(bar.p_full, g & 1);
+            if (j == 0 && it > 0) mbar_wait(bar.o_free, (it - 1) & 1);       // the epilogue warps have read the previous item's O
             tc_fence_after();
 #pragma unroll
             for (int s = 0; s < A2_BLOCK / 16; ++s) {
@@ -200,7 +217,7 @@ __device__ __forceinline__ void a2_control(uint8_t* slice, const A2Bars& bar, ui
             umma_commit(&bar.kv_empty[st]);                  // PV(g) done: stage st, P and O are free
             if (last) {
                 umma_commit(bar.o_full);
-                if (nxt < total) {                           // first S of the next item, under this item's epilogue
+                if (nxt < total) {                           // first S of the next item
                     mbar_wait(bar.q, (it + 1) & 1);
                     issue_s(g + 1);
                 }
@@ -217,60 +234,89 @@ __device__ __forceinline__ void a2_control(uint8_t* slice, const A2Bars& bar, ui
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// softmax warps of one tile: two threads per query row r; `half` selects this thread's 64 keys of every KV block
+// softmax warps of one tile: thread r owns query row r
 // ------------------------------------------------------------------------------------------------------------------
+// exp2-turn token of the warp pair (tile 0 warp q, tile 1 warp q) that shares scheduler q: `mine` completes a phase when the
+// other tile's warp has finished an exp2 phase (32 arrivals); tile 0 starts with the token (tile 1's warps pre-arrive).
+struct A2Turn {
+    uint64_t* mine;
+    uint64_t* theirs;
+    volatile int* peer_done;
+    volatile int* my_done;
+    int n;                                      // exp2 phases this warp has waited for
+    bool solo;                                  // the other tile's warp has left its stream: no more turns
+};
+__device__ __forceinline__ void a2_turn_begin(A2Turn& t) {
+#if A2_SEQUENCE
+    if (t.solo) return;
+    const uint32_t parity = t.n & 1;
+    ++t.n;
+    if (mbar_try_wait(t.mine, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(t.mine, parity)) {
+        if (*t.peer_done) { t.solo = true; return; }
+        if ((++spins & 31u) == 0 && clock64() - t0 > MOLLY_MBAR_TIMEOUT_CYCLES) {
+            printf("molly attention2: exp2-turn timeout block=%d thread=%d\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+#endif
+}
+__device__ __forceinline__ void a2_turn_end(A2Turn& t) {
+#if A2_SEQUENCE
+    if (!t.solo) mbar_arrive(t.theirs);
+#endif
+}
+
 template <int D, int NST, int POLY>
-__device__ __forceinline__ void a2_softmax(const A2Bars& bar, uint32_t tmem_tile, float* xch, int r, int half, int pair_bar,
-                                           int slot, int stride, const A2Shape& sh, const int32_t* __restrict__ kv_info,
-                                           const uint8_t* __restrict__ key_mask, __nv_bfloat16* __restrict__ out,
-                                           float* __restrict__ lse2) {
+__device__ __forceinline__ void a2_softmax(const A2Bars& bar, uint32_t tmem_tile, float2* stats, A2Turn turn, int r, int slot,
+                                           int stride, const A2Shape& sh, const int32_t* __restrict__ kv_info,
+                                           const uint8_t* __restrict__ key_mask) {
     using Cfg = A2Cfg<D, NST>;
-    constexpr int OC = D / 2;                                                 // O columns this thread rescales / writes out
     const uint32_t lane_addr = static_cast<uint32_t>(r & ~31) << 16;          // TMEM lane quarter of this warp
-    const uint32_t tmem_s = tmem_tile + Cfg::TM_S + lane_addr + half * A2_HALF;
-    const uint32_t tmem_p = tmem_tile + Cfg::TM_P + lane_addr + half * (A2_HALF / 2);
-    const uint32_t tmem_o = tmem_tile + Cfg::TM_O + lane_addr + half * OC;
-    float* const xmax = xch;                                                  // [2 (g parity)][2 (half)][128]
-    float* const xsum = xch + 2 * 2 * A2_BLOCK;                               // [2 (half)][128]
-    const int k_tokens = sh.k_tokens, h = sh.h;
+    const uint32_t tmem_s = tmem_tile + Cfg::TM_S + lane_addr, tmem_p = tmem_tile + Cfg::TM_P + lane_addr;
+    const uint32_t tmem_o = tmem_tile + Cfg::TM_O + lane_addr;
+    const int k_tokens = sh.k_tokens;
+#ifdef A2_TIMELINE
+    long long* const tl_buf = d_a2_tl;                                        // read once: a stamp must not cost a global load
+#endif
     int it = 0, g = 0;
     for (int item = slot; item < sh.total; item += stride) {
         const A2Item w = a2_decode(item, sh, kv_info);
+        if (w.nkv == 0) continue;                                             // all-pad sequence: the epilogue warps write its zeros
         const int kvl = w.kvl;
         const bool interior = w.n_nonpad != w.kvl;                            // pad ids before the last real token
         const long long row_base = static_cast<long long>(w.n) * k_tokens;
-        const bool row_ok = w.q0 + r < k_tokens;
-        __nv_bfloat16* orow = out + (row_base + w.q0 + r) * h + w.head * D + half * OC;
-        if (w.nkv == 0) {                                                     // all-pad sequence: the reference never encodes one
-            if (row_ok) {
-                for (int i = 0; i < OC / 8; ++i) reinterpret_cast<uint4*>(orow)[i] = make_uint4(0, 0, 0, 0);
-                if (lse2 != nullptr && half == 0)
-                    lse2[(static_cast<size_t>(w.n) * sh.heads + w.head) * k_tokens + w.q0 + r] = -CUDART_INF_F;
-            }
-            continue;
-        }
-        float m_run = -CUDART_INF_F;                                          // running reference max, log2 domain (both halves agree)
-        float l_run = 0.f;                                                    // row sum over THIS thread's keys
+        float m_run = -CUDART_INF_F;                                          // running reference max, log2 domain
+        float l_run = 0.f;
         for (int j = 0; j < w.nkv; ++j, ++g) {
-            const int j0 = j * A2_BLOCK + half * A2_HALF;                     // first key of this thread in the block
+            const int j0 = j * A2_BLOCK;
+#ifdef A2_TIMELINE
+            const bool tl_on = tl_buf != nullptr && r == 0 && blockIdx.x < 8 && g < 64;
+            const int tl_base = ((blockIdx.x * 2 + ((tmem_tile >> 8) & 1)) * 64 + g) * 8;
+#endif
+            TL2(0);
             mbar_wait(bar.s_full, g & 1);
+            TL2(1);
             tc_fence_after();
-            float s[A2_HALF];
+            float s[A2_BLOCK];
             {
-                uint32_t raw[A2_HALF];
-                tmem_ld32(tmem_s, raw);
-                tmem_ld32(tmem_s + 32, raw + 32);
+                uint32_t raw[A2_BLOCK];
+#pragma unroll
+                for (int c = 0; c < A2_BLOCK / 32; ++c) tmem_ld32(tmem_s + c * 32, raw + c * 32);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < A2_HALF; ++i) s[i] = __uint_as_float(raw[i]);
+                for (int i = 0; i < A2_BLOCK; ++i) s[i] = __uint_as_float(raw[i]);
             }
             tc_fence_before();
             mbar_arrive(bar.s_free);                                          // the control thread may issue S(g+1)
+            TL2(2);
             if (interior) {
                 const uint4* mk = reinterpret_cast<const uint4*>(key_mask + row_base + j0);
-                const bool vec_ok = ((row_base + j0) & 15) == 0 && j0 + A2_HALF <= k_tokens;
+                const bool vec_ok = ((row_base + j0) & 15) == 0 && j0 + A2_BLOCK <= k_tokens;
 #pragma unroll
-                for (int q = 0; q < A2_HALF / 16; ++q) {
+                for (int q = 0; q < A2_BLOCK / 16; ++q) {
                     uint32_t wd[4];
                     if (vec_ok) {
                         const uint4 u = __ldg(mk + q);
@@ -293,30 +339,24 @@ __device__ __forceinline__ void a2_softmax(const A2Bars& bar, uint32_t tmem_tile
                         if (!ok) s[q * 16 + i] = -CUDART_INF_F;
                     }
                 }
-            } else if (j0 + A2_HALF > kvl) {
+            } else if (j0 + A2_BLOCK > kvl) {
                 const int lim = kvl - j0;
 #pragma unroll
-                for (int i = 0; i < A2_HALF; ++i)
+                for (int i = 0; i < A2_BLOCK; ++i)
                     if (i >= lim) s[i] = -CUDART_INF_F;
             }
-            // row max of this thread's 64 keys: four independent FMNMX3 chains, then the other half's through shared memory
+            // row max: four independent FMNMX3 chains
             float mx4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-            for (int i = 4; i + 8 <= A2_HALF; i += 8) {
+            for (int i = 4; i + 8 <= A2_BLOCK; i += 8) {
                 mx4[0] = a2_max3(mx4[0], s[i], s[i + 1]);
                 mx4[1] = a2_max3(mx4[1], s[i + 2], s[i + 3]);
                 mx4[2] = a2_max3(mx4[2], s[i + 4], s[i + 5]);
                 mx4[3] = a2_max3(mx4[3], s[i + 6], s[i + 7]);
             }
-            mx4[0] = a2_max3(mx4[0], s[A2_HALF - 4], s[A2_HALF - 3]);
-            mx4[1] = a2_max3(mx4[1], s[A2_HALF - 2], s[A2_HALF - 1]);
-            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-            {
-                float* slot_x = xmax + (g & 1) * (2 * A2_BLOCK);
-                slot_x[half * A2_BLOCK + r] = mx;
-                named_bar_sync(pair_bar, 64);                                 // the two warps that share this lane quarter
-                mx = fmaxf(mx, slot_x[(half ^ 1) * A2_BLOCK + r]);
-            }
+            mx4[0] = a2_max3(mx4[0], s[A2_BLOCK - 4], s[A2_BLOCK - 3]);
+            mx4[1] = a2_max3(mx4[1], s[A2_BLOCK - 2], s[A2_BLOCK - 1]);
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             // Lazy rescaling (see attention.cu): the reference max moves only when the row max grew by more than 2^8, so
             // P <= 256 (exact in the fp32 sum, harmless in bf16) and O / l almost never need a correction.
             const float m_cand = fmaxf(m_run, mx * A2_LOG2E);
@@ -328,10 +368,13 @@ __device__ __forceinline__ void a2_softmax(const A2Bars& bar, uint32_t tmem_tile
             const float m_use = (m_run == -CUDART_INF_F) ? 0.f : m_run;
             const uint64_t sc2 = pack_f32x2(A2_LOG2E, A2_LOG2E), nm2 = pack_f32x2(-m_use, -m_use);
             uint64_t sum2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
+            TL2(3);
+            a2_turn_begin(turn);                                              // this warp's turn on the scheduler's MUFU
+            TL2(4);
             // P = exp2(s log2e - m) in 32-key chunks: packed bf16 pairs go to TMEM as each chunk retires
             // (column c of lane r holds keys 2c, 2c+1 of query row r: the K-major A operand of O += P V)
 #pragma unroll
-            for (int c = 0; c < A2_HALF / 32; ++c) {
+            for (int c = 0; c < A2_BLOCK / 32; ++c) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -346,9 +389,13 @@ __device__ __forceinline__ void a2_softmax(const A2Bars& bar, uint32_t tmem_tile
                     sum2[i & 1] = add_f32x2(sum2[i & 1], pack_f32x2(x0, x1));
                     pk[i] = pack_bf16x2(x0, x1);
                 }
-                if (c == 0 && j > 0) {                                        // PV(g-1) consumed P and finished O
-                    mbar_wait(&bar.kv_empty[(g - 1) % NST], ((g - 1) / NST) & 1);     // (j == 0: the previous item's o_full)
+                if (c == 0 && g > 0) {                                        // PV(g-1) consumed P and finished O
+                    mbar_wait(&bar.kv_empty[(g - 1) % NST], ((g - 1) / NST) & 1);
                     tc_fence_after();
+                }
+                if (c == A2_BLOCK / 32 - 1) {
+                    a2_turn_end(turn);                                        // the other tile's warp may start its exp2 phase
+                    TL2(5);
                 }
                 tmem_st16(tmem_p + c * 16, pk);
             }
@@ -356,47 +403,126 @@ __device__ __forceinline__ void a2_softmax(const A2Bars& bar, uint32_t tmem_tile
             unpack_f32x2(sum2[0], sa, sb);
             unpack_f32x2(sum2[1], sc, sd);
             l_run = l_run * alpha + ((sa + sb) + (sc + sd));
-            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {            // rare: rescale this thread's half of the O columns
+            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {            // rare: rescale the running O accumulator
 #pragma unroll
-                for (int c = 0; c < OC / 8; ++c) {
-                    uint32_t o[8];
-                    tmem_ld8(tmem_o + c * 8, o);
+                for (int c = 0; c < D / 16; ++c) {
+                    uint32_t o[16];
+                    tmem_ld16(tmem_o + c * 16, o);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    tmem_st8(tmem_o + c * 8, o);
+                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st16(tmem_o + c * 16, o);
                 }
             }
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(bar.p_full);
+            TL2(6);
         }
-        // item epilogue: the row sum is the two halves' sums; O / l -> bf16 -> HBM, each thread half of the columns
-        xsum[half * A2_BLOCK + r] = l_run;
-        named_bar_sync(pair_bar, 64);
-        const float l_tot = l_run + xsum[(half ^ 1) * A2_BLOCK + r];
-        mbar_wait(bar.o_full, it & 1);
+        // the item's row statistics go to the epilogue warps (buffer it & 1: the epilogue of item it-2 finished before the
+        // control thread issued the first O += P V of item it-1, see o_free)
+        stats[(it & 1) * A2_BLOCK + r] = make_float2(l_run, m_run);
+        mbar_arrive(bar.stats_full);                                          // (release: the store above is visible to the waiter)
         ++it;
-        tc_fence_after();
-        const float inv_l = 1.0f / l_tot;
-        if (lse2 != nullptr && row_ok && half == 0)                           // row log-sum-exp, log2 domain (backward)
-            lse2[(static_cast<size_t>(w.n) * sh.heads + w.head) * k_tokens + w.q0 + r] = m_run + log2f(l_tot);
+    }
+#if A2_SEQUENCE
+    // leave the turn-taking: the other tile's warp must not wait for a token that will never come
+    __syncwarp();
+    if ((r & 31) == 0) *turn.my_done = 1;
+    __threadfence_block();
+    a2_turn_end(turn);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// epilogue warps: O / l -> bf16 -> HBM for the work items of BOTH tiles, in the order the tiles finish them
+// ------------------------------------------------------------------------------------------------------------------
+template <int D, int NST>
+__device__ __forceinline__ void a2_epilogue(uint64_t* bars, uint32_t tmem_base, const float2* stats_all, int r,
+                                            const A2Shape& sh, const int32_t* __restrict__ kv_info,
+                                            __nv_bfloat16* __restrict__ out, float* __restrict__ lse2) {
+    using Cfg = A2Cfg<D, NST>;
+    const uint32_t lane_addr = static_cast<uint32_t>(r & ~31) << 16;
+    const int k_tokens = sh.k_tokens, h = sh.h;
+    const int stride = 2 * gridDim.x;
+    // The two tiles finish their items at their own pace (different kv_len), and with the exp2 turn-taking a tile that is
+    // held up holds up the other one: the items are therefore served in the order they become READY (non-blocking probes),
+    // never in a fixed tile order -- waiting for tile 0 while tile 1's finished item keeps its control thread from issuing
+    // the next O += P V would deadlock the pair.
+    int item[2] = {2 * static_cast<int>(blockIdx.x), 2 * static_cast<int>(blockIdx.x) + 1};
+    int it[2] = {0, 0};
+    A2Item w[2];
+    auto seek = [&](int t) {                                                  // next item of tile t that has keys; zero rows for the rest
+        while (item[t] < sh.total) {
+            w[t] = a2_decode(item[t], sh, kv_info);
+            if (w[t].nkv > 0) return;
+            if (w[t].q0 + r < k_tokens) {                                     // all-pad sequence: the reference never encodes one
+                __nv_bfloat16* orow = out + (static_cast<long long>(w[t].n) * k_tokens + w[t].q0 + r) * h + w[t].head * D;
+                for (int i = 0; i < D / 8; ++i) reinterpret_cast<uint4*>(orow)[i] = make_uint4(0, 0, 0, 0);
+                if (lse2 != nullptr)
+                    lse2[(static_cast<size_t>(w[t].n) * sh.heads + w[t].head) * k_tokens + w[t].q0 + r] = -CUDART_INF_F;
+            }
+            item[t] += stride;
+        }
+    };
+    seek(0);
+    seek(1);
+    long long t_idle = clock64();
+    while (item[0] < sh.total || item[1] < sh.total) {
+        bool served = false;
 #pragma unroll
-        for (int c = 0; c < OC / 8; ++c) {
-            uint32_t o[8];
-            tmem_ld8(tmem_o + c * 8, o);
-            tmem_ld_wait();
-            if (row_ok) {
-                uint4 u;
-                u.x = pack_bf16x2(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l);
-                u.y = pack_bf16x2(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l);
-                u.z = pack_bf16x2(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l);
-                u.w = pack_bf16x2(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l);
-                reinterpret_cast<uint4*>(orow)[c] = u;
+        for (int t = 0; t < 2; ++t) {
+            if (item[t] >= sh.total) continue;
+            const A2Bars bar = a2_bars<NST>(bars + t * Cfg::NBAR);
+            // warp-uniform readiness (every lane must take the same branch: tcgen05.ld is warp-wide)
+            const bool ready = mbar_test_wait(bar.stats_full, it[t] & 1) && mbar_test_wait(bar.o_full, it[t] & 1);
+            if (!__all_sync(0xffffffffu, ready)) continue;
+            served = true;
+            const bool row_ok = w[t].q0 + r < k_tokens;
+            __nv_bfloat16* orow = out + (static_cast<long long>(w[t].n) * k_tokens + w[t].q0 + r) * h + w[t].head * D;
+            float* lrow = lse2 == nullptr ? nullptr
+                                          : lse2 + (static_cast<size_t>(w[t].n) * sh.heads + w[t].head) * k_tokens + w[t].q0 + r;
+            const uint32_t tmem_o = tmem_base + t * Cfg::TM_TILE + Cfg::TM_O + lane_addr;
+            const float2 st = stats_all[(t * 2 + (it[t] & 1)) * A2_BLOCK + r];
+            ++it[t];
+            tc_fence_after();
+            const float inv_l = 1.0f / st.x;
+            if (row_ok && lrow != nullptr) *lrow = st.y + log2f(st.x);        // row log-sum-exp, log2 domain (backward)
+#pragma unroll
+            for (int c = 0; c < D / 16; ++c) {                                // 16 columns at a time: this group has 56 registers
+                uint32_t o[16];
+                tmem_ld16(tmem_o + c * 16, o);
+                tmem_ld_wait();
+                uint4 u0, u1;
+                u0.x = pack_bf16x2(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l);
+                u0.y = pack_bf16x2(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l);
+                u0.z = pack_bf16x2(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l);
+                u0.w = pack_bf16x2(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l);
+                u1.x = pack_bf16x2(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l);
+                u1.y = pack_bf16x2(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l);
+                u1.z = pack_bf16x2(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l);
+                u1.w = pack_bf16x2(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l);
+                if (c == D / 16 - 1) {                                        // O is in registers: the next item's first PV may go
+                    tc_fence_before();
+                    mbar_arrive(bar.o_free);
+                }
+                if (row_ok) {
+                    reinterpret_cast<uint4*>(orow + c * 16)[0] = u0;
+                    reinterpret_cast<uint4*>(orow + c * 16)[1] = u1;
+                }
+            }
+            item[t] += stride;
+            seek(t);
+        }
+        if (served) {
+            t_idle = clock64();
+        } else {
+            __nanosleep(200);
+            if (clock64() - t_idle > MOLLY_MBAR_TIMEOUT_CYCLES) {
+                printf("molly attention2: epilogue timeout block=%d thread=%d\n", blockIdx.x, threadIdx.x);
+                __trap();
             }
         }
-        tc_fence_before();                                                    // O is read: the next item's PV may overwrite it
-        named_bar_sync(pair_bar, 64);                                         // xsum is read: the next item may overwrite it
     }
 }
 
@@ -408,15 +534,17 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int he
     using Cfg = A2Cfg<D, NST>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::NBAR);
-    float* xch = reinterpret_cast<float*>(smem + Cfg::OFF_X);
+    uint64_t* seq = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_SEQ);
+    int* done = reinterpret_cast<int*>(smem + Cfg::OFF_DONE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_SLOT);
+    float2* stats = reinterpret_cast<float2*>(smem + Cfg::OFF_STATS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     A2Shape sh;
     sh.n_seq = n_seq; sh.heads = heads; sh.k_tokens = k_tokens; sh.h = h;
     sh.nqb = (k_tokens + A2_BLOCK - 1) / A2_BLOCK;
     sh.total = n_seq * heads * sh.nqb;
 
-    if (warp == 18) {
+    if (warp == 14) {
         if (lane == 0) {
             if ((smem_u32(smem) & 1023u) != 0) { printf("molly attention2: smem base not 1024-B aligned\n"); __trap(); }
             tma_prefetch_desc(&tma_qkv);
@@ -425,10 +553,13 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int he
                 mbar_init(b.q, 1);
                 for (int st = 0; st < NST; ++st) { mbar_init(&b.kv_full[st], 1); mbar_init(&b.kv_empty[st], 1); }
                 mbar_init(b.s_full, 1);
-                mbar_init(b.p_full, 256);
+                mbar_init(b.p_full, 128);
                 mbar_init(b.o_full, 1);
-                mbar_init(b.s_free, 256);
+                mbar_init(b.s_free, 128);
+                mbar_init(b.stats_full, 128);
+                mbar_init(b.o_free, 128);
             }
+            for (int i = 0; i < 8; ++i) { mbar_init(&seq[i], 32); done[i] = 0; }
             fence_mbar_init();
         }
         __syncwarp();
@@ -441,24 +572,36 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int he
     const uint32_t tmem_base = *tmem_slot;
     const int stride = 2 * gridDim.x;
 
-    if (warp >= 16) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(A2_REGS_CONTROL));
-        if (warp < 18 && lane == 0) {
-            const int t = warp - 16;
+    if (warp >= 12) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(A2_REGS_OTHER));
+        if (warp < 14 && lane == 0) {
+            const int t = warp - 12;
             a2_control<D, NST>(smem + t * Cfg::SLICE_BYTES, a2_bars<NST>(bars + t * Cfg::NBAR), tmem_base + t * Cfg::TM_TILE,
                                &tma_qkv, 2 * blockIdx.x + t, stride, sh, kv_info);
         }
+    } else if (warp >= 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(A2_REGS_OTHER));
+        a2_epilogue<D, NST>(bars, tmem_base, stats, threadIdx.x & 127, sh, kv_info, out, lse2);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(A2_REGS_SOFTMAX));
-        const int t = warp >> 3, half = (warp >> 2) & 1;
-        a2_softmax<D, NST, POLY>(a2_bars<NST>(bars + t * Cfg::NBAR), tmem_base + t * Cfg::TM_TILE, xch + t * Cfg::X_FLOATS,
-                                 threadIdx.x & 127, half, 1 + t * 4 + (warp & 3), 2 * blockIdx.x + t, stride, sh, kv_info,
-                                 key_mask, out, lse2);
+        const int t = warp >> 2, q = warp & 3;
+        A2Turn turn;
+        turn.mine = &seq[t * 4 + q];
+        turn.theirs = &seq[(1 - t) * 4 + q];
+        turn.my_done = &done[t * 4 + q];
+        turn.peer_done = &done[(1 - t) * 4 + q];
+        turn.n = 0;
+        turn.solo = false;
+#if A2_SEQUENCE
+        if (t == 1) mbar_arrive(turn.theirs);                                 // tile 0 has the first turn
+#endif
+        a2_softmax<D, NST, POLY>(a2_bars<NST>(bars + t * Cfg::NBAR), tmem_base + t * Cfg::TM_TILE, stats + t * 2 * A2_BLOCK,
+                                 turn, threadIdx.x & 127, 2 * blockIdx.x + t, stride, sh, kv_info, key_mask);
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 18) {
+    if (warp == 14) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }

@@ -27,6 +27,12 @@ def test_one_cta_per_item_attention():
     _run({"MOLLY_ATTN_STREAM": "0"}, "attention")
 
 
+def test_one_cta_per_sm_two_tile_attention():
+    """MOLLY_ATTN_V2=1: attention2.cu -- one CTA per SM, two 128-row tiles, P in tensor memory, an epilogue warp-group and
+    sequenced exp2 phases (FlashAttention-4 style; head_dim <= 64).  Forward, log-sum-exp and the backward that consumes it."""
+    _run({"MOLLY_ATTN_V2": "1"}, "attention")
+
+
 def test_register_pipelined_attention():
     """MOLLY_ATTN_PIPE=1: 64-key blocks, S(g+1) loaded from TMEM under the exp2 phase of block g, S issued a block ahead."""
     _run({"MOLLY_ATTN_PIPE": "1"}, "attention")

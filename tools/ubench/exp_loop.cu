@@ -12,7 +12,7 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { u
 __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-template <int MODE>       // 0: full loop, 1: MUFU only, 2: loop + bf16 pack
+template <int MODE>       // 0: full loop, 1: MUFU only, 2: loop + bf16 pack, 3: the kernel's chunked loop (FFMA2, 2 MUFU, FADD2, F2FP interleaved), 4: same with the integer-pipe pack
 __global__ void k(float* out, long long* clk, const float* in, int iters) {
     float s[128];
 #pragma unroll
@@ -24,6 +24,25 @@ __global__ void k(float* out, long long* clk, const float* in, int iters) {
     for (int it = 0; it < iters; ++it) {
         const uint64_t sc2 = pack2(1.44f, 1.44f), nm2 = pack2(-acc * 1e-30f - 3.f, -acc * 1e-30f - 3.f);
         uint64_t sum2[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)};
+        if (MODE == 3 || MODE == 4) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t pkk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float x0, x1;
+                    unpack2(fma2(pack2(s[c * 32 + 2 * i], s[c * 32 + 2 * i + 1]), sc2, nm2), x0, x1);
+                    x0 = ex2(x0); x1 = ex2(x1);
+                    sum2[i & 1] = add2(sum2[i & 1], pack2(x0, x1));
+                    if (MODE == 3) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pkk[i]) : "f"(x1), "f"(x0));
+                    else pkk[i] = __byte_perm(__float_as_uint(x0) + 0x8000u, __float_as_uint(x1) + 0x8000u, 0x7632);
+                    s[c * 32 + 2 * i] = x0 * 0.5f - 1.0f; s[c * 32 + 2 * i + 1] = x1 * 0.5f - 1.0f;
+                }
+                // stand-in for the tcgen05.st of the chunk: the 16 packed registers are consumed together
+                asm volatile("" :: "r"(pkk[0]), "r"(pkk[1]), "r"(pkk[2]), "r"(pkk[3]), "r"(pkk[4]), "r"(pkk[5]), "r"(pkk[6]), "r"(pkk[7]),
+                             "r"(pkk[8]), "r"(pkk[9]), "r"(pkk[10]), "r"(pkk[11]), "r"(pkk[12]), "r"(pkk[13]), "r"(pkk[14]), "r"(pkk[15]));
+            }
+        } else
 #pragma unroll
         for (int i = 0; i < 128; i += 4) {
 #pragma unroll
@@ -35,6 +54,9 @@ __global__ void k(float* out, long long* clk, const float* in, int iters) {
                 s[i + 2 * u + 1] = ex2(x1);
                 if (MODE != 1) sum2[u] = add2(sum2[u], pack2(s[i + 2 * u], s[i + 2 * u + 1]));
             }
+        }
+        if (MODE == 3 || MODE == 4) {
+            // nothing here: MODE 3 / 4 replace the loop above (see below)
         }
         if (MODE == 2) {
 #pragma unroll
@@ -82,5 +104,7 @@ int main() {
     for (int w : {4, 8, 12, 16}) run<1>("MUFU only", w);
     for (int w : {4, 8, 12, 16}) run<0>("FFMA2+MUFU+FADD2", w);
     for (int w : {4, 8, 12, 16}) run<2>("  ... + F2FP pack", w);
+    for (int w : {4, 8, 12, 16}) run<3>("kernel loop (F2FP)", w);
+    for (int w : {4, 8, 12, 16}) run<4>("kernel loop (int pack)", w);
     return 0;
 }
