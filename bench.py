@@ -456,9 +456,8 @@ def train_section(args, wl: dict, path, dev, rank: int, world: int, steps: int, 
     tokens_per_step = wl["B"] * 2 * wl["K"]
 
     def step(comm: bool = True):
-        for p in params:                       # zero in place (optimizer.zero_grad(set_to_none=False)): stable allocations
-            if p.grad is not None:
-                p.grad.zero_()
+        for p in params:                       # optimizer.zero_grad() (set_to_none=True, the PyTorch / HF Trainer default)
+            p.grad = None
         hs = base.clone()
         out = path.process_omic_sequences(hs, omic_ids_dev, infos, dev)
         # (the LLM forward + backward run here in the real step: they leave d_out and the LoRA gradients)

@@ -104,8 +104,25 @@ class _InjectTrainFn(torch.autograd.Function):
             reducer.finish()
         ctx.tape = None
         w_m, b_m, p_ms = ctx.metas
-        enc_grads = [grads[n].to(device=dv, dtype=dt) if (n in grads and need) else None
-                     for n, (dt, dv), need in zip(ctx.names, p_ms, ctx.needs_input_grad[8:])]
+        # every gradient goes back in its parameter's dtype / device: ONE multi-tensor cast instead of a kernel per parameter
+        enc_grads, srcs, dsts = [], [], []
+        for n, (dt, dv), need in zip(ctx.names, p_ms, ctx.needs_input_grad[8:]):
+            if n not in grads or not need:
+                enc_grads.append(None)
+                continue
+            src = grads[n]
+            if src.dtype == dt and src.device == dv:
+                enc_grads.append(src)
+                continue
+            dst = torch.empty(src.shape, dtype=dt, device=dv)
+            if dv == src.device:
+                srcs.append(src)
+                dsts.append(dst)
+            else:
+                dst.copy_(src)
+            enc_grads.append(dst)
+        if dsts:
+            torch._foreach_copy_(dsts, srcs)
         return ((g if need_h else None), dW.to(device=w_m[1], dtype=w_m[0]), db.to(device=b_m[1], dtype=b_m[0]), None, None,
                 None, None, None, *enc_grads)
 

@@ -157,7 +157,15 @@ def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor,
     glu = cfg.ffn_type == "glu"
     rope = cfg.position_embedding_type == "rotary"
     grads: Dict[str, torch.Tensor] = {}
-    z = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
+    # LayerNorm weight / bias gradients accumulate into pre-zeroed fp32 rows: one buffer (one fill) for the whole backward
+    zero_rows = torch.zeros(4 * cfg.num_hidden_layers + 2, h, dtype=torch.float32, device=dev)
+    zero_next = [0]
+
+    def z(n):
+        assert n == h
+        row = zero_rows[zero_next[0]]
+        zero_next[0] += 1
+        return row
     schedule = reduce_schedule(enc) if reducer is not None else None     # [0] projector, [1 + (L-1-i)] layer i, [-1] the rest
 
     # emb_layer_norm_after
