@@ -95,6 +95,23 @@ __device__ __forceinline__ A2Bars a2_bars(uint64_t* base) {
 struct A2Item { int n, head, q0, kvl, nkv, n_nonpad; };
 struct A2Shape { int n_seq, heads, k_tokens, h, nqb, total; };
 
+// work-item slot of tile t of this CTA and the stride of the item streams (-DA2_ONE_TILE: tile 1 idle, a bring-up experiment)
+__device__ __forceinline__ int a2_slot(int t, int total) {
+#ifdef A2_ONE_TILE
+    return t == 0 ? static_cast<int>(blockIdx.x) : total;
+#else
+    (void)total;
+    return 2 * static_cast<int>(blockIdx.x) + t;
+#endif
+}
+__device__ __forceinline__ int a2_stride() {
+#ifdef A2_ONE_TILE
+    return static_cast<int>(gridDim.x);
+#else
+    return 2 * static_cast<int>(gridDim.x);
+#endif
+}
+
 __device__ __forceinline__ A2Item a2_decode(int item, const A2Shape& sh, const int32_t* __restrict__ kv_info) {
     A2Item w;                                  // query block fastest: neighbouring tiles share one (sequence, head)'s K/V in L2
     w.q0 = (item % sh.nqb) * A2_BLOCK;
@@ -255,10 +272,14 @@ __device__ __forceinline__ void a2_turn_begin(A2Turn& t) {
     const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try_wait(t.mine, parity)) {
-        if (*t.peer_done) { t.solo = true; return; }
-        if ((++spins & 31u) == 0 && clock64() - t0 > MOLLY_MBAR_TIMEOUT_CYCLES) {
-            printf("molly attention2: exp2-turn timeout block=%d thread=%d\n", blockIdx.x, threadIdx.x);
-            __trap();
+        // the "other warp has left" flag is probed rarely: a shared-memory load per spin is an LDS stream next to the other
+        // tile's exp2 loop on the same scheduler, which slows that loop 2.5x (tools/ubench/interfere.cu); try_wait costs nothing
+        if ((++spins & 63u) == 0) {
+            if (*t.peer_done) { t.solo = true; return; }
+            if (clock64() - t0 > MOLLY_MBAR_TIMEOUT_CYCLES) {
+                printf("molly attention2: exp2-turn timeout block=%d thread=%d\n", blockIdx.x, threadIdx.x);
+                __trap();
+            }
         }
     }
 #endif
@@ -444,12 +465,12 @@ __device__ __forceinline__ void a2_epilogue(uint64_t* bars, uint32_t tmem_base, 
     using Cfg = A2Cfg<D, NST>;
     const uint32_t lane_addr = static_cast<uint32_t>(r & ~31) << 16;
     const int k_tokens = sh.k_tokens, h = sh.h;
-    const int stride = 2 * gridDim.x;
+    const int stride = a2_stride();
     // The two tiles finish their items at their own pace (different kv_len), and with the exp2 turn-taking a tile that is
     // held up holds up the other one: the items are therefore served in the order they become READY (non-blocking probes),
     // never in a fixed tile order -- waiting for tile 0 while tile 1's finished item keeps its control thread from issuing
     // the next O += P V would deadlock the pair.
-    int item[2] = {2 * static_cast<int>(blockIdx.x), 2 * static_cast<int>(blockIdx.x) + 1};
+    int item[2] = {a2_slot(0, sh.total), a2_slot(1, sh.total)};
     int it[2] = {0, 0};
     A2Item w[2];
     auto seek = [&](int t) {                                                  // next item of tile t that has keys; zero rows for the rest
@@ -570,14 +591,14 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int he
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int stride = 2 * gridDim.x;
+    const int stride = a2_stride();
 
     if (warp >= 12) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(A2_REGS_OTHER));
         if (warp < 14 && lane == 0) {
             const int t = warp - 12;
             a2_control<D, NST>(smem + t * Cfg::SLICE_BYTES, a2_bars<NST>(bars + t * Cfg::NBAR), tmem_base + t * Cfg::TM_TILE,
-                               &tma_qkv, 2 * blockIdx.x + t, stride, sh, kv_info);
+                               &tma_qkv, a2_slot(t, sh.total), stride, sh, kv_info);
         }
     } else if (warp >= 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(A2_REGS_OTHER));
@@ -596,7 +617,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int he
         if (t == 1) mbar_arrive(turn.theirs);                                 // tile 0 has the first turn
 #endif
         a2_softmax<D, NST, POLY>(a2_bars<NST>(bars + t * Cfg::NBAR), tmem_base + t * Cfg::TM_TILE, stats + t * 2 * A2_BLOCK,
-                                 turn, threadIdx.x & 127, 2 * blockIdx.x + t, stride, sh, kv_info, key_mask);
+                                 turn, threadIdx.x & 127, a2_slot(t, sh.total), stride, sh, kv_info, key_mask);
     }
 
     tc_fence_before();

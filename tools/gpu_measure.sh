@@ -16,12 +16,12 @@ if [ "${NCU:-1}" = "1" ]; then
   timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none \
       -k "regex:gemm_tcgen05_kernel|attention|layernorm_kernel|embed_kernel|rotary_kernel|mask_rows_kernel" \
       -s ${NCU_SKIP:-1506} -c ${NCU_COUNT:-502} --csv \
-      --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch.log 2>&1
+      --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --headline-only > $OUT/ncu_launch.log 2>&1
   echo "rc=$? lines=$(wc -l < $OUT/launches.csv)"
   echo "== ncu --set full: GEMMs of one encoder layer + attention"
   timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 8 -c 4 \
-      -o $OUT/prof_gemm -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_gemm.log 2>&1; echo "rc=$?"
+      -o $OUT/prof_gemm -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --headline-only > $OUT/ncu_gemm.log 2>&1; echo "rc=$?"
   timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:attention -s 2 -c 1 \
-      -o $OUT/prof_attn -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_attn.log 2>&1; echo "rc=$?"
+      -o $OUT/prof_attn -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --headline-only > $OUT/ncu_attn.log 2>&1; echo "rc=$?"
   ls -la $OUT
 fi
