@@ -387,38 +387,62 @@ __device__ __forceinline__ void a2_softmax(const A2Bars& bar, uint32_t tmem_tile
                 m_run = m_cand;
             }
             const float m_use = (m_run == -CUDART_INF_F) ? 0.f : m_run;
-            const uint64_t sc2 = pack_f32x2(A2_LOG2E, A2_LOG2E), nm2 = pack_f32x2(-m_use, -m_use);
-            uint64_t sum2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
+            // The exp2 phase proper holds the scheduler's MUFU exclusively (turn-taking), so everything that is not a
+            // MUFU.EX2 or the pack of its result stays OUT of it: the scale-and-shift FFMA2s run before the turn is taken
+            // (volatile: they must not sink below the wait), the wait for PV(g-1) too, and the row sum (FADD2) runs after
+            // the turn has been passed on, from the exponentials kept in place in s[].
+            {
+                const uint64_t sc2 = pack_f32x2(A2_LOG2E, A2_LOG2E), nm2 = pack_f32x2(-m_use, -m_use);
+#pragma unroll
+                for (int i = 0; i < A2_BLOCK; i += 2) {
+                    uint64_t v;
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(v) : "l"(pack_f32x2(s[i], s[i + 1])), "l"(sc2), "l"(nm2));
+                    unpack_f32x2(v, s[i], s[i + 1]);
+                }
+            }
+            if (g > 0) {                                                      // PV(g-1) consumed P and finished O
+                mbar_wait(&bar.kv_empty[(g - 1) % NST], ((g - 1) / NST) & 1);
+                tc_fence_after();
+            }
             TL2(3);
             a2_turn_begin(turn);                                              // this warp's turn on the scheduler's MUFU
             TL2(4);
-            // P = exp2(s log2e - m) in 32-key chunks: packed bf16 pairs go to TMEM as each chunk retires
-            // (column c of lane r holds keys 2c, 2c+1 of query row r: the K-major A operand of O += P V)
-#pragma unroll
-            for (int c = 0; c < A2_BLOCK / 32; ++c) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float x0, x1;
-                    unpack_f32x2(fma_f32x2(pack_f32x2(s[c * 32 + 2 * i], s[c * 32 + 2 * i + 1]), sc2, nm2), x0, x1);
-                    if (i % 4 < POLY) {                                       // this pair goes to the FMA pipe
+            // P = exp2(.), packed bf16 pairs go to TMEM in 32-key chunks (column c of lane r holds keys 2c, 2c+1 of query row r:
+            // the K-major A operand of O += P V).  The MUFU stream runs A2_AHEAD key pairs ahead of the pack stream, in an
+            // order pinned with volatile asm: left to itself ptxas packs a pair right behind its two MUFU.EX2, and the
+            // in-order warp then waits out the MUFU latency on every pair (measured: 14 cycles per MUFU.EX2 instead of 8).
+            {
+                constexpr int A2_AHEAD = 8, NP = A2_BLOCK / 2;
+                auto exp_pair = [&](int p) {
+                    float x0 = s[2 * p], x1 = s[2 * p + 1];
+                    if (p % 4 < POLY) {                                       // this pair goes to the FMA pipe
                         a2_exp2_poly_pair(x0, x1);
                     } else {                                                  // this pair goes to the MUFU
-                        x0 = a2_ex2(x0);
-                        x1 = a2_ex2(x1);
+                        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(x0) : "f"(x0));
+                        asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(x1) : "f"(x1));
                     }
-                    sum2[i & 1] = add_f32x2(sum2[i & 1], pack_f32x2(x0, x1));
-                    pk[i] = pack_bf16x2(x0, x1);
+                    s[2 * p] = x0;
+                    s[2 * p + 1] = x1;
+                };
+#pragma unroll
+                for (int p = 0; p < A2_AHEAD; ++p) exp_pair(p);
+                uint32_t pk[16];
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    if (p + A2_AHEAD < NP) exp_pair(p + A2_AHEAD);
+                    if (p + A2_AHEAD == NP - 1) {
+                        a2_turn_end(turn);                                    // last MUFU.EX2 issued: the other tile's warp may start
+                        TL2(5);
+                    }
+                    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[p % 16]) : "f"(s[2 * p + 1]), "f"(s[2 * p]));
+                    if (p % 16 == 15) tmem_st16(tmem_p + (p / 16) * 16, pk);
                 }
-                if (c == 0 && g > 0) {                                        // PV(g-1) consumed P and finished O
-                    mbar_wait(&bar.kv_empty[(g - 1) % NST], ((g - 1) / NST) & 1);
-                    tc_fence_after();
-                }
-                if (c == A2_BLOCK / 32 - 1) {
-                    a2_turn_end(turn);                                        // the other tile's warp may start its exp2 phase
-                    TL2(5);
-                }
-                tmem_st16(tmem_p + c * 16, pk);
+            }
+            uint64_t sum2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
+#pragma unroll
+            for (int i = 0; i < A2_BLOCK; i += 4) {
+                sum2[0] = add_f32x2(sum2[0], pack_f32x2(s[i], s[i + 1]));
+                sum2[1] = add_f32x2(sum2[1], pack_f32x2(s[i + 2], s[i + 3]));
             }
             float sa, sb, sc, sd;
             unpack_f32x2(sum2[0], sa, sb);
