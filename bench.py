@@ -479,8 +479,10 @@ def train_section(args, wl: dict, path, dev, rank: int, world: int, steps: int, 
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
+        t0 = time.perf_counter()
         for _ in range(n):
             fn()
+        host_ms[0] = (time.perf_counter() - t0) * 1e3 / n          # how long the host needs to enqueue one step
         ev1.record()
         barrier()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
@@ -488,6 +490,7 @@ def train_section(args, wl: dict, path, dev, rank: int, world: int, steps: int, 
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / n
 
+    host_ms = [0.0]
     for _ in range(max(warmup, 6)):            # the caching allocator needs a few steps to settle on the tape's block sizes
         step()
     assert all(p.grad is not None and torch.isfinite(p.grad.float()).all() for p in params)
@@ -496,6 +499,7 @@ def train_section(args, wl: dict, path, dev, rank: int, world: int, steps: int, 
     l0 = ops.kernel_launch_count()
     sampler.start()
     ms_step = timed(step, steps)
+    host_enqueue_ms = host_ms[0]
     clocks = sampler.stop()
     launches = ops.kernel_launch_count() - l0
     comm = None
@@ -536,6 +540,7 @@ def train_section(args, wl: dict, path, dev, rank: int, world: int, steps: int, 
     grad_elems = sum(p.numel() for p in params) + (lora.numel() if lora is not None else 0)
     out = {"workload": wl["desc"], "B_per_gpu": wl["B"], "K": wl["K"], "T": wl["T"], "D": wl["D"],
            "tokens_per_s": world * tokens_per_step / (ms_step * 1e-3), "ms_per_step": ms_step,
+           "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
            "parallelism": (f"sample-sharded x{world}, " + ("layer-wise grad all-reduce overlapped with the backward"
                                                             if overlap else "flat grad buckets, mean all-reduce")
                            + f" ({grad_elems} elements)"),
@@ -554,7 +559,7 @@ def run_train_step(args, wl: dict, dev, rank: int, world: int, warmup: int) -> N
             "ms_per_step": sec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {k: sec[k] for k in ("workload", "B_per_gpu", "K", "T", "D", "parallelism", "trainable")},
-            "clocks": sec["clocks"], "gpu_launches": sec["gpu_launches"], "kernels": sec["kernels"], "comm": sec["comm"]}
+            "host_enqueue_ms_per_step": sec["host_enqueue_ms_per_step"], "clocks": sec["clocks"], "gpu_launches": sec["gpu_launches"], "kernels": sec["kernels"], "comm": sec["comm"]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     path.close()

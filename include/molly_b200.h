@@ -234,6 +234,37 @@ int molly_scale_cols(void* x_dev /*bf16 [rows, ld]*/, int32_t rows, int32_t ld, 
 /* table[index[r], :] += scale[r] * src[r, :] (fp32 atomics): autograd of the embedding gathers (HF:189-236) */
 int molly_scatter_add_rows(const float* src_dev, const int32_t* index_dev, const float* scale_dev, int32_t rows, int32_t h,
                            float* table_dev, void* stream);
+/* ---- the encoder training step, orchestrated natively (--train-bio: src/utils/tools.py:313-331 sets
+ * requires_grad on every encoder parameter; the reference then runs HF EsmModel under torch autograd).  One call runs the
+ * forward of all layers and keeps what the backward needs in the caller-owned `tape`; one call runs the backward of a range
+ * of layers and writes fp32 parameter gradients into `grads_dev`, laid out as molly_encoder_grad_layout() says, in the
+ * PACKED layout of the weights (q,k,v concatenated like cat(Wq,Wk,Wv); GLU rows interleaved like w_ffn1).
+ * recompute != 0: the tape keeps only each layer's fp32 input and ONE activation slot that the backward refills layer by
+ * layer (activation checkpointing); 0: every layer's activations are kept. */
+enum molly_grad_slot {            /* per-layer gradient tensors, in layout order: vectors first, then matrices */
+    MOLLY_GRAD_LN2_W = 0, MOLLY_GRAD_LN2_B, MOLLY_GRAD_B_FFN2, MOLLY_GRAD_B_FFN1, MOLLY_GRAD_LN1_W, MOLLY_GRAD_LN1_B,
+    MOLLY_GRAD_B_O, MOLLY_GRAD_B_QKV, MOLLY_GRAD_W_FFN2, MOLLY_GRAD_W_FFN1, MOLLY_GRAD_W_O, MOLLY_GRAD_W_QKV, MOLLY_GRAD_SLOTS
+};
+enum molly_grad_tail_slot {       /* after the L layer groups */
+    MOLLY_GRAD_TAIL_FINAL_LN_W = 0, MOLLY_GRAD_TAIL_FINAL_LN_B, MOLLY_GRAD_TAIL_WORD_EMB, MOLLY_GRAD_TAIL_POS_EMB,
+    MOLLY_GRAD_TAIL_SLOTS
+};
+int molly_encoder_train_sizes(const molly_encoder_t* enc, int32_t n_seq, int32_t k_tokens, int32_t recompute,
+                              size_t* tape_bytes, size_t* workspace_bytes, int64_t* grad_floats);
+/* layer_offsets[MOLLY_GRAD_SLOTS]: float offset of each slot inside a layer group (-1: the encoder has no such parameter);
+ * layer l's group starts at l * *layer_group_floats; tail_offsets[MOLLY_GRAD_TAIL_SLOTS]: absolute float offsets (-1: none) */
+int molly_encoder_grad_layout(const molly_encoder_t* enc, int64_t* layer_offsets, int64_t* layer_group_floats,
+                              int64_t* tail_offsets, int64_t* total_floats);
+/* out_dev: bf16 [n_seq*k, h] = hidden_states[-1] (numerically the inference forward: same kernels, same order) */
+int molly_encode_train_fwd(molly_encoder_t* enc, const int64_t* ids_dev, int32_t n_seq, int32_t k_tokens, void* out_dev,
+                           void* tape_dev, size_t tape_bytes, int32_t recompute, int32_t* err_flag_dev, void* stream);
+/* Backward of layers layer_begin, layer_begin-1, ..., layer_end (layer index num_layers = emb_layer_norm_after, which needs
+ * d_out_dev = d(loss)/d(hidden_states[-1]), bf16 [n_seq*k, h]).  The running gradient of the residual stream lives in the
+ * first n_seq*k*h floats of the workspace between calls: after layer 0 it is d(embedding output), the input of
+ * molly_scatter_add_rows for the embedding tables.  The word / position embedding slots of grads_dev are not written here. */
+int molly_encode_train_bwd(molly_encoder_t* enc, int32_t n_seq, int32_t k_tokens, void* tape_dev, size_t tape_bytes,
+                           int32_t recompute, const void* d_out_dev, float* grads_dev, void* workspace_dev,
+                           size_t workspace_bytes, int32_t layer_begin, int32_t layer_end, void* stream);
 /* bring-up aid: when non-NULL, CTA 0 of the attention kernel records clock64() stamps into timeline_dev
  * (int64 [2 roles][64 iterations][8 slots]); NULL (default) disables it */
 int molly_attention_debug(long long* timeline_dev);

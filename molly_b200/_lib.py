@@ -62,6 +62,10 @@ class ProfileEntry(C.Structure):
 
 
 PROFILE_FAMILIES = 14
+# enum molly_grad_slot / molly_grad_tail_slot (include/molly_b200.h)
+(GRAD_LN2_W, GRAD_LN2_B, GRAD_B_FFN2, GRAD_B_FFN1, GRAD_LN1_W, GRAD_LN1_B, GRAD_B_O, GRAD_B_QKV, GRAD_W_FFN2, GRAD_W_FFN1,
+ GRAD_W_O, GRAD_W_QKV, GRAD_SLOTS) = range(13)
+GRAD_TAIL_FINAL_LN_W, GRAD_TAIL_FINAL_LN_B, GRAD_TAIL_WORD_EMB, GRAD_TAIL_POS_EMB, GRAD_TAIL_SLOTS = range(5)
 _i32, _i64p, _vp, _sz = C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t
 
 # name -> (restype, argtypes); must list every function declared in include/molly_b200.h (tests/test_abi.py checks)
@@ -97,6 +101,12 @@ SIGNATURES = {
     "molly_cast_f32_bf16": (C.c_int, [_vp, C.c_int64, _vp, _vp]),
     "molly_scale_cols": (C.c_int, [_vp, _i32, _i32, _i32, C.c_float, _vp]),
     "molly_scatter_add_rows": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "molly_encoder_train_sizes": (C.c_int, [C.c_void_p, _i32, _i32, _i32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                            C.POINTER(C.c_int64)]),
+    "molly_encoder_grad_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                            C.POINTER(C.c_int64)]),
+    "molly_encode_train_fwd": (C.c_int, [C.c_void_p, _vp, _i32, _i32, _vp, _vp, _sz, _i32, _vp, _vp]),
+    "molly_encode_train_bwd": (C.c_int, [C.c_void_p, _i32, _i32, _vp, _sz, _i32, _vp, _vp, _vp, _sz, _i32, _i32, _vp]),
     "molly_attention_debug": (C.c_int, [_vp]),
     "molly_merge_rows": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "molly_profile_start": (C.c_int, []),

@@ -73,8 +73,9 @@ int embed_launch(const int64_t* ids, int n_seq, int k_tokens, const EmbedArgs& a
 int mask_rows_launch(float* x, const uint8_t* key_mask, int rows, int h, cudaStream_t stream);
 int layernorm_launch(const float* x, const float* w, const float* b, int rows, int h, float eps, void* out,
                      int out_dtype, cudaStream_t stream);
+// sin_sign = -1: the inverse rotation (rotary backward); q_scale multiplies the rotated q columns (backward of q * d^-1/2)
 int rotary_launch(void* qkv, int rows, int k_tokens, int h, int heads, const float* cos_t, const float* sin_t,
-                  cudaStream_t stream);
+                  cudaStream_t stream, float sin_sign = 1.0f, float q_scale = 1.0f);
 int pool_launch(const void* enc_out, const int64_t* ids, int n_seq, int k_tokens, int h, int mode, float* out,
                 cudaStream_t stream);
 

@@ -229,7 +229,7 @@ void launch_layernorm(const float* x, const float* w, const float* b, int rows, 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 rotary_kernel(__nv_bfloat16* __restrict__ qkv, long long total_items, int k_tokens, int h, int heads,
-              const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
+              const float* __restrict__ cos_t, const float* __restrict__ sin_t, float sin_sign, float q_scale) {
     const int d = h / heads, half = d >> 1, vec_per_head = half >> 3;
     const long long item = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (item >= total_items) return;
@@ -247,6 +247,11 @@ rotary_kernel(__nv_bfloat16* __restrict__ qkv, long long total_items, int k_toke
     float c[8], s[8];
     *reinterpret_cast<float4*>(c) = __ldg(c4); *reinterpret_cast<float4*>(c + 4) = __ldg(c4 + 1);
     *reinterpret_cast<float4*>(s) = __ldg(s4); *reinterpret_cast<float4*>(s + 4) = __ldg(s4 + 1);
+    // backward: the inverse rotation (sin_sign = -1) and, on the q columns, the d^-1/2 of q = (W_q x + b_q) * d^-1/2 (HF:341);
+    // the forward passes (+1, 1): both multiplications are exact
+    const float sc = which == 0 ? q_scale : 1.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i] *= sc; s[i] *= sin_sign * sc; }
     __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&lo);
     __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&hi);
 #pragma unroll
@@ -320,13 +325,13 @@ int layernorm_launch(const float* x, const float* w, const float* b, int rows, i
 }
 
 int rotary_launch(void* qkv, int rows, int k_tokens, int h, int heads, const float* cos_t, const float* sin_t,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, float sin_sign, float q_scale) {
     const int d = h / heads;
     MOLLY_CHECK(d % 16 == 0, MOLLY_ERR_UNSUPPORTED, "rotary: head_dim %d must be a multiple of 16", d);
     const long long items = static_cast<long long>(rows) * 2 * heads * (d / 16);
     ProfScope prof(PF_ROTARY, static_cast<double>(rows) * 2.0 * h * 4.0, stream);     // q,k read + write, bf16
     rotary_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, stream>>>(
-        static_cast<__nv_bfloat16*>(qkv), items, k_tokens, h, heads, cos_t, sin_t);
+        static_cast<__nv_bfloat16*>(qkv), items, k_tokens, h, heads, cos_t, sin_t, sin_sign, q_scale);
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
     return MOLLY_OK;

@@ -137,12 +137,21 @@ class LayerwiseGradReducer:
         else:
             self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
-    def reduce_zeros_(self, numel: int, device) -> None:
+    def reduce_flat_(self, flat: torch.Tensor) -> torch.Tensor:
+        """One group that already is one contiguous buffer (the library's flat gradient layout, ``train.GradPlan``): cast to
+        the reducer's dtype (one pass), mean all-reduce on the side stream; returns the buffer the averaged values land in."""
+        g = {"_flat": flat}
+        self.reduce_(g, ["_flat"])
+        return g["_flat"]
+
+    def reduce_zeros_(self, numel: int, device) -> torch.Tensor:
         """The collective a rank issues in place of ``reduce_`` for gradients it does not have (a modality absent from its
-        micro-batch): same size, same dtype, same position in the schedule, all zeros."""
+        micro-batch): same size, same dtype, same position in the schedule, all zeros.  Returns what every rank gets back:
+        the averaged gradients of the ranks that had the modality."""
+        z = torch.zeros(max(0, int(numel)), dtype=self.dtype, device=device)
         if numel <= 0 or dist.get_world_size(self.group) == 1:
-            return
-        self.reduce_({"_zeros": torch.zeros(int(numel), dtype=self.dtype, device=device)}, ["_zeros"])
+            return z
+        return self.reduce_flat_(z)
 
     def finish(self) -> None:
         for w in self._works:

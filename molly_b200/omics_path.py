@@ -131,24 +131,27 @@ class _AbsentModalityFn(torch.autograd.Function):
     """A modality with a TRAINABLE encoder that has no sequence in this rank's micro-batch while a gradient reducer is
     attached: the other ranks all-reduce that encoder's gradients layer by layer inside their backward, so this rank must
     issue the SAME sequence of collectives at the same point of its backward, or NCCL pairs the wrong buffers / hangs.  It
-    contributes zeros laid out like ``train.reduce_schedule`` and gets back what every rank gets: the averaged gradients.
+    contributes zeros sized like the groups of ``train.GradPlan`` and gets back what every rank gets: the averaged gradients.
     Forward is the identity on ``hidden_states``."""
 
     @staticmethod
-    def forward(ctx, hidden_states, reducer, schedule, names, *params):
-        ctx.reducer, ctx.schedule, ctx.names = reducer, schedule, names
+    def forward(ctx, hidden_states, reducer, plan, names, *params):
+        ctx.reducer, ctx.plan, ctx.names = reducer, plan, names
         ctx.metas = [(p.dtype, p.device) for p in params]
         ctx.mark_dirty(hidden_states)
         return hidden_states
 
     @staticmethod
     def backward(ctx, grad_out):
+        plan, red, dev = ctx.plan, ctx.reducer, grad_out.device
         got = {}
-        for group in ctx.schedule:
-            d = {n: torch.zeros(shape, dtype=ctx.reducer.dtype, device=grad_out.device) for n, shape in group}
-            ctx.reducer.reduce_(d, [n for n, _ in group])
-            got.update(d)
-        ctx.reducer.finish()
+        flat = red.reduce_zeros_(plan.group_numel(0), dev)                   # the projector group
+        n_w = plan.proj_shapes[0][0] * plan.proj_shapes[0][1]
+        got["projector.weight"], got["projector.bias"] = flat[:n_w].view(plan.proj_shapes[0]), flat[n_w:]
+        for g in range(1, plan.L + 1):                                       # layers L-1 .. 0, as the backward produces them
+            got.update(plan.layer_views(plan.L - g, red.reduce_zeros_(plan.group_numel(g), dev)))
+        got.update(plan.tail_views(red.reduce_zeros_(plan.group_numel(plan.L + 1), dev)))
+        red.finish()
         grads = [got[n].to(device=dv, dtype=dt) if (n in got and need) else None
                  for n, (dt, dv), need in zip(ctx.names, ctx.metas, ctx.needs_input_grad[4:])]
         return (grad_out if ctx.needs_input_grad[0] else None), None, None, None, *grads
@@ -283,7 +286,7 @@ class FastOmicsPath:
             return
         from . import train
         named += [("projector.weight", proj.weight), ("projector.bias", proj.bias)]
-        _AbsentModalityFn.apply(hidden_states, self.grad_reducer, train.reduce_schedule(ops.get_encoder(enc_id)),
+        _AbsentModalityFn.apply(hidden_states, self.grad_reducer, train.grad_plan(ops.get_encoder(enc_id)),
                                 tuple(n for n, _ in named), *[prm for _, prm in named])
 
     def _inject(self, name: str, plan: planner.ModalityPlan, hidden_states: torch.Tensor, omic_ids_list, dev) -> None:

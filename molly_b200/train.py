@@ -1,7 +1,9 @@
 """Encoder training path (``--train-bio``: src/utils/tools.py:313-331 unfreezes the encoders).
 
-Forward = the same sm_100a kernels as the inference path, launched layer by layer so that each layer's fp32 input can be
-kept; backward = per-layer recompute from that input, then the autograd of every HF module the kernels replace:
+Forward = the same sm_100a kernels as the inference path, run layer by layer by ``molly_encode_train_fwd`` with what the
+backward needs kept in a tape (every layer's activations, or -- when they do not fit -- only each layer's fp32 input, the
+backward then recomputing one layer at a time); backward = ``molly_encode_train_bwd``, the autograd of every HF module the
+kernels replace:
 
     nn.Linear      dgrad: tcgen05 GEMM on the transposed weight        wgrad / bias: ``molly_linear_wgrad``
     attention      ``molly_attention_bwd`` (dQ / dK,dV kernels) from the forward's row log-sum-exp
@@ -9,12 +11,16 @@ kept; backward = per-layer recompute from that input, then the autograd of every
     rotary         the forward kernel with -sin (inverse rotation), then the q scale
     embeddings     ``molly_scatter_add_rows`` (token-dropout scale, pad / <mask> rows skipped like the forward)
 
-Gradients come back keyed by the HF ``state_dict`` names of the encoder (q / k / v and the NT-v2 gate / up halves are
-un-packed), fp32.  Orchestration is Python (one ctypes call per kernel): this is the training path, not the hot path.
+Orchestration is native (csrc/train.cu: one C call for the forward, one per range of layers for the backward); the first
+version issued one ctypes call per kernel and the step was bound by the host (133 ms to enqueue 115 ms of kernels).  The
+library writes fp32 gradients into ONE flat buffer in the packed layout of the weights (``molly_encoder_grad_layout``);
+``GradPlan`` maps it to the HF ``state_dict`` names (q / k / v are slices, the NT-v2 gate / up halves are un-interleaved).
 """
 from __future__ import annotations
 
-from typing import Dict, List, Tuple
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
@@ -40,51 +46,119 @@ def _emb_meta(enc: PackedEncoder, ids: torch.Tensor):
             mask.float().reshape(-1).contiguous())
 
 
-def reduce_schedule(enc: PackedEncoder) -> List[List[Tuple[str, Tuple[int, ...]]]]:
-    """The gradient groups ``_InjectTrainFn.backward`` hands to a ``LayerwiseGradReducer``, in order, as (HF name, shape)
-    lists: the projector, the encoder layers L-1 .. 0, then final LayerNorm + embeddings.  ``encoder_backward`` reduces
-    exactly these lists; a rank whose micro-batch lacks the modality all-reduces zeros laid out the same way
-    (``omics_path._AbsentModalityFn``) and so receives the other ranks' averaged gradients."""
-    cfg = enc.cfg
-    h, F = cfg.hidden_size, cfg.intermediate_size
-    glu = cfg.ffn_type == "glu"
-    groups = [[("projector.weight", tuple(enc.proj_w.shape)), ("projector.bias", tuple(enc.proj_b.shape))]]
-    for i in range(cfg.num_hidden_layers - 1, -1, -1):
+class GradPlan:
+    """The library's flat fp32 gradient layout of one encoder (``molly_encoder_grad_layout``) and its HF names.
+
+    ``groups`` is the reduction schedule of ``--train-bio`` at N > 1, in the order the backward produces it: the projector
+    (not part of the flat buffer), the encoder layers L-1 .. 0, then final LayerNorm + embeddings; each group is a list of
+    (HF name, shape).  A rank whose micro-batch lacks the modality all-reduces zeros of ``group_numel(g)`` elements per group
+    (``omics_path._AbsentModalityFn``) and maps what comes back with the same ``layer_views`` / ``tail_views``."""
+
+    def __init__(self, enc: PackedEncoder):
+        cfg = enc.cfg
+        self.cfg = cfg
+        self.L, self.h, self.F = cfg.num_hidden_layers, cfg.hidden_size, cfg.intermediate_size
+        self.glu = cfg.ffn_type == "glu"
+        self.F1 = 2 * self.F if self.glu else self.F
+        off = (C.c_int64 * _lib.GRAD_SLOTS)()
+        tail = (C.c_int64 * _lib.GRAD_TAIL_SLOTS)()
+        group, total = C.c_int64(), C.c_int64()
+        _lib.check(_lib.load().molly_encoder_grad_layout(enc.handle, off, C.byref(group), tail, C.byref(total)),
+                   "molly_encoder_grad_layout")
+        self.off, self.tail, self.group, self.total = list(off), list(tail), int(group.value), int(total.value)
+        self.word_shape = tuple(enc.word_emb.shape)
+        self.pos_shape = tuple(enc.pos_emb.shape) if enc.pos_emb is not None else None
+        self.proj_shapes = (tuple(enc.proj_w.shape), tuple(enc.proj_b.shape))
+        self.tail_begin = self.group * self.L
+
+    # -- (HF name, slot, offset inside the slot, shape) of one layer group, in flat order
+    def _layer_entries(self, i: int):
+        h, F, F1 = self.h, self.F, self.F1
         p = f"esm.encoder.layer.{i}."
-        ffn_bias = enc.layer_tensors[i]["b_ffn1"] is not None
-        g = [(p + "LayerNorm.weight", (h,)), (p + "LayerNorm.bias", (h,)), (p + "output.dense.weight", (h, F)),
-             (p + "intermediate.dense.weight", ((2 * F if glu else F), h))]
-        if ffn_bias:
-            g += [(p + "intermediate.dense.bias", ((2 * F if glu else F),)), (p + "output.dense.bias", (h,))]
-        g += [(p + "attention.LayerNorm.weight", (h,)), (p + "attention.LayerNorm.bias", (h,)),
-              (p + "attention.output.dense.weight", (h, h)), (p + "attention.output.dense.bias", (h,))]
-        for nm in ("query", "key", "value"):
-            g += [(p + f"attention.self.{nm}.weight", (h, h)), (p + f"attention.self.{nm}.bias", (h,))]
-        groups.append(g)
-    last = [("esm.encoder.emb_layer_norm_after.weight", (h,)), ("esm.encoder.emb_layer_norm_after.bias", (h,)),
-            ("esm.embeddings.word_embeddings.weight", tuple(enc.word_emb.shape))]
-    if enc.pos_emb is not None:
-        last.append(("esm.embeddings.position_embeddings.weight", tuple(enc.pos_emb.shape)))
-    groups.append(last)
-    return groups
+        G = _lib
+        ent = [(p + "LayerNorm.weight", G.GRAD_LN2_W, 0, (h,)), (p + "LayerNorm.bias", G.GRAD_LN2_B, 0, (h,)),
+               (p + "output.dense.bias", G.GRAD_B_FFN2, 0, (h,)), (p + "intermediate.dense.bias", G.GRAD_B_FFN1, 0, (F1,)),
+               (p + "attention.LayerNorm.weight", G.GRAD_LN1_W, 0, (h,)), (p + "attention.LayerNorm.bias", G.GRAD_LN1_B, 0, (h,)),
+               (p + "attention.output.dense.bias", G.GRAD_B_O, 0, (h,))]
+        ent += [(p + f"attention.self.{nm}.bias", G.GRAD_B_QKV, j * h, (h,)) for j, nm in enumerate(("query", "key", "value"))]
+        ent += [(p + "output.dense.weight", G.GRAD_W_FFN2, 0, (h, F)), (p + "intermediate.dense.weight", G.GRAD_W_FFN1, 0, (F1, h)),
+                (p + "attention.output.dense.weight", G.GRAD_W_O, 0, (h, h))]
+        ent += [(p + f"attention.self.{nm}.weight", G.GRAD_W_QKV, j * h * h, (h, h))
+                for j, nm in enumerate(("query", "key", "value"))]
+        return [e for e in ent if self.off[e[1]] >= 0]
+
+    def _tail_entries(self):
+        G = _lib
+        ent = [("esm.encoder.emb_layer_norm_after.weight", G.GRAD_TAIL_FINAL_LN_W, (self.h,)),
+               ("esm.encoder.emb_layer_norm_after.bias", G.GRAD_TAIL_FINAL_LN_B, (self.h,)),
+               ("esm.embeddings.word_embeddings.weight", G.GRAD_TAIL_WORD_EMB, self.word_shape)]
+        if self.pos_shape is not None:
+            ent.append(("esm.embeddings.position_embeddings.weight", G.GRAD_TAIL_POS_EMB, self.pos_shape))
+        return ent
+
+    @property
+    def groups(self) -> List[List[Tuple[str, Tuple[int, ...]]]]:
+        out = [[("projector.weight", self.proj_shapes[0]), ("projector.bias", self.proj_shapes[1])]]
+        for i in range(self.L - 1, -1, -1):
+            out.append([(n, shape) for n, _, _, shape in self._layer_entries(i)])
+        out.append([(n, shape) for n, _, shape in self._tail_entries()])
+        return out
+
+    def group_numel(self, g: int) -> int:
+        """Elements all-reduced for schedule group ``g`` (0 projector, 1 .. L layers L-1 .. 0, L+1 the tail)."""
+        if g == 0:
+            return self.proj_shapes[0][0] * self.proj_shapes[0][1] + self.proj_shapes[1][0]
+        return self.group if g <= self.L else self.total - self.tail_begin
+
+    def layer_views(self, i: int, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """HF-named gradients of layer ``i`` from its flat group (views; the NT-v2 gate / up halves are un-interleaved)."""
+        out = {}
+        for name, slot, sub, shape in self._layer_entries(i):
+            n = 1
+            for v in shape:
+                n *= v
+            t = flat[self.off[slot] + sub:self.off[slot] + sub + n].view(shape)
+            if self.glu and slot in (_lib.GRAD_W_FFN1, _lib.GRAD_B_FFN1):
+                t = glu_deinterleave(t, self.cfg.glu_gate_first)     # packed rows are (gate_0, up_0, gate_1, up_1, ...)
+            out[name] = t
+        return out
+
+    def tail_views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        out = {}
+        for name, slot, shape in self._tail_entries():
+            n = 1
+            for v in shape:
+                n *= v
+            o = self.tail[slot] - self.tail_begin
+            out[name] = flat[o:o + n].view(shape)
+        return out
+
+
+def grad_plan(enc: PackedEncoder) -> GradPlan:
+    plan = getattr(enc, "_grad_plan", None)
+    if plan is None:
+        plan = enc._grad_plan = GradPlan(enc)
+    return plan
+
+
+def reduce_schedule(enc: PackedEncoder) -> List[List[Tuple[str, Tuple[int, ...]]]]:
+    """The gradient groups handed to a ``LayerwiseGradReducer``, in order, as (HF name, shape) lists (``GradPlan.groups``)."""
+    return grad_plan(enc).groups
 
 
 class EncoderTape:
-    """What the training forward keeps for the backward.  ``saved[i]`` holds layer i's activations (ln1, qkv, attn, lse2,
-    x_mid, ln2, FFN pre-activation) when they fit the memory budget; otherwise only the fp32 layer input is kept and the
-    backward recomputes the layer (activation checkpointing per layer)."""
+    """What the training forward keeps for the backward: one device buffer laid out by the library (fp32 layer inputs,
+    key mask, and either every layer's activations or one activation slot the backward refills: ``recompute``)."""
 
     def __init__(self):
-        self.layer_inputs: List[torch.Tensor] = []
-        self.saved: List[tuple] = []
-        self.x_final = None
-        self.kv_info = self.key_mask = self.ids = None
+        self.buf: Optional[torch.Tensor] = None
+        self.recompute = False
+        self.ids = None
 
 
 def _save_activations(enc: PackedEncoder, n_tokens: int) -> bool:
     """Keep every layer's activations (no recompute) when they take less than 35 % of the free device memory;
     MOLLY_TRAIN_RECOMPUTE=1 / 0 forces per-layer recompute / saving."""
-    import os
     env = os.environ.get("MOLLY_TRAIN_RECOMPUTE")
     if env is not None:
         return env == "0"
@@ -94,150 +168,87 @@ def _save_activations(enc: PackedEncoder, n_tokens: int) -> bool:
     return per_layer * cfg.num_hidden_layers < 0.35 * torch.cuda.mem_get_info(enc.device)[0]
 
 
+def _sizes(enc: PackedEncoder, n_seq: int, K: int, recompute: bool) -> Tuple[int, int, int]:
+    tape_b, ws_b, gf = C.c_size_t(), C.c_size_t(), C.c_int64()
+    _lib.check(_lib.load().molly_encoder_train_sizes(enc.handle, n_seq, K, int(recompute), C.byref(tape_b), C.byref(ws_b),
+                                                      C.byref(gf)), "molly_encoder_train_sizes")
+    return int(tape_b.value), int(ws_b.value), int(gf.value)
+
+
+def _device_buffer(nbytes: int, dev) -> torch.Tensor:
+    """uint8 buffer whose base is 1024-B aligned (the caching allocator hands out 512-B aligned blocks)."""
+    raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+    shift = (-raw.data_ptr()) % 1024
+    return raw[shift:shift + nbytes]
+
+
 def encoder_forward_train(enc: PackedEncoder, ids: torch.Tensor) -> Tuple[torch.Tensor, EncoderTape]:
     """``hidden_states[-1]`` (bf16 [n*K, h]) with the tape; numerically the inference forward (same kernels, same order)."""
-    cfg, L = enc.cfg, _lib
+    cfg = enc.cfg
     if cfg.emb_layer_norm_before:
         raise NotImplementedError("emb_layer_norm_before encoders are not covered by the training path")
+    dev = ops._require_cuda(ids)
+    ids = ids.contiguous()
     n_seq, K = ids.shape
     tape = EncoderTape()
     tape.ids = ids
-    x, tape.kv_info, tape.key_mask = ops.embed(ids, enc.c_config, enc.word_emb, enc.pos_emb)
-    save = _save_activations(enc, n_seq * K)
-    for lt in enc.layer_tensors:
-        tape.layer_inputs.append(x.clone())
-        if save:
-            kept = _layer_forward(enc, lt, x, n_seq, K, tape.kv_info, tape.key_mask, keep=True)
-            tape.saved.append(kept[1:])
-            mid, _ = ops.act_fwd_bwd(cfg.ffn_type == "glu", kept[7], None)       # finish the layer: FFN activation + FFN2
-            ops.gemm_bf16(mid, lt["w_ffn2"], L.EPI_BIAS_RESIDUAL, bias=lt["b_ffn2"], residual=x, out=x)
-        else:
-            x = _layer_forward(enc, lt, x, n_seq, K, tape.kv_info, tape.key_mask)[0]
-    tape.x_final = x
-    out = ops.layernorm(x, enc.final_ln_w, enc.final_ln_b, cfg.layer_norm_eps, torch.bfloat16)
+    tape.recompute = not _save_activations(enc, n_seq * K)
+    tape_bytes, _, _ = _sizes(enc, n_seq, K, tape.recompute)
+    tape.buf = _device_buffer(tape_bytes, dev)
+    out = torch.empty(n_seq * K, cfg.hidden_size, dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_encode_train_fwd(enc.handle, ids.data_ptr(), n_seq, K, out.data_ptr(), tape.buf.data_ptr(),
+                                                      tape_bytes, int(tape.recompute), ops.error_flag(dev).data_ptr(),
+                                                      ops._stream(dev)), "molly_encode_train_fwd")
     return out, tape
 
 
-def _layer_forward(enc, lt, x, n_seq, K, kv_info, key_mask, keep: bool = False):
-    """One pre-LN layer on the fp32 stream ``x`` (updated in place).  ``keep``: also return what the backward needs."""
-    cfg, L = enc.cfg, _lib
-    h, H = cfg.hidden_size, cfg.num_attention_heads
-    d = h // H
-    rope = cfg.position_embedding_type == "rotary"
-    ln1 = ops.layernorm(x, lt["ln1_w"], lt["ln1_b"], cfg.layer_norm_eps, torch.bfloat16)
-    if rope and d <= 64:
-        qkv = ops.gemm_bf16(ln1, lt["w_qkv"], L.EPI_BIAS_ROPE, bias=lt["b_qkv"], seq_k=K, scale_cols=h, scale=d ** -0.5,
-                            rope_cos_t=enc.rope_cos_t, rope_sin_t=enc.rope_sin_t, rope_cols=2 * h, rope_head_dim=d)
-    else:
-        qkv = ops.gemm_bf16(ln1, lt["w_qkv"], L.EPI_BIAS, bias=lt["b_qkv"], scale_cols=h, scale=d ** -0.5)
-        if rope:
-            ops.rotary_(qkv, K, H, enc.rope_cos, enc.rope_sin)
-    attn, lse2 = ops.attention_lse(qkv, n_seq, K, H, kv_info, key_mask)
-    ops.gemm_bf16(attn, lt["w_attn_out"], L.EPI_BIAS_RESIDUAL, bias=lt["b_attn_out"], residual=x, out=x)
-    x_mid = x.clone() if keep else None
-    ln2 = ops.layernorm(x, lt["ln2_w"], lt["ln2_b"], cfg.layer_norm_eps, torch.bfloat16)
-    glu = cfg.ffn_type == "glu"
-    if keep:                                   # the backward needs the pre-activation: plain bias epilogue, activation apart
-        pre = ops.gemm_bf16(ln2, lt["w_ffn1"], L.EPI_BIAS, bias=lt["b_ffn1"])
-        return x, ln1, qkv, attn, lse2, x_mid, ln2, pre
-    mid = ops.gemm_bf16(ln2, lt["w_ffn1"], L.EPI_GLU if glu else L.EPI_BIAS_GELU, bias=lt["b_ffn1"])
-    ops.gemm_bf16(mid, lt["w_ffn2"], L.EPI_BIAS_RESIDUAL, bias=lt["b_ffn2"], residual=x, out=x)
-    return (x,)
-
-
 def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor, reducer=None) -> Dict[str, torch.Tensor]:
-    """Gradients of every encoder parameter (HF ``state_dict`` names, fp32) from ``d_out`` = d(loss)/d(hidden_states[-1]),
-    bf16 [n*K, h].  ``reducer`` (``dist.LayerwiseGradReducer``): each layer's gradients are handed to it as soon as they
-    exist, so their all-reduce overlaps the layers below; they come back averaged, in the reducer's dtype."""
-    cfg, L = enc.cfg, _lib
+    """Gradients of every encoder parameter (HF ``state_dict`` names, fp32 views of one flat buffer) from ``d_out`` =
+    d(loss)/d(hidden_states[-1]), bf16 [n*K, h].  ``reducer`` (``dist.LayerwiseGradReducer``): each layer's flat group is
+    handed to it as soon as the layer's backward is enqueued, so its all-reduce overlaps the layers below; those gradients
+    come back averaged, in the reducer's dtype."""
+    cfg = enc.cfg
     n_seq, K = tape.ids.shape
-    h, H, F = cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size
-    d = h // H
-    dev = d_out.device
-    glu = cfg.ffn_type == "glu"
-    rope = cfg.position_embedding_type == "rotary"
+    h, L = cfg.hidden_size, cfg.num_hidden_layers
+    dev = ops._require_cuda(d_out)
+    if d_out.dtype != torch.bfloat16 or tuple(d_out.shape) != (n_seq * K, h) or not d_out.is_contiguous():
+        raise ValueError("encoder_backward: d_out must be contiguous bf16 [n_seq*K, h]")
+    plan = grad_plan(enc)
+    tape_bytes, ws_bytes, grad_floats = _sizes(enc, n_seq, K, tape.recompute)
+    assert grad_floats == plan.total
+    flat = torch.empty(plan.total, dtype=torch.float32, device=dev)
+    ws = _device_buffer(ws_bytes, dev)
+    lib = _lib.load()
+
+    def run(layer_begin: int, layer_end: int) -> None:
+        with torch.cuda.device(dev):
+            _lib.check(lib.molly_encode_train_bwd(enc.handle, n_seq, K, tape.buf.data_ptr(), tape_bytes, int(tape.recompute),
+                                                  d_out.data_ptr(), flat.data_ptr(), ws.data_ptr(), ws_bytes, layer_begin,
+                                                  layer_end, ops._stream(dev)), "molly_encode_train_bwd")
+
     grads: Dict[str, torch.Tensor] = {}
-    # LayerNorm weight / bias gradients accumulate into pre-zeroed fp32 rows: one buffer (one fill) for the whole backward
-    zero_rows = torch.zeros(4 * cfg.num_hidden_layers + 2, h, dtype=torch.float32, device=dev)
-    zero_next = [0]
-
-    def z(n):
-        assert n == h
-        row = zero_rows[zero_next[0]]
-        zero_next[0] += 1
-        return row
-    schedule = reduce_schedule(enc) if reducer is not None else None     # [0] projector, [1 + (L-1-i)] layer i, [-1] the rest
-
-    # emb_layer_norm_after
-    d_x = torch.empty_like(tape.x_final)
-    g_w, g_b = z(h), z(h)
-    ops.layernorm_bwd(tape.x_final, d_out, enc.final_ln_w, cfg.layer_norm_eps, d_x, False, g_w, g_b)
-    grads["esm.encoder.emb_layer_norm_after.weight"], grads["esm.encoder.emb_layer_norm_after.bias"] = g_w, g_b
-
-    for i in range(cfg.num_hidden_layers - 1, -1, -1):
-        lt = enc.layer_tensors[i]
-        p = f"esm.encoder.layer.{i}."
-        x_in = tape.layer_inputs[i]
-        if tape.saved:
-            ln1, qkv, attn, lse2, x_mid, ln2, pre = tape.saved[i]
-            tape.saved[i] = None                                              # release as we go
-        else:
-            _, ln1, qkv, attn, lse2, x_mid, ln2, pre = _layer_forward(enc, lt, x_in.clone(), n_seq, K, tape.kv_info,
-                                                                       tape.key_mask, keep=True)
-        # ---- feed-forward block: x_out = x_mid + W2 act(W1 LN2(x_mid) + b1) + b2
-        dy = ops.cast_bf16(d_x)
-        d_act = ops.gemm_bf16(dy, ops.transpose_bf16(lt["w_ffn2"]), L.EPI_BIAS)
-        act, d_pre = ops.act_fwd_bwd(glu, pre, d_act)
-        ffn_bias = lt["b_ffn1"] is not None                                     # NT-v2's gated FFN has none (add_bias_fnn = False)
-        dW2, db2 = ops.linear_wgrad(dy, act, with_bias=ffn_bias)
-        dW1, db1 = ops.linear_wgrad(d_pre, ln2, with_bias=ffn_bias)
-        d_ln2 = ops.gemm_bf16(d_pre, ops.transpose_bf16(lt["w_ffn1"]), L.EPI_BIAS)
-        g_w, g_b = z(h), z(h)
-        ops.layernorm_bwd(x_mid, d_ln2, lt["ln2_w"], cfg.layer_norm_eps, d_x, True, g_w, g_b)      # d_x is now d(x_mid)
-        grads[p + "LayerNorm.weight"], grads[p + "LayerNorm.bias"] = g_w, g_b
-        grads[p + "output.dense.weight"] = dW2
-        if glu:                                # packed rows are (gate_0, up_0, gate_1, up_1, ...): back to the HF halves
-            grads[p + "intermediate.dense.weight"] = glu_deinterleave(dW1, cfg.glu_gate_first)
-            if ffn_bias:
-                grads[p + "intermediate.dense.bias"] = glu_deinterleave(db1, cfg.glu_gate_first)
-        else:
-            grads[p + "intermediate.dense.weight"] = dW1
-            grads[p + "intermediate.dense.bias"] = db1
-        if ffn_bias:
-            grads[p + "output.dense.bias"] = db2
-        # ---- attention block: x_mid = x_in + Wo Attn(LN1(x_in)) + bo
-        dy = ops.cast_bf16(d_x)
-        d_attn = ops.gemm_bf16(dy, ops.transpose_bf16(lt["w_attn_out"]), L.EPI_BIAS)
-        dWo, dbo = ops.linear_wgrad(dy, attn)
-        d_qkv = ops.attention_bwd(qkv, attn, d_attn, lse2, n_seq, K, H, tape.kv_info, tape.key_mask)
-        if rope:
-            ops.rotary_(d_qkv, K, H, enc.rope_cos, enc.rope_neg_sin)          # inverse rotation of d(q'), d(k')
-        ops.scale_cols_(d_qkv, h, d ** -0.5)                                  # q = (W_q x + b_q) * d^-1/2   (HF:341)
-        dWqkv, dbqkv = ops.linear_wgrad(d_qkv, ln1)
-        d_ln1 = ops.gemm_bf16(d_qkv, ops.transpose_bf16(lt["w_qkv"]), L.EPI_BIAS)
-        g_w, g_b = z(h), z(h)
-        ops.layernorm_bwd(x_in, d_ln1, lt["ln1_w"], cfg.layer_norm_eps, d_x, True, g_w, g_b)        # d_x is now d(x_in)
-        grads[p + "attention.LayerNorm.weight"], grads[p + "attention.LayerNorm.bias"] = g_w, g_b
-        grads[p + "attention.output.dense.weight"], grads[p + "attention.output.dense.bias"] = dWo, dbo
-        for j, nm in enumerate(("query", "key", "value")):
-            grads[p + f"attention.self.{nm}.weight"] = dWqkv[j * h:(j + 1) * h]
-            grads[p + f"attention.self.{nm}.bias"] = dbqkv[j * h:(j + 1) * h]
-        if reducer is not None:
-            names = [n for n, _ in schedule[cfg.num_hidden_layers - i]]
-            assert sorted(names) == sorted(n for n in grads if n.startswith(p)), "reduce_schedule is out of date"
-            reducer.reduce_(grads, names)
-
-    # ---- embeddings
+    if reducer is None:
+        run(L, 0)
+        for i in range(L):
+            grads.update(plan.layer_views(i, flat[i * plan.group:(i + 1) * plan.group]))
+    else:
+        for i in range(L - 1, -1, -1):
+            run(L if i == L - 1 else i, i)                    # (the first call also does emb_layer_norm_after)
+            grads.update(plan.layer_views(i, reducer.reduce_flat_(flat[i * plan.group:(i + 1) * plan.group])))
+    # ---- embeddings: the running gradient of the residual stream is the first M*h floats of the workspace
+    d_x = ws[:n_seq * K * h * 4].view(torch.float32).view(n_seq * K, h)
+    tail = flat[plan.tail_begin:]
+    views = plan.tail_views(tail)
     word_index, word_scale, pos_index, pos_scale = _emb_meta(enc, tape.ids)
-    d_word = torch.zeros(enc.word_emb.shape, dtype=torch.float32, device=dev)
+    d_word = views["esm.embeddings.word_embeddings.weight"]
+    d_word.zero_()
     ops.scatter_add_rows_(d_word, d_x, word_index, word_scale)
-    grads["esm.embeddings.word_embeddings.weight"] = d_word
     if pos_index is not None:
-        d_pos = torch.zeros(enc.pos_emb.shape, dtype=torch.float32, device=dev)
+        d_pos = views["esm.embeddings.position_embeddings.weight"]
+        d_pos.zero_()
         ops.scatter_add_rows_(d_pos, d_x, pos_index, pos_scale)
-        grads["esm.embeddings.position_embeddings.weight"] = d_pos
     if reducer is not None:
-        names = [n for n, _ in schedule[-1]]
-        assert sorted(names) == sorted(n for n in grads if not n.startswith("esm.encoder.layer.")), "reduce_schedule is out of date"
-        reducer.reduce_(grads, names)
+        views = plan.tail_views(reducer.reduce_flat_(tail))
+    grads.update(views)
     return grads
