@@ -2,6 +2,8 @@
 // d(hidden_states) that the forward's slice-assign wrote (omics_one.py:91-97) and X is the saved encoder output.
 // Both products contract over the token dimension, so dY and X are first transposed (smem-tiled, coalesced both ways)
 // into K-major operands and the tcgen05 GEMM of gemm.cu does the contraction; db is a warp-per-row reduction of dY^T.
+#include <stdlib.h>
+
 #include "common.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -222,22 +224,30 @@ int linear_wgrad_launch(const void* dy_bf16, const void* x_bf16, int M, int N, i
                         cudaStream_t stream) {
     MOLLY_CHECK(M > 0 && N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0, MOLLY_ERR_UNSUPPORTED,
                 "linear_wgrad: M=%d N=%d K=%d (N, K must be multiples of 8)", M, N, K);
-    CUtensorMap tdy, tx;
-    int rc = make_tma_2d(&tdy, dy_bf16, M, N, N, WG_BK, 64, 2);
-    if (rc) return rc;
-    if ((rc = make_tma_2d(&tx, x_bf16, M, K, K, WG_BK, 64, 2))) return rc;
-    static bool configured = false;
-    if (!configured) {
-        MOLLY_CUDA(cudaFuncSetAttribute(wgrad_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
-        configured = true;
+    static const bool legacy = [] { const char* e = getenv("MOLLY_WGRAD_LEGACY"); return e != nullptr && e[0] == '1'; }();
+    if (!legacy) {
+        // the main tcgen05 GEMM with both operands MN-major (CTA pairs on 256 x 256 tiles, K split across the SMs)
+        set_gemm_family(PF_GEMM_OTHER);
+        int rc = gemm_launch_mn(GEMM_OPND_MN_MN, dy_bf16, N, x_bf16, K, N, K, M, d_weight, DT_F32, K, stream);
+        if (rc) return rc;
+    } else {                                   // MOLLY_WGRAD_LEGACY=1: the first wgrad kernel (one CTA per 128 x 128 tile)
+        CUtensorMap tdy, tx;
+        int rc = make_tma_2d(&tdy, dy_bf16, M, N, N, WG_BK, 64, 2);
+        if (rc) return rc;
+        if ((rc = make_tma_2d(&tx, x_bf16, M, K, K, WG_BK, 64, 2))) return rc;
+        static bool configured = false;
+        if (!configured) {
+            MOLLY_CUDA(cudaFuncSetAttribute(wgrad_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+            configured = true;
+        }
+        const int tiles = ((N + WG_TILE - 1) / WG_TILE) * ((K + WG_TILE - 1) / WG_TILE);
+        const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+        {
+            ProfScope prof(PF_GEMM_OTHER, 2.0 * M * N * static_cast<double>(K), stream);
+            wgrad_mn_kernel<<<grid, WG_THREADS, WG_SMEM, stream>>>(tdy, tx, M, N, K, d_weight);
+        }
+        count_launch();
     }
-    const int tiles = ((N + WG_TILE - 1) / WG_TILE) * ((K + WG_TILE - 1) / WG_TILE);
-    const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-    {
-        ProfScope prof(PF_GEMM_OTHER, 2.0 * M * N * static_cast<double>(K), stream);
-        wgrad_mn_kernel<<<grid, WG_THREADS, WG_SMEM, stream>>>(tdy, tx, M, N, K, d_weight);
-    }
-    count_launch();
     if (d_bias != nullptr) {
         MOLLY_CUDA(cudaMemsetAsync(d_bias, 0, sizeof(float) * N, stream));
         const int chunks = max(1, min(64, M / 64));

@@ -69,6 +69,8 @@ struct GemmParams {
     int rope_len;
     int rope_cols;              //   columns [0, rope_cols) (= q and k) are rotated; rope_cols % 64 == 0
     int rope_head_dim;          //   16 | 32 | 64 ; position = row % seq_k  (row index inside the padded sequence, HF:103)
+    int splits;                 // split-K: the K range is cut into `splits` work items per output tile, each adding its partial
+                                //   tile into the (pre-zeroed) fp32 output with a TMA reduce-add; 1 = plain stores
 };
 
 // NeoX rotary on one 64-column chunk held by one thread (its row): x*cos + rotate_half(x)*sin per head (HF:45-54).
@@ -121,11 +123,18 @@ __device__ __forceinline__ void add_bias32(float* v, const float* bias, int col0
     }
 }
 
-template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS, bool CTA2>
+// OPND: which way the operands lie in memory.  GEMM_OPND_KK: A [M, K] and W [N, K] row-major, both K-major for the MMA (every
+// forward GEMM).  GEMM_OPND_K_MN: the second operand is given as [K, N] row-major = MN-major (dgrad: d_in = d_out W with W as
+// stored, no transpose).  GEMM_OPND_MN_MN: both operands are [K, M] / [K, N] row-major (wgrad: dW = dY^T X contracts over the
+// rows of both).  An MN-major operand arrives as 64 x 64 boxes (64 K-rows x 128 B, 128-B swizzle), one box per 64 M/N values;
+// the stage holds the same bytes, only the descriptors change (LBO = box pitch, SBO = 8 K-rows, 16 K-rows per MMA).
+template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS, bool CTA2, int OPND = GEMM_OPND_KK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
     using Cfg = GemmCfg<BLOCK_N, STG_BUFS, CTA2>;
+    constexpr bool A_MN = OPND == GEMM_OPND_MN_MN, B_MN = OPND != GEMM_OPND_KK;
+    constexpr int MN_BOX_BYTES = 64 * 128;
     constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
     const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs), 1 = peer
     const int tile_first = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
@@ -181,8 +190,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
     const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int tiles_m = (p.M + TILE_M - 1) / TILE_M;
-    const int num_tiles = tiles_m * tiles_n;
+    const int splits = p.splits > 1 ? p.splits : 1;
+    const int num_tiles = tiles_m * tiles_n * splits;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int kb_per = (num_kb + splits - 1) / splits;        // the host picks `splits` so that no split is empty
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
@@ -190,24 +201,52 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
-                const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+                const int ks = tile % splits, mn = tile / splits;
+                const int m_blk = mn / tiles_n, n_blk = mn % tiles_n;
                 const int a_row = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;
                 const int b_row = n_blk * BLOCK_N + (CTA2 ? static_cast<int>(cta_rank) * (BLOCK_N / 2) : 0);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb_end = min(num_kb, (ks + 1) * kb_per);
+                for (int kb = ks * kb_per; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* const a_dst = sA + stage * A_STAGE_BYTES;
+                    uint8_t* const b_dst = sB + stage * Cfg::B_STAGE_BYTES;
                     if constexpr (CTA2) {
                         // both CTAs' bytes are credited to the leader's barrier; only the leader arms it
                         if (cta_rank == 0)
                             mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
-                        tma_load_2d_pair(sA + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], kb * BLOCK_K, a_row);
-                        tma_load_2d_pair(sB + stage * Cfg::B_STAGE_BYTES, &tma_b, &full_bar[stage], kb * BLOCK_K, b_row);
+                        if constexpr (A_MN) {
+#pragma unroll
+                            for (int bx = 0; bx < BLOCK_M / 64; ++bx)
+                                tma_load_2d_pair(a_dst + bx * MN_BOX_BYTES, &tma_a, &full_bar[stage], a_row + bx * 64, kb * BLOCK_K);
+                        } else {
+                            tma_load_2d_pair(a_dst, &tma_a, &full_bar[stage], kb * BLOCK_K, a_row);
+                        }
+                        if constexpr (B_MN) {
+#pragma unroll
+                            for (int bx = 0; bx < BLOCK_N / 2 / 64; ++bx)
+                                tma_load_2d_pair(b_dst + bx * MN_BOX_BYTES, &tma_b, &full_bar[stage], b_row + bx * 64, kb * BLOCK_K);
+                        } else {
+                            tma_load_2d_pair(b_dst, &tma_b, &full_bar[stage], kb * BLOCK_K, b_row);
+                        }
                     } else {
                         mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
-                        tma_load_2d(sA + stage * A_STAGE_BYTES, &tma_a, &full_bar[stage], kb * BLOCK_K, a_row);
+                        if constexpr (A_MN) {
 #pragma unroll
-                        for (int bx = 0; bx < BLOCK_N / B_BOX_ROWS; ++bx)      // the weight map has 128-row boxes
-                            tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES + bx * B_BOX_ROWS * BLOCK_K * 2, &tma_b,
-                                        &full_bar[stage], kb * BLOCK_K, b_row + bx * B_BOX_ROWS);
+                            for (int bx = 0; bx < BLOCK_M / 64; ++bx)
+                                tma_load_2d(a_dst + bx * MN_BOX_BYTES, &tma_a, &full_bar[stage], a_row + bx * 64, kb * BLOCK_K);
+                        } else {
+                            tma_load_2d(a_dst, &tma_a, &full_bar[stage], kb * BLOCK_K, a_row);
+                        }
+                        if constexpr (B_MN) {
+#pragma unroll
+                            for (int bx = 0; bx < BLOCK_N / 64; ++bx)
+                                tma_load_2d(b_dst + bx * MN_BOX_BYTES, &tma_b, &full_bar[stage], b_row + bx * 64, kb * BLOCK_K);
+                        } else {
+#pragma unroll
+                            for (int bx = 0; bx < BLOCK_N / B_BOX_ROWS; ++bx)      // the weight map has 128-row boxes
+                                tma_load_2d(b_dst + bx * B_BOX_ROWS * BLOCK_K * 2, &tma_b, &full_bar[stage], kb * BLOCK_K,
+                                            b_row + bx * B_BOX_ROWS);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -216,7 +255,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
         if (lane == 0 && cta_rank == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, false, false);
+            constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, A_MN, B_MN);
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
@@ -227,21 +266,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb_begin = (tile % splits) * kb_per, kb_end = min(num_kb, kb_begin + kb_per);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint64_t a_desc =
-                        make_smem_desc(smem_u32(sA + stage * A_STAGE_BYTES), 16, 8 * BLOCK_K * 2, kLayoutSW128);
-                    const uint64_t b_desc =
-                        make_smem_desc(smem_u32(sB + stage * Cfg::B_STAGE_BYTES), 16, 8 * BLOCK_K * 2, kLayoutSW128);
+                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES), b_addr = smem_u32(sB + stage * Cfg::B_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        if constexpr (CTA2)
-                            umma_bf16_ss_pair(d_tmem, desc_advance(a_desc, k * UMMA_K * 2),
-                                              desc_advance(b_desc, k * UMMA_K * 2), idesc, (kb | k) != 0);
-                        else
-                            umma_bf16_ss(d_tmem, desc_advance(a_desc, k * UMMA_K * 2), desc_advance(b_desc, k * UMMA_K * 2),
-                                         idesc, (kb | k) != 0);
+                        // K-major: 16 K-elements = 32 B further inside the 128-B row; MN-major: 16 K-rows = 2 KB further down
+                        const uint64_t a_desc = A_MN ? make_smem_desc(a_addr + k * UMMA_K * 128, MN_BOX_BYTES, 1024, kLayoutSW128)
+                                                     : make_smem_desc(a_addr + k * UMMA_K * 2, 16, 8 * BLOCK_K * 2, kLayoutSW128);
+                        const uint64_t b_desc = B_MN ? make_smem_desc(b_addr + k * UMMA_K * 128, MN_BOX_BYTES, 1024, kLayoutSW128)
+                                                     : make_smem_desc(b_addr + k * UMMA_K * 2, 16, 8 * BLOCK_K * 2, kLayoutSW128);
+                        const uint32_t accumulate = (kb > kb_begin || k != 0) ? 1u : 0u;
+                        if constexpr (CTA2) umma_bf16_ss_pair(d_tmem, a_desc, b_desc, idesc, accumulate);
+                        else umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
                     }
                     // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
                     if constexpr (CTA2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -263,7 +302,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const uint32_t lane_tmem = static_cast<uint32_t>(q * 32) << 16;
         int local = 0;
         for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++local) {
-            const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+            const int m_blk = (tile / splits) / tiles_n, n_blk = (tile / splits) % tiles_n;
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
             const int row0 = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + q * 32;   // first row of this warp's slab
@@ -409,7 +448,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         float v[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-                        if (p.bias != nullptr) add_bias32(v, p.bias, col0);
+                        if (p.bias != nullptr && tile % splits == 0) add_bias32(v, p.bias, col0);
                         if (EPI == EPI_BIAS && col0 < p.scale_cols) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] *= p.scale;
@@ -423,7 +462,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&tma_c, stg, col0, row0);
+                            if (splits > 1) tma_reduce_add_2d(&tma_c, stg, col0, row0);     // partial tile of one K split
+                            else tma_store_2d(&tma_c, stg, col0, row0);
                             tma_store_commit();
                         }
                     } else {
@@ -493,18 +533,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
 }
 
-template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS, bool CTA2>
+template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS, bool CTA2, int OPND = GEMM_OPND_KK>
 int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
                      cudaStream_t stream) {
     using Cfg = GemmCfg<BLOCK_N, STG_BUFS, CTA2>;
-    auto kernel = gemm_tcgen05_kernel<BLOCK_N, EPI, OutT, STG_BUFS, CTA2>;
+    auto kernel = gemm_tcgen05_kernel<BLOCK_N, EPI, OutT, STG_BUFS, CTA2, OPND>;
     static bool configured = false;
     if (!configured) {
         MOLLY_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
     constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
-    const int tiles = ((p.M + TILE_M - 1) / TILE_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+    const int tiles = ((p.M + TILE_M - 1) / TILE_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * (p.splits > 1 ? p.splits : 1);
     const int slots = CTA2 ? device_sm_count() / 2 : device_sm_count();
     const int grid = (tiles < slots ? tiles : slots) * (CTA2 ? 2 : 1);
     cudaLaunchConfig_t cfg{};
@@ -653,6 +693,52 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap*
     const GemmTile tile = gemm_pick_tile(M, N, epi);
     if (tile == GEMM_TILE_128) return dispatch_epilogue<128>(ta, tb, *tc, p, epi, out_dtype, false, stream);
     return dispatch_epilogue<256>(ta, tb, *tc, p, epi, out_dtype, tile == GEMM_TILE_PAIR_256, stream);
+}
+
+int gemm_make_map_mn(CUtensorMap* t, const void* base, int rows_k, int cols_mn, int ld) {
+    MOLLY_CHECK(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, MOLLY_ERR_UNSUPPORTED,
+                "gemm: an MN-major operand needs a 16-B aligned base and a pitch that is a multiple of 8 (ld=%d)", ld);
+    return make_tma_2d(t, base, rows_k, cols_mn, ld, 64, 64, 2);
+}
+
+namespace {
+// K splits of a wgrad: fewest waves per split (ceil(tiles * s / slots) / s) with a small charge per extra partial tile
+int pick_splits(int tiles, int slots, int num_kb) {
+    int best = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= 8 && s * 4 <= num_kb; ++s) {
+        const int kb_per = (num_kb + s - 1) / s;
+        if ((num_kb + kb_per - 1) / kb_per != s) continue;                 // an empty split would leave a tile unwritten
+        const double cost = static_cast<double>((tiles * s + slots - 1) / slots) / s * (1.0 + 0.01 * (s - 1));
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+    }
+    return best;
+}
+}  // namespace
+
+int gemm_launch_mn(int opnd, const void* a, int lda, const void* b, int ldb, int M, int N, int K, void* out, int out_dtype,
+                   int ldo, cudaStream_t stream) {
+    MOLLY_CHECK(M > 0 && N > 0 && K > 0 && N % 32 == 0, MOLLY_ERR_UNSUPPORTED, "gemm_mn: M=%d N=%d K=%d (N %% 32 == 0)", M, N, K);
+    MOLLY_CHECK((opnd == GEMM_OPND_K_MN && out_dtype == DT_BF16) || (opnd == GEMM_OPND_MN_MN && out_dtype == DT_F32),
+                MOLLY_ERR_UNSUPPORTED, "gemm_mn: dgrad writes bf16, wgrad fp32 (opnd=%d dtype=%d)", opnd, out_dtype);
+    CUtensorMap ta, tb, tc;
+    int rc = opnd == GEMM_OPND_MN_MN ? gemm_make_map_mn(&ta, a, K, M, lda) : gemm_make_map_a(&ta, a, lda, M, K);
+    if (rc) return rc;
+    if ((rc = gemm_make_map_mn(&tb, b, K, N, ldb))) return rc;
+    if ((rc = gemm_make_map_c(&tc, out, out_dtype, ldo, M, N))) return rc;
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.scale = 1.0f; p.splits = 1;
+    const bool pair = g_pair_enabled() && N % 256 == 0 && M > BLOCK_M;
+    if (opnd == GEMM_OPND_K_MN) {
+        if (pair) return launch_gemm_impl<256, EPI_BIAS, __nv_bfloat16, 1, true, GEMM_OPND_K_MN>(ta, tb, tc, p, stream);
+        return launch_gemm_impl<256, EPI_BIAS, __nv_bfloat16, 1, false, GEMM_OPND_K_MN>(ta, tb, tc, p, stream);
+    }
+    const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
+    const int tiles = ((M + tile_m - 1) / tile_m) * ((N + 255) / 256);
+    p.splits = pick_splits(tiles, pair ? device_sm_count() / 2 : device_sm_count(), (K + BLOCK_K - 1) / BLOCK_K);
+    if (p.splits > 1) MOLLY_CUDA(cudaMemsetAsync(out, 0, static_cast<size_t>(M) * ldo * 4, stream));
+    if (pair) return launch_gemm_impl<256, EPI_BIAS, float, 1, true, GEMM_OPND_MN_MN>(ta, tb, tc, p, stream);
+    return launch_gemm_impl<256, EPI_BIAS, float, 1, false, GEMM_OPND_MN_MN>(ta, tb, tc, p, stream);
 }
 
 }  // namespace molly

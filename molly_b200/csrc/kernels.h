@@ -44,6 +44,15 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap*
                 const float* rope_cos_t = nullptr, const float* rope_sin_t = nullptr, int rope_len = 0, int rope_cols = 0,
                 int rope_head_dim = 0);
 
+// Backward GEMMs on the same kernel, operands taken as they lie in memory (no transposes):
+//   GEMM_OPND_K_MN   out[M, N] = a[M, K] b[K, N]        b row-major [K, N]            (dgrad: d_in = d_out W)
+//   GEMM_OPND_MN_MN  out[M, N] = a[K, M]^T b[K, N]      both row-major with K as rows  (wgrad: dW = dY^T X), fp32 out,
+//                    split over K across the SMs when M x N has too few tiles (partials meet in a TMA reduce-add)
+enum { GEMM_OPND_KK = 0, GEMM_OPND_K_MN = 1, GEMM_OPND_MN_MN = 2 };
+int gemm_make_map_mn(CUtensorMap* t, const void* base, int rows_k, int cols_mn, int ld);
+int gemm_launch_mn(int opnd, const void* a, int lda, const void* b, int ldb, int M, int N, int K, void* out, int out_dtype,
+                   int ldo, cudaStream_t stream);
+
 // ---- attention.cu ----
 void attention_set_debug(long long* buf);
 struct AttnMaps {          // views of the packed [rows, 3h] QKV activation
@@ -106,10 +115,13 @@ int attention_bwd_launch(const void* qkv, const void* out, const void* d_out, co
                          cudaStream_t stream);
 
 // ---- rowwise_bwd.cu ----
+// dy_next_bf16 (optional): bf16 copy of the new d_x; d_bias_next (optional, pre-zeroed): += column sums of dy_next
 int ln_bwd_launch(const float* x, const void* dy_bf16, const float* gamma, int rows, int h, float eps, float* d_x,
-                  int accumulate, float* stats, float* d_gamma, float* d_beta, cudaStream_t stream);
+                  int accumulate, float* stats, float* d_gamma, float* d_beta, cudaStream_t stream,
+                  void* dy_next_bf16 = nullptr, float* d_bias_next = nullptr);
+// d_bias (optional, GELU backward only, pre-zeroed fp32 [f_out]): += column sums of d_pre
 int act_fwd_bwd_launch(int glu, const void* pre, const void* d_act, long long rows, int f_out, void* act, void* d_pre,
-                       cudaStream_t stream);
+                       cudaStream_t stream, float* d_bias = nullptr);
 int cast_f32_bf16_launch(const float* in, long long n, void* out, cudaStream_t stream);
 int scale_cols_launch(void* x_bf16, int rows, int ld, int cols, float scale, cudaStream_t stream);
 int scatter_add_rows_launch(const float* src, const int32_t* index, const float* scale, int rows, int h, float* table,

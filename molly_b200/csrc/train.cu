@@ -236,8 +236,11 @@ int forward(const molly_encoder* e, const int64_t* ids, int n_seq, int k, void* 
     return layernorm_launch(x_at(d.L), e->w.final_ln_w_dev, e->w.final_ln_b_dev, M, h, c.layer_norm_eps, out, DT_BF16, s);
 }
 
-// dgrad of nn.Linear: d_in[M, K] = d_out[M, N] W[N, K]  =  GEMM against W^T [K, N] (transposed into scratch)
+// dgrad of nn.Linear: d_in[M, K] = d_out[M, N] W[N, K], W read as it is stored ([N, K] row-major = MN-major second operand).
+// MOLLY_DGRAD_TRANSPOSE=1: the first version (W^T materialised in scratch, then the K-major GEMM).
 int dgrad(const void* d_out, const void* w, int M, int N, int K, void* w_t, void* d_in, cudaStream_t s) {
+    static const bool legacy = [] { const char* e = getenv("MOLLY_DGRAD_TRANSPOSE"); return e != nullptr && e[0] == '1'; }();
+    if (!legacy) return gemm_launch_mn(GEMM_OPND_K_MN, d_out, N, w, K, M, K, N, d_in, DT_BF16, K, s);
     int rc = transpose_bf16_launch(w, N, K, w_t, s);
     if (rc) return rc;
     return gemm_plain(d_out, w_t, nullptr, M, K, N, EPI_BIAS, nullptr, d_in, K, s);
@@ -261,21 +264,23 @@ int backward_layer(const molly_encoder* e, const Dims& d, int l, const float* x_
     void* w_t = ws + sc.w_t;
     auto G = [&](int slot_id) { return gl.off[slot_id] < 0 ? nullptr : g + gl.off[slot_id]; };
     int rc;
-    MOLLY_CUDA(cudaMemsetAsync(g, 0, sizeof(float) * gl.vec_floats, s));      // LayerNorm / bias gradients accumulate
+    // On entry `dy` holds the bf16 copy of d_x = d(x_out) (written by the LayerNorm backward above this layer), this layer's
+    // vector block is zeroed and its b_ffn2 gradient (column sums of dy) is already in place.
     // ---- feed-forward block: x_out = x_mid + W2 act(W1 LN2(x_mid) + b1) + b2
-    if ((rc = cast_f32_bf16_launch(d_x, static_cast<long long>(M) * h, dy, s))) return rc;
     if ((rc = dgrad(dy, e->w_ffn2[l], M, h, F, w_t, d_act, s))) return rc;
-    if ((rc = act_fwd_bwd_launch(d.glu, slot + t.pre, d_act, M, F, act, d_pre, s))) return rc;
-    if ((rc = linear_wgrad_launch(dy, act, M, h, F, G(MOLLY_GRAD_W_FFN2), G(MOLLY_GRAD_B_FFN2), s))) return rc;
-    if ((rc = linear_wgrad_launch(d_pre, slot + t.ln2, M, F1, h, G(MOLLY_GRAD_W_FFN1), G(MOLLY_GRAD_B_FFN1), s))) return rc;
+    if ((rc = act_fwd_bwd_launch(d.glu, slot + t.pre, d_act, M, F, act, d_pre, s, d.glu ? nullptr : G(MOLLY_GRAD_B_FFN1))))
+        return rc;
+    if ((rc = linear_wgrad_launch(dy, act, M, h, F, G(MOLLY_GRAD_W_FFN2), nullptr, s))) return rc;
+    if ((rc = linear_wgrad_launch(d_pre, slot + t.ln2, M, F1, h, G(MOLLY_GRAD_W_FFN1), d.glu ? G(MOLLY_GRAD_B_FFN1) : nullptr, s)))
+        return rc;
     if ((rc = dgrad(d_pre, e->w_ffn1[l], M, F1, h, w_t, d_ln, s))) return rc;
+    // d_x becomes d(x_mid); dy its bf16 copy; b_o gradient = column sums of dy
     if ((rc = ln_bwd_launch(reinterpret_cast<const float*>(slot + t.x_mid), d_ln, e->ln2_w[l], M, h, c.layer_norm_eps, d_x, 1,
-                            stats, G(MOLLY_GRAD_LN2_W), G(MOLLY_GRAD_LN2_B), s)))
-        return rc;                                                             // d_x is now d(x_mid)
+                            stats, G(MOLLY_GRAD_LN2_W), G(MOLLY_GRAD_LN2_B), s, dy, G(MOLLY_GRAD_B_O))))
+        return rc;
     // ---- attention block: x_mid = x_in + Wo Attn(LN1(x_in)) + bo
-    if ((rc = cast_f32_bf16_launch(d_x, static_cast<long long>(M) * h, dy, s))) return rc;
     if ((rc = dgrad(dy, e->w_o[l], M, h, h, w_t, d_attn, s))) return rc;
-    if ((rc = linear_wgrad_launch(dy, slot + t.attn, M, h, h, G(MOLLY_GRAD_W_O), G(MOLLY_GRAD_B_O), s))) return rc;
+    if ((rc = linear_wgrad_launch(dy, slot + t.attn, M, h, h, G(MOLLY_GRAD_W_O), nullptr, s))) return rc;
     if ((rc = attention_bwd_launch(slot + t.qkv, slot + t.attn, d_attn, reinterpret_cast<const float*>(slot + t.lse2), d.n_seq,
                                    d.k, h, d.H, kv_info, key_mask, d_qkv, delta, s)))
         return rc;
@@ -287,8 +292,12 @@ int backward_layer(const molly_encoder* e, const Dims& d, int l, const float* x_
     }
     if ((rc = linear_wgrad_launch(d_qkv, slot + t.ln1, M, 3 * h, h, G(MOLLY_GRAD_W_QKV), G(MOLLY_GRAD_B_QKV), s))) return rc;
     if ((rc = dgrad(d_qkv, e->w_qkv[l], M, 3 * h, h, w_t, d_ln, s))) return rc;
-    return ln_bwd_launch(x_in, d_ln, e->ln1_w[l], M, h, c.layer_norm_eps, d_x, 1, stats, G(MOLLY_GRAD_LN1_W),
-                         G(MOLLY_GRAD_LN1_B), s);                             // d_x is now d(x_in)
+    // d_x becomes d(x_in) = d(x_out of layer l-1): prepare that layer's vector block and its b_ffn2 gradient
+    float* g_below = l > 0 ? g - gl.group : nullptr;
+    if (g_below != nullptr) MOLLY_CUDA(cudaMemsetAsync(g_below, 0, sizeof(float) * gl.vec_floats, s));
+    float* b2_below = (g_below != nullptr && gl.off[MOLLY_GRAD_B_FFN2] >= 0) ? g_below + gl.off[MOLLY_GRAD_B_FFN2] : nullptr;
+    return ln_bwd_launch(x_in, d_ln, e->ln1_w[l], M, h, c.layer_norm_eps, d_x, 1, stats, G(MOLLY_GRAD_LN1_W), G(MOLLY_GRAD_LN1_B),
+                         s, l > 0 ? dy : nullptr, b2_below);
 }
 
 }  // namespace
@@ -355,9 +364,12 @@ int molly_encode_train_bwd(molly_encoder_t* enc, int32_t n_seq, int32_t k_tokens
         if (l == d.L) {                            // emb_layer_norm_after: d_x = LN-backward(d_out)
             MOLLY_CHECK(d_out_dev != nullptr, MOLLY_ERR_INVALID, "molly_encode_train_bwd: d_out is needed for layer %d", d.L);
             float* gw = grads_dev + gl.tail[MOLLY_GRAD_TAIL_FINAL_LN_W];
+            float* g_top = grads_dev + gl.group * (d.L - 1);          // layer L-1: zero its vector block, fill its b_ffn2 gradient
             MOLLY_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * 2 * d.h, s));
+            MOLLY_CUDA(cudaMemsetAsync(g_top, 0, sizeof(float) * gl.vec_floats, s));
             if ((rc = ln_bwd_launch(x_at(d.L), d_out_dev, enc->w.final_ln_w_dev, d.M, d.h, enc->cfg.layer_norm_eps, d_x, 0,
-                                    reinterpret_cast<float*>(ws + sc.stats), gw, gw + d.h, s)))
+                                    reinterpret_cast<float*>(ws + sc.stats), gw, gw + d.h, s, ws + sc.dy,
+                                    gl.off[MOLLY_GRAD_B_FFN2] >= 0 ? g_top + gl.off[MOLLY_GRAD_B_FFN2] : nullptr)))
                 return rc;
             continue;
         }

@@ -43,9 +43,38 @@ def main():
         step()
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
+    n_steps = 3
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-        step()
+        for _ in range(n_steps):
+            step()
         torch.cuda.synchronize()
+    # launch -> start delay per kernel (chrome trace: runtime launch events and kernels share a correlation id): a queue that
+    # stays full shows delays of many milliseconds; delays of a few microseconds mean the GPU is waiting for the host
+    import json
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".json") as f:
+        prof.export_chrome_trace(f.name)
+        tr = json.load(open(f.name))
+    launch, kern = {}, {}
+    for ev in tr["traceEvents"]:
+        a = ev.get("args", {})
+        c = a.get("correlation")
+        if c is None or ev.get("ph") != "X":
+            continue
+        if ev.get("cat") == "cuda_runtime":
+            launch[c] = ev["ts"]
+        elif ev.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset"):
+            kern[c] = (ev["ts"], ev["dur"], ev["name"])
+    delays = sorted((kern[c][0] - launch[c], kern[c][0]) for c in kern if c in launch)
+    if delays:
+        d = [x for x, _ in delays]
+        print(f"launch->start delay over {len(d)} launches: median {d[len(d) // 2]:.0f} us, p10 {d[len(d) // 10]:.0f} us, "
+              f"p90 {d[len(d) * 9 // 10]:.0f} us; launches that started < 20 us after their launch call: "
+              f"{sum(1 for x in d if x < 20)} ({100.0 * sum(1 for x in d if x < 20) / len(d):.0f} %)")
+    ks = sorted(kern.values())
+    t_first, t_last = ks[0][0], max(k[0] + k[1] for k in ks)
+    print(f"{n_steps} steps: device span {(t_last - t_first) / 1e3 / n_steps:.2f} ms per step, busy "
+          f"{sum(k[1] for k in ks) / 1e3 / n_steps:.2f} ms per step")
     agg = collections.OrderedDict()
     kernels = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     t0 = min(e.time_range.start for e in kernels)
@@ -56,9 +85,9 @@ def main():
         a[0] += 1
         a[1] += e.time_range.elapsed_us()
         busy += e.time_range.elapsed_us()
-    print(f"span {(t1 - t0) / 1e3:.2f} ms, kernel time {busy / 1e3:.2f} ms, {len(kernels)} device activities")
-    for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
-        print(f"{us / 1e3:9.3f} ms {n:6d} x {us / n:9.1f} us  {name}")
+    print(f"span {(t1 - t0) / 1e3 / n_steps:.2f} ms, kernel time {busy / 1e3 / n_steps:.2f} ms, {len(kernels) // n_steps} device activities (per step)")
+    for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:32]:
+        print(f"{us / 1e3 / n_steps:9.3f} ms {n // n_steps:6d} x {us / n:9.1f} us  {name}")
     # gaps: idle time between consecutive device activities (single stream view)
     ev = sorted(kernels, key=lambda e: e.time_range.start)
     gaps, end = [], ev[0].time_range.end
@@ -66,7 +95,7 @@ def main():
         if e.time_range.start > end:
             gaps.append((e.time_range.start - end, e.name[:60]))
         end = max(end, e.time_range.end)
-    print(f"idle {sum(g for g, _ in gaps) / 1e3:.2f} ms in {len(gaps)} gaps; largest:")
+    print(f"idle {sum(g for g, _ in gaps) / 1e3 / n_steps:.2f} ms per step in {len(gaps) // n_steps} gaps; largest:")
     for g, n in sorted(gaps, reverse=True)[:15]:
         print(f"   {g:9.1f} us before {n}")
     path.close()
