@@ -375,17 +375,20 @@ int molly_gemm_bf16(const void* a_dev, int32_t lda, const void* w_dev, int32_t l
     int rc = gemm_make_map_a(&ta, a_dev, lda, M, K);
     if (rc) return rc;
     if ((rc = gemm_make_map_b(&tb, w_dev, ldw, N, K, epilogue))) return rc;
+    CUtensorMap tr;
+    const CUtensorMap* trp = nullptr;                                  // residual read in place unless it lives elsewhere
     if (epilogue == EPI_BIAS_RESID) {
         MOLLY_CHECK(residual_dev != nullptr, MOLLY_ERR_INVALID, "molly_gemm_bf16: residual epilogue needs a residual");
-        if (static_cast<const void*>(residual_dev) != out_dev)       // the kernel updates the fp32 stream in place
-            MOLLY_CUDA(cudaMemcpy2DAsync(out_dev, static_cast<size_t>(ldo) * 4, residual_dev, static_cast<size_t>(ldo) * 4,
-                                         static_cast<size_t>(N) * 4, M, cudaMemcpyDeviceToDevice, s));
+        if (static_cast<const void*>(residual_dev) != out_dev) {       // (same pitch as the output)
+            if ((rc = gemm_make_map_c(&tr, const_cast<float*>(residual_dev), DT_F32, ldo, M, N))) return rc;
+            trp = &tr;
+        }
     }
     if (epilogue != EPI_SCATTER)
         if ((rc = gemm_make_map_c(&tc, out_dev, out_dtype, ldo, M, epilogue == EPI_GLU ? N / 2 : N))) return rc;
     return gemm_launch(ta, tb, epilogue == EPI_SCATTER ? nullptr : &tc, M, N, K, epilogue, bias_dev, out_dev, out_dtype,
                        ldo, seq_table_dev, seq_k_tokens, B, T, k_cap, err_flag_dev, s, scale_cols, scale, rope_cos_t_dev,
-                       rope_sin_t_dev, rope_len, rope_cols, rope_head_dim);
+                       rope_sin_t_dev, rope_len, rope_cols, rope_head_dim, trp);
 }
 
 int molly_layernorm(const float* x_dev, const float* w_dev, const float* b_dev, int32_t rows, int32_t h, float eps,

@@ -10,9 +10,12 @@
 //     A operand and dQ' += dS K' uses the K tile as the MN-major B operand (exactly how the forward feeds V).
 //   * attn_bwd_dkv_kernel: CTA = 128 keys; streams query blocks with the roles swapped -- S^T = K' Q'^T, dP^T = V dO^T, so a
 //     thread owns a KEY row, P^T and dS^T are K-major A operands, and dV += P^T dO, dK' += dS^T Q' take dO / Q' as MN-major B.
-// One CTA per SM (512 TMEM columns: two 128-column score tiles + the accumulators).  The element-wise work has no row
-// reduction (P comes from the stored log-sum-exp), so TWO threads share a row, 64 columns each: warps w and w+4 address the
-// same TMEM lanes.  First version: loads are double-buffered, the score tiles are not.
+// The streamed blocks are SB = 64 rows for head_dim <= 64: the score tiles and accumulators then take 192 / 256 TMEM columns
+// and ~80 / ~97 KB of shared memory, so TWO CTAs share an SM and one CTA's MMAs / barrier hand-overs run under the other's
+// element-wise work (the first version streamed 128-row blocks with one CTA per SM: 5 500 cycles per 128 x 128 block against
+// ~1 000 of MUFU work).  head_dim 128 keeps SB = 128, one CTA per SM (512 TMEM columns).  The element-wise work has no row
+// reduction (P comes from the stored log-sum-exp), so TWO threads share a row, SB/2 columns each: warps w and w+4 address the
+// same TMEM lanes.  Loads are double-buffered, the score tiles are not.
 #include <math_constants.h>
 
 #include "common.h"
@@ -28,25 +31,34 @@ constexpr int BW_THREADS = 288;                // 8 compute warps (two per query
 constexpr int BW_COMPUTE = 256;
 constexpr float BW_LOG2E = 1.4426950408889634f;
 
-template <int D>
+template <int D, int SB>
 struct BwdCfg {
     static constexpr int BOX_D = D < 64 ? D : 64;
     static constexpr int NBOX = D / BOX_D;
     static constexpr int ROW_BYTES = BOX_D * 2;
     static constexpr uint32_t LAYOUT = ROW_BYTES == 128 ? kLayoutSW128 : (ROW_BYTES == 64 ? kLayoutSW64 : kLayoutSW32);
-    static constexpr int BOX_BYTES = BW_BLOCK * ROW_BYTES;
+    static constexpr int BOX_BYTES = BW_BLOCK * ROW_BYTES;             // resident tiles: 128 rows per TMA box
     static constexpr int TILE = NBOX * BOX_BYTES;                      // one 128 x D bf16 tile
-    static constexpr int PT_BYTES = BW_BLOCK * BW_BLOCK * 2;           // one 128 x 128 bf16 operand tile (two swizzle atoms)
+    static constexpr int SBOX_BYTES = SB * ROW_BYTES;                  // streamed tiles: SB rows per TMA box
+    static constexpr int STILE = NBOX * SBOX_BYTES;                    // one SB x D bf16 tile
+    static constexpr int PT_BYTES = BW_BLOCK * SB * 2;                 // one 128 x SB bf16 operand tile (SB/64 swizzle atoms)
     static constexpr int STAGES = D == 128 ? 1 : 2;                    // streamed-tile ring depth
-    // dQ kernel: Q | dO | K ring | V ring | dS
-    static constexpr int DQ_OFF_Q = 0, DQ_OFF_DO = TILE, DQ_OFF_K = 2 * TILE, DQ_OFF_V = DQ_OFF_K + STAGES * TILE;
-    static constexpr int DQ_OFF_DS = DQ_OFF_V + STAGES * TILE, DQ_OFF_BAR = DQ_OFF_DS + PT_BYTES;
+    static constexpr int QPH = SB / 64;                                // 32-column quarters each of a row's two threads handles
+    static constexpr int CTAS_PER_SM = SB == 64 ? 2 : 1;
+    // dQ kernel: Q | dO | K ring | V ring | dS          TMEM: S | dP | dQ
+    static constexpr int DQ_OFF_Q = 0, DQ_OFF_DO = TILE, DQ_OFF_K = 2 * TILE, DQ_OFF_V = DQ_OFF_K + STAGES * STILE;
+    static constexpr int DQ_OFF_DS = DQ_OFF_V + STAGES * STILE, DQ_OFF_BAR = DQ_OFF_DS + PT_BYTES;
     static constexpr int DQ_SMEM = DQ_OFF_BAR + 256;
+    static constexpr int DQ_TMEM = 2 * SB + D <= 256 ? 256 : 512;
     // dK/dV kernel: K | V | Q ring | dO ring | P^T | dS^T | row statistics of the streamed query block (2 x {lse2, delta})
-    static constexpr int KV_OFF_K = 0, KV_OFF_V = TILE, KV_OFF_Q = 2 * TILE, KV_OFF_DO = KV_OFF_Q + STAGES * TILE;
-    static constexpr int KV_OFF_PT = KV_OFF_DO + STAGES * TILE, KV_OFF_DST = KV_OFF_PT + PT_BYTES;
-    static constexpr int KV_OFF_STAT = KV_OFF_DST + PT_BYTES, KV_OFF_BAR = KV_OFF_STAT + 2 * 2 * BW_BLOCK * 4;
+    //                                                    TMEM: S^T | dP^T | dV | dK
+    static constexpr int KV_OFF_K = 0, KV_OFF_V = TILE, KV_OFF_Q = 2 * TILE, KV_OFF_DO = KV_OFF_Q + STAGES * STILE;
+    static constexpr int KV_OFF_PT = KV_OFF_DO + STAGES * STILE, KV_OFF_DST = KV_OFF_PT + PT_BYTES;
+    static constexpr int KV_OFF_STAT = KV_OFF_DST + PT_BYTES, KV_OFF_BAR = KV_OFF_STAT + 2 * 2 * SB * 4;
     static constexpr int KV_SMEM = KV_OFF_BAR + 256;
+    static constexpr int KV_TMEM = 2 * SB + 2 * D <= 256 ? 256 : 512;
+    static_assert(SB == 64 || SB == 128, "streamed blocks are 64 or 128 rows");
+    static_assert(2 * SB + 2 * D <= 512, "tensor memory budget");
 };
 
 __device__ __forceinline__ float bw_ex2(float x) {
@@ -126,12 +138,14 @@ __device__ __forceinline__ void zero_row(__nv_bfloat16* dst) {
 }
 
 // ------------------------------------------------------------------------------------------------- dQ'
-template <int D>
-__global__ void __launch_bounds__(BW_THREADS, 1)
-attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do, int k_tokens,
+// tma_qkv / tma_do: 128-row boxes (the CTA's own rows); tma_kv: SB-row boxes of the packed QKV activation (streamed K, V)
+template <int D, int SB>
+__global__ void __launch_bounds__(BW_THREADS, BwdCfg<D, SB>::CTAS_PER_SM)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
+                   const __grid_constant__ CUtensorMap tma_kv, int k_tokens,
                    int h, const int32_t* __restrict__ kv_info, const uint8_t* __restrict__ key_mask,
                    const float* __restrict__ lse2, const float* __restrict__ delta, __nv_bfloat16* __restrict__ d_qkv) {
-    using Cfg = BwdCfg<D>;
+    using Cfg = BwdCfg<D, SB>;
     constexpr int NST = Cfg::STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::DQ_OFF_BAR);
@@ -148,7 +162,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
     const int q0 = blockIdx.x * BW_BLOCK, head = blockIdx.y, n = blockIdx.z, heads = gridDim.y;
     const int kvl = kv_info[2 * n], n_nonpad = kv_info[2 * n + 1];
     const bool interior = n_nonpad != kvl;
-    const int nkv = (kvl + BW_BLOCK - 1) / BW_BLOCK;
+    const int nkv = (kvl + SB - 1) / SB;
     const long long row_base = static_cast<long long>(n) * k_tokens;
     if (nkv == 0) {                                          // no valid key: the forward wrote zeros, nothing flows back
         if (threadIdx.x < BW_BLOCK && q0 + threadIdx.x < k_tokens)
@@ -168,18 +182,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, Cfg::DQ_TMEM);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dq = tmem_base + 256;
+    const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + SB, tmem_dq = tmem_base + 2 * SB;
 
     if (warp == 8) {
         if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_bf16(BW_BLOCK, BW_BLOCK, false, false);
+            constexpr uint32_t idesc_s = make_idesc_bf16(BW_BLOCK, SB, false, false);
             constexpr uint32_t idesc_acc = make_idesc_bf16(BW_BLOCK, D, false, true);       // B MN-major
             const uint32_t s_q = smem_u32(smem + Cfg::DQ_OFF_Q), s_do = smem_u32(smem + Cfg::DQ_OFF_DO);
             const uint32_t s_k = smem_u32(smem + Cfg::DQ_OFF_K), s_v = smem_u32(smem + Cfg::DQ_OFF_V);
@@ -189,13 +203,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                 for (int b = 0; b < Cfg::NBOX; ++b)
                     tma_load_2d(smem + off + b * Cfg::BOX_BYTES, map, bar, col + b * Cfg::BOX_D, row);
             };
+            auto load_stile = [&](int off, uint64_t* bar, int col, int row) {
+#pragma unroll
+                for (int b = 0; b < Cfg::NBOX; ++b)
+                    tma_load_2d(smem + off + b * Cfg::SBOX_BYTES, &tma_kv, bar, col + b * Cfg::BOX_D, row);
+            };
             auto load_kv = [&](int blk) {
                 const int st = blk % NST;
-                mbar_arrive_expect_tx(&bar_kv_full[st], 2 * Cfg::TILE);
-                load_tile(Cfg::DQ_OFF_K + st * Cfg::TILE, &tma_qkv, &bar_kv_full[st], h + head * D,
-                          static_cast<int>(row_base) + blk * BW_BLOCK);
-                load_tile(Cfg::DQ_OFF_V + st * Cfg::TILE, &tma_qkv, &bar_kv_full[st], 2 * h + head * D,
-                          static_cast<int>(row_base) + blk * BW_BLOCK);
+                mbar_arrive_expect_tx(&bar_kv_full[st], 2 * Cfg::STILE);
+                load_stile(Cfg::DQ_OFF_K + st * Cfg::STILE, &bar_kv_full[st], h + head * D, static_cast<int>(row_base) + blk * SB);
+                load_stile(Cfg::DQ_OFF_V + st * Cfg::STILE, &bar_kv_full[st], 2 * h + head * D, static_cast<int>(row_base) + blk * SB);
             };
             auto issue_scores = [&](int blk) {               // S = Q K^T and dP = dO V^T (all four operands K-major)
                 const int st = blk % NST;
@@ -204,15 +221,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
 #pragma unroll
                 for (int s = 0; s < D / 16; ++s) {
                     const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
+                    const uint32_t soff = ((s * 16) / Cfg::BOX_D) * Cfg::SBOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
                     umma_bf16_ss(tmem_s, make_smem_desc(s_q + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT),
-                                 make_smem_desc(s_k + st * Cfg::TILE + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT), idesc_s,
+                                 make_smem_desc(s_k + st * Cfg::STILE + soff, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT), idesc_s,
                                  s != 0);
                 }
 #pragma unroll
                 for (int s = 0; s < D / 16; ++s) {
                     const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
+                    const uint32_t soff = ((s * 16) / Cfg::BOX_D) * Cfg::SBOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
                     umma_bf16_ss(tmem_dp, make_smem_desc(s_do + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT),
-                                 make_smem_desc(s_v + st * Cfg::TILE + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT), idesc_s,
+                                 make_smem_desc(s_v + st * Cfg::STILE + soff, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT), idesc_s,
                                  s != 0);
                 }
                 umma_commit(bar_sdp_full);
@@ -233,9 +252,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                 mbar_wait(bar_ds_full, j & 1);               // dS(j) is in smem
                 tc_fence_after();
 #pragma unroll
-                for (int s = 0; s < BW_BLOCK / 16; ++s) {    // dQ += dS K : A K-major (two 64-key atoms), B = K tile MN-major
+                for (int s = 0; s < SB / 16; ++s) {          // dQ += dS K : A K-major (SB/64 atoms of 64 keys), B = K tile MN-major
                     const uint64_t ad = make_smem_desc(s_ds + (s >> 2) * (BW_BLOCK * 128) + (s & 3) * 32, 16, 1024, kLayoutSW128);
-                    const uint64_t bd = make_smem_desc(s_k + st * Cfg::TILE + s * 16 * Cfg::ROW_BYTES, Cfg::BOX_BYTES,
+                    const uint64_t bd = make_smem_desc(s_k + st * Cfg::STILE + s * 16 * Cfg::ROW_BYTES, Cfg::SBOX_BYTES,
                                                        8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
                     umma_bf16_ss(tmem_dq, ad, bd, idesc_acc, (j | s) != 0);
                 }
@@ -270,20 +289,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                 tc_fence_after();
             }
 #pragma unroll
-            for (int qq = 0; qq < 2; ++qq) {                 // 32 keys at a time
-                const int qt = 2 * half + qq;
+            for (int qq = 0; qq < Cfg::QPH; ++qq) {          // 32 keys at a time
+                const int qt = Cfg::QPH * half + qq;
                 uint32_t sr[32], pr[32];
                 tmem_ld32(tmem_s + lane_addr + qt * 32, sr);
                 tmem_ld32(tmem_dp + lane_addr + qt * 32, pr);
                 tmem_ld_wait();
-                if (qq == 1) {
+                if (qq == Cfg::QPH - 1) {
                     tc_fence_before();
                     mbar_arrive(bar_s_free);                 // S / dP are in registers: the next block's scores may be issued
                 }
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const int key = j * BW_BLOCK + qt * 32 + i;
+                    const int key = j * SB + qt * 32 + i;
                     bool ok = key < kvl;
                     if (interior && ok) ok = key_mask[row_base + key] != 0;
                     const float p = ok ? bw_ex2(__uint_as_float(sr[i]) * BW_LOG2E - my_lse) : 0.f;
@@ -305,17 +324,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, Cfg::DQ_TMEM);
     }
 }
 
 // ------------------------------------------------------------------------------------------------- dK', dV
-template <int D>
-__global__ void __launch_bounds__(BW_THREADS, 1)
-attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do, int k_tokens,
+// tma_qkv: 128-row boxes (the CTA's K, V); tma_q / tma_do: SB-row boxes (streamed Q', dO)
+template <int D, int SB>
+__global__ void __launch_bounds__(BW_THREADS, BwdCfg<D, SB>::CTAS_PER_SM)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_q,
+                    const __grid_constant__ CUtensorMap tma_do, int k_tokens,
                     int h, const int32_t* __restrict__ kv_info, const uint8_t* __restrict__ key_mask,
                     const float* __restrict__ lse2, const float* __restrict__ delta, __nv_bfloat16* __restrict__ d_qkv) {
-    using Cfg = BwdCfg<D>;
+    using Cfg = BwdCfg<D, SB>;
     constexpr int NST = Cfg::STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::KV_OFF_BAR);
@@ -333,7 +354,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     const int kvl = kv_info[2 * n], n_nonpad = kv_info[2 * n + 1];
     const bool interior = n_nonpad != kvl;
     const long long row_base = static_cast<long long>(n) * k_tokens;
-    const int nq = (k_tokens + BW_BLOCK - 1) / BW_BLOCK;     // every query row of the sequence attends (pad queries too)
+    const int nq = (k_tokens + SB - 1) / SB;                 // every query row of the sequence attends (pad queries too)
     if (k0 >= kvl) {                                         // keys past the last valid one never receive probability mass
         if (threadIdx.x < BW_BLOCK && k0 + threadIdx.x < k_tokens) {
             __nv_bfloat16* row = d_qkv + (row_base + k0 + threadIdx.x) * 3 * h + head * D;
@@ -345,6 +366,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     if (warp == 8) {
         if (lane == 0) {
             tma_prefetch_desc(&tma_qkv);
+            tma_prefetch_desc(&tma_q);
             tma_prefetch_desc(&tma_do);
             mbar_init(bar_kv, 1);
             for (int s = 0; s < NST; ++s) { mbar_init(&bar_q_full[s], 1); mbar_init(&bar_q_empty[s], 1); }
@@ -355,18 +377,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, Cfg::KV_TMEM);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_st = tmem_base, tmem_dpt = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 384;
+    const uint32_t tmem_st = tmem_base, tmem_dpt = tmem_base + SB, tmem_dv = tmem_base + 2 * SB, tmem_dk = tmem_dv + D;
 
     if (warp == 8) {
         if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_bf16(BW_BLOCK, BW_BLOCK, false, false);
+            constexpr uint32_t idesc_s = make_idesc_bf16(BW_BLOCK, SB, false, false);
             constexpr uint32_t idesc_acc = make_idesc_bf16(BW_BLOCK, D, false, true);       // B MN-major
             const uint32_t s_k = smem_u32(smem + Cfg::KV_OFF_K), s_v = smem_u32(smem + Cfg::KV_OFF_V);
             const uint32_t s_q = smem_u32(smem + Cfg::KV_OFF_Q), s_do = smem_u32(smem + Cfg::KV_OFF_DO);
@@ -376,13 +398,16 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
                 for (int b = 0; b < Cfg::NBOX; ++b)
                     tma_load_2d(smem + off + b * Cfg::BOX_BYTES, map, bar, col + b * Cfg::BOX_D, row);
             };
+            auto load_stile = [&](int off, const CUtensorMap* map, uint64_t* bar, int col, int row) {
+#pragma unroll
+                for (int b = 0; b < Cfg::NBOX; ++b)
+                    tma_load_2d(smem + off + b * Cfg::SBOX_BYTES, map, bar, col + b * Cfg::BOX_D, row);
+            };
             auto load_q = [&](int blk) {
                 const int st = blk % NST;
-                mbar_arrive_expect_tx(&bar_q_full[st], 2 * Cfg::TILE);
-                load_tile(Cfg::KV_OFF_Q + st * Cfg::TILE, &tma_qkv, &bar_q_full[st], head * D,
-                          static_cast<int>(row_base) + blk * BW_BLOCK);
-                load_tile(Cfg::KV_OFF_DO + st * Cfg::TILE, &tma_do, &bar_q_full[st], head * D,
-                          static_cast<int>(row_base) + blk * BW_BLOCK);
+                mbar_arrive_expect_tx(&bar_q_full[st], 2 * Cfg::STILE);
+                load_stile(Cfg::KV_OFF_Q + st * Cfg::STILE, &tma_q, &bar_q_full[st], head * D, static_cast<int>(row_base) + blk * SB);
+                load_stile(Cfg::KV_OFF_DO + st * Cfg::STILE, &tma_do, &bar_q_full[st], head * D, static_cast<int>(row_base) + blk * SB);
             };
             auto issue_scores = [&](int blk) {               // S^T = K Q^T and dP^T = V dO^T
                 const int st = blk % NST;
@@ -391,15 +416,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
 #pragma unroll
                 for (int s = 0; s < D / 16; ++s) {
                     const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
+                    const uint32_t soff = ((s * 16) / Cfg::BOX_D) * Cfg::SBOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
                     umma_bf16_ss(tmem_st, make_smem_desc(s_k + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT),
-                                 make_smem_desc(s_q + st * Cfg::TILE + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT), idesc_s,
+                                 make_smem_desc(s_q + st * Cfg::STILE + soff, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT), idesc_s,
                                  s != 0);
                 }
 #pragma unroll
                 for (int s = 0; s < D / 16; ++s) {
                     const uint32_t off = ((s * 16) / Cfg::BOX_D) * Cfg::BOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
+                    const uint32_t soff = ((s * 16) / Cfg::BOX_D) * Cfg::SBOX_BYTES + ((s * 16) % Cfg::BOX_D) * 2;
                     umma_bf16_ss(tmem_dpt, make_smem_desc(s_v + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT),
-                                 make_smem_desc(s_do + st * Cfg::TILE + off, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT), idesc_s,
+                                 make_smem_desc(s_do + st * Cfg::STILE + soff, 16, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT), idesc_s,
                                  s != 0);
                 }
                 umma_commit(bar_sdp_full);
@@ -420,13 +447,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
                 mbar_wait(bar_pt_full, i & 1);
                 tc_fence_after();
 #pragma unroll
-                for (int s = 0; s < BW_BLOCK / 16; ++s) {    // contraction over the 128 queries of the block
+                for (int s = 0; s < SB / 16; ++s) {          // contraction over the SB queries of the block
                     const uint32_t a_off = (s >> 2) * (BW_BLOCK * 128) + (s & 3) * 32;
                     const uint64_t pd = make_smem_desc(s_pt + a_off, 16, 1024, kLayoutSW128);
                     const uint64_t dd = make_smem_desc(s_dst + a_off, 16, 1024, kLayoutSW128);
-                    const uint64_t bo = make_smem_desc(s_do + st * Cfg::TILE + s * 16 * Cfg::ROW_BYTES, Cfg::BOX_BYTES,
+                    const uint64_t bo = make_smem_desc(s_do + st * Cfg::STILE + s * 16 * Cfg::ROW_BYTES, Cfg::SBOX_BYTES,
                                                        8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
-                    const uint64_t bq = make_smem_desc(s_q + st * Cfg::TILE + s * 16 * Cfg::ROW_BYTES, Cfg::BOX_BYTES,
+                    const uint64_t bq = make_smem_desc(s_q + st * Cfg::STILE + s * 16 * Cfg::ROW_BYTES, Cfg::SBOX_BYTES,
                                                        8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
                     umma_bf16_ss(tmem_dv, pd, bo, idesc_acc, (i | s) != 0);      // dV  += P^T  dO
                     umma_bf16_ss(tmem_dk, dd, bq, idesc_acc, (i | s) != 0);      // dK' += dS^T Q'
@@ -457,12 +484,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
         uint8_t* dst_tile = smem + Cfg::KV_OFF_DST;
         const size_t stat_base = (static_cast<size_t>(n) * heads + head) * k_tokens;
         for (int i = 0; i < nq; ++i) {
-            // row statistics of the 128 queries of this block -> smem (thread r brings query i*128 + r)
-            float* st_lse = stats + (i & 1) * 2 * BW_BLOCK;
-            float* st_delta = st_lse + BW_BLOCK;
-            const int q = i * BW_BLOCK + r;
-            if (half == 0) st_lse[r] = q < k_tokens ? lse2[stat_base + q] : CUDART_INF_F;    // +inf: P = 0 beyond the sequence
-            else st_delta[r] = q < k_tokens ? delta[stat_base + q] : 0.f;
+            // row statistics of the SB queries of this block -> smem (thread r brings query i*SB + r)
+            float* st_lse = stats + (i & 1) * 2 * SB;
+            float* st_delta = st_lse + SB;
+            const int q = i * SB + r;
+            if (r < SB) {
+                if (half == 0) st_lse[r] = q < k_tokens ? lse2[stat_base + q] : CUDART_INF_F;    // +inf: P = 0 beyond the sequence
+                else st_delta[r] = q < k_tokens ? delta[stat_base + q] : 0.f;
+            }
             named_bar_sync(1, BW_COMPUTE);
             mbar_wait(bar_sdp_full, i & 1);
             tc_fence_after();
@@ -471,13 +500,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
                 tc_fence_after();
             }
 #pragma unroll
-            for (int qq = 0; qq < 2; ++qq) {                 // 32 queries at a time
-                const int qt = 2 * half + qq;
+            for (int qq = 0; qq < Cfg::QPH; ++qq) {          // 32 queries at a time
+                const int qt = Cfg::QPH * half + qq;
                 uint32_t sr[32], pr[32];
                 tmem_ld32(tmem_st + lane_addr + qt * 32, sr);
                 tmem_ld32(tmem_dpt + lane_addr + qt * 32, pr);
                 tmem_ld_wait();
-                if (qq == 1) {
+                if (qq == Cfg::QPH - 1) {
                     tc_fence_before();
                     mbar_arrive(bar_s_free);
                 }
@@ -506,29 +535,37 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, Cfg::KV_TMEM);
     }
 }
 
 template <int D>
-int launch_attention_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, int n_seq, int k_tokens, int h, int heads,
+int launch_attention_bwd(const void* qkv, const void* d_out, int n_seq, int k_tokens, int h, int heads,
                          const int32_t* kv_info, const uint8_t* key_mask, const float* lse2, const float* delta,
                          __nv_bfloat16* d_qkv, cudaStream_t stream) {
-    using Cfg = BwdCfg<D>;
+    constexpr int SB = D <= 64 ? 64 : 128;
+    using Cfg = BwdCfg<D, SB>;
     static bool configured = false;
     if (!configured) {
-        MOLLY_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::DQ_SMEM));
-        MOLLY_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::KV_SMEM));
+        MOLLY_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<D, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::DQ_SMEM));
+        MOLLY_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<D, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::KV_SMEM));
         configured = true;
     }
+    const int rows = n_seq * k_tokens;
+    CUtensorMap tq, tdo, tq_s, tdo_s;          // 128-row boxes for the CTA's own tile, SB-row boxes for the streamed ones
+    int rc = make_tma_2d(&tq, qkv, rows, 3 * h, 3 * h, BW_BLOCK, Cfg::BOX_D, 2);
+    if (rc) return rc;
+    if ((rc = make_tma_2d(&tdo, d_out, rows, h, h, BW_BLOCK, Cfg::BOX_D, 2))) return rc;
+    if ((rc = make_tma_2d(&tq_s, qkv, rows, 3 * h, 3 * h, SB, Cfg::BOX_D, 2))) return rc;
+    if ((rc = make_tma_2d(&tdo_s, d_out, rows, h, h, SB, Cfg::BOX_D, 2))) return rc;
     dim3 grid((k_tokens + BW_BLOCK - 1) / BW_BLOCK, heads, n_seq);
     {   // 4 MMAs of 2*K*K*d each per (sequence, head) in each kernel... dense-equivalent 2.5x the forward in total
         prof_attention_work(kv_info, n_seq, k_tokens, h, 10.0, stream);     // work = 10 h K sum(kv_len), known on the device only
         ProfScope prof(PF_ATTENTION_BWD, 10.0 * n_seq * k_tokens * static_cast<double>(k_tokens) * h, stream);
-        attn_bwd_dq_kernel<D><<<grid, BW_THREADS, Cfg::DQ_SMEM, stream>>>(tq, tdo, k_tokens, h, kv_info, key_mask, lse2, delta,
-                                                                          d_qkv);
-        attn_bwd_dkv_kernel<D><<<grid, BW_THREADS, Cfg::KV_SMEM, stream>>>(tq, tdo, k_tokens, h, kv_info, key_mask, lse2, delta,
-                                                                           d_qkv);
+        attn_bwd_dq_kernel<D, SB><<<grid, BW_THREADS, Cfg::DQ_SMEM, stream>>>(tq, tdo, tq_s, k_tokens, h, kv_info, key_mask, lse2,
+                                                                              delta, d_qkv);
+        attn_bwd_dkv_kernel<D, SB><<<grid, BW_THREADS, Cfg::KV_SMEM, stream>>>(tq, tq_s, tdo_s, k_tokens, h, kv_info, key_mask,
+                                                                               lse2, delta, d_qkv);
     }
     count_launch();
     count_launch();
@@ -552,18 +589,12 @@ int attention_bwd_launch(const void* qkv, const void* out, const void* d_out, co
         static_cast<const __nv_bfloat16*>(d_out), static_cast<const __nv_bfloat16*>(out), n_seq, k_tokens, heads, d, delta_ws);
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
-    const int box_d = d < 64 ? d : 64;
-    CUtensorMap tq, tdo;
-    int rc = make_tma_2d(&tq, qkv, n_seq * k_tokens, 3 * h, 3 * h, BW_BLOCK, box_d, 2);
-    if (rc) return rc;
-    rc = make_tma_2d(&tdo, d_out, n_seq * k_tokens, h, h, BW_BLOCK, box_d, 2);
-    if (rc) return rc;
     __nv_bfloat16* dq = static_cast<__nv_bfloat16*>(d_qkv);
     switch (d) {
-        case 16: return launch_attention_bwd<16>(tq, tdo, n_seq, k_tokens, h, heads, kv_info, key_mask, lse2, delta_ws, dq, stream);
-        case 32: return launch_attention_bwd<32>(tq, tdo, n_seq, k_tokens, h, heads, kv_info, key_mask, lse2, delta_ws, dq, stream);
-        case 64: return launch_attention_bwd<64>(tq, tdo, n_seq, k_tokens, h, heads, kv_info, key_mask, lse2, delta_ws, dq, stream);
-        default: return launch_attention_bwd<128>(tq, tdo, n_seq, k_tokens, h, heads, kv_info, key_mask, lse2, delta_ws, dq, stream);
+        case 16: return launch_attention_bwd<16>(qkv, d_out, n_seq, k_tokens, h, heads, kv_info, key_mask, lse2, delta_ws, dq, stream);
+        case 32: return launch_attention_bwd<32>(qkv, d_out, n_seq, k_tokens, h, heads, kv_info, key_mask, lse2, delta_ws, dq, stream);
+        case 64: return launch_attention_bwd<64>(qkv, d_out, n_seq, k_tokens, h, heads, kv_info, key_mask, lse2, delta_ws, dq, stream);
+        default: return launch_attention_bwd<128>(qkv, d_out, n_seq, k_tokens, h, heads, kv_info, key_mask, lse2, delta_ws, dq, stream);
     }
 }
 

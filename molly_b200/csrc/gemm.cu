@@ -131,7 +131,8 @@ __device__ __forceinline__ void add_bias32(float* v, const float* bias, int col0
 template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS, bool CTA2, int OPND = GEMM_OPND_KK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r,
+                    const GemmParams p) {
     using Cfg = GemmCfg<BLOCK_N, STG_BUFS, CTA2>;
     constexpr bool A_MN = OPND == GEMM_OPND_MN_MN, B_MN = OPND != GEMM_OPND_KK;
     constexpr int MN_BOX_BYTES = 64 * 128;
@@ -165,6 +166,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         if constexpr (EPI != EPI_SCATTER) tma_prefetch_desc(&tma_c);
+        if constexpr (EPI == EPI_BIAS_RESID) tma_prefetch_desc(&tma_r);     // the residual source (== tma_c when in place)
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -351,7 +353,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 if (lane == 0 && nchunks > 0) {             // chunk 0 is fetched while the main loop still runs
                     tma_store_wait_read<0>();               // buffer 0 may still be read by an earlier store
                     mbar_arrive_expect_tx(&rbar[0], STG_BUF_BYTES);
-                    tma_load_2d(stg, &tma_c, &rbar[0], colw, row0);
+                    tma_load_2d(stg, &tma_r, &rbar[0], colw, row0);
                 }
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
@@ -363,13 +365,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         if (lane == 0 && c + 1 < nchunks) {  // prefetch the next residual chunk into the other buffer
                             tma_store_wait_read<0>();        // ... once the store that last used it has read it out
                             mbar_arrive_expect_tx(&rbar[buf ^ 1], STG_BUF_BYTES);
-                            tma_load_2d(stg + (buf ^ 1) * STG_BUF_BYTES, &tma_c, &rbar[buf ^ 1], colw + (c + 1) * 32, row0);
+                            tma_load_2d(stg + (buf ^ 1) * STG_BUF_BYTES, &tma_r, &rbar[buf ^ 1], colw + (c + 1) * 32, row0);
                         }
                     } else {
                         if (lane == 0 && c > 0) {
                             tma_store_wait_read<0>();
                             mbar_arrive_expect_tx(&rbar[0], STG_BUF_BYTES);
-                            tma_load_2d(stg, &tma_c, &rbar[0], colw + c * 32, row0);
+                            tma_load_2d(stg, &tma_r, &rbar[0], colw + c * 32, row0);
                         }
                     }
                     const int col0 = colw + c * 32;
@@ -535,7 +537,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
 template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS, bool CTA2, int OPND = GEMM_OPND_KK>
 int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const CUtensorMap* tr = nullptr) {
     using Cfg = GemmCfg<BLOCK_N, STG_BUFS, CTA2>;
     auto kernel = gemm_tcgen05_kernel<BLOCK_N, EPI, OutT, STG_BUFS, CTA2, OPND>;
     static bool configured = false;
@@ -561,7 +563,7 @@ int launch_gemm_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     cfg.numAttrs = 1;
     {
         ProfScope prof(gemm_family(), 2.0 * p.M * p.N * p.K, stream);
-        MOLLY_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, p));
+        MOLLY_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, tr != nullptr ? *tr : tc, p));
     }
     count_launch();
     MOLLY_CUDA(cudaGetLastError());
@@ -579,16 +581,16 @@ bool g_pair_enabled() {
 
 template <int BLOCK_N, int EPI, typename OutT, int STG_BUFS = 1>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, bool pair,
-                cudaStream_t stream) {
+                cudaStream_t stream, const CUtensorMap* tr = nullptr) {
     if constexpr (BLOCK_N == 256 && EPI != EPI_SCATTER) {
-        if (pair) return launch_gemm_impl<256, EPI, OutT, STG_BUFS, true>(ta, tb, tc, p, stream);
+        if (pair) return launch_gemm_impl<256, EPI, OutT, STG_BUFS, true>(ta, tb, tc, p, stream, tr);
     }
-    return launch_gemm_impl<BLOCK_N, EPI, OutT, STG_BUFS, false>(ta, tb, tc, p, stream);
+    return launch_gemm_impl<BLOCK_N, EPI, OutT, STG_BUFS, false>(ta, tb, tc, p, stream, tr);
 }
 
 template <int BLOCK_N>
 int dispatch_epilogue(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int epi,
-                      int out_dtype, bool pair, cudaStream_t stream) {
+                      int out_dtype, bool pair, cudaStream_t stream, const CUtensorMap* tr) {
     const bool f32 = out_dtype == DT_F32;
     switch (epi) {
         case EPI_BIAS:
@@ -597,8 +599,8 @@ int dispatch_epilogue(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
         case EPI_BIAS_GELU:
             return launch_gemm<BLOCK_N, EPI_BIAS_GELU, __nv_bfloat16>(ta, tb, tc, p, pair, stream);
         case EPI_BIAS_RESID:       // short K: the epilogue is a large share -> prefetch residual chunks; long K: deeper ring
-            return p.K >= 2048 ? launch_gemm<BLOCK_N, EPI_BIAS_RESID, float, 1>(ta, tb, tc, p, pair, stream)
-                               : launch_gemm<BLOCK_N, EPI_BIAS_RESID, float, 2>(ta, tb, tc, p, pair, stream);
+            return p.K >= 2048 ? launch_gemm<BLOCK_N, EPI_BIAS_RESID, float, 1>(ta, tb, tc, p, pair, stream, tr)
+                               : launch_gemm<BLOCK_N, EPI_BIAS_RESID, float, 2>(ta, tb, tc, p, pair, stream, tr);
         case EPI_BIAS_ROPE:
             return launch_gemm<BLOCK_N, EPI_BIAS_ROPE, __nv_bfloat16>(ta, tb, tc, p, pair, stream);
         case EPI_GLU:
@@ -658,7 +660,7 @@ int gemm_make_map_c(CUtensorMap* tc, void* out, int out_dtype, int ldo, int M, i
 int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tc, int M, int N, int K, int epi,
                 const float* bias, void* out, int out_dtype, int ldo, const int32_t* seq_table, int seq_k, int B, int T,
                 int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols, float scale, const float* rope_cos_t,
-                const float* rope_sin_t, int rope_len, int rope_cols, int rope_head_dim) {
+                const float* rope_sin_t, int rope_len, int rope_cols, int rope_head_dim, const CUtensorMap* tr) {
     MOLLY_CHECK(M > 0 && N > 0 && K > 0, MOLLY_ERR_INVALID, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     if (epi == EPI_BIAS_ROPE) {
         MOLLY_CHECK(out_dtype == DT_BF16 && rope_cos_t != nullptr && rope_sin_t != nullptr && seq_k > 0 &&
@@ -691,8 +693,8 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap*
     GemmParams p{M, N, K, bias, out, ldo, seq_table, seq_k, B, T, k_cap, err_flag, scale_cols, scale,
                  rope_cos_t, rope_sin_t, rope_len, rope_cols, rope_head_dim};
     const GemmTile tile = gemm_pick_tile(M, N, epi);
-    if (tile == GEMM_TILE_128) return dispatch_epilogue<128>(ta, tb, *tc, p, epi, out_dtype, false, stream);
-    return dispatch_epilogue<256>(ta, tb, *tc, p, epi, out_dtype, tile == GEMM_TILE_PAIR_256, stream);
+    if (tile == GEMM_TILE_128) return dispatch_epilogue<128>(ta, tb, *tc, p, epi, out_dtype, false, stream, tr);
+    return dispatch_epilogue<256>(ta, tb, *tc, p, epi, out_dtype, tile == GEMM_TILE_PAIR_256, stream, tr);
 }
 
 int gemm_make_map_mn(CUtensorMap* t, const void* base, int rows_k, int cols_mn, int ld) {

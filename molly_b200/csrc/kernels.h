@@ -37,12 +37,13 @@ GemmTile gemm_pick_tile(int M, int N, int epi);
 int gemm_make_map_a(CUtensorMap* ta, const void* a, int lda, int M, int K);
 int gemm_make_map_b(CUtensorMap* tb, const void* w, int ldw, int N, int K, int epi);
 int gemm_make_map_c(CUtensorMap* tc, void* out, int out_dtype, int ldo, int M, int n_out);
-// EPI_BIAS_RESID reads the residual through `tc` too: the update is in place on the fp32 stream.
+// EPI_BIAS_RESID reads the residual through `tr` (a map shaped like `tc` over the residual tensor); tr == nullptr: through
+// `tc`, i.e. the update is in place on the fp32 stream.
 int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tc, int M, int N, int K, int epi,
                 const float* bias, void* out, int out_dtype, int ldo, const int32_t* seq_table, int seq_k, int B, int T,
                 int k_cap, int32_t* err_flag, cudaStream_t stream, int scale_cols = 0, float scale = 1.0f,
                 const float* rope_cos_t = nullptr, const float* rope_sin_t = nullptr, int rope_len = 0, int rope_cols = 0,
-                int rope_head_dim = 0);
+                int rope_head_dim = 0, const CUtensorMap* tr = nullptr);
 
 // Backward GEMMs on the same kernel, operands taken as they lie in memory (no transposes):
 //   GEMM_OPND_K_MN   out[M, N] = a[M, K] b[K, N]        b row-major [K, N]            (dgrad: d_in = d_out W)

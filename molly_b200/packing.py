@@ -63,17 +63,20 @@ class PackedEncoder:
 
         self._recipes = []          # (kept tensor, builder(state_dict) -> source tensor): replayed by reload()
 
-        def mat(build):   # bf16 matrix on device
+        def mat(build, parts=None):   # bf16 matrix on device
             o = build(state_dict).detach().to(device=device, dtype=torch.float32).to(torch.bfloat16).contiguous()
             self._keep.append(o)
-            self._recipes.append((o, build))
+            self._recipes.append((o, build, parts))
             return o
 
-        def vec(build):   # fp32 vector on device
+        def vec(build, parts=None):   # fp32 vector on device
             o = build(state_dict).detach().to(device=device, dtype=torch.float32).contiguous()
             self._keep.append(o)
-            self._recipes.append((o, build))
+            self._recipes.append((o, build, parts))
             return o
+
+        def qkv_parts(p, kind):       # reload() copies q, k, v straight into their row blocks of the packed tensor (no cat)
+            return lambda sd_: [sd_[p + f"attention.self.{n}.{kind}"] for n in ("query", "key", "value")]
 
         def key(name):
             return lambda sd_: sd_[name]
@@ -118,9 +121,9 @@ class PackedEncoder:
             arrays["ln1_w"].append(_ptr(vec(key(p + "attention.LayerNorm.weight"))))
             arrays["ln1_b"].append(_ptr(vec(key(p + "attention.LayerNorm.bias"))))
             arrays["w_qkv"].append(_ptr(mat(lambda sd_, p=p: torch.cat(
-                [sd_[p + f"attention.self.{n}.weight"] for n in ("query", "key", "value")], dim=0))))
+                [sd_[p + f"attention.self.{n}.weight"] for n in ("query", "key", "value")], dim=0), qkv_parts(p, "weight"))))
             arrays["b_qkv"].append(_ptr(vec(lambda sd_, p=p: torch.cat(
-                [sd_[p + f"attention.self.{n}.bias"] for n in ("query", "key", "value")], dim=0))))
+                [sd_[p + f"attention.self.{n}.bias"] for n in ("query", "key", "value")], dim=0), qkv_parts(p, "bias"))))
             arrays["w_attn_out"].append(_ptr(mat(key(p + "attention.output.dense.weight"))))
             arrays["b_attn_out"].append(_ptr(vec(key(p + "attention.output.dense.bias"))))
             arrays["ln2_w"].append(_ptr(vec(key(p + "LayerNorm.weight"))))
@@ -184,14 +187,25 @@ class PackedEncoder:
         handle and its cached TMA descriptors stay valid.  SURVEY.md 8b: packed copies are caches that must follow the
         ``nn.Module`` weights when the encoders train (``--train-bio``) or a checkpoint is loaded after construction."""
         same_d, same_s, conv_d, conv_s = [], [], [], []
-        for dst, build in self._recipes:
-            src = build(state_dict).detach()
+        def put(dst, src):
+            src = src.detach()
             if tuple(src.shape) != tuple(dst.shape):
                 raise ValueError(f"reload: shape {tuple(src.shape)} does not match the packed {tuple(dst.shape)}")
             if src.device != dst.device:
                 src = src.to(dst.device, non_blocking=True)
             (same_d if src.dtype == dst.dtype else conv_d).append(dst)
             (same_s if src.dtype == dst.dtype else conv_s).append(src)
+
+        for dst, build, parts in self._recipes:
+            if parts is None:
+                put(dst, build(state_dict))
+                continue
+            row = 0
+            for src in parts(state_dict):              # row blocks of dst, in order
+                put(dst[row:row + src.shape[0]], src)
+                row += src.shape[0]
+            if row != dst.shape[0]:
+                raise ValueError(f"reload: parts cover {row} of {dst.shape[0]} rows")
         # trainable encoders are re-packed on EVERY call (omics_path.refresh_encoders): a few multi-tensor launches instead
         # of ~800 single copies (bf16 parameters under DeepSpeed bf16 go straight into the bf16 matrices)
         if same_d:

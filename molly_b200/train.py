@@ -162,10 +162,13 @@ def _save_activations(enc: PackedEncoder, n_tokens: int) -> bool:
     env = os.environ.get("MOLLY_TRAIN_RECOMPUTE")
     if env is not None:
         return env == "0"
-    cfg = enc.cfg
-    f_pre = cfg.intermediate_size * (2 if cfg.ffn_type == "glu" else 1)
-    per_layer = n_tokens * (cfg.hidden_size * (4 + 2 + 6 + 2 + 4 + 2) + f_pre * 2)
-    return per_layer * cfg.num_hidden_layers < 0.35 * torch.cuda.mem_get_info(enc.device)[0]
+    cache = enc.__dict__.setdefault("_save_activations_cache", {})
+    if n_tokens not in cache:          # decided once per batch size: cudaMemGetInfo costs ~0.5 ms of device idle time per call
+        cfg = enc.cfg
+        f_pre = cfg.intermediate_size * (2 if cfg.ffn_type == "glu" else 1)
+        per_layer = n_tokens * (cfg.hidden_size * (4 + 2 + 6 + 2 + 4 + 2) + f_pre * 2)
+        cache[n_tokens] = per_layer * cfg.num_hidden_layers < 0.35 * torch.cuda.mem_get_info(enc.device)[0]
+    return cache[n_tokens]
 
 
 def _sizes(enc: PackedEncoder, n_seq: int, K: int, recompute: bool) -> Tuple[int, int, int]:
