@@ -53,6 +53,9 @@ __device__ long long* d_attn_tl = nullptr;
 #define ATT_MAX2 0
 #endif
 #ifndef ATT_THREAD_ARRIVE
+#ifndef ATT_ELECT
+#define ATT_ELECT 1
+#endif
 #define ATT_THREAD_ARRIVE 1       // measured (profiles/r02_attention.md): one elected arrival per warp is SLOWER with the staged epilogue
 #endif
 constexpr int ATT_ARRIVALS = ATT_THREAD_ARRIVE ? 128 : 4;       // arrivals per phase of s_free / p_full
@@ -404,7 +407,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
     const uint32_t tmem_o = tmem_base + KVB;
 
     if (warp == 4) {
-        if (lane == 0) {
+        // elect.sync, not `lane == 0`: ptxas then knows ONE thread runs this region and issues the tcgen05 / TMA instructions
+        // back to back; under a lane test it wraps EACH of them in an elect / branch loop over the "active" threads (13
+        // instructions and a taken branch per MMA -- the control thread, not the tensor pipe, paced the small MMAs)
+        if (ATT_ELECT ? elect_one() : lane == 0) {
             // ---------------- control thread: TMA producer + MMA issuer ----------------
             constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK, KVB, false, false);
             constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK, D, false, true);      // B (= V) is MN-major
@@ -749,7 +755,10 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_
     const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + KVB;
 
     if (warp == 4) {
-        if (lane == 0) {
+        // elect.sync, not `lane == 0`: ptxas then knows ONE thread runs this region and issues the tcgen05 / TMA instructions
+        // back to back; under a lane test it wraps EACH of them in an elect / branch loop over the "active" threads (13
+        // instructions and a taken branch per MMA -- the control thread, not the tensor pipe, paced the small MMAs)
+        if (ATT_ELECT ? elect_one() : lane == 0) {
             // ---------------- control thread: TMA producer + MMA issuer ----------------
             constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK, KVB, false, false);
             constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK, D, false, true);      // B (= V) is MN-major

@@ -619,7 +619,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, int n_seq, int he
 
     if (warp >= 12) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(A2_REGS_OTHER));
-        if (warp < 14 && lane == 0) {
+        if (warp < 14 && elect_one()) {      // (elect.sync, not a lane test: see the control thread of attention.cu)
             const int t = warp - 12;
             a2_control<D, NST>(smem + t * Cfg::SLICE_BYTES, a2_bars<NST>(bars + t * Cfg::NBAR), tmem_base + t * Cfg::TM_TILE,
                                &tma_qkv, a2_slot(t, sh.total), stride, sh, kv_info);

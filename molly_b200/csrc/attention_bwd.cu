@@ -30,6 +30,26 @@ constexpr int BW_BLOCK = 128;
 constexpr int BW_THREADS = 288;                // 8 compute warps (two per query / key row: 64 columns each) + 1 control warp
 constexpr int BW_COMPUTE = 256;
 constexpr float BW_LOG2E = 1.4426950408889634f;
+#ifndef BW_DS2
+#define BW_DS2 1                               // 1: the dQ kernel double-buffers its dS tile (block j+1 is not held up by dQ MMA j)
+#endif
+#ifndef BW_ELECT
+#define BW_ELECT 1                             // the control thread is chosen with elect.sync (see the note at the MMA loops)
+#endif
+#ifndef BW_WARP_ARRIVE
+#define BW_WARP_ARRIVE 0                       // 1: one elected mbarrier.arrive per warp instead of one per thread
+#endif
+constexpr int BW_ARRIVALS = BW_WARP_ARRIVE ? BW_COMPUTE / 32 : BW_COMPUTE;
+
+// every compute thread has done its part (TMEM reads fenced / smem writes published): signal the control thread
+__device__ __forceinline__ void bw_arrive(uint64_t* bar) {
+#if BW_WARP_ARRIVE
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+#else
+    mbar_arrive(bar);
+#endif
+}
 
 template <int D, int SB>
 struct BwdCfg {
@@ -42,24 +62,41 @@ struct BwdCfg {
     static constexpr int SBOX_BYTES = SB * ROW_BYTES;                  // streamed tiles: SB rows per TMA box
     static constexpr int STILE = NBOX * SBOX_BYTES;                    // one SB x D bf16 tile
     static constexpr int PT_BYTES = BW_BLOCK * SB * 2;                 // one 128 x SB bf16 operand tile (SB/64 swizzle atoms)
-    static constexpr int STAGES = D == 128 ? 1 : 2;                    // streamed-tile ring depth
+    // streamed-tile ring depth.  Three stages when the blocks are small: a stage is refilled when the MMAs of the block BEFORE
+    // the current one have completed, i.e. two iterations before its data is needed -- with two stages the TMA load was
+    // issued one short iteration ahead and the control thread sat ~900 cycles on the full barrier (clock64 timeline)
+    static constexpr int STAGES = D == 128 ? 1 : 3;                    // dK/dV kernel (shared memory: 2 x 112 KB per SM)
+    static constexpr int DQ_STAGES = D == 128 ? 1 : 3;                 // dQ kernel (+ two dS tiles: 2 x 112 KB per SM)
     static constexpr int QPH = SB / 64;                                // 32-column quarters each of a row's two threads handles
     static constexpr int CTAS_PER_SM = SB == 64 ? 2 : 1;
     // dQ kernel: Q | dO | K ring | V ring | dS          TMEM: S | dP | dQ
-    static constexpr int DQ_OFF_Q = 0, DQ_OFF_DO = TILE, DQ_OFF_K = 2 * TILE, DQ_OFF_V = DQ_OFF_K + STAGES * STILE;
-    static constexpr int DQ_OFF_DS = DQ_OFF_V + STAGES * STILE, DQ_OFF_BAR = DQ_OFF_DS + PT_BYTES;
+    static constexpr int DQ_OFF_Q = 0, DQ_OFF_DO = TILE, DQ_OFF_K = 2 * TILE, DQ_OFF_V = DQ_OFF_K + DQ_STAGES * STILE;
+    static constexpr int DS_BUFS = (BW_DS2 && DQ_STAGES >= 2) ? 2 : 1; // (the wait below pairs dS buffers with K/V stages)
+    static constexpr int DQ_OFF_DS = DQ_OFF_V + DQ_STAGES * STILE, DQ_OFF_BAR = DQ_OFF_DS + DS_BUFS * PT_BYTES;
     static constexpr int DQ_SMEM = DQ_OFF_BAR + 256;
     static constexpr int DQ_TMEM = 2 * SB + D <= 256 ? 256 : 512;
-    // dK/dV kernel: K | V | Q ring | dO ring | P^T | dS^T | row statistics of the streamed query block (2 x {lse2, delta})
+    // dK/dV kernel: K | V | Q ring | dO ring | P^T | dS^T | row statistics of the streamed query block
     //                                                    TMEM: S^T | dP^T | dV | dK
     static constexpr int KV_OFF_K = 0, KV_OFF_V = TILE, KV_OFF_Q = 2 * TILE, KV_OFF_DO = KV_OFF_Q + STAGES * STILE;
     static constexpr int KV_OFF_PT = KV_OFF_DO + STAGES * STILE, KV_OFF_DST = KV_OFF_PT + PT_BYTES;
-    static constexpr int KV_OFF_STAT = KV_OFF_DST + PT_BYTES, KV_OFF_BAR = KV_OFF_STAT + 2 * 2 * SB * 4;
+    static constexpr int KV_OFF_STAT = KV_OFF_DST + PT_BYTES, KV_OFF_BAR = KV_OFF_STAT + 2 * SB * 4;   // {lse2, delta} of SB queries
     static constexpr int KV_SMEM = KV_OFF_BAR + 256;
     static constexpr int KV_TMEM = 2 * SB + 2 * D <= 256 ? 256 : 512;
     static_assert(SB == 64 || SB == 128, "streamed blocks are 64 or 128 rows");
     static_assert(2 * SB + 2 * D <= 512, "tensor memory budget");
 };
+
+#ifdef BW_TIMELINE
+// bring-up aid (-DBW_TIMELINE): clock64 stamps of the dQ kernel's compute thread 0 and control thread, first 16 CTAs
+__device__ long long g_bw_tl[16 * 2 * 32 * 8];
+#define BW_TL(role, it, slot)                                                                                         \
+    do {                                                                                                              \
+        const int _cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);                              \
+        if (_cta < 16 && (it) < 32) g_bw_tl[((_cta * 2 + (role)) * 32 + (it)) * 8 + (slot)] = clock64();               \
+    } while (0)
+#else
+#define BW_TL(role, it, slot) do {} while (0)
+#endif
 
 __device__ __forceinline__ float bw_ex2(float x) {
     float y;
@@ -146,17 +183,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                    int h, const int32_t* __restrict__ kv_info, const uint8_t* __restrict__ key_mask,
                    const float* __restrict__ lse2, const float* __restrict__ delta, __nv_bfloat16* __restrict__ d_qkv) {
     using Cfg = BwdCfg<D, SB>;
-    constexpr int NST = Cfg::STAGES;
+    constexpr int NST = Cfg::DQ_STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::DQ_OFF_BAR);
     uint64_t* bar_qdo = bars + 0;
-    uint64_t* bar_kv_full = bars + 1;        // [NST]
-    uint64_t* bar_kv_empty = bars + 3;       // [NST]  dQ MMA of the block done: the K/V stage and the dS tile are free
-    uint64_t* bar_sdp_full = bars + 5;       // S and dP of the block are in TMEM
-    uint64_t* bar_s_free = bars + 6;         // 256 arrivals: both are in registers
-    uint64_t* bar_ds_full = bars + 7;        // 256 arrivals: dS is in smem
-    uint64_t* bar_dq_full = bars + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* bar_kv_full = bars + 1;        // [NST <= 4]
+    uint64_t* bar_kv_empty = bars + 5;       // [NST <= 4]  dQ MMA of the block done: the K/V stage and the dS tile are free
+    uint64_t* bar_sdp_full = bars + 9;       // S and dP of the block are in TMEM
+    uint64_t* bar_s_free = bars + 10;        // 256 arrivals: both are in registers
+    uint64_t* bar_ds_full = bars + 11;       // 256 arrivals: dS is in smem
+    uint64_t* bar_dq_full = bars + 12;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BW_BLOCK, head = blockIdx.y, n = blockIdx.z, heads = gridDim.y;
@@ -176,8 +213,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
             mbar_init(bar_qdo, 1);
             for (int s = 0; s < NST; ++s) { mbar_init(&bar_kv_full[s], 1); mbar_init(&bar_kv_empty[s], 1); }
             mbar_init(bar_sdp_full, 1);
-            mbar_init(bar_s_free, BW_COMPUTE);
-            mbar_init(bar_ds_full, BW_COMPUTE);
+            mbar_init(bar_s_free, BW_ARRIVALS);
+            mbar_init(bar_ds_full, BW_ARRIVALS);
             mbar_init(bar_dq_full, 1);
             fence_mbar_init();
         }
@@ -192,7 +229,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
     const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + SB, tmem_dq = tmem_base + 2 * SB;
 
     if (warp == 8) {
-        if (lane == 0) {
+        if (BW_ELECT ? elect_one() : lane == 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16(BW_BLOCK, SB, false, false);
             constexpr uint32_t idesc_acc = make_idesc_bf16(BW_BLOCK, D, false, true);       // B MN-major
             const uint32_t s_q = smem_u32(smem + Cfg::DQ_OFF_Q), s_do = smem_u32(smem + Cfg::DQ_OFF_DO);
@@ -244,21 +281,34 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
             issue_scores(0);
             for (int j = 0; j < nkv; ++j) {
                 const int st = j % NST;
-                if (NST == 2 && j + 1 < nkv) {               // scores of block j+1 run under the element-wise work of block j
+                BW_TL(1, j, 0);
+                // refill the stage of block j-1 as soon as its dQ MMA (issued at the end of the previous iteration) is done:
+                // the TMA load takes ~1 450 cycles to land and its block is needed NST-2 iterations from now
+                if (NST >= 2 && j >= 1 && j - 1 + NST < nkv) {
+                    mbar_wait(&bar_kv_empty[(j - 1) % NST], ((j - 1) / NST) & 1);
+                    BW_TL(1, j, 5);
+                    load_kv(j - 1 + NST);
+                }
+                if (NST >= 2 && j + 1 < nkv) {               // scores of block j+1 run under the element-wise work of block j
                     mbar_wait(bar_s_free, j & 1);
+                    BW_TL(1, j, 1);
                     tc_fence_after();
                     issue_scores(j + 1);
+                    BW_TL(1, j, 2);
                 }
                 mbar_wait(bar_ds_full, j & 1);               // dS(j) is in smem
+                BW_TL(1, j, 3);
                 tc_fence_after();
 #pragma unroll
                 for (int s = 0; s < SB / 16; ++s) {          // dQ += dS K : A K-major (SB/64 atoms of 64 keys), B = K tile MN-major
-                    const uint64_t ad = make_smem_desc(s_ds + (s >> 2) * (BW_BLOCK * 128) + (s & 3) * 32, 16, 1024, kLayoutSW128);
+                    const uint64_t ad = make_smem_desc(s_ds + (j % Cfg::DS_BUFS) * Cfg::PT_BYTES + (s >> 2) * (BW_BLOCK * 128) +
+                                                           (s & 3) * 32, 16, 1024, kLayoutSW128);
                     const uint64_t bd = make_smem_desc(s_k + st * Cfg::STILE + s * 16 * Cfg::ROW_BYTES, Cfg::SBOX_BYTES,
                                                        8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
                     umma_bf16_ss(tmem_dq, ad, bd, idesc_acc, (j | s) != 0);
                 }
                 umma_commit(&bar_kv_empty[st]);
+                BW_TL(1, j, 4);
                 if (j == nkv - 1) umma_commit(bar_dq_full);
                 if (NST == 1 && j + 1 < nkv) {               // single stage: the next K/V overwrite this one after its dQ MMA
                     mbar_wait(&bar_kv_empty[0], j & 1);
@@ -266,10 +316,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                     mbar_wait(bar_s_free, j & 1);
                     tc_fence_after();
                     issue_scores(j + 1);
-                }
-                if (NST == 2 && j + 2 < nkv) {
-                    mbar_wait(&bar_kv_empty[st], (j >> 1) & 1);
-                    load_kv(j + 2);
                 }
             }
         }
@@ -280,14 +326,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
         const size_t stat = (static_cast<size_t>(n) * heads + head) * k_tokens + (row_ok ? q0 + r : 0);
         const float my_lse = row_ok ? lse2[stat] : CUDART_INF_F;             // +inf: P = 0 for rows outside the sequence
         const float my_delta = row_ok ? delta[stat] : 0.f;
-        uint8_t* ds_tile = smem + Cfg::DQ_OFF_DS;
+        const float neg_lse = -my_lse;
         for (int j = 0; j < nkv; ++j) {
+            if (threadIdx.x == 0) BW_TL(0, j, 0);
             mbar_wait(bar_sdp_full, j & 1);
+            if (threadIdx.x == 0) BW_TL(0, j, 1);
             tc_fence_after();
-            if (j > 0) {                                     // dQ MMA (j-1) has drained the dS tile
-                mbar_wait(&bar_kv_empty[(j - 1) % NST], ((j - 1) / NST) & 1);
+            if (j >= Cfg::DS_BUFS) {                         // dQ MMA (j - DS_BUFS) has drained this dS tile
+                const int jp = j - Cfg::DS_BUFS;
+                mbar_wait(&bar_kv_empty[jp % NST], (jp / NST) & 1);
                 tc_fence_after();
             }
+            if (threadIdx.x == 0) BW_TL(0, j, 2);
+            uint8_t* ds_tile = smem + Cfg::DQ_OFF_DS + (j % Cfg::DS_BUFS) * Cfg::PT_BYTES;
 #pragma unroll
             for (int qq = 0; qq < Cfg::QPH; ++qq) {          // 32 keys at a time
                 const int qt = Cfg::QPH * half + qq;
@@ -295,24 +346,36 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                 tmem_ld32(tmem_s + lane_addr + qt * 32, sr);
                 tmem_ld32(tmem_dp + lane_addr + qt * 32, pr);
                 tmem_ld_wait();
+                if (threadIdx.x == 0) BW_TL(0, j, 3);
                 if (qq == Cfg::QPH - 1) {
                     tc_fence_before();
-                    mbar_arrive(bar_s_free);                 // S / dP are in registers: the next block's scores may be issued
+                    bw_arrive(bar_s_free);                   // S / dP are in registers: the next block's scores may be issued
                 }
                 float v[32];
+                if (!interior && (j + 1) * SB <= kvl) {      // every key of the block is valid (all but the last block): no masks
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int key = j * SB + qt * 32 + i;
-                    bool ok = key < kvl;
-                    if (interior && ok) ok = key_mask[row_base + key] != 0;
-                    const float p = ok ? bw_ex2(__uint_as_float(sr[i]) * BW_LOG2E - my_lse) : 0.f;
-                    v[i] = p * (__uint_as_float(pr[i]) - my_delta);
+                    for (int i = 0; i < 32; ++i) {
+                        const float p = bw_ex2(fmaf(__uint_as_float(sr[i]), BW_LOG2E, neg_lse));
+                        v[i] = p * (__uint_as_float(pr[i]) - my_delta);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int key = j * SB + qt * 32 + i;
+                        bool ok = key < kvl;
+                        if (interior && ok) ok = key_mask[row_base + key] != 0;
+                        const float p = ok ? bw_ex2(fmaf(__uint_as_float(sr[i]), BW_LOG2E, neg_lse)) : 0.f;
+                        v[i] = p * (__uint_as_float(pr[i]) - my_delta);
+                    }
                 }
+                if (threadIdx.x == 0) BW_TL(0, j, 4);
                 store_quarter_row(ds_tile, r, qt, v);
             }
+            if (threadIdx.x == 0) BW_TL(0, j, 5);
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(bar_ds_full);
+            bw_arrive(bar_ds_full);
+            if (threadIdx.x == 0) BW_TL(0, j, 6);
         }
         if (half == 0) {
             mbar_wait(bar_dq_full, 0);
@@ -341,13 +404,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::KV_OFF_BAR);
     uint64_t* bar_kv = bars + 0;
-    uint64_t* bar_q_full = bars + 1;         // [NST]  Q_i and dO_i landed
-    uint64_t* bar_q_empty = bars + 3;        // [NST]  dV / dK MMAs of the block done: stage, P^T and dS^T tiles are free
-    uint64_t* bar_sdp_full = bars + 5;
-    uint64_t* bar_s_free = bars + 6;         // 256 arrivals
-    uint64_t* bar_pt_full = bars + 7;        // 256 arrivals
-    uint64_t* bar_out_full = bars + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* bar_q_full = bars + 1;         // [NST <= 3]  Q_i and dO_i landed
+    uint64_t* bar_q_empty = bars + 4;        // [NST <= 3]  dV / dK MMAs of the block done: stage, P^T and dS^T tiles are free
+    uint64_t* bar_sdp_full = bars + 7;
+    uint64_t* bar_s_free = bars + 8;         // 256 arrivals
+    uint64_t* bar_pt_full = bars + 9;        // 256 arrivals
+    uint64_t* bar_out_full = bars + 10;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k0 = blockIdx.x * BW_BLOCK, head = blockIdx.y, n = blockIdx.z, heads = gridDim.y;
@@ -371,8 +434,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
             mbar_init(bar_kv, 1);
             for (int s = 0; s < NST; ++s) { mbar_init(&bar_q_full[s], 1); mbar_init(&bar_q_empty[s], 1); }
             mbar_init(bar_sdp_full, 1);
-            mbar_init(bar_s_free, BW_COMPUTE);
-            mbar_init(bar_pt_full, BW_COMPUTE);
+            mbar_init(bar_s_free, BW_ARRIVALS);
+            mbar_init(bar_pt_full, BW_ARRIVALS);
             mbar_init(bar_out_full, 1);
             fence_mbar_init();
         }
@@ -387,7 +450,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     const uint32_t tmem_st = tmem_base, tmem_dpt = tmem_base + SB, tmem_dv = tmem_base + 2 * SB, tmem_dk = tmem_dv + D;
 
     if (warp == 8) {
-        if (lane == 0) {
+        if (BW_ELECT ? elect_one() : lane == 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16(BW_BLOCK, SB, false, false);
             constexpr uint32_t idesc_acc = make_idesc_bf16(BW_BLOCK, D, false, true);       // B MN-major
             const uint32_t s_k = smem_u32(smem + Cfg::KV_OFF_K), s_v = smem_u32(smem + Cfg::KV_OFF_V);
@@ -439,7 +502,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
             issue_scores(0);
             for (int i = 0; i < nq; ++i) {
                 const int st = i % NST;
-                if (NST == 2 && i + 1 < nq) {
+                if (NST >= 2 && i >= 1 && i - 1 + NST < nq) {            // refill the stage of block i-1 (see the dQ kernel)
+                    mbar_wait(&bar_q_empty[(i - 1) % NST], ((i - 1) / NST) & 1);
+                    load_q(i - 1 + NST);
+                }
+                if (NST >= 2 && i + 1 < nq) {
                     mbar_wait(bar_s_free, i & 1);
                     tc_fence_after();
                     issue_scores(i + 1);
@@ -467,10 +534,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
                     tc_fence_after();
                     issue_scores(i + 1);
                 }
-                if (NST == 2 && i + 2 < nq) {
-                    mbar_wait(&bar_q_empty[st], (i >> 1) & 1);
-                    load_q(i + 2);
-                }
             }
         }
     } else {
@@ -479,26 +542,30 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
         const int key = k0 + r;
         bool key_ok = key < kvl;
         if (interior && key_ok) key_ok = key_mask[row_base + key] != 0;
-        float* stats = reinterpret_cast<float*>(smem + Cfg::KV_OFF_STAT);
         uint8_t* pt_tile = smem + Cfg::KV_OFF_PT;
         uint8_t* dst_tile = smem + Cfg::KV_OFF_DST;
         const size_t stat_base = (static_cast<size_t>(n) * heads + head) * k_tokens;
+        float* st_lse = reinterpret_cast<float*>(smem + Cfg::KV_OFF_STAT);
+        float* st_delta = st_lse + SB;
         for (int i = 0; i < nq; ++i) {
-            // row statistics of the SB queries of this block -> smem (thread r brings query i*SB + r)
-            float* st_lse = stats + (i & 1) * 2 * SB;
-            float* st_delta = st_lse + SB;
+            // row statistics of the SB queries of this block: thread r brings query i*SB + r (the load is in flight during the
+            // waits below)
             const int q = i * SB + r;
+            float my_stat = 0.f;
             if (r < SB) {
-                if (half == 0) st_lse[r] = q < k_tokens ? lse2[stat_base + q] : CUDART_INF_F;    // +inf: P = 0 beyond the sequence
-                else st_delta[r] = q < k_tokens ? delta[stat_base + q] : 0.f;
+                if (half == 0) my_stat = q < k_tokens ? lse2[stat_base + q] : CUDART_INF_F;      // +inf: P = 0 beyond the sequence
+                else my_stat = q < k_tokens ? delta[stat_base + q] : 0.f;
             }
-            named_bar_sync(1, BW_COMPUTE);
             mbar_wait(bar_sdp_full, i & 1);
             tc_fence_after();
-            if (i > 0) {                                     // dV / dK MMAs (i-1) have drained the P^T / dS^T tiles
+            if (i > 0) {                                     // dV / dK MMAs (i-1) have drained the P^T / dS^T tiles ...
                 mbar_wait(&bar_q_empty[(i - 1) % NST], ((i - 1) / NST) & 1);
                 tc_fence_after();
             }
+            // ... and, since they only ran after all 256 arrivals on pt_full(i-1), every thread is done reading the previous
+            // block's statistics: the single buffer can be overwritten
+            if (r < SB) (half == 0 ? st_lse : st_delta)[r] = my_stat;
+            named_bar_sync(1, BW_COMPUTE);
 #pragma unroll
             for (int qq = 0; qq < Cfg::QPH; ++qq) {          // 32 queries at a time
                 const int qt = Cfg::QPH * half + qq;
@@ -508,22 +575,33 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
                 tmem_ld_wait();
                 if (qq == Cfg::QPH - 1) {
                     tc_fence_before();
-                    mbar_arrive(bar_s_free);
+                    bw_arrive(bar_s_free);
                 }
                 float pv[32], dv[32];
+                if (!key_ok) {                               // a key past the sequence / masked: its whole row of P^T is zero
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float l = st_lse[qt * 32 + c], dl = st_delta[qt * 32 + c];
-                    const float p = key_ok ? bw_ex2(__uint_as_float(sr[c]) * BW_LOG2E - l) : 0.f;
-                    pv[c] = p;
-                    dv[c] = p * (__uint_as_float(pr[c]) - dl);
+                    for (int c = 0; c < 32; ++c) sr[c] = 0xff800000u;             // S = -inf -> P = exp2(-inf) = 0
+                }
+                const float4* l4 = reinterpret_cast<const float4*>(st_lse + qt * 32);          // (broadcast reads)
+                const float4* d4 = reinterpret_cast<const float4*>(st_delta + qt * 32);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 l = l4[c4], dl = d4[c4];
+                    const float ls[4] = {l.x, l.y, l.z, l.w}, ds[4] = {dl.x, dl.y, dl.z, dl.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = c4 * 4 + e;
+                        const float p = bw_ex2(fmaf(__uint_as_float(sr[c]), BW_LOG2E, -ls[e]));
+                        pv[c] = p;
+                        dv[c] = p * (__uint_as_float(pr[c]) - ds[e]);
+                    }
                 }
                 store_quarter_row(pt_tile, r, qt, pv);
                 store_quarter_row(dst_tile, r, qt, dv);
             }
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(bar_pt_full);
+            bw_arrive(bar_pt_full);
         }
         mbar_wait(bar_out_full, 0);
         tc_fence_after();
@@ -549,6 +627,11 @@ int launch_attention_bwd(const void* qkv, const void* d_out, int n_seq, int k_to
     if (!configured) {
         MOLLY_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<D, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::DQ_SMEM));
         MOLLY_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<D, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::KV_SMEM));
+        // two CTAs per SM need the whole shared-memory carve-out
+        MOLLY_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<D, SB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
+        MOLLY_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<D, SB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
     const int rows = n_seq * k_tokens;
@@ -599,3 +682,9 @@ int attention_bwd_launch(const void* qkv, const void* out, const void* d_out, co
 }
 
 }  // namespace molly
+
+#ifdef BW_TIMELINE
+extern "C" __attribute__((visibility("default"))) int molly_debug_bw_timeline(long long* host_out) {
+    return static_cast<int>(cudaMemcpyFromSymbol(host_out, molly::g_bw_tl, sizeof(molly::g_bw_tl)));
+}
+#endif

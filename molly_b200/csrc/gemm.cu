@@ -27,6 +27,9 @@ namespace molly {
 
 namespace {
 
+#ifndef GEMM_ELECT
+#define GEMM_ELECT 1
+#endif
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                      // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
@@ -199,7 +202,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
-        if (lane == 0) {
+        if (GEMM_ELECT ? elect_one() : lane == 0) {   // (elect.sync: ptxas issues the TMA / MMA instructions of a one-thread region back to back)
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
@@ -256,7 +259,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
-        if (lane == 0 && cta_rank == 0) {
+        if (cta_rank == 0 && (GEMM_ELECT ? elect_one() : lane == 0)) {
             constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, A_MN, B_MN);
             int stage = 0;
             uint32_t phase = 0;
