@@ -152,6 +152,7 @@ class _AbsentModalityFn(torch.autograd.Function):
             got.update(plan.layer_views(plan.L - g, red.reduce_zeros_(plan.group_numel(g), dev)))
         got.update(plan.tail_views(red.reduce_zeros_(plan.group_numel(plan.L + 1), dev)))
         red.finish()
+        plan.finalize_(got)                                                  # (copies: only after the collectives are done)
         grads = [got[n].to(device=dv, dtype=dt) if (n in got and need) else None
                  for n, (dt, dv), need in zip(ctx.names, ctx.metas, ctx.needs_input_grad[4:])]
         return (grad_out if ctx.needs_input_grad[0] else None), None, None, None, *grads

@@ -111,17 +111,26 @@ class GradPlan:
         return self.group if g <= self.L else self.total - self.tail_begin
 
     def layer_views(self, i: int, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """HF-named gradients of layer ``i`` from its flat group (views; the NT-v2 gate / up halves are un-interleaved)."""
+        """HF-named gradients of layer ``i`` from its flat group: VIEWS only (no kernel reads ``flat`` here, so this is safe
+        while an all-reduce of ``flat`` is still in flight).  The NT-v2 ``intermediate.dense`` entries are still in the packed
+        row order (gate_0, up_0, gate_1, up_1, ...): ``finalize_`` un-interleaves them once the values are final."""
         out = {}
         for name, slot, sub, shape in self._layer_entries(i):
             n = 1
             for v in shape:
                 n *= v
-            t = flat[self.off[slot] + sub:self.off[slot] + sub + n].view(shape)
-            if self.glu and slot in (_lib.GRAD_W_FFN1, _lib.GRAD_B_FFN1):
-                t = glu_deinterleave(t, self.cfg.glu_gate_first)     # packed rows are (gate_0, up_0, gate_1, up_1, ...)
-            out[name] = t
+            out[name] = flat[self.off[slot] + sub:self.off[slot] + sub + n].view(shape)
         return out
+
+    def finalize_(self, grads: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Packed -> HF layout for the tensors whose layouts differ (copies): call after the last collective has finished."""
+        if self.glu:
+            for i in range(self.L):
+                for suffix in ("intermediate.dense.weight", "intermediate.dense.bias"):
+                    name = f"esm.encoder.layer.{i}.{suffix}"
+                    if name in grads:
+                        grads[name] = glu_deinterleave(grads[name], self.cfg.glu_gate_first)
+        return grads
 
     def tail_views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
         out = {}
@@ -210,7 +219,8 @@ def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor,
     """Gradients of every encoder parameter (HF ``state_dict`` names, fp32 views of one flat buffer) from ``d_out`` =
     d(loss)/d(hidden_states[-1]), bf16 [n*K, h].  ``reducer`` (``dist.LayerwiseGradReducer``): each layer's flat group is
     handed to it as soon as the layer's backward is enqueued, so its all-reduce overlaps the layers below; those gradients
-    come back averaged, in the reducer's dtype."""
+    come back averaged, in the reducer's dtype (the reducer is finished -- current stream ordered after every collective --
+    before this returns)."""
     cfg = enc.cfg
     n_seq, K = tape.ids.shape
     h, L = cfg.hidden_size, cfg.num_hidden_layers
@@ -253,5 +263,6 @@ def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor,
         ops.scatter_add_rows_(d_pos, d_x, pos_index, pos_scale)
     if reducer is not None:
         views = plan.tail_views(reducer.reduce_flat_(tail))
+        reducer.finish()                       # every group is averaged before anything reads the flat buffers
     grads.update(views)
-    return grads
+    return plan.finalize_(grads)

@@ -52,6 +52,18 @@ den = sum(float(b.pow(2).sum()) for b in ref) ** 0.5
 mb = path.grad_reducer.bytes_reduced / 2 ** 20
 print(f"rank {rank}/{world}: {len(params)} parameter gradients, averaged vs single-rank: relative error of the whole "
       f"gradient {num / den:.2e}, {mb:.0f} MiB all-reduced in layer-wise buckets", flush=True)
+if num / den >= 2e-3:            # diagnostics: which tensors, and is it the local reference or the reduced run that moved?
+    pnames = ([f"proj.{m}.{n}" for m in ("dna_rna", "protein") for n in ("weight", "bias")]
+              + [f"{m}.{n}" for m in ("dna_rna", "protein") for n, _ in path._enc_modules[m].named_parameters()])
+    errs = sorted(((float((a - b).norm() / (b.norm() + 1e-30)), n, float(a.norm()), float(b.norm()))
+                   for n, a, b in zip(pnames, red, ref)), reverse=True)
+    for e, n, na, nb in errs[:12]:
+        print(f"rank {rank}: {n}: rel err {e:.3e}  |reduced| {na:.4e}  |reference| {nb:.4e}", flush=True)
+for tag, gl in (("reference", ref), ("reduced", red)):
+    chk = torch.tensor([float(sum(t.double().abs().sum() for t in gl))], device=dev, dtype=torch.float64)
+    both = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(both, chk)
+    print(f"rank {rank}: checksum of the {tag} gradients per rank: {[float(b) for b in both]}", flush=True)
 assert num / den < 2e-3, num / den
 
 # ---- asymmetric micro-batches: rank 1's batch has NO protein sequence.  Its backward must issue zero
