@@ -167,28 +167,37 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap tma_dy, const __grid_constan
     }
 }
 
-// out[c] += sum_r in[r, c]  (bf16 [rows, cols], cols even -> fp32): block = 64 columns (one bf16x2 per thread) x 32 row lanes
-// per row chunk, one atomicAdd per (chunk, column)
-__global__ void __launch_bounds__(1024)
+// out[c] += sum_r in[r, c]  (bf16 [rows, cols], cols % 8 == 0 -> fp32): a thread sums 8 columns (one 16-B load per row)
+// over every 8th row of its chunk, the 8 row lanes of a block meet in shared memory, one atomicAdd per (chunk, column)
+__global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, int rows, int cols, int rows_per_chunk, float* __restrict__ out) {
-    __shared__ float2 sm[32][33];
+    __shared__ float sm[8][256 + 8];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int c = blockIdx.x * 64 + tx * 2;
+    const int c = blockIdx.x * 256 + tx * 8;
     const int r0 = blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
-    float2 a = make_float2(0.f, 0.f);
-    if (c < cols)
-        for (int r = r0 + ty; r < r1; r += 32) {
-            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(in + static_cast<size_t>(r) * cols + c));
-            a.x += v.x;
-            a.y += v.y;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c < cols) {
+#pragma unroll 4
+        for (int r = r0 + ty; r < r1; r += 8) {
+            const uint4 v = *reinterpret_cast<const uint4*>(in + static_cast<size_t>(r) * cols + c);
+            const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __bfloat1622float2(p[k]);
+                a[2 * k] += f.x;
+                a[2 * k + 1] += f.y;
+            }
         }
-    sm[ty][tx] = a;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm[ty][tx * 8 + k] = a[k];
     __syncthreads();
-    if (ty == 0 && c < cols) {
-        float2 t = make_float2(0.f, 0.f);
-        for (int i = 0; i < 32; ++i) { t.x += sm[i][tx].x; t.y += sm[i][tx].y; }
-        atomicAdd(out + c, t.x);
-        atomicAdd(out + c + 1, t.y);
+    const int col = blockIdx.x * 256 + threadIdx.x;
+    if (col < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+        atomicAdd(out + col, t);
     }
 }
 
@@ -221,14 +230,14 @@ int project_bwd_launch(const void* dy_bf16, const void* x_bf16, int M, int D, in
 
 // dW[N, K] = dy[M, N]^T x[M, K], db[N] = colsum(dy), no transposes (wgrad_mn_kernel).  N and K must be multiples of 8.
 int linear_wgrad_launch(const void* dy_bf16, const void* x_bf16, int M, int N, int K, float* d_weight, float* d_bias,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, bool zeroed) {
     MOLLY_CHECK(M > 0 && N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0, MOLLY_ERR_UNSUPPORTED,
                 "linear_wgrad: M=%d N=%d K=%d (N, K must be multiples of 8)", M, N, K);
     static const bool legacy = [] { const char* e = getenv("MOLLY_WGRAD_LEGACY"); return e != nullptr && e[0] == '1'; }();
     if (!legacy) {
         // the main tcgen05 GEMM with both operands MN-major (CTA pairs on 256 x 256 tiles, K split across the SMs)
         set_gemm_family(PF_GEMM_OTHER);
-        int rc = gemm_launch_mn(GEMM_OPND_MN_MN, dy_bf16, N, x_bf16, K, N, K, M, d_weight, DT_F32, K, stream);
+        int rc = gemm_launch_mn(GEMM_OPND_MN_MN, dy_bf16, N, x_bf16, K, N, K, M, d_weight, DT_F32, K, stream, zeroed);
         if (rc) return rc;
     } else {                                   // MOLLY_WGRAD_LEGACY=1: the first wgrad kernel (one CTA per 128 x 128 tile)
         CUtensorMap tdy, tx;
@@ -249,12 +258,12 @@ int linear_wgrad_launch(const void* dy_bf16, const void* x_bf16, int M, int N, i
         count_launch();
     }
     if (d_bias != nullptr) {
-        MOLLY_CUDA(cudaMemsetAsync(d_bias, 0, sizeof(float) * N, stream));
-        const int chunks = max(1, min(64, M / 64));
+        if (!zeroed) MOLLY_CUDA(cudaMemsetAsync(d_bias, 0, sizeof(float) * N, stream));
+        const int chunks = max(1, min(128, M / 64));
         const int rpc = (M + chunks - 1) / chunks;
         ProfScope prof(PF_ROWWISE_BWD, static_cast<double>(M) * N * 2.0, stream);
-        colsum_bf16_kernel<<<dim3((N + 63) / 64, chunks), 1024, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy_bf16), M, N,
-                                                                           rpc, d_bias);
+        colsum_bf16_kernel<<<dim3((N + 255) / 256, chunks), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy_bf16), M, N,
+                                                                            rpc, d_bias);
         count_launch();
     }
     MOLLY_CUDA(cudaGetLastError());

@@ -722,7 +722,7 @@ int pick_splits(int tiles, int slots, int num_kb) {
 }  // namespace
 
 int gemm_launch_mn(int opnd, const void* a, int lda, const void* b, int ldb, int M, int N, int K, void* out, int out_dtype,
-                   int ldo, cudaStream_t stream) {
+                   int ldo, cudaStream_t stream, bool out_zeroed) {
     MOLLY_CHECK(M > 0 && N > 0 && K > 0 && N % 32 == 0, MOLLY_ERR_UNSUPPORTED, "gemm_mn: M=%d N=%d K=%d (N %% 32 == 0)", M, N, K);
     MOLLY_CHECK((opnd == GEMM_OPND_K_MN && out_dtype == DT_BF16) || (opnd == GEMM_OPND_MN_MN && out_dtype == DT_F32),
                 MOLLY_ERR_UNSUPPORTED, "gemm_mn: dgrad writes bf16, wgrad fp32 (opnd=%d dtype=%d)", opnd, out_dtype);
@@ -741,7 +741,7 @@ int gemm_launch_mn(int opnd, const void* a, int lda, const void* b, int ldb, int
     const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
     const int tiles = ((M + tile_m - 1) / tile_m) * ((N + 255) / 256);
     p.splits = pick_splits(tiles, pair ? device_sm_count() / 2 : device_sm_count(), (K + BLOCK_K - 1) / BLOCK_K);
-    if (p.splits > 1) MOLLY_CUDA(cudaMemsetAsync(out, 0, static_cast<size_t>(M) * ldo * 4, stream));
+    if (p.splits > 1 && !out_zeroed) MOLLY_CUDA(cudaMemsetAsync(out, 0, static_cast<size_t>(M) * ldo * 4, stream));
     if (pair) return launch_gemm_impl<256, EPI_BIAS, float, 1, true, GEMM_OPND_MN_MN>(ta, tb, tc, p, stream);
     return launch_gemm_impl<256, EPI_BIAS, float, 1, false, GEMM_OPND_MN_MN>(ta, tb, tc, p, stream);
 }

@@ -51,8 +51,9 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap*
 //                    split over K across the SMs when M x N has too few tiles (partials meet in a TMA reduce-add)
 enum { GEMM_OPND_KK = 0, GEMM_OPND_K_MN = 1, GEMM_OPND_MN_MN = 2 };
 int gemm_make_map_mn(CUtensorMap* t, const void* base, int rows_k, int cols_mn, int ld);
+// out_zeroed: the caller has already zeroed `out` (a split-K wgrad accumulates into it)
 int gemm_launch_mn(int opnd, const void* a, int lda, const void* b, int ldb, int M, int N, int K, void* out, int out_dtype,
-                   int ldo, cudaStream_t stream);
+                   int ldo, cudaStream_t stream, bool out_zeroed = false);
 
 // ---- attention.cu ----
 void attention_set_debug(long long* buf);
@@ -130,8 +131,9 @@ int scatter_add_rows_launch(const float* src, const int32_t* index, const float*
 
 // ---- bwd.cu ----
 int transpose_bf16_launch(const void* in, int rows, int cols, void* out, cudaStream_t stream);
+// zeroed: d_weight and d_bias are already zero (the training step clears a whole layer's gradient group with one memset)
 int linear_wgrad_launch(const void* dy_bf16, const void* x_bf16, int M, int N, int K, float* d_weight, float* d_bias,
-                        cudaStream_t stream);
+                        cudaStream_t stream, bool zeroed = false);
 int project_bwd_launch(const void* dy_bf16, const void* x_bf16, int M, int D, int h, float* d_weight, float* d_bias,
                        void* workspace, size_t workspace_bytes, cudaStream_t stream);
 

@@ -266,14 +266,15 @@ int backward_layer(const molly_encoder* e, const Dims& d, int l, const float* x_
     auto G = [&](int slot_id) { return gl.off[slot_id] < 0 ? nullptr : g + gl.off[slot_id]; };
     int rc;
     // On entry `dy` holds the bf16 copy of d_x = d(x_out) (written by the LayerNorm backward above this layer), this layer's
-    // vector block is zeroed and its b_ffn2 gradient (column sums of dy) is already in place.
+    // whole gradient group is zeroed (ONE memset: LayerNorm / bias gradients accumulate with atomics, split-K weight gradients
+    // with TMA reduce-adds) and its b_ffn2 gradient (column sums of dy) is already in place.
     // ---- feed-forward block: x_out = x_mid + W2 act(W1 LN2(x_mid) + b1) + b2
     if ((rc = dgrad(dy, e->w_ffn2[l], M, h, F, w_t, d_act, s))) return rc;
     if ((rc = act_fwd_bwd_launch(d.glu, slot + t.pre, d_act, M, F, act, d_pre, s))) return rc;
-    if ((rc = linear_wgrad_launch(dy, act, M, h, F, G(MOLLY_GRAD_W_FFN2), nullptr, s))) return rc;
+    if ((rc = linear_wgrad_launch(dy, act, M, h, F, G(MOLLY_GRAD_W_FFN2), nullptr, s, true))) return rc;
     // (the GELU backward is bound by instruction issue: with the b_ffn1 column sums fused in it took 92 us against 45 + 17 us
     //  for the plain kernel and a separate column-sum pass over d_pre, so the bias gradient stays with the wgrad)
-    if ((rc = linear_wgrad_launch(d_pre, slot + t.ln2, M, F1, h, G(MOLLY_GRAD_W_FFN1), G(MOLLY_GRAD_B_FFN1), s))) return rc;
+    if ((rc = linear_wgrad_launch(d_pre, slot + t.ln2, M, F1, h, G(MOLLY_GRAD_W_FFN1), G(MOLLY_GRAD_B_FFN1), s, true))) return rc;
     if ((rc = dgrad(d_pre, e->w_ffn1[l], M, F1, h, w_t, d_ln, s))) return rc;
     // d_x becomes d(x_mid); dy its bf16 copy; b_o gradient = column sums of dy
     if ((rc = ln_bwd_launch(reinterpret_cast<const float*>(slot + t.x_mid), d_ln, e->ln2_w[l], M, h, c.layer_norm_eps, d_x, 1,
@@ -281,7 +282,7 @@ int backward_layer(const molly_encoder* e, const Dims& d, int l, const float* x_
         return rc;
     // ---- attention block: x_mid = x_in + Wo Attn(LN1(x_in)) + bo
     if ((rc = dgrad(dy, e->w_o[l], M, h, h, w_t, d_attn, s))) return rc;
-    if ((rc = linear_wgrad_launch(dy, slot + t.attn, M, h, h, G(MOLLY_GRAD_W_O), nullptr, s))) return rc;
+    if ((rc = linear_wgrad_launch(dy, slot + t.attn, M, h, h, G(MOLLY_GRAD_W_O), nullptr, s, true))) return rc;
     if ((rc = attention_bwd_launch(slot + t.qkv, slot + t.attn, d_attn, reinterpret_cast<const float*>(slot + t.lse2), d.n_seq,
                                    d.k, h, d.H, kv_info, key_mask, d_qkv, delta, s)))
         return rc;
@@ -291,11 +292,11 @@ int backward_layer(const molly_encoder* e, const Dims& d, int l, const float* x_
     } else if ((rc = scale_cols_launch(d_qkv, M, 3 * h, h, e->q_scale, s))) {
         return rc;
     }
-    if ((rc = linear_wgrad_launch(d_qkv, slot + t.ln1, M, 3 * h, h, G(MOLLY_GRAD_W_QKV), G(MOLLY_GRAD_B_QKV), s))) return rc;
+    if ((rc = linear_wgrad_launch(d_qkv, slot + t.ln1, M, 3 * h, h, G(MOLLY_GRAD_W_QKV), G(MOLLY_GRAD_B_QKV), s, true))) return rc;
     if ((rc = dgrad(d_qkv, e->w_qkv[l], M, 3 * h, h, w_t, d_ln, s))) return rc;
     // d_x becomes d(x_in) = d(x_out of layer l-1): prepare that layer's vector block and its b_ffn2 gradient
     float* g_below = l > 0 ? g - gl.group : nullptr;
-    if (g_below != nullptr) MOLLY_CUDA(cudaMemsetAsync(g_below, 0, sizeof(float) * gl.vec_floats, s));
+    if (g_below != nullptr) MOLLY_CUDA(cudaMemsetAsync(g_below, 0, sizeof(float) * gl.group, s));
     float* b2_below = (g_below != nullptr && gl.off[MOLLY_GRAD_B_FFN2] >= 0) ? g_below + gl.off[MOLLY_GRAD_B_FFN2] : nullptr;
     return ln_bwd_launch(x_in, d_ln, e->ln1_w[l], M, h, c.layer_norm_eps, d_x, 1, stats, G(MOLLY_GRAD_LN1_W), G(MOLLY_GRAD_LN1_B),
                          s, l > 0 ? dy : nullptr, b2_below);
@@ -367,7 +368,7 @@ int molly_encode_train_bwd(molly_encoder_t* enc, int32_t n_seq, int32_t k_tokens
             float* gw = grads_dev + gl.tail[MOLLY_GRAD_TAIL_FINAL_LN_W];
             float* g_top = grads_dev + gl.group * (d.L - 1);          // layer L-1: zero its vector block, fill its b_ffn2 gradient
             MOLLY_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * 2 * d.h, s));
-            MOLLY_CUDA(cudaMemsetAsync(g_top, 0, sizeof(float) * gl.vec_floats, s));
+            MOLLY_CUDA(cudaMemsetAsync(g_top, 0, sizeof(float) * gl.group, s));
             if ((rc = ln_bwd_launch(x_at(d.L), d_out_dev, enc->w.final_ln_w_dev, d.M, d.h, enc->cfg.layer_norm_eps, d_x, 0,
                                     reinterpret_cast<float*>(ws + sc.stats), gw, gw + d.h, s, ws + sc.dy,
                                     gl.off[MOLLY_GRAD_B_FFN2] >= 0 ? g_top + gl.off[MOLLY_GRAD_B_FFN2] : nullptr)))
