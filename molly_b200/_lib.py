@@ -11,7 +11,8 @@ import re
 from typing import List
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmolly_b200.so")
+# MOLLY_LIB=<path>: load another build of the same library (A/B runs of kernel variants, tools/build_variant.sh)
+LIB_PATH = os.environ.get("MOLLY_LIB") or os.path.join(_HERE, "libmolly_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "molly_b200.h")
 
 # status codes (enum molly_status)
