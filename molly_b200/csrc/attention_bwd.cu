@@ -191,9 +191,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
     uint64_t* bar_kv_empty = bars + 5;       // [NST <= 4]  dQ MMA of the block done: the K/V stage and the dS tile are free
     uint64_t* bar_sdp_full = bars + 9;       // S and dP of the block are in TMEM
     uint64_t* bar_s_free = bars + 10;        // 256 arrivals: both are in registers
-    uint64_t* bar_ds_full = bars + 11;       // 256 arrivals: dS is in smem
-    uint64_t* bar_dq_full = bars + 12;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    // 256 arrivals: dS is in smem.  ONE barrier per dS tile: with two tiles a fast thread finishes block j+1 while a slow one is
+    // still inside block j, and on a single barrier its second arrival would complete block j's phase in the slow thread's place
+    // (found by running the parity tests under compute-sanitizer, whose instrumentation spreads the threads that far apart)
+    uint64_t* bar_ds_full = bars + 11;       // [DS_BUFS <= 2]
+    uint64_t* bar_dq_full = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BW_BLOCK, head = blockIdx.y, n = blockIdx.z, heads = gridDim.y;
@@ -214,7 +217,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
             for (int s = 0; s < NST; ++s) { mbar_init(&bar_kv_full[s], 1); mbar_init(&bar_kv_empty[s], 1); }
             mbar_init(bar_sdp_full, 1);
             mbar_init(bar_s_free, BW_ARRIVALS);
-            mbar_init(bar_ds_full, BW_ARRIVALS);
+            for (int b = 0; b < Cfg::DS_BUFS; ++b) mbar_init(&bar_ds_full[b], BW_ARRIVALS);
             mbar_init(bar_dq_full, 1);
             fence_mbar_init();
         }
@@ -296,7 +299,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                     issue_scores(j + 1);
                     BW_TL(1, j, 2);
                 }
-                mbar_wait(bar_ds_full, j & 1);               // dS(j) is in smem
+                mbar_wait(&bar_ds_full[j % Cfg::DS_BUFS], (j / Cfg::DS_BUFS) & 1);     // dS(j) is in smem
                 BW_TL(1, j, 3);
                 tc_fence_after();
 #pragma unroll
@@ -374,7 +377,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
             if (threadIdx.x == 0) BW_TL(0, j, 5);
             fence_proxy_async_smem();
             tc_fence_before();
-            bw_arrive(bar_ds_full);
+            bw_arrive(&bar_ds_full[j % Cfg::DS_BUFS]);
             if (threadIdx.x == 0) BW_TL(0, j, 6);
         }
         if (half == 0) {

@@ -142,3 +142,73 @@ def test_encoder_backward_full_size_models(enc_name):
         assert total <= TOL and worst <= 0.10, (total, worst, worst_name)
     finally:
         enc.close()
+
+
+def test_native_train_abi_contract():
+    """``molly_encoder_train_sizes`` / ``molly_encoder_grad_layout`` / ``molly_encode_train_fwd|bwd`` (include/molly_b200.h): the
+    flat gradient layout covers every encoder parameter exactly once, a tape / workspace that is too small and a layer range
+    outside the encoder are refused with a status and a message (no kernel is launched), and a backward issued layer range by
+    layer range (what the reducer path does) equals the one-call backward."""
+    import ctypes as C
+    from molly_b200 import _lib, ops, train
+    from molly_b200.config import EncoderConfig
+    from molly_b200.packing import PackedEncoder
+    for spec_name in ("tiny_esm2", "tiny_ntv2", "tiny_ntv1"):
+        spec = SPECS[spec_name]
+        W = init_encoder_weights(spec, 3)
+        enc = PackedEncoder(EncoderConfig.from_mapping(spec.as_dict()), W, init_projector(spec.hidden_size, 64, 4), 64,
+                            torch.device(DEV))
+        try:
+            plan = train.grad_plan(enc)
+            n_params = sum(v.numel() for k, v in W.items() if v.dtype.is_floating_point and not k.endswith("inv_freq")
+                           and "contact_head" not in k and "lm_head" not in k and "pooler" not in k)
+            assert plan.total == n_params, (spec_name, plan.total, n_params)
+            spans = []
+            for i in range(plan.L):
+                for name, slot, sub, shape in plan._layer_entries(i):
+                    n = 1
+                    for v in shape:
+                        n *= v
+                    assert tuple(W[name].shape) == shape or plan.glu, name
+                    spans.append((i * plan.group + plan.off[slot] + sub, n))
+            for name, slot, shape in plan._tail_entries():
+                n = 1
+                for v in shape:
+                    n *= v
+                spans.append((plan.tail[slot], n))
+            spans.sort()
+            assert spans[0][0] == 0 and all(a + n == b for (a, n), (b, _) in zip(spans, spans[1:]))      # a partition
+            assert spans[-1][0] + spans[-1][1] == plan.total
+            K, n_seq = 64, 2
+            ids = _ids(spec, K, [64, 30], 5).to(DEV)
+            tape_b, ws_b, gf = train._sizes(enc, n_seq, K, False)
+            assert gf == plan.total and tape_b > 0 and ws_b > 0
+            assert train._sizes(enc, n_seq, K, True)[0] < tape_b                  # the recompute tape keeps one activation slot
+            lib = _lib.load()
+            out = torch.empty(n_seq * K, spec.hidden_size, dtype=torch.bfloat16, device=DEV)
+            small = train._device_buffer(tape_b - 1024, torch.device(DEV))
+            rc = lib.molly_encode_train_fwd(enc.handle, ids.data_ptr(), n_seq, K, out.data_ptr(), small.data_ptr(), tape_b - 1024, 0,
+                                            ops.error_flag(torch.device(DEV)).data_ptr(), ops._stream(torch.device(DEV)))
+            assert rc == 4 and b"tape" in lib.molly_last_error()                   # MOLLY_STATUS_WORKSPACE
+            out, tape = train.encoder_forward_train(enc, ids)
+            g = torch.Generator().manual_seed(1)
+            d_out = (torch.randn(n_seq * K, spec.hidden_size, generator=g) * 0.1).to(torch.bfloat16).to(DEV)
+            flat = torch.zeros(plan.total, dtype=torch.float32, device=DEV)
+            ws = train._device_buffer(ws_b, torch.device(DEV))
+
+            def bwd(lb, le, ws_bytes=ws_b):
+                return lib.molly_encode_train_bwd(enc.handle, n_seq, K, tape.buf.data_ptr(), tape_b, 0, d_out.data_ptr(),
+                                                  flat.data_ptr(), ws.data_ptr(), ws_bytes, lb, le, ops._stream(torch.device(DEV)))
+            assert bwd(plan.L + 1, 0) == 1 and bwd(0, 1) == 1 and bwd(plan.L, -1) == 1      # MOLLY_STATUS_INVALID
+            assert bwd(plan.L, 0, ws_b - 1024) == 4
+            whole = train.encoder_backward(enc, tape, d_out)
+            assert bwd(plan.L, plan.L - 1) == 0                                              # range by range, top down
+            for i in range(plan.L - 2, -1, -1):
+                assert bwd(i, i) == 0
+            torch.cuda.synchronize()
+            for i in range(plan.L):
+                part = plan.finalize_(plan.layer_views(i, flat[i * plan.group:(i + 1) * plan.group]))
+                for name, t in part.items():
+                    assert_close(f"{spec_name} {name} (layer ranges vs one call)", t.float().cpu(), whole[name].float().cpu(), 1e-3)
+        finally:
+            enc.close()
