@@ -290,6 +290,9 @@ int molly_profile_stop(molly_profile_entry* out, int32_t max_entries);
 const char* molly_last_error(void);
 int molly_abi_version(void);
 int molly_kernel_launch_count(void); /* kernels launched by this library since load (bench `gpu_launches`) */
+/* A host that captured this library's launches into a CUDA graph reports each replay here (n = launches counted while
+ * capturing), so that the counter keeps meaning "kernels of this library that ran" */
+int molly_add_kernel_launches(int32_t n);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

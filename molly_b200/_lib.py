@@ -115,6 +115,7 @@ SIGNATURES = {
     "molly_last_error": (C.c_char_p, []),
     "molly_abi_version": (C.c_int, []),
     "molly_kernel_launch_count": (C.c_int, []),
+    "molly_add_kernel_launches": (C.c_int, [_i32]),
 }
 
 _lib = None

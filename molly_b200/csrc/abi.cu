@@ -165,6 +165,11 @@ extern "C" {
 const char* molly_last_error(void) { return get_last_error(); }
 int molly_abi_version(void) { return MOLLY_ABI_VERSION; }
 int molly_kernel_launch_count(void) { return launch_count(); }
+int molly_add_kernel_launches(int32_t n) {
+    MOLLY_CHECK(n >= 0, MOLLY_ERR_INVALID, "molly_add_kernel_launches: n=%d", n);
+    add_launches(n);
+    return MOLLY_OK;
+}
 
 int molly_profile_start(void) { prof_start(); return MOLLY_OK; }
 int molly_profile_stop(molly_profile_entry* out, int32_t max_entries) {

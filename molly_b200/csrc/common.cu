@@ -116,6 +116,7 @@ int prof_stop(int* launches, double* ms, double* work) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int launch_count() { return g_launches.load(std::memory_order_relaxed); }
+void add_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int device_sm_count() {
     static int sms = 0;

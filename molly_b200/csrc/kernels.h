@@ -11,6 +11,7 @@ enum { DT_BF16 = 0, DT_F32 = 1 };
 
 void count_launch();
 int launch_count();
+void add_launches(int n);     // kernels replayed from a CUDA graph the host captured around this library's launches
 
 // ---- optional per-launch profiling (CUDA events on the launching stream; off by default) ----
 enum ProfFamily {

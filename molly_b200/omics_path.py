@@ -99,6 +99,7 @@ class _InjectTrainFn(torch.autograd.Function):
             pg = {"projector.weight": dW, "projector.bias": db}
             reducer.reduce_(pg, list(pg))
             dW, db = pg["projector.weight"], pg["projector.bias"]
+        static = ctx.tape.graph is not None          # gradients are views of a graph's buffer: never hand those to autograd
         grads = train.encoder_backward(enc, ctx.tape, d_enc, reducer)
         if reducer is not None:
             reducer.finish()
@@ -111,7 +112,7 @@ class _InjectTrainFn(torch.autograd.Function):
                 enc_grads.append(None)
                 continue
             src = grads[n]
-            if src.dtype == dt and src.device == dv:
+            if src.dtype == dt and src.device == dv and not static:
                 enc_grads.append(src)
                 continue
             dst = torch.empty(src.shape, dtype=dt, device=dv)

@@ -150,13 +150,29 @@ def kernel_launch_count() -> int:
     return int(_lib.load().molly_kernel_launch_count())
 
 
+_profiling = False            # per-launch events cannot be recorded inside a replayed graph: graphed paths check this
+
+
+def profiling_active() -> bool:
+    return _profiling
+
+
+def add_kernel_launches(n: int) -> None:
+    """Report the replay of a CUDA graph that holds ``n`` of this library's launches (keeps ``kernel_launch_count`` honest)."""
+    _lib.check(_lib.load().molly_add_kernel_launches(int(n)), "molly_add_kernel_launches")
+
+
 def profile_start() -> None:
     """Bracket every kernel the library launches from now on with CUDA events on the launching stream."""
+    global _profiling
     _lib.check(_lib.load().molly_profile_start(), "molly_profile_start")
+    _profiling = True
 
 
 def profile_stop() -> Dict[str, dict]:
     """Per kernel family: launches, total ms, algorithmic work (FLOP or HBM bytes) since profile_start()."""
+    global _profiling
+    _profiling = False
     arr = (_lib.ProfileEntry * _lib.PROFILE_FAMILIES)()
     _lib.check(_lib.load().molly_profile_stop(arr, _lib.PROFILE_FAMILIES), "molly_profile_stop")
     out = {}

@@ -15,11 +15,13 @@ Orchestration is native (csrc/train.cu: one C call for the forward, one per rang
 version issued one ctypes call per kernel and the step was bound by the host (133 ms to enqueue 115 ms of kernels).  The
 library writes fp32 gradients into ONE flat buffer in the packed layout of the weights (``molly_encoder_grad_layout``);
 ``GradPlan`` maps it to the HF ``state_dict`` names (q / k / v are slices, the NT-v2 gate / up halves are un-interleaved).
+Once a shape is steady state the two calls are replayed from CUDA graphs (``_GraphedStep``).
 """
 from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -163,6 +165,7 @@ class EncoderTape:
         self.buf: Optional[torch.Tensor] = None
         self.recompute = False
         self.ids = None
+        self.graph = None                      # the _GraphedStep whose buffers this tape borrows (None: eager)
 
 
 def _save_activations(enc: PackedEncoder, n_tokens: int) -> bool:
@@ -194,8 +197,95 @@ def _device_buffer(nbytes: int, dev) -> torch.Tensor:
     return raw[shift:shift + nbytes]
 
 
+class _GraphedStep:
+    """CUDA graphs of one encoder's training forward and backward for one (n_seq, K): the ~35 launches per layer are
+    replayed as two graphs instead of being enqueued one by one (the ``--train-bio`` step had ~7 ms of inter-kernel gaps over
+    ~1 960 launches).  The buffers the graphs touch are owned here: ids, the forward output, the tape, the backward
+    workspace, d_out and the flat gradient buffer.  ``busy`` is set between a forward and its backward; a second forward in
+    between (re-entrant use) takes the eager path."""
+
+    def __init__(self, enc: PackedEncoder, n_seq: int, K: int, recompute: bool, dev):
+        h = enc.cfg.hidden_size
+        self.n_seq, self.K, self.recompute = n_seq, K, recompute
+        self.tape_bytes, self.ws_bytes, gf = _sizes(enc, n_seq, K, recompute)
+        self.ids = torch.ones(n_seq, K, dtype=torch.int64, device=dev)
+        self.out = torch.empty(n_seq * K, h, dtype=torch.bfloat16, device=dev)
+        self.d_out = torch.empty(n_seq * K, h, dtype=torch.bfloat16, device=dev)
+        self.tape = _device_buffer(self.tape_bytes, dev)
+        self.ws = _device_buffer(self.ws_bytes, dev)
+        self.flat = torch.empty(gf, dtype=torch.float32, device=dev)
+        self.fwd = self.bwd = None
+        self.fwd_launches = self.bwd_launches = 0
+        self._owner = None                     # weak reference to the tape of the forward whose backward is still to come
+
+    @property
+    def busy(self) -> bool:
+        return self._owner is not None and self._owner() is not None
+
+    def acquire(self, tape) -> None:
+        self._owner = weakref.ref(tape)
+
+    def release(self) -> None:
+        self._owner = None
+
+
+def _graphs_enabled() -> bool:
+    """MOLLY_TRAIN_GRAPH=0 turns the graphed training step off; it is also off while per-launch profiling is on (events cannot
+    be recorded inside a replay) and inside somebody else's capture."""
+    return (os.environ.get("MOLLY_TRAIN_GRAPH", "1") != "0" and not ops.profiling_active()
+            and not torch.cuda.is_current_stream_capturing())
+
+
+_GRAPH_MIN_SIGHTINGS = 3       # a shape is captured on its third use ...
+_GRAPH_SHAPES = 2              # ... at most two shapes are held per encoder (the tape is gigabytes) ...
+_GRAPH_MAX_CAPTURES = 8        # ... and an encoder whose shapes keep changing stops capturing (a capture costs ~0.1 s)
+
+
+def _graphed_step(enc: PackedEncoder, n_seq: int, K: int, recompute: bool, dev) -> Optional[_GraphedStep]:
+    """The graphed step for this shape once it is steady state: the first two uses run eagerly (they configure the kernels and
+    tell one-off shapes -- a training set whose number of omics sequences per micro-batch varies -- from the steady state);
+    a new shape replaces a held one only when it has been seen twice as often."""
+    if not _graphs_enabled():
+        return None
+    key = (n_seq, K, recompute)
+    seen = enc.__dict__.setdefault("_train_shapes_seen", {})
+    seen[key] = seen.get(key, 0) + 1
+    cache = enc.__dict__.setdefault("_train_graphs", {})
+    gs = cache.get(key)
+    if gs is None:
+        captures = enc.__dict__.get("_train_captures", 0)
+        if seen[key] < _GRAPH_MIN_SIGHTINGS or captures >= _GRAPH_MAX_CAPTURES:
+            return None
+        if len(cache) >= _GRAPH_SHAPES:
+            coldest = min(cache, key=lambda k: seen.get(k, 0))
+            if cache[coldest].busy or seen[key] < 2 * seen.get(coldest, 0):
+                return None
+            del cache[coldest]
+        enc._train_captures = captures + 1
+        gs = cache[key] = _GraphedStep(enc, n_seq, K, recompute, dev)
+    return None if gs.busy else gs
+
+
+def _capture(fn):
+    """Capture ``fn`` (kernel launches on the current stream only) into a CUDA graph; returns (graph, launches captured)."""
+    g = torch.cuda.CUDAGraph()
+    l0 = ops.kernel_launch_count()
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):       # (the backward is captured on autograd's thread)
+        fn()
+    return g, ops.kernel_launch_count() - l0
+
+
+def _call_fwd(enc: PackedEncoder, ids, n_seq, K, out, tape_buf, tape_bytes, recompute, dev) -> None:
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().molly_encode_train_fwd(enc.handle, ids.data_ptr(), n_seq, K, out.data_ptr(), tape_buf.data_ptr(),
+                                                      tape_bytes, int(recompute), ops.error_flag(dev).data_ptr(),
+                                                      ops._stream(dev)), "molly_encode_train_fwd")
+
+
 def encoder_forward_train(enc: PackedEncoder, ids: torch.Tensor) -> Tuple[torch.Tensor, EncoderTape]:
-    """``hidden_states[-1]`` (bf16 [n*K, h]) with the tape; numerically the inference forward (same kernels, same order)."""
+    """``hidden_states[-1]`` (bf16 [n*K, h]) with the tape; numerically the inference forward (same kernels, same order).
+    From the third call with a shape on, the launches are replayed from a CUDA graph (``_GraphedStep``): the returned tensor
+    and the tape are then buffers of that graph, valid until the next training forward of this encoder with the same shape."""
     cfg = enc.cfg
     if cfg.emb_layer_norm_before:
         raise NotImplementedError("emb_layer_norm_before encoders are not covered by the training path")
@@ -203,57 +293,31 @@ def encoder_forward_train(enc: PackedEncoder, ids: torch.Tensor) -> Tuple[torch.
     ids = ids.contiguous()
     n_seq, K = ids.shape
     tape = EncoderTape()
-    tape.ids = ids
     tape.recompute = not _save_activations(enc, n_seq * K)
+    gs = _graphed_step(enc, n_seq, K, tape.recompute, dev)
+    if gs is not None:
+        gs.ids.copy_(ids)
+        if gs.fwd is None:                     # (the launches were counted while capturing: this first replay is not added)
+            gs.fwd, gs.fwd_launches = _capture(lambda: _call_fwd(enc, gs.ids, n_seq, K, gs.out, gs.tape, gs.tape_bytes,
+                                                                 gs.recompute, dev))
+        else:
+            ops.add_kernel_launches(gs.fwd_launches)
+        gs.fwd.replay()
+        gs.acquire(tape)                       # (a tape that dies without a backward frees the step as well)
+        tape.ids, tape.buf, tape.graph = gs.ids, gs.tape, gs
+        return gs.out, tape
+    tape.ids = ids
     tape_bytes, _, _ = _sizes(enc, n_seq, K, tape.recompute)
     tape.buf = _device_buffer(tape_bytes, dev)
     out = torch.empty(n_seq * K, cfg.hidden_size, dtype=torch.bfloat16, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(_lib.load().molly_encode_train_fwd(enc.handle, ids.data_ptr(), n_seq, K, out.data_ptr(), tape.buf.data_ptr(),
-                                                      tape_bytes, int(tape.recompute), ops.error_flag(dev).data_ptr(),
-                                                      ops._stream(dev)), "molly_encode_train_fwd")
+    _call_fwd(enc, ids, n_seq, K, out, tape.buf, tape_bytes, tape.recompute, dev)
     return out, tape
 
 
-def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor, reducer=None) -> Dict[str, torch.Tensor]:
-    """Gradients of every encoder parameter (HF ``state_dict`` names, fp32 views of one flat buffer) from ``d_out`` =
-    d(loss)/d(hidden_states[-1]), bf16 [n*K, h].  ``reducer`` (``dist.LayerwiseGradReducer``): each layer's flat group is
-    handed to it as soon as the layer's backward is enqueued, so its all-reduce overlaps the layers below; those gradients
-    come back averaged, in the reducer's dtype (the reducer is finished -- current stream ordered after every collective --
-    before this returns)."""
-    cfg = enc.cfg
-    n_seq, K = tape.ids.shape
-    h, L = cfg.hidden_size, cfg.num_hidden_layers
-    dev = ops._require_cuda(d_out)
-    if d_out.dtype != torch.bfloat16 or tuple(d_out.shape) != (n_seq * K, h) or not d_out.is_contiguous():
-        raise ValueError("encoder_backward: d_out must be contiguous bf16 [n_seq*K, h]")
-    plan = grad_plan(enc)
-    tape_bytes, ws_bytes, grad_floats = _sizes(enc, n_seq, K, tape.recompute)
-    assert grad_floats == plan.total
-    flat = torch.empty(plan.total, dtype=torch.float32, device=dev)
-    ws = _device_buffer(ws_bytes, dev)
-    lib = _lib.load()
-
-    def run(layer_begin: int, layer_end: int) -> None:
-        with torch.cuda.device(dev):
-            _lib.check(lib.molly_encode_train_bwd(enc.handle, n_seq, K, tape.buf.data_ptr(), tape_bytes, int(tape.recompute),
-                                                  d_out.data_ptr(), flat.data_ptr(), ws.data_ptr(), ws_bytes, layer_begin,
-                                                  layer_end, ops._stream(dev)), "molly_encode_train_bwd")
-
-    grads: Dict[str, torch.Tensor] = {}
-    if reducer is None:
-        run(L, 0)
-        for i in range(L):
-            grads.update(plan.layer_views(i, flat[i * plan.group:(i + 1) * plan.group]))
-    else:
-        for i in range(L - 1, -1, -1):
-            run(L if i == L - 1 else i, i)                    # (the first call also does emb_layer_norm_after)
-            grads.update(plan.layer_views(i, reducer.reduce_flat_(flat[i * plan.group:(i + 1) * plan.group])))
-    # ---- embeddings: the running gradient of the residual stream is the first M*h floats of the workspace
-    d_x = ws[:n_seq * K * h * 4].view(torch.float32).view(n_seq * K, h)
-    tail = flat[plan.tail_begin:]
+def _embedding_backward(enc: PackedEncoder, plan: "GradPlan", ids: torch.Tensor, d_x: torch.Tensor, tail: torch.Tensor) -> None:
+    """Embedding tables: scatter-add of the residual-stream gradient (token-dropout scale, pad / <mask> rows skipped)."""
     views = plan.tail_views(tail)
-    word_index, word_scale, pos_index, pos_scale = _emb_meta(enc, tape.ids)
+    word_index, word_scale, pos_index, pos_scale = _emb_meta(enc, ids)
     d_word = views["esm.embeddings.word_embeddings.weight"]
     d_word.zero_()
     ops.scatter_add_rows_(d_word, d_x, word_index, word_scale)
@@ -261,8 +325,71 @@ def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor,
         d_pos = views["esm.embeddings.position_embeddings.weight"]
         d_pos.zero_()
         ops.scatter_add_rows_(d_pos, d_x, pos_index, pos_scale)
-    if reducer is not None:
-        views = plan.tail_views(reducer.reduce_flat_(tail))
-        reducer.finish()                       # every group is averaged before anything reads the flat buffers
-    grads.update(views)
+
+
+def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor, reducer=None) -> Dict[str, torch.Tensor]:
+    """Gradients of every encoder parameter (HF ``state_dict`` names, fp32 views of one flat buffer) from ``d_out`` =
+    d(loss)/d(hidden_states[-1]), bf16 [n*K, h].  ``reducer`` (``dist.LayerwiseGradReducer``): each layer's flat group is
+    handed to it as soon as the layer's backward is enqueued, so its all-reduce overlaps the layers below; those gradients
+    come back averaged, in the reducer's dtype (the reducer is finished -- current stream ordered after every collective --
+    before this returns).  After a graphed forward (and without a reducer) the backward is one graph replay as well and the
+    returned tensors are views of that graph's gradient buffer: consume them before the next backward of this encoder."""
+    cfg = enc.cfg
+    n_seq, K = tape.ids.shape
+    h, L = cfg.hidden_size, cfg.num_hidden_layers
+    dev = ops._require_cuda(d_out)
+    if d_out.dtype != torch.bfloat16 or tuple(d_out.shape) != (n_seq * K, h) or not d_out.is_contiguous():
+        raise ValueError("encoder_backward: d_out must be contiguous bf16 [n_seq*K, h]")
+    plan = grad_plan(enc)
+    gs: Optional[_GraphedStep] = tape.graph
+    tape_bytes, ws_bytes, grad_floats = _sizes(enc, n_seq, K, tape.recompute)
+    assert grad_floats == plan.total
+    graphed = gs is not None and reducer is None and _graphs_enabled()
+    if graphed:
+        flat, ws, d_src = gs.flat, gs.ws, gs.d_out
+        d_src.copy_(d_out)
+    else:
+        flat = torch.empty(plan.total, dtype=torch.float32, device=dev)
+        ws = _device_buffer(ws_bytes, dev)
+        d_src = d_out
+    lib = _lib.load()
+
+    def run(layer_begin: int, layer_end: int) -> None:
+        with torch.cuda.device(dev):
+            _lib.check(lib.molly_encode_train_bwd(enc.handle, n_seq, K, tape.buf.data_ptr(), tape_bytes, int(tape.recompute),
+                                                  d_src.data_ptr(), flat.data_ptr(), ws.data_ptr(), ws_bytes, layer_begin,
+                                                  layer_end, ops._stream(dev)), "molly_encode_train_bwd")
+
+    # the running gradient of the residual stream is the first M*h floats of the workspace: d(embedding output) after layer 0
+    d_x = ws[:n_seq * K * h * 4].view(torch.float32).view(n_seq * K, h)
+    tail = flat[plan.tail_begin:]
+    grads: Dict[str, torch.Tensor] = {}
+    try:
+        if graphed:
+            if gs.bwd is None:
+                def whole():
+                    run(L, 0)
+                    _embedding_backward(enc, plan, tape.ids, d_x, tail)
+                gs.bwd, gs.bwd_launches = _capture(whole)
+            else:
+                ops.add_kernel_launches(gs.bwd_launches)
+            gs.bwd.replay()
+        elif reducer is None:
+            run(L, 0)
+        else:
+            for i in range(L - 1, -1, -1):
+                run(L if i == L - 1 else i, i)                    # (the first call also does emb_layer_norm_after)
+                grads.update(plan.layer_views(i, reducer.reduce_flat_(flat[i * plan.group:(i + 1) * plan.group])))
+        if reducer is None:
+            for i in range(L):
+                grads.update(plan.layer_views(i, flat[i * plan.group:(i + 1) * plan.group]))
+        if not graphed:
+            _embedding_backward(enc, plan, tape.ids, d_x, tail)
+        if reducer is not None:
+            tail = reducer.reduce_flat_(tail)
+            reducer.finish()                       # every group is averaged before anything reads the flat buffers
+        grads.update(plan.tail_views(tail))
+    finally:
+        if gs is not None:
+            gs.release()
     return plan.finalize_(grads)

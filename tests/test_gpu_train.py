@@ -212,3 +212,68 @@ def test_native_train_abi_contract():
                     assert_close(f"{spec_name} {name} (layer ranges vs one call)", t.float().cpu(), whole[name].float().cpu(), 1e-3)
         finally:
             enc.close()
+
+
+@pytest.mark.parametrize("spec_name", ["tiny_esm2", "tiny_ntv2", "tiny_ntv1"])
+def test_graphed_training_step_equals_eager(spec_name):
+    """From the third call with a shape on, ``encoder_forward_train`` / ``encoder_backward`` replay CUDA graphs (``_GraphedStep``):
+    same outputs and gradients as the eager launches (column sums and split-K partials meet in fp32 atomics / reduce-adds, so
+    equal up to their order), also when the ids and d_out CHANGE between replays (the graphs read static buffers), the forward
+    output of a graphed step survives until its backward, and a re-entrant forward falls back to the eager path."""
+    from molly_b200.config import EncoderConfig
+    from molly_b200.packing import PackedEncoder
+    from molly_b200 import ops, train
+    spec = SPECS[spec_name]
+    W = init_encoder_weights(spec, 11)
+    K, valid_sets = 96, ([96, 50, 70], [33, 96, 96], [96, 96, 5])
+    g = torch.Generator().manual_seed(12)
+    d_outs = [(torch.randn(3 * K, spec.hidden_size, generator=g) * 0.1).to(torch.bfloat16).to(DEV) for _ in range(3)]
+    idss = [_ids(spec, K, v, 20 + i).to(DEV) for i, v in enumerate(valid_sets)]
+
+    def one(enc, i):
+        out, tape = train.encoder_forward_train(enc, idss[i])
+        out = out.clone()
+        grads = train.encoder_backward(enc, tape, d_outs[i])
+        return out, {k: v.float().clone() for k, v in grads.items()}, tape
+
+    import os
+    os.environ["MOLLY_TRAIN_GRAPH"] = "0"
+    enc = PackedEncoder(EncoderConfig.from_mapping(spec.as_dict()), W, init_projector(spec.hidden_size, 64, 4), K, torch.device(DEV))
+    try:
+        eager = [one(enc, i)[:2] for i in range(3)]
+    finally:
+        enc.close()
+        del os.environ["MOLLY_TRAIN_GRAPH"]
+    enc = PackedEncoder(EncoderConfig.from_mapping(spec.as_dict()), W, init_projector(spec.hidden_size, 64, 4), K, torch.device(DEV))
+    try:
+        for _ in range(2):                                         # the first two calls with this shape: eager
+            l0 = ops.kernel_launch_count()
+            o0, g0, t0 = one(enc, 0)
+            per_step = ops.kernel_launch_count() - l0
+            assert t0.graph is None
+        for i in (1, 2, 0):                                        # capture + replay, replay, replay with the first inputs again
+            l0 = ops.kernel_launch_count()
+            out, grads, tape = one(enc, i)
+            assert tape.graph is not None and tape.graph.fwd is not None and tape.graph.bwd is not None
+            assert ops.kernel_launch_count() - l0 == per_step, "replays must be counted like the eager launches"
+            assert torch.equal(out, eager[i][0]), "graphed forward differs from the eager forward"
+            for name, ref in eager[i][1].items():
+                assert_close(f"{spec_name} graphed d {name} (inputs {i})", grads[name].cpu(), ref.cpu(), 1e-4)
+        # a second forward before the first one's backward must not touch the first one's buffers
+        out_a, tape_a = train.encoder_forward_train(enc, idss[1])
+        out_b, tape_b = train.encoder_forward_train(enc, idss[2])
+        assert tape_a.graph is not None and tape_b.graph is None
+        assert torch.equal(out_a, eager[1][0]) and torch.equal(out_b, eager[2][0])
+        gb = train.encoder_backward(enc, tape_b, d_outs[2])
+        ga = train.encoder_backward(enc, tape_a, d_outs[1])
+        for name in ("esm.encoder.layer.0.attention.self.value.weight", "esm.embeddings.word_embeddings.weight"):
+            assert_close(f"{spec_name} re-entrant a {name}", ga[name].float().cpu(), eager[1][1][name].cpu(), 1e-4)
+            assert_close(f"{spec_name} re-entrant b {name}", gb[name].float().cpu(), eager[2][1][name].cpu(), 1e-4)
+        del tape_a, tape_b
+        # a forward whose backward never comes (its tape dies) does not block the graphs for good
+        out_c, tape_c = train.encoder_forward_train(enc, idss[0])
+        del out_c, tape_c
+        _, tape_d = train.encoder_forward_train(enc, idss[0])
+        assert tape_d.graph is not None
+    finally:
+        enc.close()
