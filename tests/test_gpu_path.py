@@ -528,3 +528,61 @@ def test_frozen_projector_still_zeroes_the_overwritten_rows_of_the_embedding_gra
         assert int(written.sum()) > 0
     finally:
         path.close()
+
+
+def test_train_bio_steps_through_cuda_graphs_match_the_eager_step_and_accumulate():
+    """``--train-bio`` stepped repeatedly with one batch shape: from the third step on the encoder forward / backward are CUDA
+    graph replays (``train._GraphedStep``).  The parameter gradients of a replayed step equal those of the first (eager) step,
+    the step follows an in-place weight update in between, and gradients ACCUMULATE across steps (what autograd receives is
+    never a view of a graph's buffer)."""
+    from molly_b200 import train
+    from molly_b200.omics_path import FastOmicsPath
+    case = cases.golden_cases()["tiny_rotary_glu"]
+    om = _omics_one_like(case)
+    for mod in (om.dna_rna_model, om.protein_model, om.dna_rna_projector, om.protein_projector):
+        mod.to(DEV)
+    path = FastOmicsPath.from_omics_one(om, DEV, strict=True)
+    params = [p for m in (om.dna_rna_model, om.protein_model, om.dna_rna_projector, om.protein_projector)
+              for p in m.parameters() if p.requires_grad]
+    gw = torch.randn(case.batch.hidden_states.shape, generator=torch.Generator().manual_seed(61)).to(DEV)
+
+    def step(zero=True):
+        if zero:
+            for p in params:
+                p.grad = None
+        hs = case.batch.hidden_states.to(DEV) * 1.0
+        out = path.process_omic_sequences(hs, case.batch.omic_ids, case.batch.omic_info_list, hs.device)
+        (out * gw).sum().backward()
+        return [None if p.grad is None else p.grad.float().clone() for p in params]
+
+    try:
+        first = step()
+        assert sum(g is not None and float(g.abs().sum()) > 0 for g in first) > 20
+        step()
+        third = step()                                             # captured and replayed
+        graphs = [g for name in ("dna_rna", "protein") for g in getattr(path, name).__dict__.get("_train_graphs", {}).values()]
+        assert graphs and all(g.fwd is not None and g.bwd is not None for g in graphs), "the steady-state step was not graphed"
+        for a, b in zip(third, first):
+            if b is not None:
+                assert_close("graphed step vs eager step", a.cpu(), b.cpu(), 1e-4)
+        doubled = step(zero=False)                                 # accumulate on top of the third step's gradients
+        for a, b in zip(doubled, first):
+            if b is not None:
+                assert_close("accumulated over two steps", a.cpu(), 2 * b.cpu(), 1e-3)
+        with torch.no_grad():                                      # an optimizer step written through .data
+            for p in om.protein_model.parameters():
+                if p.dim() == 2:
+                    p.data.mul_(1.05)
+        moved = step()
+        assert any(b is not None and float((a - b).abs().max()) > 1e-3 * float(b.abs().max()) for a, b in zip(moved, first)), \
+            "the graphed step did not follow the weight update"
+        os.environ["MOLLY_TRAIN_GRAPH"] = "0"
+        try:
+            eager_moved = step()
+        finally:
+            del os.environ["MOLLY_TRAIN_GRAPH"]
+        for a, b in zip(moved, eager_moved):
+            if b is not None:
+                assert_close("graphed vs eager after the update", a.cpu(), b.cpu(), 1e-4)
+    finally:
+        path.close()

@@ -69,3 +69,16 @@ def test_encoder_backward_with_per_layer_recompute():
 def test_wgrad_through_transposes():
     """MOLLY_WGRAD_TRANSPOSE=1: the first wgrad version (explicit bf16 transposes + the K-major GEMM)."""
     _run({"MOLLY_WGRAD_TRANSPOSE": "1"}, "linear_wgrad")
+
+
+def test_backward_gemms_legacy_kernels():
+    """MOLLY_WGRAD_LEGACY=1 + MOLLY_DGRAD_TRANSPOSE=1: the round-1 backward GEMMs (single-CTA 128x128 MN-major wgrad kernel,
+    weight transposes + K-major dgrad) instead of the main tcgen05 kernel with MN-major operands and split-K."""
+    _run({"MOLLY_WGRAD_LEGACY": "1", "MOLLY_DGRAD_TRANSPOSE": "1"}, "linear_wgrad or tiny", files=("tests/test_gpu_kernels.py", "tests/test_gpu_train.py"))
+
+
+def test_training_step_without_graphs():
+    """MOLLY_TRAIN_GRAPH=0: the encoder training forward / backward always launched eagerly (a live nn.Module stepped several
+    times: the path-level training tests)."""
+    _run({"MOLLY_TRAIN_GRAPH": "0"}, "(train or backward or grad) and not cuda_graphs",
+         files=("tests/test_gpu_path.py", "tests/test_gpu_real_class.py"))
