@@ -104,20 +104,19 @@ __device__ __forceinline__ float bw_ex2(float x) {
     return y;
 }
 
-// delta[n, head, t] = sum_d dO[row, head*D + d] * O[row, head*D + d]      (one thread per (row, head))
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ d_out, const __nv_bfloat16* __restrict__ out, int n_seq,
-                                  int k_tokens, int heads, int d, float* __restrict__ delta) {
-    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long total = static_cast<long long>(n_seq) * k_tokens * heads;
-    if (idx >= total) return;
-    const int head = static_cast<int>(idx % heads);
-    const long long row = idx / heads;
-    const int h = heads * d;
-    const uint4* a = reinterpret_cast<const uint4*>(d_out + row * h + head * d);
-    const uint4* b = reinterpret_cast<const uint4*>(out + row * h + head * d);
+// delta[n, head, t] = sum_d dO[row, head*D + d] * O[row, head*D + d].  d/8 lanes share a (row, head) pair, 16 B each, so a warp
+// reads 512 contiguous bytes of dO and of O per load instruction; the partial dot products meet in d/8-lane xor shuffles.
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ d_out, const __nv_bfloat16* __restrict__ out, int n_seq, int k_tokens,
+                  int heads, int d, float* __restrict__ delta) {
+    const int lpp = d >> 3;                                             // lanes per (row, head) pair: 2, 4, 8 or 16
+    const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long idx = gid / lpp, total = static_cast<long long>(n_seq) * k_tokens * heads;
+    const int sub = static_cast<int>(gid % lpp);
     float acc = 0.f;
-    for (int v = 0; v < d / 8; ++v) {
-        const uint4 x = __ldg(a + v), y = __ldg(b + v);
+    if (idx < total) {                                                  // (pairs are contiguous: element offset = idx * d)
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(d_out + idx * d) + sub);
+        const uint4 y = __ldg(reinterpret_cast<const uint4*>(out + idx * d) + sub);
         const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&x);
         const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(&y);
 #pragma unroll
@@ -126,8 +125,13 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ d_out, const
             acc += xf.x * yf.x + xf.y * yf.y;
         }
     }
-    const long long n = row / k_tokens, t = row % k_tokens;
-    delta[(n * heads + head) * k_tokens + t] = acc;
+    for (int o = lpp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (idx < total && sub == 0) {
+        const int head = static_cast<int>(idx % heads);
+        const long long row = idx / heads;
+        const long long n = row / k_tokens, t = row % k_tokens;
+        delta[(n * heads + head) * k_tokens + t] = acc;
+    }
 }
 
 // store 32 bf16 values of operand-tile row r (K-major, 128-B swizzle, atom = 64 columns): columns [qt*32, qt*32 + 32)
@@ -670,7 +674,7 @@ int attention_bwd_launch(const void* qkv, const void* out, const void* d_out, co
     MOLLY_CHECK(d == 16 || d == 32 || d == 64 || d == 128, MOLLY_ERR_UNSUPPORTED, "attention_bwd: head_dim %d unsupported", d);
     MOLLY_CHECK(static_cast<long long>(n_seq) * k_tokens < (1ll << 31) && n_seq <= 65535 && heads <= 65535,
                 MOLLY_ERR_UNSUPPORTED, "attention_bwd: problem too large for the grid / TMA coordinates");
-    const long long items = static_cast<long long>(n_seq) * k_tokens * heads;
+    const long long items = static_cast<long long>(n_seq) * k_tokens * heads * (d / 8);       // one thread per 16 B
     attn_delta_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(d_out), static_cast<const __nv_bfloat16*>(out), n_seq, k_tokens, heads, d, delta_ws);
     count_launch();

@@ -94,47 +94,62 @@ ln_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
 // Column sums of one LayerNorm backward, one pass over x, dy and dy_next:
 //   d_gamma[c] += sum_r dy * xhat,   d_beta[c] += sum_r dy,   d_bias[c] += sum_r dy_next  (the bias of the linear layer whose
 //   output gradient dy_next is; optional)
-// block = 32 column pairs x 32 row lanes over one chunk of rows, one atomicAdd per (chunk, column) into pre-zeroed fp32.
-__global__ void __launch_bounds__(1024)
+// A thread owns 4 columns (one 16-B load of x, one 8-B load of dy / dy_next per row) and walks every 8th row of its chunk; the
+// 8 row lanes of a block meet in shared memory, one atomicAdd per (chunk, column) into pre-zeroed fp32.
+__global__ void __launch_bounds__(256)
 ln_colstats_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const float* __restrict__ stats,
                    const __nv_bfloat16* __restrict__ dy_next, int rows, int h, int rows_per_chunk, float* __restrict__ d_gamma,
                    float* __restrict__ d_beta, float* __restrict__ d_bias) {
-    __shared__ float2 sg[32][33], sb[32][33], sn[32][33];
+    __shared__ float sm[3][8][128 + 4];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int c = blockIdx.x * 64 + tx * 2;
+    const int c = blockIdx.x * 128 + tx * 4;
     const int r0 = blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
     const bool bias = d_bias != nullptr;
-    float2 ag = make_float2(0.f, 0.f), ab = ag, an = ag;
+    float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f}, an[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < h) {
 #pragma unroll 4
-        for (int r = r0 + ty; r < r1; r += 32) {
+        for (int r = r0 + ty; r < r1; r += 8) {
             const size_t o = static_cast<size_t>(r) * h + c;
-            const float2 xv = *reinterpret_cast<const float2*>(x + o);
-            const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy + o));
+            const float4 xv = *reinterpret_cast<const float4*>(x + o);
+            const uint2 du = *reinterpret_cast<const uint2*>(dy + o);
             const float2 st = *reinterpret_cast<const float2*>(stats + 2 * r);
-            ag.x += d.x * (xv.x - st.x) * st.y;
-            ag.y += d.y * (xv.y - st.x) * st.y;
-            ab.x += d.x;
-            ab.y += d.y;
+            const float2 d0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&du.x));
+            const float2 d1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&du.y));
+            ag[0] += d0.x * (xv.x - st.x) * st.y;
+            ag[1] += d0.y * (xv.y - st.x) * st.y;
+            ag[2] += d1.x * (xv.z - st.x) * st.y;
+            ag[3] += d1.y * (xv.w - st.x) * st.y;
+            ab[0] += d0.x; ab[1] += d0.y; ab[2] += d1.x; ab[3] += d1.y;
             if (bias) {
-                const float2 n = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy_next + o));
-                an.x += n.x;
-                an.y += n.y;
+                const uint2 nu = *reinterpret_cast<const uint2*>(dy_next + o);
+                const float2 n0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&nu.x));
+                const float2 n1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&nu.y));
+                an[0] += n0.x; an[1] += n0.y; an[2] += n1.x; an[3] += n1.y;
             }
         }
     }
-    sg[ty][tx] = ag;
-    sb[ty][tx] = ab;
-    sn[ty][tx] = an;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        sm[0][ty][tx * 4 + k] = ag[k];
+        sm[1][ty][tx * 4 + k] = ab[k];
+        sm[2][ty][tx * 4 + k] = an[k];
+    }
     __syncthreads();
-    if (ty < 3 && c < h) {                    // warp 0: d_gamma, warp 1: d_beta, warp 2: d_bias
-        float2 (*src)[33] = ty == 0 ? sg : (ty == 1 ? sb : sn);
-        float* dst = ty == 0 ? d_gamma : (ty == 1 ? d_beta : d_bias);
-        if (dst != nullptr) {
-            float2 t = make_float2(0.f, 0.f);
-            for (int i = 0; i < 32; ++i) { t.x += src[i][tx].x; t.y += src[i][tx].y; }
-            atomicAdd(dst + c, t.x);
-            atomicAdd(dst + c + 1, t.y);
+    // 256 threads: threads 0..127 finish d_gamma and d_bias of column blockIdx.x*128 + t, threads 128..255 d_beta
+    const int t = threadIdx.x & 127, which = threadIdx.x >> 7;
+    const int col = blockIdx.x * 128 + t;
+    if (col < h) {
+        if (which == 0) {
+            float g = 0.f, n = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { g += sm[0][i][t]; n += sm[2][i][t]; }
+            atomicAdd(d_gamma + col, g);
+            if (bias) atomicAdd(d_bias + col, n);
+        } else {
+            float b = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b += sm[1][i][t];
+            atomicAdd(d_beta + col, b);
         }
     }
 }
@@ -310,11 +325,11 @@ int ln_bwd_launch(const float* x, const void* dy_bf16, const float* gamma, int r
     }
     count_launch();
     if (d_gamma != nullptr && d_beta != nullptr) {
-        const int chunks = max(1, min(64, rows / 64));
+        const int chunks = max(1, min(128, rows / 64));
         const int rpc = (rows + chunks - 1) / chunks;
         ProfScope prof(PF_ROWWISE_BWD, static_cast<double>(rows) * h * (d_bias_next ? 8.0 : 6.0), stream);
-        ln_colstats_kernel<<<dim3((h + 63) / 64, chunks), 1024, 0, stream>>>(x, dy, stats, d_bias_next ? dy_next : nullptr, rows,
-                                                                            h, rpc, d_gamma, d_beta, d_bias_next);
+        ln_colstats_kernel<<<dim3((h + 127) / 128, chunks), 256, 0, stream>>>(x, dy, stats, d_bias_next ? dy_next : nullptr, rows,
+                                                                             h, rpc, d_gamma, d_beta, d_bias_next);
         count_launch();
     }
     MOLLY_CUDA(cudaGetLastError());

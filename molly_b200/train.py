@@ -261,6 +261,10 @@ def _graphed_step(enc: PackedEncoder, n_seq: int, K: int, recompute: bool, dev) 
             if cache[coldest].busy or seen[key] < 2 * seen.get(coldest, 0):
                 return None
             del cache[coldest]
+        tape_b, ws_b, gf = _sizes(enc, n_seq, K, recompute)
+        if tape_b + ws_b + 4 * gf > 0.4 * torch.cuda.mem_get_info(dev)[0]:    # the graph's buffers stay allocated: only when
+            seen[key] = -(1 << 30)                                             # they fit comfortably (decided once per shape)
+            return None
         enc._train_captures = captures + 1
         gs = cache[key] = _GraphedStep(enc, n_seq, K, recompute, dev)
     return None if gs.busy else gs
