@@ -23,12 +23,13 @@ __device__ __forceinline__ float wsum(float v) {
 // d_x (fp32) receives dx (accumulate == 0) or has it added (accumulate != 0: the residual branch); dy_next (optional) gets
 // the bf16 copy of the NEW d_x: the output gradient of the linear layer below, which the dgrad / wgrad GEMMs read.
 // stats[row] = (mean, rstd) for ln_colstats_kernel.
+// Wide rows (VPL >= 10: ~150 registers) run 128-thread blocks so that three of them share an SM (12 warps instead of 8).
 template <int VPL>
-__global__ void __launch_bounds__(256, VPL <= 10 ? 2 : 1)
+__global__ void __launch_bounds__(VPL >= 10 ? 128 : 256)
 ln_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const float* __restrict__ gamma, int rows,
               int h, float eps, float* __restrict__ d_x, int accumulate, float* __restrict__ stats,
               __nv_bfloat16* __restrict__ dy_next) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31, nvec = h >> 2;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * h);
@@ -319,7 +320,8 @@ int ln_bwd_launch(const float* x, const void* dy_bf16, const float* gamma, int r
                        stream);
         const int vpl = (h / 4 + 31) / 32;
 #define MOLLY_LNB_CASE(V) \
-        if (vpl <= V) ln_bwd_kernel<V><<<(rows + 7) / 8, 256, 0, stream>>>(x, dy, gamma, rows, h, eps, d_x, accumulate, stats, dy_next); else
+        if (vpl <= V) ln_bwd_kernel<V><<<(rows + (V >= 10 ? 3 : 7)) / (V >= 10 ? 4 : 8), V >= 10 ? 128 : 256, 0, stream>>>( \
+            x, dy, gamma, rows, h, eps, d_x, accumulate, stats, dy_next); else
         MOLLY_LNB_CASE(1) MOLLY_LNB_CASE(2) MOLLY_LNB_CASE(4) MOLLY_LNB_CASE(8) MOLLY_LNB_CASE(10) MOLLY_LNB_CASE(20) {}
 #undef MOLLY_LNB_CASE
     }
