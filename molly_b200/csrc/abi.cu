@@ -17,6 +17,17 @@ using namespace molly;
 
 namespace {
 
+// MOLLY_RESID_REDUCE=1: the two residual GEMMs of a layer add (acc + bias) into the fp32 stream with TMA reduce-adds instead of
+// loading the residual tile, adding and storing it (bit-identical: one fp32 add per element either way)
+int residual_epilogue() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOLLY_RESID_REDUCE");
+        v = (e != nullptr && e[0] == '1') ? EPI_BIAS_ACCUM : EPI_BIAS_RESID;
+    }
+    return v;
+}
+
 constexpr size_t kAlign = 1024;
 size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
@@ -127,7 +138,7 @@ int encode(molly_encoder* e, const int64_t* ids, int n_seq, int k, void* final_o
             if ((rc = rotary_launch(qkv, M, k, h, c.num_heads, e->w.rope_cos_dev, e->w.rope_sin_dev, stream))) return rc;
         if ((rc = attention_launch(p.tm_qkv, n_seq, k, h, c.num_heads, kv_info, key_mask, attn, stream))) return rc;
         set_gemm_family(PF_GEMM_ATTN_OUT);
-        if ((rc = gemm_launch(p.tm_attn, e->tm_wo[l], &p.tc_x, M, h, h, EPI_BIAS_RESID, e->b_o[l], x, DT_F32, h, nullptr, 0,
+        if ((rc = gemm_launch(p.tm_attn, e->tm_wo[l], &p.tc_x, M, h, h, residual_epilogue(), e->b_o[l], x, DT_F32, h, nullptr, 0,
                               0, 0, 0, nullptr, stream)))
             return rc;
         // --- feed-forward block: x = x + W2 * act(W1 * LN(x) + b1) + b2   (HF:478-482)
@@ -138,7 +149,7 @@ int encode(molly_encoder* e, const int64_t* ids, int n_seq, int k, void* final_o
                               nullptr, 0, 0, 0, 0, nullptr, stream)))
             return rc;
         set_gemm_family(PF_GEMM_FFN2);
-        if ((rc = gemm_launch(p.tm_mid, e->tm_w2[l], &p.tc_x, M, h, F, EPI_BIAS_RESID, e->b_ffn2[l], x, DT_F32, h, nullptr,
+        if ((rc = gemm_launch(p.tm_mid, e->tm_w2[l], &p.tc_x, M, h, F, residual_epilogue(), e->b_ffn2[l], x, DT_F32, h, nullptr,
                               0, 0, 0, 0, nullptr, stream)))
             return rc;
     }

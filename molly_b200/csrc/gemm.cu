@@ -74,6 +74,7 @@ struct GemmParams {
     int rope_head_dim;          //   16 | 32 | 64 ; position = row % seq_k  (row index inside the padded sequence, HF:103)
     int splits;                 // split-K: the K range is cut into `splits` work items per output tile, each adding its partial
                                 //   tile into the (pre-zeroed) fp32 output with a TMA reduce-add; 1 = plain stores
+    int reduce_out;             // 1: fp32 output tiles are ADDED to what `out` holds (EPI_BIAS_ACCUM) even without a K split
 };
 
 // NeoX rotary on one 64-column chunk held by one thread (its row): x*cos + rotate_half(x)*sin per head (HF:45-54).
@@ -467,7 +468,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            if (splits > 1) tma_reduce_add_2d(&tma_c, stg, col0, row0);     // partial tile of one K split
+                            if (splits > 1 || p.reduce_out) tma_reduce_add_2d(&tma_c, stg, col0, row0);   // partial tile / accumulate
                             else tma_store_2d(&tma_c, stg, col0, row0);
                             tma_store_commit();
                         }
@@ -695,6 +696,11 @@ int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap*
     }
     GemmParams p{M, N, K, bias, out, ldo, seq_table, seq_k, B, T, k_cap, err_flag, scale_cols, scale,
                  rope_cos_t, rope_sin_t, rope_len, rope_cols, rope_head_dim};
+    if (epi == EPI_BIAS_ACCUM) {
+        MOLLY_CHECK(out_dtype == DT_F32, MOLLY_ERR_UNSUPPORTED, "gemm: the accumulating epilogue writes fp32");
+        p.reduce_out = 1;
+        epi = EPI_BIAS;
+    }
     const GemmTile tile = gemm_pick_tile(M, N, epi);
     if (tile == GEMM_TILE_128) return dispatch_epilogue<128>(ta, tb, *tc, p, epi, out_dtype, false, stream, tr);
     return dispatch_epilogue<256>(ta, tb, *tc, p, epi, out_dtype, tile == GEMM_TILE_PAIR_256, stream, tr);

@@ -6,7 +6,8 @@
 
 namespace molly {
 
-enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_GLU = 3, EPI_SCATTER = 4, EPI_BIAS_ROPE = 5 };
+enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_GLU = 3, EPI_SCATTER = 4, EPI_BIAS_ROPE = 5,
+       EPI_BIAS_ACCUM = 6 };   // fp32 out += acc + bias through a TMA reduce-add: the in-place residual update without reading it
 enum { DT_BF16 = 0, DT_F32 = 1 };
 
 void count_launch();

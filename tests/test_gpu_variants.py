@@ -82,3 +82,9 @@ def test_training_step_without_graphs():
     times: the path-level training tests)."""
     _run({"MOLLY_TRAIN_GRAPH": "0"}, "(train or backward or grad) and not cuda_graphs",
          files=("tests/test_gpu_path.py", "tests/test_gpu_real_class.py"))
+
+
+def test_residual_gemms_through_reduce_add():
+    """MOLLY_RESID_REDUCE=1: the in-place residual GEMMs add (acc + bias) into the fp32 stream with TMA reduce-adds
+    (EPI_BIAS_ACCUM) instead of loading the residual tile; the golden fixtures must still match."""
+    _run({"MOLLY_RESID_REDUCE": "1"}, "golden", files=("tests/test_gpu_path.py",))
