@@ -33,6 +33,9 @@ constexpr float BW_LOG2E = 1.4426950408889634f;
 #ifndef BW_DS2
 #define BW_DS2 1                               // 1: the dQ kernel double-buffers its dS tile (block j+1 is not held up by dQ MMA j)
 #endif
+#ifndef BW_TS
+#define BW_TS 1                                // 1: the dK'/dV kernel keeps P^T / dS^T in tensor memory (A operand of the TS-form MMA)
+#endif
 #ifndef BW_ELECT
 #define BW_ELECT 1                             // the control thread is chosen with elect.sync (see the note at the MMA loops)
 #endif
@@ -234,6 +237,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + SB, tmem_dq = tmem_base + 2 * SB;
+    // TS: dS (bf16, 32 packed columns per tile, two tiles) lives in the 64 tensor-memory columns the accumulators leave free and
+    // feeds dQ += dS K as the A operand from tensor memory: no dS stores to shared memory, no proxy fence, a third of the
+    // operand reads of that MMA.  Nothing is aliased, so S, dP of the next block are still issued under this block's work.
+    constexpr bool TS = BW_TS && SB == 64 && Cfg::DS_BUFS == 2 && 2 * SB + D + 64 <= Cfg::DQ_TMEM;
+    const uint32_t tmem_ds = tmem_base + 2 * SB + D;
 
     if (warp == 8) {
         if (BW_ELECT ? elect_one() : lane == 0) {
@@ -308,11 +316,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                 tc_fence_after();
 #pragma unroll
                 for (int s = 0; s < SB / 16; ++s) {          // dQ += dS K : A K-major (SB/64 atoms of 64 keys), B = K tile MN-major
-                    const uint64_t ad = make_smem_desc(s_ds + (j % Cfg::DS_BUFS) * Cfg::PT_BYTES + (s >> 2) * (BW_BLOCK * 128) +
-                                                           (s & 3) * 32, 16, 1024, kLayoutSW128);
                     const uint64_t bd = make_smem_desc(s_k + st * Cfg::STILE + s * 16 * Cfg::ROW_BYTES, Cfg::SBOX_BYTES,
                                                        8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
-                    umma_bf16_ss(tmem_dq, ad, bd, idesc_acc, (j | s) != 0);
+                    if constexpr (TS) {
+                        umma_bf16_ts(tmem_dq, tmem_ds + (j % Cfg::DS_BUFS) * 32 + s * 8, bd, idesc_acc, (j | s) != 0);
+                    } else {
+                        const uint64_t ad = make_smem_desc(s_ds + (j % Cfg::DS_BUFS) * Cfg::PT_BYTES + (s >> 2) * (BW_BLOCK * 128) +
+                                                               (s & 3) * 32, 16, 1024, kLayoutSW128);
+                        umma_bf16_ss(tmem_dq, ad, bd, idesc_acc, (j | s) != 0);
+                    }
                 }
                 umma_commit(&bar_kv_empty[st]);
                 BW_TL(1, j, 4);
@@ -376,10 +388,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                     }
                 }
                 if (threadIdx.x == 0) BW_TL(0, j, 4);
-                store_quarter_row(ds_tile, r, qt, v);
+                if constexpr (TS) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) pk[c] = pack_bf16x2(v[2 * c], v[2 * c + 1]);
+                    tmem_st16(tmem_ds + lane_addr + (j % Cfg::DS_BUFS) * 32 + half * 16, pk);
+                } else {
+                    store_quarter_row(ds_tile, r, qt, v);
+                }
             }
             if (threadIdx.x == 0) BW_TL(0, j, 5);
-            fence_proxy_async_smem();
+            if constexpr (TS) tmem_st_wait(); else fence_proxy_async_smem();
             tc_fence_before();
             bw_arrive(&bar_ds_full[j % Cfg::DS_BUFS]);
             if (threadIdx.x == 0) BW_TL(0, j, 6);
@@ -408,6 +427,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
                     const float* __restrict__ lse2, const float* __restrict__ delta, __nv_bfloat16* __restrict__ d_qkv) {
     using Cfg = BwdCfg<D, SB>;
     constexpr int NST = Cfg::STAGES;
+    // TS: P^T and dS^T (bf16, 32 packed columns each) overwrite the first half of the fp32 S^T / dP^T columns they were computed
+    // from and feed dV += P^T dO, dK' += dS^T Q' as the A operand FROM TENSOR MEMORY: no operand-tile stores, half the
+    // shared-memory reads per accumulate MMA.  The next block's scores are then issued AFTER those MMAs (same thread: they
+    // execute in order), so inside a CTA the block is a serial chain and the overlap comes from the second CTA of the SM.
+    constexpr bool TS = BW_TS && SB == 64;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::KV_OFF_BAR);
     uint64_t* bar_kv = bars + 0;
@@ -513,7 +537,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
                     mbar_wait(&bar_q_empty[(i - 1) % NST], ((i - 1) / NST) & 1);
                     load_q(i - 1 + NST);
                 }
-                if (NST >= 2 && i + 1 < nq) {
+                if (!TS && NST >= 2 && i + 1 < nq) {
                     mbar_wait(bar_s_free, i & 1);
                     tc_fence_after();
                     issue_scores(i + 1);
@@ -522,18 +546,24 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
                 tc_fence_after();
 #pragma unroll
                 for (int s = 0; s < SB / 16; ++s) {          // contraction over the SB queries of the block
-                    const uint32_t a_off = (s >> 2) * (BW_BLOCK * 128) + (s & 3) * 32;
-                    const uint64_t pd = make_smem_desc(s_pt + a_off, 16, 1024, kLayoutSW128);
-                    const uint64_t dd = make_smem_desc(s_dst + a_off, 16, 1024, kLayoutSW128);
                     const uint64_t bo = make_smem_desc(s_do + st * Cfg::STILE + s * 16 * Cfg::ROW_BYTES, Cfg::SBOX_BYTES,
                                                        8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
                     const uint64_t bq = make_smem_desc(s_q + st * Cfg::STILE + s * 16 * Cfg::ROW_BYTES, Cfg::SBOX_BYTES,
                                                        8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
-                    umma_bf16_ss(tmem_dv, pd, bo, idesc_acc, (i | s) != 0);      // dV  += P^T  dO
-                    umma_bf16_ss(tmem_dk, dd, bq, idesc_acc, (i | s) != 0);      // dK' += dS^T Q'
+                    if constexpr (TS) {                      // A = 16 queries = 8 packed columns of tensor memory
+                        umma_bf16_ts(tmem_dv, tmem_st + s * 8, bo, idesc_acc, (i | s) != 0);     // dV  += P^T  dO
+                        umma_bf16_ts(tmem_dk, tmem_dpt + s * 8, bq, idesc_acc, (i | s) != 0);    // dK' += dS^T Q'
+                    } else {
+                        const uint32_t a_off = (s >> 2) * (BW_BLOCK * 128) + (s & 3) * 32;
+                        const uint64_t pd = make_smem_desc(s_pt + a_off, 16, 1024, kLayoutSW128);
+                        const uint64_t dd = make_smem_desc(s_dst + a_off, 16, 1024, kLayoutSW128);
+                        umma_bf16_ss(tmem_dv, pd, bo, idesc_acc, (i | s) != 0);
+                        umma_bf16_ss(tmem_dk, dd, bq, idesc_acc, (i | s) != 0);
+                    }
                 }
                 umma_commit(&bar_q_empty[st]);
                 if (i == nq - 1) umma_commit(bar_out_full);
+                if (TS && i + 1 < nq) issue_scores(i + 1);   // behind the MMAs that read the columns S^T / dP^T(i+1) overwrite
                 if (NST == 1 && i + 1 < nq) {
                     mbar_wait(&bar_q_empty[0], i & 1);
                     load_q(i + 1);
@@ -565,10 +595,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
             }
             mbar_wait(bar_sdp_full, i & 1);
             tc_fence_after();
-            if (i > 0) {                                     // dV / dK MMAs (i-1) have drained the P^T / dS^T tiles ...
+            if (!TS && i > 0) {                              // dV / dK MMAs (i-1) have drained the P^T / dS^T tiles ...
                 mbar_wait(&bar_q_empty[(i - 1) % NST], ((i - 1) / NST) & 1);
                 tc_fence_after();
-            }
+            }                                                // (TS: sdp_full(i) was committed behind those MMAs by the same thread)
             // ... and, since they only ran after all 256 arrivals on pt_full(i-1), every thread is done reading the previous
             // block's statistics: the single buffer can be overwritten
             if (r < SB) (half == 0 ? st_lse : st_delta)[r] = my_stat;
@@ -580,7 +610,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
                 tmem_ld32(tmem_st + lane_addr + qt * 32, sr);
                 tmem_ld32(tmem_dpt + lane_addr + qt * 32, pr);
                 tmem_ld_wait();
-                if (qq == Cfg::QPH - 1) {
+                if (!TS && qq == Cfg::QPH - 1) {
                     tc_fence_before();
                     bw_arrive(bar_s_free);
                 }
@@ -603,10 +633,24 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
                         dv[c] = p * (__uint_as_float(pr[c]) - ds[e]);
                     }
                 }
-                store_quarter_row(pt_tile, r, qt, pv);
-                store_quarter_row(dst_tile, r, qt, dv);
+                if constexpr (TS) {
+                    uint32_t pp[16], dp[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        pp[c] = pack_bf16x2(pv[2 * c], pv[2 * c + 1]);
+                        dp[c] = pack_bf16x2(dv[2 * c], dv[2 * c + 1]);
+                    }
+                    // warps w and w+4 share these TMEM lanes: the other half's thread must have READ columns 16..31 of S^T / dP^T
+                    // before this one's packed words land there
+                    named_bar_sync(2, BW_COMPUTE);
+                    tmem_st16(tmem_st + lane_addr + half * 16, pp);
+                    tmem_st16(tmem_dpt + lane_addr + half * 16, dp);
+                } else {
+                    store_quarter_row(pt_tile, r, qt, pv);
+                    store_quarter_row(dst_tile, r, qt, dv);
+                }
             }
-            fence_proxy_async_smem();
+            if constexpr (TS) tmem_st_wait(); else fence_proxy_async_smem();
             tc_fence_before();
             bw_arrive(bar_pt_full);
         }

@@ -715,9 +715,10 @@ int gemm_make_map_mn(CUtensorMap* t, const void* base, int rows_k, int cols_mn, 
 namespace {
 // K splits of a wgrad: fewest waves per split (ceil(tiles * s / slots) / s) with a small charge per extra partial tile
 int pick_splits(int tiles, int slots, int num_kb) {
+    static const int max_splits = [] { const char* e = getenv("MOLLY_WGRAD_MAX_SPLITS"); return e ? atoi(e) : 8; }();
     int best = 1;
     double best_cost = 1e30;
-    for (int s = 1; s <= 8 && s * 4 <= num_kb; ++s) {
+    for (int s = 1; s <= max_splits && s * 4 <= num_kb; ++s) {
         const int kb_per = (num_kb + s - 1) / s;
         if ((num_kb + kb_per - 1) / kb_per != s) continue;                 // an empty split would leave a tile unwritten
         const double cost = static_cast<double>((tiles * s + slots - 1) / slots) / s * (1.0 + 0.01 * (s - 1));

@@ -166,6 +166,7 @@ class EncoderTape:
         self.recompute = False
         self.ids = None
         self.graph = None                      # the _GraphedStep whose buffers this tape borrows (None: eager)
+        self.gen = 0                           # ... and the generation of that loan
 
 
 def _save_activations(enc: PackedEncoder, n_tokens: int) -> bool:
@@ -217,16 +218,31 @@ class _GraphedStep:
         self.fwd = self.bwd = None
         self.fwd_launches = self.bwd_launches = 0
         self._owner = None                     # weak reference to the tape of the forward whose backward is still to come
+        self.gen = 0                           # bumped by every forward that takes the buffers: a tape knows if it was overtaken
+        self._passed_over = 0
+
+    def try_acquire(self, tape) -> bool:
+        """Take the buffers for ``tape``'s forward.  Refused while an earlier forward still waits for its backward (its tape is
+        alive) -- the caller then runs eagerly -- except that a forward which has been passed over ``_GRAPH_ABANDON`` times is
+        taken for abandoned (a forward in training mode whose loss was never back-propagated) and loses the buffers: its
+        backward, should it still come, raises."""
+        if self._owner is not None and self._owner() is not None:
+            self._passed_over += 1
+            if self._passed_over <= _GRAPH_ABANDON:
+                return False
+        self._owner = weakref.ref(tape)
+        self._passed_over = 0
+        self.gen += 1
+        tape.gen = self.gen
+        return True
 
     @property
     def busy(self) -> bool:
         return self._owner is not None and self._owner() is not None
 
-    def acquire(self, tape) -> None:
-        self._owner = weakref.ref(tape)
-
-    def release(self) -> None:
-        self._owner = None
+    def release(self, tape) -> None:
+        if tape.gen == self.gen:
+            self._owner = None
 
 
 def _graphs_enabled() -> bool:
@@ -239,6 +255,7 @@ def _graphs_enabled() -> bool:
 _GRAPH_MIN_SIGHTINGS = 3       # a shape is captured on its third use ...
 _GRAPH_SHAPES = 2              # ... at most two shapes are held per encoder (the tape is gigabytes) ...
 _GRAPH_MAX_CAPTURES = 8        # ... and an encoder whose shapes keep changing stops capturing (a capture costs ~0.1 s)
+_GRAPH_ABANDON = 3             # forwards that may pass over a pending one before its buffers are reclaimed
 
 
 def _graphed_step(enc: PackedEncoder, n_seq: int, K: int, recompute: bool, dev) -> Optional[_GraphedStep]:
@@ -267,7 +284,7 @@ def _graphed_step(enc: PackedEncoder, n_seq: int, K: int, recompute: bool, dev) 
             return None
         enc._train_captures = captures + 1
         gs = cache[key] = _GraphedStep(enc, n_seq, K, recompute, dev)
-    return None if gs.busy else gs
+    return gs
 
 
 def _capture(fn):
@@ -299,7 +316,7 @@ def encoder_forward_train(enc: PackedEncoder, ids: torch.Tensor) -> Tuple[torch.
     tape = EncoderTape()
     tape.recompute = not _save_activations(enc, n_seq * K)
     gs = _graphed_step(enc, n_seq, K, tape.recompute, dev)
-    if gs is not None:
+    if gs is not None and gs.try_acquire(tape):
         gs.ids.copy_(ids)
         if gs.fwd is None:                     # (the launches were counted while capturing: this first replay is not added)
             gs.fwd, gs.fwd_launches = _capture(lambda: _call_fwd(enc, gs.ids, n_seq, K, gs.out, gs.tape, gs.tape_bytes,
@@ -307,7 +324,6 @@ def encoder_forward_train(enc: PackedEncoder, ids: torch.Tensor) -> Tuple[torch.
         else:
             ops.add_kernel_launches(gs.fwd_launches)
         gs.fwd.replay()
-        gs.acquire(tape)                       # (a tape that dies without a backward frees the step as well)
         tape.ids, tape.buf, tape.graph = gs.ids, gs.tape, gs
         return gs.out, tape
     tape.ids = ids
@@ -346,6 +362,9 @@ def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor,
         raise ValueError("encoder_backward: d_out must be contiguous bf16 [n_seq*K, h]")
     plan = grad_plan(enc)
     gs: Optional[_GraphedStep] = tape.graph
+    if gs is not None and tape.gen != gs.gen:
+        raise RuntimeError("encoder_backward: the CUDA-graph buffers of this forward were taken over by a later training forward "
+                           f"of the same encoder and shape (it was passed over more than {_GRAPH_ABANDON} times)")
     tape_bytes, ws_bytes, grad_floats = _sizes(enc, n_seq, K, tape.recompute)
     assert grad_floats == plan.total
     graphed = gs is not None and reducer is None and _graphs_enabled()
@@ -395,5 +414,5 @@ def encoder_backward(enc: PackedEncoder, tape: EncoderTape, d_out: torch.Tensor,
         grads.update(plan.tail_views(tail))
     finally:
         if gs is not None:
-            gs.release()
+            gs.release(tape)
     return plan.finalize_(grads)

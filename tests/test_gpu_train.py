@@ -270,10 +270,20 @@ def test_graphed_training_step_equals_eager(spec_name):
             assert_close(f"{spec_name} re-entrant a {name}", ga[name].float().cpu(), eager[1][1][name].cpu(), 1e-4)
             assert_close(f"{spec_name} re-entrant b {name}", gb[name].float().cpu(), eager[2][1][name].cpu(), 1e-4)
         del tape_a, tape_b
-        # a forward whose backward never comes (its tape dies) does not block the graphs for good
+        # a forward whose backward never comes does not block the graphs for good: it is passed over a few times (eager steps),
+        # then its buffers are reclaimed, and its backward -- should it still come -- is refused
         out_c, tape_c = train.encoder_forward_train(enc, idss[0])
-        del out_c, tape_c
-        _, tape_d = train.encoder_forward_train(enc, idss[0])
-        assert tape_d.graph is not None
+        assert tape_c.graph is not None
+        for _ in range(train._GRAPH_ABANDON):
+            _, t, = train.encoder_forward_train(enc, idss[1])
+            assert t.graph is None
+            train.encoder_backward(enc, t, d_outs[1])
+        out_d, tape_d = train.encoder_forward_train(enc, idss[2])
+        assert tape_d.graph is not None and torch.equal(out_d, eager[2][0])
+        gd = train.encoder_backward(enc, tape_d, d_outs[2])
+        assert_close(f"{spec_name} after reclaiming", gd["esm.embeddings.word_embeddings.weight"].float().cpu(),
+                     eager[2][1]["esm.embeddings.word_embeddings.weight"].cpu(), 1e-4)
+        with pytest.raises(RuntimeError, match="taken over"):
+            train.encoder_backward(enc, tape_c, d_outs[0])
     finally:
         enc.close()
