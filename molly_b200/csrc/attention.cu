@@ -53,6 +53,11 @@ __device__ long long* d_attn_tl = nullptr;
 #define ATT_MAX2 0
 #endif
 #ifndef ATT_THREAD_ARRIVE
+#ifndef ATT_TS
+#define ATT_TS 0        // 1: P (bf16) lives in the tensor-memory columns S and O leave free and feeds O += P V as the A operand
+#endif                  //    from tensor memory (TS-form MMA) when they fit: KVB + D + KVB/2 <= 256 (head_dim <= 64 at 128 keys).
+                        //    Measured 555 us against 542 (it costs 80 B of spills at the 168-register cap): off.  The same change
+                        //    is worth 11-13 % in the attention BACKWARD kernels, whose small MMAs are bound by operand reads.
 #ifndef ATT_ELECT
 #define ATT_ELECT 1
 #endif
@@ -269,6 +274,8 @@ __device__ __forceinline__ void softmax_block(uint64_t* bar_s_full, uint32_t s_p
     const float m_use = (m_run == -CUDART_INF_F) ? 0.f : m_run;
     // exp2(s*log2e - m) and the row sum with packed fp32x2 FMA / ADD (FFMA2 / FADD2): half the issue slots
     if (tl_on) TL(tl_base + 2);
+    constexpr bool TS = ATT_TS && (KVB + D + KVB / 2 <= AttnCfg<D, KVB>::TMEM_COLS);
+    uint32_t pk[TS ? KVB / 2 : 1];                    // TS: P is packed to bf16 pairs as it is produced (half the live registers)
     const uint64_t sc2 = pack_f32x2(LOG2E, LOG2E), nm2 = pack_f32x2(-m_use, -m_use);
     uint64_t sum2[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
 #pragma unroll
@@ -291,6 +298,7 @@ __device__ __forceinline__ void softmax_block(uint64_t* bar_s_full, uint32_t s_p
 #endif
             }
             sum2[u] = add_f32x2(sum2[u], pack_f32x2(s[i + 2 * u], s[i + 2 * u + 1]));
+            if constexpr (TS) pk[(i >> 1) + u] = pack_bf16x2(s[i + 2 * u], s[i + 2 * u + 1]);
         }
     }
     float sa, sb, sc, sd;
@@ -303,6 +311,12 @@ __device__ __forceinline__ void softmax_block(uint64_t* bar_s_full, uint32_t s_p
         mbar_wait(bar_pv_done, pv_parity);
         tc_fence_after();
     }
+    if constexpr (TS) {
+        // P -> tensor memory, bf16, two keys per 32-bit column, right behind O
+        const uint32_t tmem_p = tmem_o + D;
+#pragma unroll
+        for (int c = 0; c < KVB / 16; ++c) tmem_st8(tmem_p + lane_addr + c * 8, pk + c * 8);
+    } else {
     // P -> smem, bf16, K-major with the 128-B swizzle: 16-B chunk c of row r lands at chunk (c ^ (r & 7))
 #if ATT_ABLATE & 2
     if (l_run == 123.456f)
@@ -320,6 +334,7 @@ __device__ __forceinline__ void softmax_block(uint64_t* bar_s_full, uint32_t s_p
             *reinterpret_cast<uint4*>(p_row + a * (ATT_BLOCK * 128) + ((c ^ sw) << 4)) = u;
         }
     }
+    }
     // rescale the running O accumulator (complete through block j-1, see the wait above)
     if (!first && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll
@@ -331,9 +346,9 @@ __device__ __forceinline__ void softmax_block(uint64_t* bar_s_full, uint32_t s_p
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tmem_st16(tmem_o + lane_addr + c * 16, o);
         }
-        tmem_st_wait();
+        if constexpr (!TS) tmem_st_wait();
     }
-    fence_proxy_async_smem();
+    if constexpr (TS) tmem_st_wait(); else fence_proxy_async_smem();
     tc_fence_before();
     warp_arrive(bar_p_full);
     if (tl_on) TL(tl_base + 4);
@@ -497,11 +512,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
                     tc_fence_after();
 #pragma unroll
                     for (int s = 0; s < ((ATT_ABLATE & 4) ? 1 : KVB / 16); ++s) {
-                        const uint64_t pd = make_smem_desc(s_p + (s >> 2) * (ATT_BLOCK * 128) + (s & 3) * 32, 16, 1024,
-                                                           kLayoutSW128);
                         const uint64_t vd = make_smem_desc(s_v + st * Cfg::KV_TILE_BYTES + s * 16 * Cfg::ROW_BYTES,
                                                            Cfg::KV_BOX_BYTES, 8 * Cfg::ROW_BYTES, Cfg::LAYOUT);
-                        umma_bf16_ss(tmem_o, pd, vd, idesc_pv, (j | s) != 0);
+                        if constexpr (ATT_TS && (KVB + D + KVB / 2 <= Cfg::TMEM_COLS)) {   // A = 16 keys = 8 packed TMEM columns
+                            umma_bf16_ts(tmem_o, tmem_o + D + s * 8, vd, idesc_pv, (j | s) != 0);
+                        } else {
+                            const uint64_t pd = make_smem_desc(s_p + (s >> 2) * (ATT_BLOCK * 128) + (s & 3) * 32, 16, 1024,
+                                                               kLayoutSW128);
+                            umma_bf16_ss(tmem_o, pd, vd, idesc_pv, (j | s) != 0);
+                        }
                     }
                     umma_commit(&bar_kv_empty[st]);          // PV(g) done: stage st, the P buffer and O are free
                     if (last) {
