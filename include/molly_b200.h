@@ -261,7 +261,9 @@ int molly_encode_train_fwd(molly_encoder_t* enc, const int64_t* ids_dev, int32_t
 /* Backward of layers layer_begin, layer_begin-1, ..., layer_end (layer index num_layers = emb_layer_norm_after, which needs
  * d_out_dev = d(loss)/d(hidden_states[-1]), bf16 [n_seq*k, h]).  The running gradient of the residual stream lives in the
  * first n_seq*k*h floats of the workspace between calls: after layer 0 it is d(embedding output), the input of
- * molly_scatter_add_rows for the embedding tables.  The word / position embedding slots of grads_dev are not written here. */
+ * molly_scatter_add_rows for the embedding tables.  The word / position embedding slots of grads_dev are not written here.
+ * Calls must walk the layers top-down without gaps (num_layers first): each layer's backward zeroes the gradient group of the
+ * layer below it and deposits that layer's b_ffn2 gradient there before that layer's own call accumulates into the group. */
 int molly_encode_train_bwd(molly_encoder_t* enc, int32_t n_seq, int32_t k_tokens, void* tape_dev, size_t tape_bytes,
                            int32_t recompute, const void* d_out_dev, float* grads_dev, void* workspace_dev,
                            size_t workspace_bytes, int32_t layer_begin, int32_t layer_end, void* stream);

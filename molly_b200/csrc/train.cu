@@ -1,11 +1,12 @@
 // Native orchestration of the encoder TRAINING step (`--train-bio`: src/utils/tools.py:313-331 unfreezes
 // the encoders): one C call runs the forward of every layer and keeps what the backward needs in a caller-owned tape; one
 // C call runs the backward of a range of layers and leaves every parameter gradient in a flat fp32 buffer whose layout the
-// library defines (molly_encoder_grad_layout).  The host enqueues ~35 launches per layer from C++ at a few microseconds
-// each; the first version did this from Python, one ctypes call per kernel, and the step was bound by the host.
+// library defines (molly_encoder_grad_layout).  The host enqueues ~27 launches per layer from C++ (the first version did this
+// from Python, one ctypes call per kernel); once a shape is steady state the Python side captures the two calls into CUDA graphs.
 //
 // Autograd of the HF modules the kernels replace (HF EsmLayer, HF:446-482):
-//     nn.Linear   dgrad: the tcgen05 GEMM on the transposed weight        wgrad / bias: linear_wgrad_launch
+//     nn.Linear   dgrad / wgrad: the main tcgen05 GEMM with MN-major operands (gemm_launch_mn: the weight and the activations
+//                 are read as they lie in memory, the wgrad is split over K); bias: column sums
 //     attention   attention_bwd_launch (dQ / dK,dV kernels) from the forward's row log-sum-exp
 //     LayerNorm   ln_bwd_launch        GELU / gated SiLU   act_fwd_bwd_launch
 //     rotary      the forward kernel with -sin (inverse rotation) and the q scale folded in
