@@ -228,6 +228,8 @@ class PackedEncoder:
         return int(self._lib.molly_encoder_workspace_bytes(self.handle, n_seq, k_tokens))
 
     def close(self) -> None:
+        for attr in ("_train_graphs", "_train_shapes_seen", "_grad_plan"):     # graphs of the training step hold gigabytes
+            self.__dict__.pop(attr, None)
         if getattr(self, "_handle", None):
             self._lib.molly_encoder_destroy(self._handle)
             self._handle = C.c_void_p()
