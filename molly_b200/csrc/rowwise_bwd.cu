@@ -205,7 +205,7 @@ gelu_fwd_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* 
     if (d_act != nullptr) dv = *reinterpret_cast<const uint4*>(d_act + i);
     uint4 av, gv;
     gelu_eight(pv, dv, av, gv, nullptr);
-    *reinterpret_cast<uint4*>(act + i) = av;
+    if (act != nullptr) *reinterpret_cast<uint4*>(act + i) = av;          // (the training tape may already hold act)
     if (d_act != nullptr) *reinterpret_cast<uint4*>(d_pre + i) = gv;
 }
 
@@ -259,7 +259,7 @@ glu_fwd_bwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __r
         ap[k] = __float2bfloat16(sl * ab.y);
         gp[k] = __floats2bfloat162_rn(d * ab.y * sig * (1.0f + ab.x * (1.0f - sig)), d * sl);
     }
-    *reinterpret_cast<uint4*>(act + i) = av;
+    if (act != nullptr) *reinterpret_cast<uint4*>(act + i) = av;
     if (d_act != nullptr) {
         *reinterpret_cast<uint4*>(d_u + 2 * i) = gv[0];
         *reinterpret_cast<uint4*>(d_u + 2 * i + 8) = gv[1];

@@ -43,7 +43,7 @@ Dims dims_of(const molly_encoder* e, int n_seq, int k) {
 // the per-layer activations for every layer (recompute == 0) or one slot the backward refills layer by layer.
 struct Tape {
     size_t x_in, x_stride, kv_info, key_mask, mid, slot0, slot_stride, total;
-    size_t ln1, qkv, attn, lse2, x_mid, ln2, pre;          // offsets inside a slot
+    size_t ln1, qkv, attn, lse2, x_mid, ln2, pre, act;     // offsets inside a slot
     int slots;
 };
 
@@ -55,7 +55,7 @@ Tape tape_layout(const Dims& d, int recompute) {
     t.x_in = o;     o += t.x_stride * (d.L + 1);
     t.kv_info = o;  o += align_up(static_cast<size_t>(d.n_seq) * 2 * 4);
     t.key_mask = o; o += align_up(M);
-    t.mid = o;      o += align_up(M * d.F * 2);              // forward scratch: act(pre), the A operand of the FFN2 GEMM
+    t.mid = o;      o += align_up(M * d.F * 2);              // forward scratch (recompute mode): act(pre), the A operand of FFN2
     size_t s = 0;
     t.ln1 = s;   s += align_up(M * h * 2);
     t.qkv = s;   s += align_up(M * 3 * h * 2);
@@ -64,7 +64,8 @@ Tape tape_layout(const Dims& d, int recompute) {
     t.x_mid = s; s += align_up(M * h * 4);
     t.ln2 = s;   s += align_up(M * h * 2);
     t.pre = s;   s += align_up(M * d.F1 * 2);
-    t.slot_stride = s;
+    t.act = s;   s += recompute ? 0 : align_up(M * d.F * 2);   // act(pre): the forward produces it anyway; kept, the backward
+    t.slot_stride = s;                                          // neither recomputes nor rewrites it (recompute mode: scratch)
     t.slots = recompute ? 1 : d.L;
     t.slot0 = o;    o += s * t.slots;
     t.total = o;
@@ -229,8 +230,9 @@ int forward(const molly_encoder* e, const int64_t* ids, int n_seq, int k, void* 
         uint8_t* slot = tape + t.slot0 + (recompute ? 0 : t.slot_stride * l);
         if ((rc = layer_forward_keep(e, d, l, x_at(l), slot, t, kv_info, key_mask, s))) return rc;
         // finish the layer: FFN activation + FFN2 on top of x_mid
-        if ((rc = act_fwd_bwd_launch(d.glu, slot + t.pre, nullptr, M, d.F, mid, nullptr, s))) return rc;
-        if ((rc = gemm_residual(mid, e->tm_w2[l], M, h, d.F, e->b_ffn2[l], reinterpret_cast<float*>(slot + t.x_mid),
+        void* act = recompute ? mid : static_cast<void*>(slot + t.act);
+        if ((rc = act_fwd_bwd_launch(d.glu, slot + t.pre, nullptr, M, d.F, act, nullptr, s))) return rc;
+        if ((rc = gemm_residual(act, e->tm_w2[l], M, h, d.F, e->b_ffn2[l], reinterpret_cast<float*>(slot + t.x_mid),
                                 x_at(l + 1), s)))
             return rc;
     }
@@ -250,7 +252,7 @@ int dgrad(const void* d_out, const void* w, int M, int N, int K, void* w_t, void
 
 int backward_layer(const molly_encoder* e, const Dims& d, int l, const float* x_in, const uint8_t* slot, const Tape& t,
                    const int32_t* kv_info, const uint8_t* key_mask, uint8_t* ws, const Scratch& sc, float* g, const GradLayout& gl,
-                   cudaStream_t s) {
+                   bool act_kept, cudaStream_t s) {
     const auto& c = e->cfg;
     const int M = d.M, h = d.h, F = d.F, F1 = d.F1;
     float* d_x = reinterpret_cast<float*>(ws + sc.d_x);
@@ -271,8 +273,10 @@ int backward_layer(const molly_encoder* e, const Dims& d, int l, const float* x_
     // with TMA reduce-adds) and its b_ffn2 gradient (column sums of dy) is already in place.
     // ---- feed-forward block: x_out = x_mid + W2 act(W1 LN2(x_mid) + b1) + b2
     if ((rc = dgrad(dy, e->w_ffn2[l], M, h, F, w_t, d_act, s))) return rc;
-    if ((rc = act_fwd_bwd_launch(d.glu, slot + t.pre, d_act, M, F, act, d_pre, s))) return rc;
-    if ((rc = linear_wgrad_launch(dy, act, M, h, F, G(MOLLY_GRAD_W_FFN2), nullptr, s, true))) return rc;
+    // d_pre = d_act * act'(pre); act itself comes from the tape when the forward kept it, else it is rebuilt in the same pass
+    const void* act_in = act_kept ? static_cast<const void*>(slot + t.act) : act;
+    if ((rc = act_fwd_bwd_launch(d.glu, slot + t.pre, d_act, M, F, act_kept ? nullptr : act, d_pre, s))) return rc;
+    if ((rc = linear_wgrad_launch(dy, act_in, M, h, F, G(MOLLY_GRAD_W_FFN2), nullptr, s, true))) return rc;
     // (the GELU backward is bound by instruction issue: with the b_ffn1 column sums fused in it took 92 us against 45 + 17 us
     //  for the plain kernel and a separate column-sum pass over d_pre, so the bias gradient stays with the wgrad)
     if ((rc = linear_wgrad_launch(d_pre, slot + t.ln2, M, F1, h, G(MOLLY_GRAD_W_FFN1), G(MOLLY_GRAD_B_FFN1), s, true))) return rc;
@@ -378,7 +382,8 @@ int molly_encode_train_bwd(molly_encoder_t* enc, int32_t n_seq, int32_t k_tokens
         }
         uint8_t* slot = tape + t.slot0 + (recompute ? 0 : t.slot_stride * l);
         if (recompute && (rc = layer_forward_keep(enc, d, l, x_at(l), slot, t, kv_info, key_mask, s))) return rc;
-        if ((rc = backward_layer(enc, d, l, x_at(l), slot, t, kv_info, key_mask, ws, sc, grads_dev + gl.group * l, gl, s)))
+        if ((rc = backward_layer(enc, d, l, x_at(l), slot, t, kv_info, key_mask, ws, sc, grads_dev + gl.group * l, gl, !recompute,
+                                 s)))
             return rc;
     }
     return MOLLY_OK;

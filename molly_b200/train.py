@@ -159,7 +159,8 @@ def reduce_schedule(enc: PackedEncoder) -> List[List[Tuple[str, Tuple[int, ...]]
 
 class EncoderTape:
     """What the training forward keeps for the backward: one device buffer laid out by the library (fp32 layer inputs,
-    key mask, and either every layer's activations or one activation slot the backward refills: ``recompute``)."""
+    key mask, and either every layer's activations -- LN outputs, q/k/v, attention output, log-sum-exp, the FFN pre-activation
+    and its activation -- or one activation slot the backward refills: ``recompute``)."""
 
     def __init__(self):
         self.buf: Optional[torch.Tensor] = None
@@ -179,7 +180,7 @@ def _save_activations(enc: PackedEncoder, n_tokens: int) -> bool:
     if n_tokens not in cache:          # decided once per batch size: cudaMemGetInfo costs ~0.5 ms of device idle time per call
         cfg = enc.cfg
         f_pre = cfg.intermediate_size * (2 if cfg.ffn_type == "glu" else 1)
-        per_layer = n_tokens * (cfg.hidden_size * (4 + 2 + 6 + 2 + 4 + 2) + f_pre * 2)
+        per_layer = n_tokens * (cfg.hidden_size * (4 + 2 + 6 + 2 + 4 + 2) + f_pre * 2 + cfg.intermediate_size * 2)
         cache[n_tokens] = per_layer * cfg.num_hidden_layers < 0.35 * torch.cuda.mem_get_info(enc.device)[0]
     return cache[n_tokens]
 
