@@ -320,3 +320,33 @@ def test_nt_v2_loader_variants_pack_what_the_module_computes():
     stock = EncoderConfig.from_hf_config(hf_cfg(), {"esm.encoder.layer.0.intermediate.dense.weight": W[:F],
                                                     "esm.encoder.layer.0.intermediate.dense.bias": b[:F]})
     assert (stock.ffn_type, stock.ffn_bias) == ("gelu", True)
+
+
+def test_graphed_step_ownership_protocol():
+    """``train._GraphedStep`` (buffers of the CUDA-graphed training step): one forward owns them until its backward releases
+    them; a second forward in between is refused (it runs eagerly); a tape that dies frees them; a forward that is passed over
+    more than ``_GRAPH_ABANDON`` times loses them and its late backward is detectable by its generation.  Pure host logic."""
+    from molly_b200 import train
+
+    class Tape:
+        gen = 0
+
+    gs = object.__new__(train._GraphedStep)                # no device buffers: only the ownership state
+    gs._owner, gs.gen, gs._passed_over = None, 0, 0
+    a, b = Tape(), Tape()
+    assert gs.try_acquire(a) and a.gen == 1 and gs.busy
+    assert not gs.try_acquire(b) and b.gen == 0            # re-entrant forward: refused, buffers untouched
+    gs.release(a)
+    assert not gs.busy
+    assert gs.try_acquire(b) and b.gen == 2
+    del b                                                  # its backward never comes and the tape dies
+    assert not gs.busy
+    c = Tape()
+    assert gs.try_acquire(c) and c.gen == 3
+    others = [Tape() for _ in range(train._GRAPH_ABANDON + 1)]
+    assert [gs.try_acquire(t) for t in others] == [False] * train._GRAPH_ABANDON + [True]
+    assert others[-1].gen == 4 and c.gen != gs.gen         # c was taken for abandoned: its backward must refuse (gen mismatch)
+    gs.release(c)                                          # a stale release does not free the new owner
+    assert gs.busy
+    gs.release(others[-1])
+    assert not gs.busy
