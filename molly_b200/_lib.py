@@ -69,7 +69,7 @@ PROFILE_FAMILIES = 14
 GRAD_TAIL_FINAL_LN_W, GRAD_TAIL_FINAL_LN_B, GRAD_TAIL_WORD_EMB, GRAD_TAIL_POS_EMB, GRAD_TAIL_SLOTS = range(5)
 _i32, _i64p, _vp, _sz = C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t
 
-# name -> (restype, argtypes); must list every function declared in include/molly_b200.h (tests/test_abi.py checks)
+# name -> (restype, argtypes); must list every function declared in include/molly_b200.h (tests/test_host_logic.py::test_abi_library_exports_every_declared_symbol checks)
 SIGNATURES = {
     "molly_encoder_create": (C.c_int, [C.POINTER(EncoderConfig), C.POINTER(EncoderWeights), C.POINTER(C.c_void_p)]),
     "molly_encoder_destroy": (None, [C.c_void_p]),
